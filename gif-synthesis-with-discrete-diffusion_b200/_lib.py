@@ -1,0 +1,99 @@
+"""ctypes binding of `csrc/libd3pm_b200.so` (the C ABI declared in `include/d3pm_b200.h`).
+
+There is no fallback: if the library is missing or a call fails, `D3PMError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libd3pm_b200.so"
+
+# every symbol include/d3pm_b200.h declares (tests check the built library exports exactly these)
+EXPORTED_SYMBOLS = (
+    "d3pm_version", "d3pm_last_error", "d3pm_build_coef_table", "d3pm_fused_step", "d3pm_philox_uniform",
+    "d3pm_q_posterior", "d3pm_gumbel_argmax", "d3pm_tokens_to_log_onehot", "d3pm_argmax_classes",
+    "d3pm_to_token_major",
+)
+
+COEF_STRIDE = 32
+SAMPLE_NONE, SAMPLE_GUMBEL, SAMPLE_PHILOX, SAMPLE_PHILOX_EXACT = 0, 1, 2, 3
+STATUS_BAD_T, STATUS_BAD_TOKEN, STATUS_FALLBACK = 1, 2, 4
+
+
+class D3PMError(RuntimeError):
+    """Raised when libd3pm_b200.so is missing or one of its entry points returns an error."""
+
+
+class StepDesc(ctypes.Structure):
+    """Mirror of `d3pm_step_desc`."""
+    _fields_ = [
+        ("logits_c", c_void_p), ("logits_u", c_void_p), ("x_t", c_void_p), ("t", c_void_p),
+        ("coef_table", c_void_p), ("gumbel", c_void_p),
+        ("x_prev", c_void_p), ("post", c_void_p), ("recon", c_void_p), ("gap", c_void_p), ("status", c_void_p),
+        ("B", c_int32), ("N", c_int32), ("K", c_int32), ("T", c_int32),
+        ("pitch_logits", c_int64), ("pitch_gumbel", c_int64), ("pitch_out", c_int64),
+        ("guidance_scale", c_float), ("sample_mode", c_int32), ("gumbel_is_uniform", c_int32),
+        ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64),
+        ("thin_factor", c_float), ("stream", c_void_p),
+    ]
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.environ.get("D3PM_B200_LIB", os.path.join(_HERE, "csrc", _LIB_NAME))
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the shared library once; raise `D3PMError` (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.isfile(path):
+        raise D3PMError(
+            f"{path} not found: build it with `python __graft_entry__.py build` (or `make -C "
+            f"{os.path.join(_HERE, 'csrc')}`); this package has no non-CUDA fallback")
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as exc:  # e.g. libcudart missing
+        raise D3PMError(f"cannot load {path}: {exc}") from exc
+    missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise D3PMError(f"{path} lacks symbols {missing}; rebuild it")
+
+    lib.d3pm_version.restype = c_int
+    lib.d3pm_version.argtypes = []
+    lib.d3pm_last_error.restype = c_char_p
+    lib.d3pm_last_error.argtypes = []
+    lib.d3pm_build_coef_table.restype = c_int
+    lib.d3pm_build_coef_table.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.d3pm_fused_step.restype = c_int
+    lib.d3pm_fused_step.argtypes = [POINTER(StepDesc)]
+    lib.d3pm_philox_uniform.restype = c_int
+    lib.d3pm_philox_uniform.argtypes = [c_void_p, c_int64, c_int, c_int64, c_uint64, c_uint64, c_int64, c_void_p]
+    lib.d3pm_q_posterior.restype = c_int
+    lib.d3pm_q_posterior.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.d3pm_gumbel_argmax.restype = c_int
+    lib.d3pm_gumbel_argmax.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                                       c_int, c_uint64, c_uint64, c_int64, c_void_p]
+    lib.d3pm_tokens_to_log_onehot.restype = c_int
+    lib.d3pm_tokens_to_log_onehot.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]
+    lib.d3pm_argmax_classes.restype = c_int
+    lib.d3pm_argmax_classes.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
+                                        c_void_p]
+    lib.d3pm_to_token_major.restype = c_int
+    lib.d3pm_to_token_major.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().d3pm_last_error().decode("utf-8", "replace")
+        raise D3PMError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,199 @@
+// C ABI of libd3pm_b200.so (see include/d3pm_b200.h).  Host side only validates, picks a kernel
+// instantiation and launches on the caller's stream; nothing here allocates, synchronises or keeps
+// state beyond a thread-local error string.
+#include <cstdarg>
+#include <cstdio>
+
+#include "d3pm_ops.cuh"
+#include "d3pm_step_rows.cuh"
+#include "d3pm_step_stream.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(D3PM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return D3PM_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int64_t kMaxGrid = 2147483647LL;
+
+template <int V, bool HAS_U>
+void launch_rows(const d3pm::StepParams& p, cudaStream_t s) {
+  const dim3 grid(static_cast<unsigned>(p.rows)), block(d3pm::kRowThreads);
+  if (p.sample_mode == D3PM_SAMPLE_PHILOX && p.post == nullptr && p.recon == nullptr)
+    d3pm::step_rows_kernel<V, HAS_U, true><<<grid, block, 0, s>>>(p);
+  else
+    d3pm::step_rows_kernel<V, HAS_U, false><<<grid, block, 0, s>>>(p);
+}
+
+template <int V>
+void launch_rows_u(const d3pm::StepParams& p, cudaStream_t s) {
+  if (p.logits_u != nullptr) launch_rows<V, true>(p, s);
+  else launch_rows<V, false>(p, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int d3pm_version(void) { return D3PM_VERSION; }
+
+const char* d3pm_last_error(void) { return g_err; }
+
+int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_stream_t stream) {
+  if (sched == nullptr || table == nullptr) return fail(D3PM_ERR_INVALID, "coef_table: null pointer");
+  if (T <= 0 || K <= 0) return fail(D3PM_ERR_INVALID, "coef_table: T=%d K=%d must be positive", T, K);
+  if (!aligned16(table)) return fail(D3PM_ERR_ALIGN, "coef_table: table must be 16-byte aligned");
+  d3pm::coef_table_kernel<<<(T + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sched, T, K, table);
+  return check_launch("coef_table");
+}
+
+int d3pm_fused_step(const d3pm_step_desc* d) {
+  if (d == nullptr) return fail(D3PM_ERR_INVALID, "fused_step: null descriptor");
+  if (d->logits_c == nullptr || d->x_t == nullptr || d->t == nullptr || d->coef_table == nullptr)
+    return fail(D3PM_ERR_INVALID, "fused_step: logits_c, x_t, t and coef_table are required");
+  if (d->B <= 0 || d->N <= 0 || d->K <= 0 || d->T <= 0)
+    return fail(D3PM_ERR_INVALID, "fused_step: B=%d N=%d K=%d T=%d must be positive", d->B, d->N, d->K, d->T);
+  if (d->K % 4 != 0 || d->K > 8192)
+    return fail(D3PM_ERR_UNSUPPORTED, "fused_step: K=%d must be a multiple of 4 and <= 8192", d->K);
+  const int64_t rows = static_cast<int64_t>(d->B) * d->N;
+  if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "fused_step: B*N=%lld exceeds the grid limit", (long long)rows);
+  if (d->pitch_logits < d->K || d->pitch_logits % 4 != 0)
+    return fail(D3PM_ERR_ALIGN, "fused_step: pitch_logits=%lld must be >= K and a multiple of 4", (long long)d->pitch_logits);
+  if (!aligned16(d->logits_c) || !aligned16(d->logits_u) || !aligned16(d->coef_table))
+    return fail(D3PM_ERR_ALIGN, "fused_step: logits and coef_table must be 16-byte aligned");
+  const int mode = d->sample_mode;
+  if (mode < D3PM_SAMPLE_NONE || mode > D3PM_SAMPLE_PHILOX_EXACT)
+    return fail(D3PM_ERR_INVALID, "fused_step: unknown sample_mode %d", mode);
+  if (mode == D3PM_SAMPLE_NONE && d->post == nullptr && d->recon == nullptr)
+    return fail(D3PM_ERR_INVALID, "fused_step: nothing to do (no sampling and no output requested)");
+  if (mode != D3PM_SAMPLE_NONE && d->x_prev == nullptr)
+    return fail(D3PM_ERR_INVALID, "fused_step: x_prev is required when sampling");
+  if (mode == D3PM_SAMPLE_GUMBEL) {
+    if (d->gumbel == nullptr) return fail(D3PM_ERR_INVALID, "fused_step: D3PM_SAMPLE_GUMBEL needs the gumbel tensor");
+    if (d->pitch_gumbel < d->K + 1 || d->pitch_gumbel % 4 != 0 || !aligned16(d->gumbel))
+      return fail(D3PM_ERR_ALIGN, "fused_step: gumbel rows need pitch >= K+1, pitch %% 4 == 0, 16-byte base");
+  }
+  if (d->post != nullptr || d->recon != nullptr) {
+    if (d->pitch_out < d->K + 1 || d->pitch_out % 4 != 0 || !aligned16(d->post) || !aligned16(d->recon))
+      return fail(D3PM_ERR_ALIGN, "fused_step: output rows need pitch >= K+1, pitch %% 4 == 0, 16-byte base");
+  }
+  if (d->gap != nullptr && (mode == D3PM_SAMPLE_NONE || mode == D3PM_SAMPLE_PHILOX))
+    return fail(D3PM_ERR_INVALID, "fused_step: gap is produced only by the GUMBEL and PHILOX_EXACT modes");
+  if (d->thin_factor < 0.f) return fail(D3PM_ERR_INVALID, "fused_step: thin_factor must be >= 0");
+
+  d3pm::StepParams p;
+  p.logits_c = d->logits_c, p.logits_u = d->logits_u, p.x_t = d->x_t, p.t = d->t, p.coef_table = d->coef_table;
+  p.gumbel = d->gumbel, p.x_prev = d->x_prev, p.post = d->post, p.recon = d->recon, p.gap = d->gap;
+  p.status = d->status;
+  p.B = d->B, p.N = d->N, p.K = d->K, p.T = d->T;
+  p.pitch_logits = d->pitch_logits, p.pitch_gumbel = d->pitch_gumbel, p.pitch_out = d->pitch_out;
+  p.guidance_scale = d->guidance_scale, p.sample_mode = mode, p.gumbel_is_uniform = d->gumbel_is_uniform;
+  p.seed = d->seed, p.offset = d->offset, p.row_offset = d->row_offset, p.thin_factor = d->thin_factor;
+  p.rows = rows;
+  const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+
+  if (d3pm::stream_kernel_eligible(p)) {
+    const int rc = d3pm::launch_step_stream(p, s);
+    if (rc != D3PM_OK) return fail(rc, "fused_step: stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return check_launch("fused_step(stream)");
+  }
+  const int chunks = (d->K / 4 + d3pm::kRowThreads - 1) / d3pm::kRowThreads;
+  if (chunks <= 1) launch_rows_u<1>(p, s);
+  else if (chunks <= 2) launch_rows_u<2>(p, s);
+  else if (chunks <= 4) launch_rows_u<4>(p, s);
+  else launch_rows_u<8>(p, s);
+  return check_launch("fused_step");
+}
+
+int d3pm_philox_uniform(float* u, int64_t rows, int K, int64_t pitch, uint64_t seed, uint64_t offset,
+                        int64_t row_offset, d3pm_stream_t stream) {
+  if (u == nullptr || rows <= 0 || K <= 0 || pitch < K + 1 || rows > kMaxGrid)
+    return fail(D3PM_ERR_INVALID, "philox_uniform: bad arguments (rows=%lld K=%d pitch=%lld)", (long long)rows, K, (long long)pitch);
+  d3pm::philox_uniform_kernel<<<static_cast<unsigned>(rows), d3pm::kOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      u, K, pitch, seed, offset, row_offset);
+  return check_launch("philox_uniform");
+}
+
+int d3pm_q_posterior(const float* log_x_start, int64_t pitch_in, const int64_t* x_t, const int64_t* t,
+                     const float* coef_table, float* post, int64_t pitch_out, int B, int N, int K, int T,
+                     uint32_t* status, d3pm_stream_t stream) {
+  if (log_x_start == nullptr || x_t == nullptr || t == nullptr || coef_table == nullptr || post == nullptr)
+    return fail(D3PM_ERR_INVALID, "q_posterior: null pointer");
+  if (B <= 0 || N <= 0 || K <= 0 || T <= 0) return fail(D3PM_ERR_INVALID, "q_posterior: sizes must be positive");
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "q_posterior: B*N too large");
+  if (pitch_in < K || pitch_out < K + 1) return fail(D3PM_ERR_INVALID, "q_posterior: pitch_in >= K and pitch_out >= K+1 required");
+  if (!aligned16(coef_table)) return fail(D3PM_ERR_ALIGN, "q_posterior: coef_table must be 16-byte aligned");
+  d3pm::q_posterior_rows_kernel<<<static_cast<unsigned>(rows), d3pm::kOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      log_x_start, pitch_in, x_t, t, coef_table, post, pitch_out, N, K, T, status);
+  return check_launch("q_posterior");
+}
+
+int d3pm_gumbel_argmax(const float* logits, int64_t pitch_logits, const float* noise, int64_t pitch_noise,
+                       int noise_kind, int64_t* x, float* gap, int64_t rows, int C, uint64_t seed,
+                       uint64_t offset, int64_t row_offset, d3pm_stream_t stream) {
+  if (logits == nullptr || x == nullptr || rows <= 0 || C <= 0 || pitch_logits < C || rows > kMaxGrid)
+    return fail(D3PM_ERR_INVALID, "gumbel_argmax: bad arguments");
+  if (noise_kind < 0 || noise_kind > 2) return fail(D3PM_ERR_INVALID, "gumbel_argmax: noise_kind %d", noise_kind);
+  if (noise_kind != 2 && (noise == nullptr || pitch_noise < C))
+    return fail(D3PM_ERR_INVALID, "gumbel_argmax: noise tensor required for noise_kind %d", noise_kind);
+  const dim3 grid(static_cast<unsigned>(rows)), block(d3pm::kOpThreads);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (noise_kind == 0)
+    d3pm::gumbel_argmax_rows_kernel<0><<<grid, block, 0, s>>>(logits, pitch_logits, noise, pitch_noise, x, gap, C, seed, offset, row_offset);
+  else if (noise_kind == 1)
+    d3pm::gumbel_argmax_rows_kernel<1><<<grid, block, 0, s>>>(logits, pitch_logits, noise, pitch_noise, x, gap, C, seed, offset, row_offset);
+  else
+    d3pm::gumbel_argmax_rows_kernel<2><<<grid, block, 0, s>>>(logits, pitch_logits, nullptr, 0, x, gap, C, seed, offset, row_offset);
+  return check_launch("gumbel_argmax");
+}
+
+int d3pm_tokens_to_log_onehot(const int64_t* x, float* out, int64_t pitch, int64_t rows, int C, uint32_t* status,
+                              d3pm_stream_t stream) {
+  if (x == nullptr || out == nullptr || rows <= 0 || C <= 0 || pitch < C || rows > kMaxGrid)
+    return fail(D3PM_ERR_INVALID, "tokens_to_log_onehot: bad arguments");
+  d3pm::tokens_to_log_onehot_kernel<<<static_cast<unsigned>(rows), d3pm::kOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, out, pitch, C, status);
+  return check_launch("tokens_to_log_onehot");
+}
+
+int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stride, int64_t token_stride,
+                        int64_t* idx, int B, int C, int N, d3pm_stream_t stream) {
+  if (x == nullptr || idx == nullptr || B <= 0 || C <= 0 || N <= 0)
+    return fail(D3PM_ERR_INVALID, "argmax_classes: bad arguments");
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  if (class_stride == 1) {
+    if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "argmax_classes: B*N too large");
+    d3pm::argmax_rows_kernel<<<static_cast<unsigned>(rows), d3pm::kOpThreads, 0, s>>>(x, batch_stride, token_stride, idx, C, N);
+  } else {
+    if (B > 65535) return fail(D3PM_ERR_UNSUPPORTED, "argmax_classes: B > 65535 in the strided layout");
+    const dim3 grid((N + d3pm::kOpThreads - 1) / d3pm::kOpThreads, B);
+    d3pm::argmax_strided_kernel<<<grid, d3pm::kOpThreads, 0, s>>>(x, batch_stride, class_stride, token_stride, idx, C, N);
+  }
+  return check_launch("argmax_classes");
+}
+
+int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N, d3pm_stream_t stream) {
+  if (src == nullptr || dst == nullptr || B <= 0 || C <= 0 || N <= 0 || pitch < C || B > 65535)
+    return fail(D3PM_ERR_INVALID, "to_token_major: bad arguments");
+  const dim3 grid((N + 31) / 32, (C + 31) / 32, B);
+  d3pm::to_token_major_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, pitch, C, N);
+  return check_launch("to_token_major");
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// Fine-grained operators of the reverse-diffusion path (one CTA per token row, coalesced scalar
+// accesses so that any pitch — including the reference's unaligned K+1 = 4097 — is accepted).
+// These back the method-level drop-ins (q_posterior, log_sample_categorical, index<->log-one-hot);
+// the production path is the fused step.
+#pragma once
+
+#include "d3pm_common.cuh"
+
+namespace d3pm {
+
+constexpr int kOpThreads = 256;
+
+// ---------------------------------------------------------------- coefficient table
+__device__ __forceinline__ double lae64(double a, double b) {  // log_add_exp (:32-34), -inf safe
+  const double m = fmax(a, b);
+  if (isinf(m) && m < 0) return m;
+  return m + log(exp(a - m) + exp(b - m));
+}
+
+__global__ void coef_table_kernel(const float* __restrict__ sched, int T, int K, float* __restrict__ table) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int P = T + 1;
+  const int tp = (t + T) % P;  // t-1 with the modulo of q_pred (:203): t = 0 -> identity slot T
+  const double Z = static_cast<double>(kLogTiny);
+  const double la = sched[0 * P + t], lb = sched[1 * P + t], lc = sched[2 * P + t];
+  const double lA = sched[4 * P + t], lB = sched[5 * P + t], lC = sched[6 * P + t];
+  const double Ap = exp(static_cast<double>(sched[4 * P + tp])), Bp = exp(static_cast<double>(sched[5 * P + tp]));
+  const double Cp = exp(static_cast<double>(sched[6 * P + tp])), omCp = exp(static_cast<double>(sched[7 * P + tp]));
+  const double Wm = exp(-lC), Om = exp(lc);
+  const double Wo = exp(-lae64(Z + lA, lB)), Ws = exp(-lae64(lA, lB));
+  const double Oo = exp(lae64(Z + la, lb)), Os = exp(lae64(la, lb));
+  float* row = table + static_cast<size_t>(t) * D3PM_COEF_STRIDE;
+  for (int i = 0; i < D3PM_COEF_STRIDE; ++i) row[i] = 0.f;
+  row[C_AM] = static_cast<float>(Wm * Ap * Om);
+  row[C_BOM] = static_cast<float>(Bp * Om);
+  row[C_WM] = static_cast<float>(Wm);
+  row[C_C1] = static_cast<float>(1e-30 * omCp);
+  row[C_CP] = static_cast<float>(Cp);
+  row[C_AO] = static_cast<float>(Wo * Ap * Oo);
+  row[C_AS] = static_cast<float>(Ws * Ap * Os);
+  row[C_BOO] = static_cast<float>(Bp * Oo);
+  row[C_BOS] = static_cast<float>(Bp * Os);
+  row[C_WO] = static_cast<float>(Wo);
+  row[C_WS] = static_cast<float>(Ws);
+  row[C_PK1] = static_cast<float>(Cp * 1e-30);
+}
+
+// ---------------------------------------------------------------- small block reductions
+template <int NW>
+__device__ __forceinline__ float block_sum(float x, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  x = warp_sum(x);
+  if (lane == 0) scratch[warp] = x;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s += scratch[w];
+  return s;
+}
+
+__device__ __forceinline__ bool fetch_row_scalars(const int64_t* t, const int64_t* x_t, int64_t row, int N, int K,
+                                                  int T, uint32_t* status, int& tt_out, uint32_t& j_out) {
+  long long tt = t[row / N];
+  long long jj = x_t[row];
+  uint32_t st = 0;
+  if (tt < 0 || tt >= T) {
+    st |= D3PM_STATUS_BAD_T;
+    tt = tt < 0 ? 0 : T - 1;
+  }
+  if (jj < 0 || jj > K) {
+    st |= D3PM_STATUS_BAD_TOKEN;
+    jj = K;
+  }
+  if (st != 0 && threadIdx.x == 0 && status != nullptr) atomicOr(status, st);
+  tt_out = static_cast<int>(tt);
+  j_out = static_cast<uint32_t>(jj);
+  return jj == K;
+}
+
+// ---------------------------------------------------------------- q_posterior on arbitrary log p(x0)
+__global__ void __launch_bounds__(kOpThreads) q_posterior_rows_kernel(
+    const float* __restrict__ lxs, int64_t pitch_in, const int64_t* __restrict__ x_t, const int64_t* __restrict__ t,
+    const float* __restrict__ table, float* __restrict__ post, int64_t pitch_out, int N, int K, int T,
+    uint32_t* status) {
+  __shared__ float scratch[kOpThreads / 32];
+  const int64_t row = blockIdx.x;
+  int tt;
+  uint32_t j;
+  const bool masked = fetch_row_scalars(t, x_t, row, N, K, T, status, tt, j);
+  const RowCoef cf = load_row_coef(table, tt, masked);
+  const float* __restrict__ in = lxs + row * pitch_in;
+  float* __restrict__ out = post + row * pitch_out;
+
+  float sum = 0.f;
+  for (int k = threadIdx.x; k < K; k += kOpThreads) sum += ex2(in[k] * kLog2e);
+  sum = block_sum<kOpThreads / 32>(sum, scratch);
+  const float pj = masked ? 0.f : ex2(in[j] * kLog2e);
+  const float eL = masked ? fmaf(cf.W, sum, kTiny) : fmaf(cf.W, sum - pj, fmaf(cf.WS, pj, kTiny));
+  const float Bc = cf.BO * eL;
+  const float Pj = fmaf(pj, cf.AS, cf.BOS * eL);
+  for (int k = threadIdx.x; k < K; k += kOpThreads) {
+    const float pk = ex2(in[k] * kLog2e);
+    const float P = (static_cast<uint32_t>(k) == j) ? Pj : fmaf(pk, cf.A, Bc);
+    out[k] = log_prob_clamped(P);
+  }
+  if (threadIdx.x == 0) out[K] = log_prob_clamped(fmaf(cf.PK1, eL, cf.PK0));
+}
+
+// ---------------------------------------------------------------- Gumbel-max over rows of C classes
+template <int KIND>  // 0 gumbel given, 1 uniform given, 2 Philox
+__global__ void __launch_bounds__(kOpThreads) gumbel_argmax_rows_kernel(
+    const float* __restrict__ logits, int64_t pitch_logits, const float* __restrict__ noise, int64_t pitch_noise,
+    int64_t* __restrict__ x, float* __restrict__ gap, int C, uint64_t seed, uint64_t offset, int64_t row_offset) {
+  constexpr int NW = kOpThreads / 32;
+  __shared__ unsigned long long skey[NW];
+  __shared__ float sgap[NW];
+  const int64_t row = blockIdx.x;
+  const float* __restrict__ lg = logits + row * pitch_logits;
+  const float* __restrict__ nz = KIND == 2 ? nullptr : noise + row * pitch_noise;
+  const PhiloxStream rng(seed, offset);
+  const uint64_t grow = static_cast<uint64_t>(row_offset + row);
+  unsigned long long best = 0ull;
+  float second = -CUDART_INF_F;
+  const int nq = (C + 3) >> 2;
+  for (int q = threadIdx.x; q < nq; q += kOpThreads) {
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (KIND == 2) w = rng.words(q, grow);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * q + e;
+      if (k < C) {
+        float g;
+        if (KIND == 0) g = nz[k];
+        else if (KIND == 1) g = gumbel_from_uniform(nz[k]);
+        else g = gumbel_from_uniform(uniform_from_word(word_of(w, e)));
+        const float sc = g + lg[k];
+        const unsigned long long key = pack_key(sc, k);
+        if (key > best) {
+          if (best != 0ull) second = fmaxf(second, key_score(best));
+          best = key;
+        } else {
+          second = fmaxf(second, sc);
+        }
+      }
+    }
+  }
+  const unsigned long long win = group_max_u64<NW>(best, skey, CtaSync());
+  if (threadIdx.x == 0) x[row] = key_class(win);
+  if (gap != nullptr) {
+    float cand = (best == win) ? second : (best != 0ull ? key_score(best) : -CUDART_INF_F);
+    cand = group_max_f32<NW>(cand, sgap, CtaSync());
+    if (threadIdx.x == 0) gap[row] = key_score(win) - cand;
+  }
+}
+
+__global__ void __launch_bounds__(kOpThreads) philox_uniform_kernel(float* __restrict__ u, int K, int64_t pitch,
+                                                                    uint64_t seed, uint64_t offset,
+                                                                    int64_t row_offset) {
+  const int64_t row = blockIdx.x;
+  const PhiloxStream rng(seed, offset);
+  const uint64_t grow = static_cast<uint64_t>(row_offset + row);
+  float* __restrict__ out = u + row * pitch;
+  const int C = K + 1, nq = (C + 3) >> 2;
+  for (int q = threadIdx.x; q < nq; q += kOpThreads) {
+    const uint4 w = rng.words(q, grow);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (4 * q + e < C) out[4 * q + e] = uniform_from_word(word_of(w, e));
+  }
+}
+
+// ---------------------------------------------------------------- index <-> log one-hot
+__global__ void __launch_bounds__(kOpThreads) tokens_to_log_onehot_kernel(const int64_t* __restrict__ x,
+                                                                          float* __restrict__ out, int64_t pitch,
+                                                                          int C, uint32_t* status) {
+  const int64_t row = blockIdx.x;
+  const long long j = x[row];
+  if ((j < 0 || j >= C) && threadIdx.x == 0 && status != nullptr) atomicOr(status, D3PM_STATUS_BAD_TOKEN);
+  float* __restrict__ o = out + row * pitch;
+  for (int k = threadIdx.x; k < C; k += kOpThreads) o[k] = (k == j) ? 0.0f : kLogTiny;
+}
+
+// class_stride == 1: one CTA per token
+__global__ void __launch_bounds__(kOpThreads) argmax_rows_kernel(const float* __restrict__ x, int64_t batch_stride,
+                                                                 int64_t token_stride, int64_t* __restrict__ idx,
+                                                                 int C, int N) {
+  constexpr int NW = kOpThreads / 32;
+  __shared__ unsigned long long skey[NW];
+  const int64_t row = blockIdx.x;
+  const float* __restrict__ r = x + (row / N) * batch_stride + (row % N) * token_stride;
+  unsigned long long best = 0ull;
+  for (int k = threadIdx.x; k < C; k += kOpThreads) {
+    const unsigned long long key = pack_key(r[k], k);
+    best = key > best ? key : best;
+  }
+  best = group_max_u64<NW>(best, skey, CtaSync());
+  if (threadIdx.x == 0) idx[row] = key_class(best);
+}
+
+// any strides: one thread per token, classes visited in order (coalesced when token_stride == 1)
+__global__ void __launch_bounds__(kOpThreads) argmax_strided_kernel(const float* __restrict__ x,
+                                                                    int64_t batch_stride, int64_t class_stride,
+                                                                    int64_t token_stride, int64_t* __restrict__ idx,
+                                                                    int C, int N) {
+  const int n = blockIdx.x * kOpThreads + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= N) return;
+  const float* __restrict__ r = x + b * batch_stride + n * token_stride;
+  float best = r[0];
+  int arg = 0;
+  for (int k = 1; k < C; ++k) {
+    const float v = r[k * class_stride];
+    if (v > best) best = v, arg = k;
+  }
+  idx[static_cast<int64_t>(b) * N + n] = arg;
+}
+
+// [B, C, N] contiguous -> [B*N][pitch] rows, 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) to_token_major_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int64_t pitch, int C, int N) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* __restrict__ s = src + static_cast<int64_t>(b) * C * N;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, n = n0 + tx;
+    if (c < C && n < N) tile[ty + i][tx] = s[static_cast<int64_t>(c) * N + n];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int n = n0 + ty + i, c = c0 + tx;
+    if (c < C && n < N) dst[(static_cast<int64_t>(b) * N + n) * pitch + c] = tile[tx][ty + i];
+  }
+}
+
+}  // namespace d3pm

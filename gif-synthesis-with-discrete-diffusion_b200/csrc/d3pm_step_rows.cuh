@@ -1,0 +1,401 @@
+// Fused reverse step, general kernel: one CTA of 256 threads per token row, the row held in registers.
+//
+// This is the shape-general implementation (any K % 4 == 0 up to 8192, every output / sampling
+// mode).  d3pm_step_stream.cuh holds the persistent TMA-pipelined kernel used for the production
+// mode on large batches; both share the per-row mathematics below (RowMath), so they agree bit for
+// bit on the quantities they both compute.
+#pragma once
+
+#include "d3pm_common.cuh"
+
+namespace d3pm {
+
+struct StepParams {
+  const float* logits_c;
+  const float* logits_u;
+  const int64_t* x_t;
+  const int64_t* t;
+  const float* coef_table;
+  const float* gumbel;
+  int64_t* x_prev;
+  float* post;
+  float* recon;
+  float* gap;
+  uint32_t* status;
+  int32_t B, N, K, T;
+  int64_t pitch_logits, pitch_gumbel, pitch_out;
+  float guidance_scale;
+  int32_t sample_mode;
+  int32_t gumbel_is_uniform;
+  uint64_t seed, offset;
+  int64_t row_offset;
+  float thin_factor;
+  int64_t rows;
+};
+
+// exact residual of the fp32 product m*log2e (natural-log units -> log2 units)
+__device__ __forceinline__ float to_log2_units(float m) { return __fmul_rn(m, kLog2e); }
+
+// ln(sum_k exp(x_k - M)) from S = sum_k 2^(x_k*log2e - fl(M*log2e)): corrects the rounding of M*log2e
+__device__ __forceinline__ float ln_rel_sum(float M, float S) {
+  const float m2 = to_log2_units(M);
+  const float delta = -fmaf(M, kLog2e, -m2);  // m2 - M*log2e, exact
+  return kLn2 * (lg2(S) + delta);
+}
+
+// Everything a row needs once the softmax statistics are known.  Identical in every kernel.
+struct RowMath {
+  float A, Bc;      // P_k = p_k*A + Bc           (k != x_t)
+  float Pj;         // P at k == x_t (unmasked rows)
+  float PK;         // P at the [MASK] class
+  float Ptot;       // sum of all K+1 P's (for the thinning threshold)
+  uint32_t j;       // x_t (== K when masked)
+
+  // p_j = exp(recon_j) as a probability in [exp(-70), 1]; ignored for masked rows
+  __device__ __forceinline__ void init(const RowCoef& cf, bool masked, float pj, uint32_t jj, int K) {
+    j = jj;
+    const float eL = masked ? cf.W + kTiny : fmaf(cf.W, 1.0f - pj, fmaf(cf.WS, pj, kTiny));
+    A = cf.A;
+    Bc = cf.BO * eL;
+    Pj = masked ? 0.0f : fmaf(pj, cf.AS, cf.BOS * eL);
+    PK = fmaf(cf.PK1, eL, cf.PK0);
+    Ptot = masked ? fmaf(static_cast<float>(K), Bc, A) + PK
+                  : fmaf(static_cast<float>(K - 1), Bc, A * (1.0f - pj)) + Pj + PK;
+  }
+  // posterior log-prob of class k (< K) given its softmax numerator e and the thread's scale r
+  __device__ __forceinline__ float post_of(uint32_t k, float e, float r) const {
+    const float p = fminf(fmaxf(e * r, kPFloor), 1.0f);
+    const float P = (k == j) ? Pj : fmaf(p, A, Bc);
+    return log_prob_clamped(P);
+  }
+  __device__ __forceinline__ float post_self() const { return log_prob_clamped(Pj); }
+  __device__ __forceinline__ float post_mask() const { return log_prob_clamped(PK); }
+};
+
+constexpr int kRowThreads = 256;
+
+template <int NV, int NW, typename Sync>
+__device__ __forceinline__ void group_max_sum_n(float (&m)[NV], float (&s)[NV], float* scratch, Sync sync) {
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) % NW;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float mw = warp_max(m[v]);
+    const float sw =
+        warp_sum(m[v] == -CUDART_INF_F ? 0.0f : s[v] * ex2(to_log2_units(m[v]) - to_log2_units(mw)));
+    if (lane == 0) {
+      scratch[(2 * v) * NW + warp] = mw;
+      scratch[(2 * v + 1) * NW + warp] = sw;
+    }
+  }
+  sync();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float M = scratch[(2 * v) * NW];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) M = fmaxf(M, scratch[(2 * v) * NW + w]);
+    const float M2 = to_log2_units(M);
+    float S = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float mwv = scratch[(2 * v) * NW + w];
+      S += (mwv == -CUDART_INF_F) ? 0.0f : scratch[(2 * v + 1) * NW + w] * ex2(to_log2_units(mwv) - M2);
+    }
+    m[v] = M;
+    s[v] = S;
+  }
+}
+
+// V = float4 chunks per thread; THIN = production Philox mode (thinned exponential race, token only)
+template <int V, bool HAS_U, bool THIN>
+__global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams p) {
+  constexpr int NW = kRowThreads / 32;
+  __shared__ float sred[2][4 * NW];
+  __shared__ unsigned long long skey[2][NW];
+  __shared__ float sgap[NW];
+  const CtaSync sync;
+
+  const int tid = threadIdx.x;
+  const int64_t row = blockIdx.x;
+  const int b = static_cast<int>(row / p.N);
+  const int K = p.K, nq = K >> 2;
+
+  // ---- row scalars --------------------------------------------------------------------------
+  long long tt = p.t[b];
+  long long jj = p.x_t[row];
+  uint32_t st = 0;
+  if (tt < 0 || tt >= p.T) {
+    st |= D3PM_STATUS_BAD_T;
+    tt = tt < 0 ? 0 : p.T - 1;
+  }
+  if (jj < 0 || jj > K) {
+    st |= D3PM_STATUS_BAD_TOKEN;
+    jj = K;
+  }
+  if (st != 0 && tid == 0 && p.status != nullptr) atomicOr(p.status, st);
+  const bool masked = (jj == K);
+  const uint32_t j = static_cast<uint32_t>(jj);
+  const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
+
+  const float* __restrict__ rc = p.logits_c + row * p.pitch_logits;
+  const float* __restrict__ ru = HAS_U ? p.logits_u + row * p.pitch_logits : nullptr;
+
+  // ---- load the row: x = conditional logits, z = unconditional ---------------------------------
+  float x[V][4], z[V][4];
+  int nvalid = 0;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int q = tid + i * kRowThreads;
+    if (q < nq) {
+      nvalid = i + 1;
+      const float4 a = ld_stream4(rc + 4 * q);
+      x[i][0] = a.x, x[i][1] = a.y, x[i][2] = a.z, x[i][3] = a.w;
+      if (HAS_U) {
+        const float4 c = ld_stream4(ru + 4 * q);
+        z[i][0] = c.x, z[i][1] = c.y, z[i][2] = c.z, z[i][3] = c.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[i][e] = -CUDART_INF_F, z[i][e] = -CUDART_INF_F;
+    }
+  }
+  float xj = 0.f, zj = 0.f;  // the logits of class x_t (unmasked rows), same for every thread
+  if (!masked) {
+    xj = __ldg(rc + j);
+    if (HAS_U) zj = __ldg(ru + j);
+  }
+
+  // ---- softmax statistics of the raw logits (:231) -------------------------------------------
+  float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      m[0] = fmaxf(m[0], x[i][e]);
+      if (HAS_U) m[1] = fmaxf(m[1], z[i][e]);
+    }
+  {
+    const float m0 = to_log2_units(m[0]), m1 = to_log2_units(m[1]);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (i < nvalid) {
+          const float ec = ex2(fmaf(x[i][e], kLog2e, -m0));
+          s[0] += ec;
+          if (HAS_U) s[1] += ex2(fmaf(z[i][e], kLog2e, -m1));
+          else z[i][e] = ec;  // guidance off: these are already the softmax numerators
+        }
+      }
+  }
+  const float m_local_c2 = to_log2_units(m[0]);
+  if (HAS_U) {
+    group_max_sum_n<2, NW>(m, s, sred[0], sync);
+  } else {
+    float m1[1] = {m[0]}, s1[1] = {s[0]};
+    group_max_sum_n<1, NW>(m1, s1, sred[0], sync);
+    m[0] = m1[0], s[0] = s1[0];
+  }
+
+  // ---- guidance combine + renormalisation (:245-247), or pass-through when guidance is off ------
+  float My, Sy, lnSy, r, yj;
+  if (HAS_U) {
+    const float lnSc = ln_rel_sum(m[0], s[0]), lnSu = ln_rel_sum(m[1], s[1]);
+    const float gs = p.guidance_scale;
+    float my = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (i < nvalid) {
+          const float lc = fmaxf((x[i][e] - m[0]) - lnSc, kClampLo);  // clamp of :236 (upper bound is automatic)
+          const float lu = fmaxf((z[i][e] - m[1]) - lnSu, kClampLo);
+          const float y = fmaf(gs, lc - lu, lu);
+          x[i][e] = y;
+          my = fmaxf(my, y);
+        }
+      }
+    {
+      const float lc = fmaxf((xj - m[0]) - lnSc, kClampLo), lu = fmaxf((zj - m[1]) - lnSu, kClampLo);
+      yj = fmaf(gs, lc - lu, lu);
+    }
+    const float my2 = to_log2_units(my);
+    float sy = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (i < nvalid) {
+          const float ey = ex2(fmaf(x[i][e], kLog2e, -my2));
+          z[i][e] = ey;
+          sy += ey;
+        }
+      }
+    float mm[1] = {my}, ss[1] = {sy};
+    group_max_sum_n<1, NW>(mm, ss, sred[1], sync);
+    My = mm[0], Sy = ss[0];
+    r = (nvalid > 0) ? ex2(my2 - to_log2_units(My)) / Sy : 0.f;
+  } else {
+    My = m[0], Sy = s[0];
+    yj = xj;
+    r = (nvalid > 0) ? ex2(m_local_c2 - to_log2_units(My)) / Sy : 0.f;
+  }
+  lnSy = ln_rel_sum(My, Sy);
+
+  // ---- per-row posterior coefficients (:251-283 collapsed, see d3pm_common.cuh) ------------------
+  const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -to_log2_units(My))) / Sy, kPFloor), 1.0f);
+  RowMath rm;
+  rm.init(cf, masked, pj, j, K);
+
+  const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
+  const PhiloxStream rng(p.seed, p.offset);
+  unsigned long long best = 0ull;
+
+  if (!THIN) {
+    // ================= log-domain pass: optional outputs + exact Gumbel-max =====================
+    const int mode = p.sample_mode;
+    float* __restrict__ rpost = p.post ? p.post + row * p.pitch_out : nullptr;
+    float* __restrict__ rrec = p.recon ? p.recon + row * p.pitch_out : nullptr;
+    const float* __restrict__ rg = (mode == D3PM_SAMPLE_GUMBEL) ? p.gumbel + row * p.pitch_gumbel : nullptr;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (i < nvalid) {
+        const int q = tid + i * kRowThreads;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rm.post_of(4 * q + e, z[i][e], r);
+        if (rpost) st_stream4(rpost + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
+        if (rrec) {
+          float rc4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rc4[e] = fminf(fmaxf((x[i][e] - My) - lnSy, kClampLo), 0.0f);
+          st_stream4(rrec + 4 * q, make_float4(rc4[0], rc4[1], rc4[2], rc4[3]));
+        }
+        if (mode != D3PM_SAMPLE_NONE) {
+          float g[4];
+          if (mode == D3PM_SAMPLE_GUMBEL) {
+            const float4 gv = ld_stream4(rg + 4 * q);
+            g[0] = gv.x, g[1] = gv.y, g[2] = gv.z, g[3] = gv.w;
+            if (p.gumbel_is_uniform) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) g[e] = gumbel_from_uniform(g[e]);
+            }
+          } else {
+            const uint4 w = rng.words(q, grow);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g[e] = gumbel_from_uniform(uniform_from_word(word_of(w, e)));
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sc = g[e] + o[e];
+            z[i][e] = sc;  // kept for the near-tie gap
+            const unsigned long long key = pack_key(sc, 4 * q + e);
+            best = key > best ? key : best;
+          }
+        }
+      }
+    }
+    float scoreK = 0.f;
+    if (tid == 0) {  // the [MASK] class
+      const float oK = rm.post_mask();
+      if (rpost) rpost[K] = oK;
+      if (rrec) rrec[K] = kClampLo;  // constant -70 row of :235, :248
+      if (mode != D3PM_SAMPLE_NONE) {
+        float gK;
+        if (mode == D3PM_SAMPLE_GUMBEL) gK = p.gumbel_is_uniform ? gumbel_from_uniform(__ldg(rg + K)) : __ldg(rg + K);
+        else gK = gumbel_from_uniform(uniform_from_word(word_of(rng.words(K >> 2, grow), K & 3)));
+        scoreK = gK + oK;
+        const unsigned long long key = pack_key(scoreK, K);
+        best = key > best ? key : best;
+      }
+    }
+    if (mode == D3PM_SAMPLE_NONE) return;
+    best = group_max_u64<NW>(best, skey[0], sync);
+    if (tid == 0 && p.x_prev) p.x_prev[row] = key_class(best);
+    if (p.gap != nullptr) {  // runner-up score, for the near-tie log
+      const uint32_t win = key_class(best);
+      float second = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (i < nvalid) {
+          const int q = tid + i * kRowThreads;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (static_cast<uint32_t>(4 * q + e) != win) second = fmaxf(second, z[i][e]);
+        }
+      if (tid == 0 && win != static_cast<uint32_t>(K)) second = fmaxf(second, scoreK);
+      second = group_max_f32<NW>(second, sgap, sync);
+      if (tid == 0) p.gap[row] = key_score(best) - second;
+    }
+    return;
+  }
+
+  // ================= production sampling: thinned exponential race ===============================
+  // argmax_k (post_k + g_k) = argmax_k P_k / E_k with E_k = -log u_k.  A class can only win if
+  // E_k < c * P_k / Ptot for a modest c (the winner's ratio is Ptot / Exp(1)); since E_k >= v_k = 1 - u_k,
+  // testing the raw uniform v_k against that bound discards ~(1 - c/K) of the classes before any
+  // logarithm is taken.  Survivors are scored exactly as in the log-domain pass, so the result is the
+  // same argmax; if the best survivor does not clear the bound (probability e^-c per row) the row is
+  // rescored exhaustively.
+  const float c_thin = p.thin_factor > 0.f ? p.thin_factor : 16.0f;
+  const float inv = c_thin / rm.Ptot;
+  // +2^-22: two ulps of slack in [1,2) so that the roundings of the threshold can only admit more classes
+  const float thrA = r * rm.A * inv, thrB = fmaf(rm.Bc, inv, 1.0f) + 2.384185791015625e-7f;
+  const float accept = -logf(inv) + 0.02f;  // ln(Ptot / c) plus slack for rounding in the filter
+
+  auto score_exact = [&](uint32_t k, float e, uint32_t word) {
+    return rm.post_of(k, e, r) + gumbel_from_uniform(uniform_from_word(word));
+  };
+
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if (i < nvalid) {
+      const int q = tid + i * kRowThreads;
+      const uint4 w = rng.words(q, grow);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t word = word_of(w, e);
+        const float f = __uint_as_float(0x3f800000u | (word & 0x007fffffu));  // 1 + m/2^23
+        if (f <= fmaf(z[i][e], thrA, thrB)) {
+          const unsigned long long key = pack_key(score_exact(4 * q + e, z[i][e], word), 4 * q + e);
+          best = key > best ? key : best;
+        }
+      }
+    }
+  }
+  if (tid == 0) {  // the two classes with their own coefficients are always scored
+    const unsigned long long kK =
+        pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_word(word_of(rng.words(K >> 2, grow), K & 3))), K);
+    best = kK > best ? kK : best;
+    if (!masked) {
+      const unsigned long long kj = pack_key(
+          rm.post_self() + gumbel_from_uniform(uniform_from_word(word_of(rng.words(j >> 2, grow), j & 3))), j);
+      best = kj > best ? kj : best;
+    }
+  }
+  best = group_max_u64<NW>(best, skey[0], sync);
+  if (!(key_score(best) >= accept)) {  // exhaustive rescoring (row-uniform branch)
+    best = 0ull;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (i < nvalid) {
+        const int q = tid + i * kRowThreads;
+        const uint4 w = rng.words(q, grow);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned long long key = pack_key(score_exact(4 * q + e, z[i][e], word_of(w, e)), 4 * q + e);
+          best = key > best ? key : best;
+        }
+      }
+    }
+    if (tid == 0) {
+      const unsigned long long kK = pack_key(
+          rm.post_mask() + gumbel_from_uniform(uniform_from_word(word_of(rng.words(K >> 2, grow), K & 3))), K);
+      best = kK > best ? kK : best;
+      if (p.status != nullptr) atomicOr(p.status, D3PM_STATUS_FALLBACK);
+    }
+    best = group_max_u64<NW>(best, skey[1], sync);
+  }
+  if (tid == 0 && p.x_prev) p.x_prev[row] = key_class(best);
+}
+
+}  // namespace d3pm

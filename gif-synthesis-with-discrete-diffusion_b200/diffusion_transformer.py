@@ -1,0 +1,362 @@
+"""`FusedDiffusionTransformer`: host-side mirror of the reference's `DiffusionTransformer`.
+
+Same constructor keywords, same registered buffer / parameter names (so reference checkpoints load)
+and the same sampling-time method signatures as
+`src/models/motionencoder/diffusion_transformer.py` (reference file:line cited per method), with
+the per-step mathematics executed by `libd3pm_b200.so`.  Select it through the Hydra `_target_` of
+`configs/model/motionencoder/diffusion_transformer.yaml:1`.
+
+Tensors returned where the reference returns `[B, K+1, N]` are `[B, K+1, N]`-shaped strided views of
+token-major storage; integer tokens, not log-one-hots, are carried between reverse steps inside
+`sample()` (the reference arg-maxes its log-one-hot immediately, :221, :255, :639).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from d3pm_b200 import _lib, ops
+from d3pm_b200._lib import D3PMError
+
+_SCHEDULE_BUFFERS = ("log_at", "log_bt", "log_ct", "log_1_min_ct",
+                     "log_cumprod_at", "log_cumprod_bt", "log_cumprod_ct", "log_1_min_cumprod_ct")
+
+
+def alpha_schedule(time_step, N=100, att_1=0.99999, att_T=0.000009, ctt_1=0.000009, ctt_T=0.99999):
+    """Mask-and-replace schedule, same signature and return order as the reference (:56-69).
+
+    Returns `(at, bt, ct, att, btt, ctt)`: per-step keep / replace / mask probabilities (length T) and
+    their cumulative versions (length T+1, last slot = the identity "t = -1").  The arithmetic keeps
+    the reference's operation order so the float64 values, and hence the float32 buffers, are
+    bit-identical (checked in tests/test_host.py against the golden-pinned oracle).
+    """
+    frac = np.arange(0, time_step) / (time_step - 1)
+    keep_cum = np.concatenate(([1], frac * (att_T - att_1) + att_1))
+    mask_cum = np.concatenate(([0], frac * (ctt_T - ctt_1) + ctt_1))
+    at = keep_cum[1:] / keep_cum[:-1]
+    not_masked = 1 - mask_cum
+    ct = 1 - not_masked[1:] / not_masked[:-1]
+    bt = (1 - at - ct) / N
+    att = np.concatenate((keep_cum[1:], [1]))
+    ctt = np.concatenate((mask_cum[1:], [0]))
+    btt = (1 - att - ctt) / N
+    return at, bt, ct, att, btt, ctt
+
+
+class FusedDiffusionTransformer(nn.Module):
+    """Drop-in for `DiffusionTransformer` (:71-164) whose reverse step runs as one CUDA kernel."""
+
+    def __init__(
+        self,
+        *,
+        condition_emb_config=None,
+        transformer=None,
+        diffusion_step=100,
+        alpha_init_type="cos",
+        auxiliary_loss_weight=0,
+        adaptive_auxiliary_loss=False,
+        mask_weight=[1, 1],
+        learnable_cf=False,
+        guidance_scale=5,
+        content_seq_len=1024,
+    ):
+        super().__init__()
+        self.condition_emb = None  # the reference never instantiates one either (:92-98)
+        self.transformer = transformer
+        self.content_seq_len = content_seq_len
+        self.amp = False
+        self.num_classes = self.transformer.content_emb.num_embed  # K + 1 (:106)
+        self.loss_type = "vb_stochastic"
+        self.shape = content_seq_len
+        self.num_timesteps = diffusion_step
+        self.parametrization = "x0"
+        self.auxiliary_loss_weight = auxiliary_loss_weight
+        self.adaptive_auxiliary_loss = adaptive_auxiliary_loss
+        self.mask_weight = mask_weight
+        if alpha_init_type != "alpha1":  # the reference prints and then dies on an undefined name (:115-120)
+            raise ValueError("alpha_init_type must be 'alpha1' (the only schedule the reference defines)")
+
+        at, bt, ct, att, btt, ctt = alpha_schedule(self.num_timesteps, N=self.num_classes - 1)
+        with np.errstate(divide="ignore"):
+            as64 = lambda a: torch.tensor(np.asarray(a, dtype="float64"))  # noqa: E731
+            log_at, log_bt, log_ct = torch.log(as64(at)), torch.log(as64(bt)), torch.log(as64(ct))
+            log_cumprod_at, log_cumprod_bt = torch.log(as64(att)), torch.log(as64(btt))
+            log_cumprod_ct = torch.log(as64(ctt))
+        log_1_min_ct = torch.log(1 - log_ct.exp() + 1e-40)                  # log_1_min_a (:29-30)
+        log_1_min_cumprod_ct = torch.log(1 - log_cumprod_ct.exp() + 1e-40)
+        for lhs, rhs in ((log_ct, log_1_min_ct), (log_cumprod_ct, log_1_min_cumprod_ct)):  # (:136-137)
+            top = torch.max(lhs, rhs)
+            total = top + torch.log(torch.exp(lhs - top) + torch.exp(rhs - top))
+            assert total.abs().sum().item() < 1.0e-5
+
+        self.diffusion_acc_list = [0] * self.num_timesteps
+        self.diffusion_keep_list = [0] * self.num_timesteps
+        self.register_buffer("log_at", log_at.float())
+        self.register_buffer("log_bt", log_bt.float())
+        self.register_buffer("log_ct", log_ct.float())
+        self.register_buffer("log_cumprod_at", log_cumprod_at.float())
+        self.register_buffer("log_cumprod_bt", log_cumprod_bt.float())
+        self.register_buffer("log_cumprod_ct", log_cumprod_ct.float())
+        self.register_buffer("log_1_min_ct", log_1_min_ct.float())
+        self.register_buffer("log_1_min_cumprod_ct", log_1_min_cumprod_ct.float())
+        self.register_buffer("Lt_history", torch.zeros(self.num_timesteps))
+        self.register_buffer("Lt_count", torch.zeros(self.num_timesteps))
+        self.zero_vector = None
+        self.empty_text_embed = nn.Parameter(torch.randn(size=(77, 512), requires_grad=True, dtype=torch.float64))
+
+        self.prior_rule = 0     # only rule 0 (VQ-Diffusion v1 Gumbel sampling) is reachable in the reference (:157)
+        self.prior_ps = 1024
+        self.prior_weight = 0
+        self.update_n_sample()
+        self.learnable_cf = learnable_cf
+        self.guidance_scale = guidance_scale
+
+        # --- state of the CUDA path (not part of the reference surface) ---
+        self.rng_seed = int(torch.initial_seed()) & (2**63 - 1)
+        self.rng_offset = 0          # advanced by one per sampling call: every call draws fresh noise
+        self.row_offset = 0          # global index of local row 0 when the batch is sharded across ranks
+        self.inject_uniform: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
+        self._coef_cache = None
+        self._status = None
+
+    # ------------------------------------------------------------------ bookkeeping
+    def update_n_sample(self):
+        """Tokens to reveal per step for the purity prior (:166-179); only its length matters for rule 0."""
+        T = self.num_timesteps
+        few = self.prior_ps <= 10
+        table = {
+            100: [1, 6 if few else 10] + [11, 10, 10] * 32 + [11, 15 if few else 11],
+            50: [10] + [21, 20] * 24 + [30],
+            25: [21] + [41] * 23 + [60],
+            10: [69] + [102] * 8 + [139],
+            200: [1, 3] + [6, 6, 4, 4] * 49 + [6, 9],
+        }
+        if T in table:
+            self.n_sample = table[T]
+
+    @property
+    def device(self):
+        return self.log_at.device
+
+    def manual_seed(self, seed: int, offset: int = 0):
+        """Re-key the in-kernel Philox stream."""
+        self.rng_seed, self.rng_offset = int(seed) & (2**63 - 1), int(offset)
+        return self
+
+    def _next_offset(self) -> int:
+        off = self.rng_offset
+        self.rng_offset += 1
+        return off
+
+    def coef_table(self) -> torch.Tensor:
+        """Device coefficient table derived from the *registered buffers* (so a loaded checkpoint's
+        schedule is honoured); rebuilt when a buffer is replaced, moved or modified in place."""
+        bufs = [getattr(self, n) for n in _SCHEDULE_BUFFERS]
+        key = tuple((b.data_ptr(), b._version, str(b.device)) for b in bufs)
+        if self._coef_cache is None or self._coef_cache[0] != key:
+            T1 = self.num_timesteps + 1
+            sched = torch.zeros(8, T1, dtype=torch.float32, device=self.device)
+            for i, b in enumerate(bufs):
+                sched[i, : b.numel()] = b
+            self._coef_cache = (key, ops.build_coef_table(sched, self.num_timesteps, self.num_classes - 1))
+        return self._coef_cache[1]
+
+    def _status_word(self) -> torch.Tensor:
+        if self._status is None or self._status.device != self.device:
+            self._status = ops.new_status(self.device)
+        return self._status
+
+    def check_status(self):
+        """One host sync: raise if any kernel since the last check saw an out-of-range t or token
+        (the reference asserts these eagerly with `.item()` syncs, :45-46, :253)."""
+        if self._status is None:
+            return
+        word = int(self._status.item())
+        self._status.zero_()
+        if word & _lib.STATUS_BAD_T:
+            raise AssertionError("t outside [0, num_timesteps)")
+        if word & _lib.STATUS_BAD_TOKEN:
+            raise AssertionError(f"token index >= num_classes ({self.num_classes})")
+
+    # ------------------------------------------------------------------ helpers
+    def _denoise_rows(self, x_t: torch.Tensor, cond_emb, t: torch.Tensor) -> torch.Tensor:
+        """Run the denoiser (:222-230) and hand its logits over as token-major rows `[B, N, K]`.
+        The reference transformer returns a `[B, K, N]` permuted view of `[B, N, K]`
+        (transformer_utils.py:442-443), so this is normally zero-copy."""
+        if self.amp:
+            with torch.autocast("cuda"):
+                out = self.transformer(x_t, cond_emb, t)
+        else:
+            out = self.transformer(x_t, cond_emb, t)
+        assert out.size(0) == x_t.size(0)
+        assert out.size(1) == self.num_classes - 1
+        assert out.size()[2:] == x_t.size()[1:]
+        out = out.float()
+        got = ops.rows_of(out)
+        if got is not None and got[1] % 4 == 0 and out.data_ptr() % 16 == 0:
+            return got[0]
+        return out.permute(0, 2, 1).contiguous()
+
+    def _tokens_of(self, log_x: torch.Tensor) -> torch.Tensor:
+        """log_onehot_to_index (:53-54) on any layout."""
+        if log_x.dtype == torch.int64 and log_x.dim() == 2:
+            return log_x.contiguous()
+        return ops.argmax_classes(log_x.float())
+
+    def _noise_rows(self, B: int, N: int):
+        """Uniform noise rows when a test injects the reference's `rand_like` tensor, else None (Philox)."""
+        if self.inject_uniform is None:
+            return None
+        u = self.inject_uniform((B, self.num_classes, N), self.device)
+        return ops.to_rows(u.to(self.device, torch.float32))
+
+    def _guidance_off(self) -> bool:
+        # the reference's own |s-1|<1e-3 branch raises AttributeError (:242-243); "off" here means the
+        # result of predict_start alone, which is what that branch was written to return
+        return abs(self.guidance_scale - 1) < 1e-3
+
+    def _step(self, x_t, cond_emb, cf_cond_emb, t, *, sample_mode, want_post=False, want_recon=False,
+              want_gap=False, guidance=True, x_prev_out=None, thin_factor=0.0):
+        logits_c = self._denoise_rows(x_t, cond_emb, t)
+        logits_u = None
+        if guidance and not self._guidance_off():
+            logits_u = self._denoise_rows(x_t, cf_cond_emb.type_as(cond_emb) if cond_emb is not None else cf_cond_emb, t)
+            if logits_u.stride() != logits_c.stride():
+                logits_u = logits_u.contiguous()
+                logits_c = logits_c.contiguous()
+        B, N = x_t.shape
+        gumbel = None
+        uniform_given = False
+        if sample_mode in (_lib.SAMPLE_PHILOX, _lib.SAMPLE_PHILOX_EXACT):
+            noise = self._noise_rows(B, N)
+            if noise is not None:
+                gumbel, uniform_given, sample_mode = noise[0], True, _lib.SAMPLE_GUMBEL
+        return ops.fused_step(
+            logits_c, logits_u, x_t, t.contiguous(), self.coef_table(), guidance_scale=self.guidance_scale,
+            sample_mode=sample_mode, gumbel=gumbel, gumbel_is_uniform=uniform_given, seed=self.rng_seed,
+            offset=self._next_offset() if sample_mode != _lib.SAMPLE_NONE else 0, row_offset=self.row_offset,
+            want_post=want_post, want_recon=want_recon, want_gap=want_gap, status=self._status_word(),
+            x_prev_out=x_prev_out, thin_factor=thin_factor)
+
+    # ------------------------------------------------------------------ reference method surface
+    @torch.no_grad()
+    def predict_start(self, log_x_t, cond_emb, t):
+        """p(x0 | x_t): float64-accurate log-softmax of the denoiser logits, -70 [MASK] row, clamp (:220-238)."""
+        x_t = self._tokens_of(log_x_t)
+        out = self._step(x_t, cond_emb, None, t, sample_mode=_lib.SAMPLE_NONE, want_recon=True, guidance=False)
+        return ops.as_logical(out["recon"], self.num_classes)
+
+    @torch.no_grad()
+    def cf_predict_start(self, log_x_t, cond_emb, cf_cond_emb, t):
+        """Classifier-free guidance combine + renormalise + clamp (:240-249)."""
+        x_t = self._tokens_of(log_x_t)
+        out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_NONE, want_recon=True)
+        return ops.as_logical(out["recon"], self.num_classes)
+
+    def q_posterior(self, log_x_start, log_x_t, t):
+        """p_theta(x_{t-1} | x_t) from an arbitrary log p(x0) (:251-283), forward only.
+
+        The differentiable use inside `_train_loss` (:405) is SURVEY.md §8 f1 ("next"): it is refused
+        here rather than silently routed through a slow path."""
+        if torch.is_grad_enabled() and log_x_start.requires_grad:
+            raise NotImplementedError("q_posterior backward (training, SURVEY §8 f1) is not built yet; "
+                                      "call under torch.no_grad() or detach log_x_start")
+        x_t = self._tokens_of(log_x_t)
+        rows, pitch = ops.to_rows(log_x_start.detach().float())
+        post = ops.q_posterior_rows(rows, pitch, x_t, t.contiguous(), self.coef_table(), self.num_classes - 1,
+                                    self._status_word())
+        return ops.as_logical(post, self.num_classes)
+
+    @torch.no_grad()
+    def p_pred(self, log_x, cond_emb, cf_cond_emb, t):
+        """(:285-296) -> (log_model_pred, log_x_recon), both `[B, K+1, N]`."""
+        if self.parametrization != "x0":
+            raise ValueError
+        x_t = self._tokens_of(log_x)
+        out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_NONE, want_post=True, want_recon=True)
+        return ops.as_logical(out["post"], self.num_classes), ops.as_logical(out["recon"], self.num_classes)
+
+    @torch.no_grad()
+    def p_sample(self, log_x, cond_emb, cf_cond_emb, t, sampled, to_sample):
+        """One reverse step (:304-352): returns (log one-hot of x_{t-1} `[B, K+1, N]`, `[1024]*B`)."""
+        if self.prior_rule != 0:
+            raise NotImplementedError("purity-prior sampling (prior_rule 1/2, :309-346) is SURVEY §8 f2 (next)")
+        x_prev = self.p_sample_tokens(self._tokens_of(log_x), cond_emb, cf_cond_emb, t)
+        out = ops.tokens_to_log_onehot_rows(x_prev, self.num_classes, self._status_word())
+        return ops.as_logical(out, self.num_classes), [1024] * log_x.shape[0]
+
+    @torch.no_grad()
+    def p_sample_tokens(self, x_t, cond_emb, cf_cond_emb, t, x_prev_out=None):
+        """The same step on integer tokens: int64 `[B, N]` in, int64 `[B, N]` out (fast path of `sample`)."""
+        out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_PHILOX, x_prev_out=x_prev_out)
+        return out["x_prev"]
+
+    @torch.no_grad()
+    def log_sample_categorical(self, logits):
+        """Gumbel-max draw over dim 1 of `[B, C, N]` log-probs, returned as a log one-hot (:354-359)."""
+        B, C, N = logits.shape
+        rows, pitch = ops.to_rows(logits.float())
+        noise = self._noise_rows(B, N) if C == self.num_classes else None
+        if noise is not None:
+            x = ops.gumbel_argmax_rows(rows, pitch, C, noise_rows=noise[0], pitch_noise=noise[1], noise_kind=1)
+        else:
+            x = ops.gumbel_argmax_rows(rows, pitch, C, noise_kind=2, seed=self.rng_seed, offset=self._next_offset(),
+                                       row_offset=self.row_offset)
+        return ops.as_logical(ops.tokens_to_log_onehot_rows(x, C, self._status_word()), C)
+
+    @torch.no_grad()
+    def sample(
+        self,
+        condition_token,
+        condition_mask,
+        condition_embed,
+        cf_condition_embed,
+        content_token=None,
+        filter_ratio=0.5,
+        temperature=1.0,
+        return_att_weight=False,
+        return_logits=False,
+        content_logits=None,
+        print_log=True,
+        **kwargs,
+    ):
+        """Full reverse chain from the all-[MASK] state (:568-644) -> {'content_token': int64 [B, N]}.
+
+        `filter_ratio > 0` (start from a noised `content_token`) calls `p_sample` with a stale
+        signature in the reference and raises there (:628-636); it is refused here too."""
+        if condition_token is not None:
+            batch_size = len(condition_token)
+        else:
+            batch_size = kwargs["batch_size"]
+        device = self.log_at.device
+        start_step = int(self.num_timesteps * filter_ratio)
+        if start_step != 0:
+            raise NotImplementedError("sample(filter_ratio > 0) is unreachable in the reference (:628-636)")
+        if condition_embed is None or cf_condition_embed is None:
+            raise ValueError("condition_embed and cf_condition_embed are required (the reference leaves "
+                             "cf_cond_emb undefined otherwise, :607-611)")
+        cond_emb = condition_embed.float()
+        cf_cond_emb = cf_condition_embed.float()
+
+        N, K = self.shape, self.num_classes - 1
+        x = torch.full((batch_size, N), K, dtype=torch.int64, device=device)  # all [MASK] (:615-618)
+        x_next = torch.empty_like(x)
+        for diffusion_index in range(self.num_timesteps - 1, -1, -1):
+            t = torch.full((batch_size,), diffusion_index, device=device, dtype=torch.long)
+            # with prior_rule == 0 the reference's `while min(sampled) < n_sample[...]` body runs once (:624-626)
+            self.p_sample_tokens(x, cond_emb, cf_cond_emb, t, x_prev_out=x_next)
+            x, x_next = x_next, x
+        self.check_status()
+        output = {"content_token": x}
+        if return_logits:
+            log_z = ops.as_logical(ops.tokens_to_log_onehot_rows(x, self.num_classes), self.num_classes)
+            output["logits"] = torch.exp(log_z)
+        return output
+
+    # ------------------------------------------------------------------ explicitly out of scope this round
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("training forward/_train_loss (:391-457, :520-565) is SURVEY §8 f1 (next); "
+                                  "this class accelerates the sampling path")

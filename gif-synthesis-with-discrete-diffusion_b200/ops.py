@@ -1,0 +1,277 @@
+"""Tensor-level wrappers of the C ABI: torch tensors in, torch tensors out, CUDA only.
+
+Layout vocabulary (see include/d3pm_b200.h): the reference's logical `[B, C, N]` tensors (class
+dim = 1) are held as *token-major rows* `[B, N, pitch]` with the class index contiguous.
+`as_logical` / `rows_of` convert between the two without copying whenever the strides allow it.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from d3pm_b200 import _lib
+from d3pm_b200._lib import D3PMError
+
+LOG_TINY = -69.07755278982137  # log(1e-30), the reference's one-hot "zero" (diffusion_transformer.py:50)
+
+
+# --------------------------------------------------------------------------- plumbing
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for x in tensors:
+        if x is None:
+            continue
+        if not x.is_cuda:
+            raise D3PMError("d3pm_b200 operates on CUDA tensors only (there is no CPU path)")
+        if dev is not None and x.device != dev:
+            raise D3PMError(f"tensors on different devices: {dev} vs {x.device}")
+        dev = x.device
+    if dev is None:
+        raise D3PMError("no tensor given")
+    return dev
+
+
+def _ptr(x: Optional[torch.Tensor]) -> Optional[int]:
+    return None if x is None else x.data_ptr()
+
+
+def padded_pitch(num_classes: int) -> int:
+    """Row pitch (floats) for a row of `num_classes` entries: next multiple of 4."""
+    return (num_classes + 3) // 4 * 4
+
+
+def alloc_rows(B: int, N: int, num_classes: int, device, dtype=torch.float32) -> torch.Tensor:
+    """Uninitialised token-major storage `[B, N, pitch]`, rows 16-byte aligned."""
+    return torch.empty(B, N, padded_pitch(num_classes), device=device, dtype=dtype)
+
+
+def as_logical(rows: torch.Tensor, num_classes: int) -> torch.Tensor:
+    """`[B, N, pitch]` rows -> the reference's logical `[B, C, N]` view (no copy)."""
+    B, N, pitch = rows.shape
+    return torch.as_strided(rows, (B, num_classes, N), (rows.stride(0), 1, rows.stride(1)), rows.storage_offset())
+
+
+def rows_of(x: torch.Tensor) -> Optional[Tuple[torch.Tensor, int]]:
+    """If logical `[B, C, N]` tensor `x` is a view of token-major rows, return `(rows [B,N,C], pitch)`."""
+    if x.dim() != 3 or x.dtype != torch.float32:
+        return None
+    B, C, N = x.shape
+    sb, sc, sn = x.stride()
+    if sc != 1 or (N > 1 and sn < C) or (B > 1 and sb != N * sn):
+        return None
+    return x.permute(0, 2, 1), (sn if N > 1 else C)
+
+
+def to_rows(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Logical `[B, C, N]` float32 -> token-major `(rows, pitch)`; copies (transposes on device) only
+    when `x` is stored class-major like the reference's own `[B, K+1, N]` intermediates."""
+    got = rows_of(x)
+    if got is not None:
+        return got
+    dev = _need_cuda(x)
+    B, C, N = x.shape
+    src = x.contiguous().float()
+    dst = alloc_rows(B, N, C, dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_to_token_major(src.data_ptr(), dst.data_ptr(), dst.shape[2], B, C, N, _stream(dev)),
+               "d3pm_to_token_major")
+    return dst[:, :, :C], dst.shape[2]
+
+
+def new_status(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+# --------------------------------------------------------------------------- schedule
+def build_coef_table(sched8: torch.Tensor, T: int, K: int) -> torch.Tensor:
+    """`[8, T+1]` float32 device schedule -> `[T, 32]` coefficient table (d3pm_build_coef_table)."""
+    dev = _need_cuda(sched8)
+    if sched8.shape != (8, T + 1) or sched8.dtype != torch.float32 or not sched8.is_contiguous():
+        raise D3PMError(f"schedule must be a contiguous float32 [8, {T + 1}] tensor, got {tuple(sched8.shape)}")
+    table = torch.empty(T, _lib.COEF_STRIDE, dtype=torch.float32, device=dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_build_coef_table(sched8.data_ptr(), T, K, table.data_ptr(), _stream(dev)),
+               "d3pm_build_coef_table")
+    return table
+
+
+# --------------------------------------------------------------------------- fused step
+def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: torch.Tensor, t: torch.Tensor,
+               coef_table: torch.Tensor, *, guidance_scale: float, sample_mode: int,
+               gumbel: Optional[torch.Tensor] = None, gumbel_is_uniform: bool = False, seed: int = 0, offset: int = 0, row_offset: int = 0,
+               want_post: bool = False, want_recon: bool = False, want_gap: bool = False,
+               status: Optional[torch.Tensor] = None, thin_factor: float = 0.0,
+               x_prev_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """One fused reverse step over token-major logits `[B, N, K]` (d3pm_fused_step).
+
+    `logits_u=None` is guidance off.  `gumbel` is `[B, N, >=K+1]` rows (entry K = [MASK]).
+    Returns a dict with the requested tensors: `x_prev` int64 `[B, N]`, `post` / `recon` as
+    `[B, N, pitch]` rows (use `as_logical(rows, K+1)` for the reference's `[B, K+1, N]`), `gap` `[B, N]`.
+    """
+    dev = _need_cuda(logits_c, logits_u, x_t, t, coef_table, gumbel, status)
+    if logits_c.dim() != 3 or logits_c.dtype != torch.float32 or logits_c.stride(2) != 1:
+        raise D3PMError("logits_c must be float32 [B, N, K] rows with the class index contiguous")
+    B, N, K = logits_c.shape
+    pitch = logits_c.stride(1) if N > 1 else K
+    if B > 1 and logits_c.stride(0) != N * pitch:
+        raise D3PMError("logits_c rows must be uniformly pitched across the batch")
+    if logits_u is not None and (logits_u.shape != logits_c.shape or logits_u.stride() != logits_c.stride()
+                                 or logits_u.dtype != torch.float32):
+        raise D3PMError("logits_u must match logits_c in shape, strides and dtype")
+    if x_t.shape != (B, N) or x_t.dtype != torch.int64 or not x_t.is_contiguous():
+        raise D3PMError("x_t must be a contiguous int64 [B, N] tensor")
+    if t.shape != (B,) or t.dtype != torch.int64 or not t.is_contiguous():
+        raise D3PMError("t must be a contiguous int64 [B] tensor")
+    T = coef_table.shape[0]
+
+    d = _lib.StepDesc()
+    d.logits_c, d.logits_u = _ptr(logits_c), _ptr(logits_u)
+    d.x_t, d.t, d.coef_table = _ptr(x_t), _ptr(t), _ptr(coef_table)
+    out: Dict[str, torch.Tensor] = {}
+    if sample_mode != _lib.SAMPLE_NONE:
+        if x_prev_out is None:
+            x_prev_out = torch.empty(B, N, dtype=torch.int64, device=dev)
+        elif x_prev_out.shape != (B, N) or x_prev_out.dtype != torch.int64 or not x_prev_out.is_contiguous():
+            raise D3PMError("x_prev_out must be a contiguous int64 [B, N] tensor")
+        out["x_prev"] = x_prev_out
+        d.x_prev = _ptr(x_prev_out)
+    if sample_mode == _lib.SAMPLE_GUMBEL:
+        if gumbel is None or gumbel.dim() != 3 or gumbel.shape[:2] != (B, N) or gumbel.stride(2) != 1 \
+                or gumbel.dtype != torch.float32:
+            raise D3PMError("SAMPLE_GUMBEL needs float32 gumbel rows [B, N, >=K+1]")
+        d.gumbel = _ptr(gumbel)
+        d.pitch_gumbel = gumbel.stride(1) if N > 1 else gumbel.shape[2]
+        d.gumbel_is_uniform = 1 if gumbel_is_uniform else 0
+    pitch_out = padded_pitch(K + 1)
+    if want_post:
+        out["post"] = torch.empty(B, N, pitch_out, dtype=torch.float32, device=dev)
+        d.post = _ptr(out["post"])
+    if want_recon:
+        out["recon"] = torch.empty(B, N, pitch_out, dtype=torch.float32, device=dev)
+        d.recon = _ptr(out["recon"])
+    if want_gap:
+        out["gap"] = torch.empty(B, N, dtype=torch.float32, device=dev)
+        d.gap = _ptr(out["gap"])
+    d.status = _ptr(status)
+    d.B, d.N, d.K, d.T = B, N, K, T
+    d.pitch_logits, d.pitch_out = pitch, pitch_out
+    d.guidance_scale, d.sample_mode = float(guidance_scale), int(sample_mode)
+    d.seed, d.offset, d.row_offset = seed & (2**64 - 1), offset & (2**64 - 1), int(row_offset)
+    d.thin_factor = float(thin_factor)
+    d.stream = _stream(dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_fused_step(ctypes.byref(d)), "d3pm_fused_step")
+    return out
+
+
+def philox_uniform(B: int, N: int, K: int, *, seed: int, offset: int, row_offset: int = 0,
+                   device="cuda") -> torch.Tensor:
+    """The uniforms SAMPLE_PHILOX draws, as rows `[B, N, pitch]` (first K+1 valid)."""
+    dev = torch.device(device)
+    u = alloc_rows(B, N, K + 1, dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_philox_uniform(u.data_ptr(), B * N, K, u.shape[2], seed & (2**64 - 1),
+                                       offset & (2**64 - 1), row_offset, _stream(dev)), "d3pm_philox_uniform")
+    return u
+
+
+# --------------------------------------------------------------------------- fine-grained operators
+def q_posterior_rows(log_x_start_rows: torch.Tensor, pitch_in: int, x_t: torch.Tensor, t: torch.Tensor,
+                     coef_table: torch.Tensor, K: int, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q_posterior on arbitrary log p(x0) rows `[B, N, >=K]`; returns posterior rows `[B, N, pitch]`."""
+    dev = _need_cuda(log_x_start_rows, x_t, t, coef_table, status)
+    B, N = x_t.shape
+    post = alloc_rows(B, N, K + 1, dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_q_posterior(log_x_start_rows.data_ptr(), pitch_in, x_t.data_ptr(), t.data_ptr(),
+                                    coef_table.data_ptr(), post.data_ptr(), post.shape[2], B, N, K,
+                                    coef_table.shape[0], _ptr(status), _stream(dev)), "d3pm_q_posterior")
+    return post
+
+
+def gumbel_argmax_rows(logits_rows: torch.Tensor, pitch_logits: int, num_classes: int, *,
+                       noise_rows: Optional[torch.Tensor] = None, pitch_noise: int = 0, noise_kind: int = 2,
+                       seed: int = 0, offset: int = 0, row_offset: int = 0, want_gap: bool = False):
+    """log_sample_categorical over rows: `noise_kind` 0 = Gumbel given, 1 = uniform given, 2 = Philox."""
+    dev = _need_cuda(logits_rows, noise_rows)
+    B, N = logits_rows.shape[:2]
+    x = torch.empty(B, N, dtype=torch.int64, device=dev)
+    gap = torch.empty(B, N, dtype=torch.float32, device=dev) if want_gap else None
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_gumbel_argmax(logits_rows.data_ptr(), pitch_logits, _ptr(noise_rows), pitch_noise,
+                                      noise_kind, x.data_ptr(), _ptr(gap), B * N, num_classes,
+                                      seed & (2**64 - 1), offset & (2**64 - 1), row_offset, _stream(dev)),
+               "d3pm_gumbel_argmax")
+    return (x, gap) if want_gap else x
+
+
+def tokens_to_log_onehot_rows(x: torch.Tensor, num_classes: int, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """index_to_log_onehot: int64 `[B, N]` -> rows `[B, N, pitch]` holding {0, log 1e-30}."""
+    dev = _need_cuda(x, status)
+    if x.dtype != torch.int64 or x.dim() != 2 or not x.is_contiguous():
+        raise D3PMError("tokens must be a contiguous int64 [B, N] tensor")
+    B, N = x.shape
+    out = alloc_rows(B, N, num_classes, dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_tokens_to_log_onehot(x.data_ptr(), out.data_ptr(), out.shape[2], B * N, num_classes,
+                                             _ptr(status), _stream(dev)), "d3pm_tokens_to_log_onehot")
+    return out
+
+
+def argmax_classes(x: torch.Tensor) -> torch.Tensor:
+    """log_onehot_to_index for any strided float32 `[B, C, N]` view -> int64 `[B, N]`."""
+    dev = _need_cuda(x)
+    if x.dim() != 3 or x.dtype != torch.float32:
+        raise D3PMError("argmax_classes expects a float32 [B, C, N] tensor")
+    B, C, N = x.shape
+    idx = torch.empty(B, N, dtype=torch.int64, device=dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_argmax_classes(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), idx.data_ptr(),
+                                       B, C, N, _stream(dev)), "d3pm_argmax_classes")
+    return idx
+
+
+# --------------------------------------------------------------------------- host-buffer entry (end-to-end path)
+class HostStep:
+    """The fused step for callers whose logits live in HOST memory (the reference's CPU tensors).
+
+    Owns the device staging buffers for one batch shape; `__call__` copies the pinned host inputs to
+    the device, runs `d3pm_fused_step` (production Philox sampling) and copies the int64 tokens back,
+    all on the current stream, then waits for the result.  Per call it moves
+    `h2d_bytes` up and `d2h_bytes` down; this is the path `bench.py` reports as `e2e`.
+    """
+
+    def __init__(self, B: int, N: int, K: int, coef_table: torch.Tensor, guidance: bool = True):
+        dev = coef_table.device
+        self.coef_table, self.guidance = coef_table, guidance
+        self.logits_c = torch.empty(B, N, K, dtype=torch.float32, device=dev)
+        self.logits_u = torch.empty(B, N, K, dtype=torch.float32, device=dev) if guidance else None
+        self.x_t = torch.empty(B, N, dtype=torch.int64, device=dev)
+        self.t = torch.empty(B, dtype=torch.int64, device=dev)
+        self.x_prev = torch.empty(B, N, dtype=torch.int64, device=dev)
+        self.x_prev_host = torch.empty(B, N, dtype=torch.int64).pin_memory()
+        self.h2d_bytes = (self.logits_c.numel() * 4 * (2 if guidance else 1) + self.x_t.numel() * 8 + self.t.numel() * 8)
+        self.d2h_bytes = self.x_prev.numel() * 8
+
+    def __call__(self, logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: torch.Tensor, t: torch.Tensor,
+                 *, guidance_scale: float, seed: int, offset: int, row_offset: int = 0) -> torch.Tensor:
+        for src in (logits_c, logits_u, x_t, t):
+            if src is not None and src.is_cuda:
+                raise D3PMError("HostStep takes host tensors; use fused_step for device-resident inputs")
+        self.logits_c.copy_(logits_c, non_blocking=True)
+        if self.guidance:
+            self.logits_u.copy_(logits_u, non_blocking=True)
+        self.x_t.copy_(x_t, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        fused_step(self.logits_c, self.logits_u, self.x_t, self.t, self.coef_table, guidance_scale=guidance_scale,
+                   sample_mode=_lib.SAMPLE_PHILOX, seed=seed, offset=offset, row_offset=row_offset,
+                   x_prev_out=self.x_prev)
+        self.x_prev_host.copy_(self.x_prev, non_blocking=True)
+        torch.cuda.current_stream(self.x_prev.device).synchronize()
+        return self.x_prev_host

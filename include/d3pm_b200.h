@@ -1,0 +1,133 @@
+/*
+ * d3pm_b200.h — C ABI of the B200-native D3PM / VQ-Diffusion reverse-diffusion token update.
+ *
+ * The reference (Developer-Zer0/GIF-synthesis-with-Discrete-Diffusion) is 100 % Python: the
+ * "FFI" of this path is the method surface of
+ *     src/models/motionencoder/diffusion_transformer.py  class DiffusionTransformer
+ * Each entry point below names the reference method(s) (file:line) it replaces.  All pointers are
+ * DEVICE pointers owned by the caller (PyTorch); the library allocates nothing persistent, keeps no
+ * pointer past return, launches asynchronously on the given CUDA stream and never synchronises.
+ * Return value: 0 (D3PM_OK) or a negative error code; d3pm_last_error() gives the text.
+ *
+ * Memory layout ("token-major rows"): a logical [B, C, N] tensor of the reference (class dim = 1)
+ * is stored as B*N rows of `pitch` floats, class index contiguous, pitch % 4 == 0, base 16-byte
+ * aligned.  The denoiser's logits are already physically [B, N, K] (transformer_utils.py:442-443
+ * returns a permuted view), so they are consumed in place with pitch = K.  Tensors that carry the
+ * [MASK] class (K+1 entries) use pitch >= K+1 (K+4 for K = 4096): entry K of a row is the [MASK]
+ * class, the padding is never read.
+ */
+#ifndef D3PM_B200_H
+#define D3PM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3PM_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define D3PM_OK 0
+#define D3PM_ERR_INVALID (-1)     /* null pointer, non-positive size, t/K/T inconsistent */
+#define D3PM_ERR_ALIGN (-2)       /* pointer not 16-byte aligned or pitch % 4 != 0 */
+#define D3PM_ERR_UNSUPPORTED (-3) /* shape outside what the kernels cover (K % 4 != 0, K > 8192) */
+#define D3PM_ERR_CUDA (-4)        /* a CUDA runtime call failed (text holds cudaGetErrorString) */
+
+/* bits OR-ed into the optional device status word by the kernels (the reference asserts these on
+ * the host with .item() syncs, diffusion_transformer.py:45-46, :253) */
+#define D3PM_STATUS_BAD_T 1u     /* some t[b] outside [0, T) */
+#define D3PM_STATUS_BAD_TOKEN 2u /* some x_t outside [0, K] */
+#define D3PM_STATUS_FALLBACK 4u  /* informational: a row needed the exhaustive sampling pass */
+
+typedef void* d3pm_stream_t; /* cudaStream_t */
+
+int d3pm_version(void);
+const char* d3pm_last_error(void);
+
+/* ---------------------------------------------------------------- schedule
+ * Replaces: the eight registered buffers built in DiffusionTransformer.__init__
+ * (diffusion_transformer.py:120-149) and every `extract(...)` gather on them (:36-39,
+ * :186-189, :204-207, :263, :271).
+ * `sched` = [8][T+1] floats in the order log_at, log_bt, log_ct, log_1_min_ct, log_cumprod_at,
+ * log_cumprod_bt, log_cumprod_ct, log_1_min_cumprod_ct (per-step rows padded to T+1).
+ * Writes table[T][D3PM_COEF_STRIDE]: per-timestep linear-domain coefficients (computed in
+ * float64 on the device) that the step kernels index with t[b].                                  */
+#define D3PM_COEF_STRIDE 32
+int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_stream_t stream);
+
+/* ---------------------------------------------------------------- fused reverse step
+ * Replaces, in ONE pass over the logits: predict_start's log-softmax/clamp (:231-236),
+ * cf_predict_start (:240-249), q_posterior (:251-283) incl. q_pred / q_pred_one_timestep
+ * (:185-218), log_sample_categorical (:354-359) and the index<->log-one-hot round trips
+ * (:44-54) — i.e. p_pred (:285-296) + the prior_rule==0 branch of p_sample (:304-352).        */
+#define D3PM_SAMPLE_NONE 0         /* outputs only (p_pred) */
+#define D3PM_SAMPLE_GUMBEL 1       /* argmax(gumbel + posterior), noise injected by the caller */
+#define D3PM_SAMPLE_PHILOX 2       /* in-kernel Philox4x32-10 noise, thinned exponential race (production) */
+#define D3PM_SAMPLE_PHILOX_EXACT 3 /* same noise, every class scored in log space (verification) */
+
+typedef struct d3pm_step_desc {
+  /* inputs */
+  const float* logits_c;   /* [B*N][pitch_logits] conditional denoiser logits (first K valid) */
+  const float* logits_u;   /* same shape, unconditional; NULL = guidance off (predict_start only) */
+  const int64_t* x_t;      /* [B*N] current tokens in [0, K]; K = [MASK] */
+  const int64_t* t;        /* [B] timestep per video, in [0, T) */
+  const float* coef_table; /* from d3pm_build_coef_table */
+  const float* gumbel;     /* [B*N][pitch_gumbel] Gumbel noise, entry K = [MASK]; D3PM_SAMPLE_GUMBEL only */
+  /* outputs (each nullable) */
+  int64_t* x_prev;     /* [B*N] sampled x_{t-1} */
+  float* post;         /* [B*N][pitch_out] posterior log-probs, K+1 valid (q_posterior's return, clamp(-70,0)) */
+  float* recon;        /* [B*N][pitch_out] log p(x0|x_t), K+1 valid (cf_predict_start's return) */
+  float* gap;          /* [B*N] top-1 minus top-2 sampling score (near-tie log); GUMBEL / PHILOX_EXACT only */
+  uint32_t* status;    /* one word, OR of D3PM_STATUS_* */
+  /* sizes */
+  int32_t B, N, K, T;
+  int64_t pitch_logits, pitch_gumbel, pitch_out; /* in floats */
+  /* parameters */
+  float guidance_scale;
+  int32_t sample_mode;   /* D3PM_SAMPLE_* */
+  int32_t gumbel_is_uniform; /* 1: `gumbel` holds uniforms u (torch.rand_like's tensor); g = -log(-log(u+1e-30)+1e-30) in-kernel */
+  uint64_t seed, offset; /* Philox key / per-call stream offset */
+  int64_t row_offset;    /* global index of local row 0 (b_global*N + n): shards reproduce the 1-GPU stream */
+  float thin_factor;     /* PHILOX thinning constant c (0 = default 16); smaller forces the exhaustive fallback */
+  d3pm_stream_t stream;
+} d3pm_step_desc;
+
+int d3pm_fused_step(const d3pm_step_desc* desc);
+
+/* The uniforms D3PM_SAMPLE_PHILOX* draw, written as fp32 rows [rows][pitch] (K+1 valid) so a test can
+ * inject the very same noise into the reference through torch.rand_like (:355).                     */
+int d3pm_philox_uniform(float* u, int64_t rows, int K, int64_t pitch, uint64_t seed, uint64_t offset,
+                        int64_t row_offset, d3pm_stream_t stream);
+
+/* ---------------------------------------------------------------- fine-grained operators
+ * q_posterior (:251-283) on an arbitrary log p(x0) (e.g. the one-hot truth of _train_loss :420).
+ * log_x_start: [B*N][pitch_in], first K entries used (entry K is ignored, like the reference :278). */
+int d3pm_q_posterior(const float* log_x_start, int64_t pitch_in, const int64_t* x_t, const int64_t* t,
+                     const float* coef_table, float* post, int64_t pitch_out, int B, int N, int K, int T,
+                     uint32_t* status, d3pm_stream_t stream);
+
+/* log_sample_categorical (:354-359): x[row] = argmax_k(noise_k + logits[row][k]) over C classes.
+ * noise_kind 0: `noise` holds Gumbel values; 1: `noise` holds uniforms u, g = -log(-log(u+1e-30)+1e-30);
+ * 2: noise == NULL, Philox stream (seed, offset, row_offset) as in d3pm_fused_step.               */
+int d3pm_gumbel_argmax(const float* logits, int64_t pitch_logits, const float* noise, int64_t pitch_noise,
+                       int noise_kind, int64_t* x, float* gap, int64_t rows, int C, uint64_t seed,
+                       uint64_t offset, int64_t row_offset, d3pm_stream_t stream);
+
+/* index_to_log_onehot (:44-51): rows of C entries, 0 at x[row], log(1e-30) elsewhere. */
+int d3pm_tokens_to_log_onehot(const int64_t* x, float* out, int64_t pitch, int64_t rows, int C,
+                              uint32_t* status, d3pm_stream_t stream);
+
+/* log_onehot_to_index (:53-54): first maximal class per token.
+ * class_stride / token_stride / batch_stride in floats describe ANY [B, C, N] view:
+ * token-major rows (class_stride 1) or the reference's contiguous layout (token_stride 1).        */
+int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stride, int64_t token_stride,
+                        int64_t* idx, int B, int C, int N, d3pm_stream_t stream);
+
+/* [B, C, N] contiguous (reference layout) -> token-major rows [B*N][pitch]. */
+int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N,
+                        d3pm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3PM_B200_H */
