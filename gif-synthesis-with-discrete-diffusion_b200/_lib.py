@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = (
 COEF_STRIDE = 32
 SAMPLE_NONE, SAMPLE_GUMBEL, SAMPLE_PHILOX, SAMPLE_PHILOX_EXACT = 0, 1, 2, 3
 STATUS_BAD_T, STATUS_BAD_TOKEN, STATUS_FALLBACK = 1, 2, 4
+KERNEL_AUTO, KERNEL_ROWS, KERNEL_STREAM = 0, 1, 2
 
 
 class D3PMError(RuntimeError):
@@ -37,7 +38,7 @@ class StepDesc(ctypes.Structure):
         ("pitch_logits", c_int64), ("pitch_gumbel", c_int64), ("pitch_out", c_int64),
         ("guidance_scale", c_float), ("sample_mode", c_int32), ("gumbel_is_uniform", c_int32),
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64),
-        ("thin_factor", c_float), ("stream", c_void_p),
+        ("thin_factor", c_float), ("kernel", c_int32), ("stream", c_void_p),
     ]
 
 

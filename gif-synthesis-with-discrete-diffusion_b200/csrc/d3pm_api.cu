@@ -106,7 +106,12 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   p.rows = rows;
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
 
-  if (d3pm::stream_kernel_eligible(p)) {
+  if (d->kernel < D3PM_KERNEL_AUTO || d->kernel > D3PM_KERNEL_STREAM)
+    return fail(D3PM_ERR_INVALID, "fused_step: unknown kernel selector %d", d->kernel);
+  const bool can_stream = d3pm::stream_kernel_supports(p);
+  if (d->kernel == D3PM_KERNEL_STREAM && !can_stream)
+    return fail(D3PM_ERR_UNSUPPORTED, "fused_step: the stream kernel needs PHILOX sampling, no outputs and K in {1024,2048,4096}");
+  if (d->kernel == D3PM_KERNEL_STREAM || (d->kernel == D3PM_KERNEL_AUTO && can_stream && rows >= d3pm::kStreamMinRows)) {
     const int rc = d3pm::launch_step_stream(p, s);
     if (rc != D3PM_OK) return fail(rc, "fused_step: stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("fused_step(stream)");

@@ -110,50 +110,75 @@ __device__ __forceinline__ float key_score(unsigned long long key) {
   return __uint_as_float(b);
 }
 
-// ---- Philox4x32-10 (Salmon et al. 2011), counter = (class/4, row, offset), key = seed ----------
-// One call yields the noise of four consecutive classes of one token row, so a row's stream does not
-// depend on which GPU or CTA processes it.
+// ---- noise: Philox4x32-10 (Salmon et al. 2011) -----------------------------------------------------
+// Every class k of every global token row draws a 23-bit integer m from a counter-based stream, so a
+// row's noise does not depend on which GPU, CTA or kernel variant processes it:
+//   * 16 high bits h from a COARSE call, counter (coarse_call(k), row, offset), eight 16-bit halves per
+//     call.  The production kernel decides with h alone whether a class can still win the race.
+//   * 7 low bits from a FINE call, counter (k >> 4, row, offset | 2^63), one byte per class; only classes
+//     that survive the coarse test (and the verification paths) ever compute it.
+// m = h << 7 | low7, v = (2m+1) / 2^24 in (0,1) is the "distance from 1" and u = 1 - v is the uniform
+// torch.rand_like would have returned (:355); both are exact in fp32.
+// A coarse call serves the two float4 chunks c and c+128 of a 1024-class block (the pair one thread of a
+// 128-thread group owns): coarse_call = (c / 256) * 128 + c % 128, half = 4 * ((c / 128) % 2) + k % 4.
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+constexpr int kPhiloxRounds = 10;
 
-template <int ROUNDS = 10>
-__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                            uint32_t k1) {
+struct NoiseStream {
+  uint32_t rk0[kPhiloxRounds], rk1[kPhiloxRounds];  // round keys (uniform across the grid)
+  uint32_t off_lo, off_hi;
+
+  __device__ __forceinline__ NoiseStream(uint64_t seed, uint64_t offset)
+      : off_lo(static_cast<uint32_t>(offset)), off_hi(static_cast<uint32_t>(offset >> 32) & 0x7fffffffu) {
+    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
 #pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
-    const unsigned long long p0 = static_cast<unsigned long long>(kPhiloxM0) * c0;
-    const unsigned long long p1 = static_cast<unsigned long long>(kPhiloxM1) * c2;
-    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
-    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
-    c1 = static_cast<uint32_t>(p1);
-    c3 = static_cast<uint32_t>(p0);
-    c0 = n0;
-    c2 = n2;
-    k0 += kPhiloxW0;
-    k1 += kPhiloxW1;
+    for (int r = 0; r < kPhiloxRounds; ++r) {
+      rk0[r] = k0, rk1[r] = k1;
+      k0 += kPhiloxW0, k1 += kPhiloxW1;
+    }
   }
-  return make_uint4(c0, c1, c2, c3);
-}
-
-struct PhiloxStream {
-  uint32_t k0, k1, off_lo, off_hi;
-  __device__ __forceinline__ PhiloxStream(uint64_t seed, uint64_t offset)
-      : k0(static_cast<uint32_t>(seed)), k1(static_cast<uint32_t>(seed >> 32)),
-        off_lo(static_cast<uint32_t>(offset)), off_hi(static_cast<uint32_t>(offset >> 32)) {}
-  // the four 32-bit words for classes 4*quad .. 4*quad+3 of global token row `row`
-  __device__ __forceinline__ uint4 words(uint32_t quad, uint64_t row) const {
-    return philox4x32<10>(quad, static_cast<uint32_t>(row), off_lo ^ static_cast<uint32_t>(row >> 32), off_hi, k0,
-                          k1);
+  __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+#pragma unroll
+    for (int r = 0; r < kPhiloxRounds; ++r) {
+      const uint32_t lo0 = kPhiloxM0 * c0, hi0 = __umulhi(kPhiloxM0, c0);
+      const uint32_t lo1 = kPhiloxM1 * c2, hi1 = __umulhi(kPhiloxM1, c2);
+      c0 = hi1 ^ c1 ^ rk0[r];
+      c2 = hi0 ^ c3 ^ rk1[r];
+      c1 = lo1;
+      c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  __device__ __forceinline__ uint4 coarse(uint32_t call, uint64_t row) const {
+    return philox(call, static_cast<uint32_t>(row), off_lo ^ static_cast<uint32_t>(row >> 32), off_hi);
+  }
+  __device__ __forceinline__ uint4 fine(uint32_t call, uint64_t row) const {
+    return philox(call, static_cast<uint32_t>(row), off_lo ^ static_cast<uint32_t>(row >> 32), off_hi | 0x80000000u);
+  }
+  static __device__ __forceinline__ uint32_t coarse_call_of_chunk(uint32_t chunk) {
+    return ((chunk >> 8) << 7) | (chunk & 127u);
+  }
+  static __device__ __forceinline__ uint32_t coarse_half_of(uint32_t k) { return (((k >> 9) & 1u) << 2) | (k & 3u); }
+  // the 23-bit draw of class k (both calls; slow paths only)
+  __device__ __forceinline__ uint32_t draw(uint32_t k, uint64_t row) const {
+    const uint4 cw = coarse(coarse_call_of_chunk(k >> 2), row);
+    const uint4 fw = fine(k >> 4, row);
+    return (half_of(cw, coarse_half_of(k)) << 7) | low7_of(fw, k & 15u);
+  }
+  static __device__ __forceinline__ uint32_t word_of(const uint4& w, uint32_t i) {
+    return i == 0 ? w.x : i == 1 ? w.y : i == 2 ? w.z : w.w;
+  }
+  static __device__ __forceinline__ uint32_t half_of(const uint4& w, uint32_t h) {
+    const uint32_t x = word_of(w, h >> 1);
+    return (h & 1u) ? (x >> 16) : (x & 0xffffu);
+  }
+  static __device__ __forceinline__ uint32_t low7_of(const uint4& w, uint32_t byte) {
+    return (word_of(w, byte >> 2) >> (8u * (byte & 3u))) & 0x7fu;
   }
 };
-__device__ __forceinline__ uint32_t word_of(const uint4& w, int e) {
-  return e == 0 ? w.x : e == 1 ? w.y : e == 2 ? w.z : w.w;
-}
 
-// A 32-bit word -> uniform.  The low 23 bits m give v = (2m+1)/2^24 in (0,1) ("distance from 1") and
-// u = 1 - v, both exactly representable in fp32; u is what torch.rand_like would have returned (:355).
-__device__ __forceinline__ float uniform_from_word(uint32_t w) {
-  const uint32_t m = w & 0x007fffffu;
+__device__ __forceinline__ float uniform_from_draw(uint32_t m) {
   return __uint2float_rn(0x1000000u - (2u * m + 1u)) * kTwoPowM24;
 }
 // Gumbel noise exactly as the reference forms it from u (:356), in accurate fp32.

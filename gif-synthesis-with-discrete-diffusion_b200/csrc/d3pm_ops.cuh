@@ -118,14 +118,14 @@ __global__ void __launch_bounds__(kOpThreads) gumbel_argmax_rows_kernel(
   const int64_t row = blockIdx.x;
   const float* __restrict__ lg = logits + row * pitch_logits;
   const float* __restrict__ nz = KIND == 2 ? nullptr : noise + row * pitch_noise;
-  const PhiloxStream rng(seed, offset);
+  const NoiseStream rng(seed, offset);
   const uint64_t grow = static_cast<uint64_t>(row_offset + row);
   unsigned long long best = 0ull;
   float second = -CUDART_INF_F;
   const int nq = (C + 3) >> 2;
   for (int q = threadIdx.x; q < nq; q += kOpThreads) {
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (KIND == 2) w = rng.words(q, grow);
+    uint4 cw = make_uint4(0, 0, 0, 0), fw = cw;
+    if (KIND == 2) cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow), fw = rng.fine(q >> 2, grow);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = 4 * q + e;
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(kOpThreads) gumbel_argmax_rows_kernel(
         float g;
         if (KIND == 0) g = nz[k];
         else if (KIND == 1) g = gumbel_from_uniform(nz[k]);
-        else g = gumbel_from_uniform(uniform_from_word(word_of(w, e)));
+        else g = gumbel_from_uniform(uniform_from_draw(
+                 (NoiseStream::half_of(cw, (((q >> 7) & 1) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3) << 2) | e)));
         const float sc = g + lg[k];
         const unsigned long long key = pack_key(sc, k);
         if (key > best) {
@@ -158,16 +159,11 @@ __global__ void __launch_bounds__(kOpThreads) philox_uniform_kernel(float* __res
                                                                     uint64_t seed, uint64_t offset,
                                                                     int64_t row_offset) {
   const int64_t row = blockIdx.x;
-  const PhiloxStream rng(seed, offset);
+  const NoiseStream rng(seed, offset);
   const uint64_t grow = static_cast<uint64_t>(row_offset + row);
   float* __restrict__ out = u + row * pitch;
-  const int C = K + 1, nq = (C + 3) >> 2;
-  for (int q = threadIdx.x; q < nq; q += kOpThreads) {
-    const uint4 w = rng.words(q, grow);
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (4 * q + e < C) out[4 * q + e] = uniform_from_word(word_of(w, e));
-  }
+  const int C = K + 1;
+  for (int k = threadIdx.x; k < C; k += kOpThreads) out[k] = uniform_from_draw(rng.draw(k, grow));
 }
 
 // ---------------------------------------------------------------- index <-> log one-hot

@@ -72,6 +72,22 @@ struct RowMath {
   __device__ __forceinline__ float post_mask() const { return log_prob_clamped(PK); }
 };
 
+// Thinning rule of the production sampler (shared by every kernel so they take identical decisions).
+// A class is kept when its 16 coarse noise bits h satisfy 1 + h*2^-23 <= e_k*(r*scaleA) + thrB, i.e.
+// h/2^16 <= c*P_k/Ptot up to rounding slack that can only admit more classes; the best survivor is
+// accepted when its exact score reaches `accept` = ln(Ptot/c) + slack, which no discarded class can.
+constexpr float kDefaultThin = 8.0f;
+struct ThinRule {
+  float scaleA, thrB, accept;
+  __device__ __forceinline__ ThinRule(const RowMath& rm, float thin_factor) {
+    const float c = thin_factor > 0.f ? thin_factor : kDefaultThin;
+    const float inv = c / rm.Ptot;
+    scaleA = rm.A * inv * 0.0078125f;                                  // * 2^-7: h sits in the low mantissa bits
+    thrB = fmaf(rm.Bc * inv, 0.0078125f, 1.0f) + 2.384185791015625e-7f;  // + 2 ulps of slack
+    accept = -logf(inv) + 0.02f;
+  }
+};
+
 constexpr int kRowThreads = 256;
 
 template <int NV, int NW, typename Sync>
@@ -247,8 +263,21 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
   rm.init(cf, masked, pj, j, K);
 
   const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
-  const PhiloxStream rng(p.seed, p.offset);
+  const NoiseStream rng(p.seed, p.offset);
   unsigned long long best = 0ull;
+
+  // exact Gumbel score of class k from its softmax numerator e and its 23-bit draw m (:356-357)
+  auto score_exact = [&](uint32_t k, float e, uint32_t m) {
+    return rm.post_of(k, e, r) + gumbel_from_uniform(uniform_from_draw(m));
+  };
+  // the noise of the four classes of chunk q: 16 coarse bits each, plus (exact paths) the 7 fine bits
+  auto chunk_draws = [&](int q, uint32_t (&m)[4]) {
+    const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
+    const uint4 fw = rng.fine(q >> 2, grow);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      m[e] = (NoiseStream::half_of(cw, (((q >> 7) & 1) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3) << 2) | e);
+  };
 
   if (!THIN) {
     // ================= log-domain pass: optional outputs + exact Gumbel-max =====================
@@ -280,9 +309,10 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
               for (int e = 0; e < 4; ++e) g[e] = gumbel_from_uniform(g[e]);
             }
           } else {
-            const uint4 w = rng.words(q, grow);
+            uint32_t m[4];
+            chunk_draws(q, m);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) g[e] = gumbel_from_uniform(uniform_from_word(word_of(w, e)));
+            for (int e = 0; e < 4; ++e) g[e] = gumbel_from_uniform(uniform_from_draw(m[e]));
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -302,7 +332,7 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
       if (mode != D3PM_SAMPLE_NONE) {
         float gK;
         if (mode == D3PM_SAMPLE_GUMBEL) gK = p.gumbel_is_uniform ? gumbel_from_uniform(__ldg(rg + K)) : __ldg(rg + K);
-        else gK = gumbel_from_uniform(uniform_from_word(word_of(rng.words(K >> 2, grow), K & 3)));
+        else gK = gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow)));
         scoreK = gK + oK;
         const unsigned long long key = pack_key(scoreK, K);
         best = key > best ? key : best;
@@ -331,65 +361,59 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
 
   // ================= production sampling: thinned exponential race ===============================
   // argmax_k (post_k + g_k) = argmax_k P_k / E_k with E_k = -log u_k.  A class can only win if
-  // E_k < c * P_k / Ptot for a modest c (the winner's ratio is Ptot / Exp(1)); since E_k >= v_k = 1 - u_k,
-  // testing the raw uniform v_k against that bound discards ~(1 - c/K) of the classes before any
-  // logarithm is taken.  Survivors are scored exactly as in the log-domain pass, so the result is the
-  // same argmax; if the best survivor does not clear the bound (probability e^-c per row) the row is
-  // rescored exhaustively.
-  const float c_thin = p.thin_factor > 0.f ? p.thin_factor : 16.0f;
-  const float inv = c_thin / rm.Ptot;
-  // +2^-22: two ulps of slack in [1,2) so that the roundings of the threshold can only admit more classes
-  const float thrA = r * rm.A * inv, thrB = fmaf(rm.Bc, inv, 1.0f) + 2.384185791015625e-7f;
-  const float accept = -logf(inv) + 0.02f;  // ln(Ptot / c) plus slack for rounding in the filter
-
-  auto score_exact = [&](uint32_t k, float e, uint32_t word) {
-    return rm.post_of(k, e, r) + gumbel_from_uniform(uniform_from_word(word));
-  };
+  // E_k < c * P_k / Ptot for a modest c (the winner's ratio is distributed as Ptot / Exp(1)); since
+  // E_k >= v_k = 1 - u_k >= h_k / 2^16, testing the 16 coarse noise bits against that bound discards all but
+  // ~c of the K classes before any logarithm is taken.  Survivors are scored exactly as in the log-domain
+  // pass, so the result is the same argmax; if the best survivor does not clear the bound (probability
+  // e^-c per row) the row is rescored exhaustively.
+  const ThinRule thin(rm, p.thin_factor);
+  const float thrA = r * thin.scaleA;
 
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     if (i < nvalid) {
       const int q = tid + i * kRowThreads;
-      const uint4 w = rng.words(q, grow);
+      const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const uint32_t word = word_of(w, e);
-        const float f = __uint_as_float(0x3f800000u | (word & 0x007fffffu));  // 1 + m/2^23
-        if (f <= fmaf(z[i][e], thrA, thrB)) {
-          const unsigned long long key = pack_key(score_exact(4 * q + e, z[i][e], word), 4 * q + e);
+        const uint32_t h = NoiseStream::half_of(cw, (((q >> 7) & 1) << 2) | e);
+        if (__uint_as_float(0x3f800000u | h) <= fmaf(z[i][e], thrA, thin.thrB)) {
+          const uint32_t k = 4 * q + e;
+          const uint32_t m = (h << 7) | NoiseStream::low7_of(rng.fine(k >> 4, grow), k & 15u);
+          const unsigned long long key = pack_key(score_exact(k, z[i][e], m), k);
           best = key > best ? key : best;
         }
       }
     }
   }
   if (tid == 0) {  // the two classes with their own coefficients are always scored
-    const unsigned long long kK =
-        pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_word(word_of(rng.words(K >> 2, grow), K & 3))), K);
+    const unsigned long long kK = pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
     best = kK > best ? kK : best;
     if (!masked) {
-      const unsigned long long kj = pack_key(
-          rm.post_self() + gumbel_from_uniform(uniform_from_word(word_of(rng.words(j >> 2, grow), j & 3))), j);
+      const unsigned long long kj =
+          pack_key(rm.post_self() + gumbel_from_uniform(uniform_from_draw(rng.draw(j, grow))), j);
       best = kj > best ? kj : best;
     }
   }
   best = group_max_u64<NW>(best, skey[0], sync);
-  if (!(key_score(best) >= accept)) {  // exhaustive rescoring (row-uniform branch)
+  if (!(key_score(best) >= thin.accept)) {  // exhaustive rescoring (row-uniform branch)
     best = 0ull;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       if (i < nvalid) {
         const int q = tid + i * kRowThreads;
-        const uint4 w = rng.words(q, grow);
+        uint32_t m[4];
+        chunk_draws(q, m);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const unsigned long long key = pack_key(score_exact(4 * q + e, z[i][e], word_of(w, e)), 4 * q + e);
+          const unsigned long long key = pack_key(score_exact(4 * q + e, z[i][e], m[e]), 4 * q + e);
           best = key > best ? key : best;
         }
       }
     }
     if (tid == 0) {
-      const unsigned long long kK = pack_key(
-          rm.post_mask() + gumbel_from_uniform(uniform_from_word(word_of(rng.words(K >> 2, grow), K & 3))), K);
+      const unsigned long long kK =
+          pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
       best = kK > best ? kK : best;
       if (p.status != nullptr) atomicOr(p.status, D3PM_STATUS_FALLBACK);
     }

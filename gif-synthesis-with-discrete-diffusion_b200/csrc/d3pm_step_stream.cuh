@@ -1,11 +1,426 @@
-// Persistent TMA-pipelined fused step for the production mode (placeholder until the kernel lands).
+// Fused reverse step, production kernel: persistent CTAs, TMA-staged rows, register-resident math.
+//
+// One CTA per SM, four independent groups of 128 threads.  A group owns every G-th token row (G = number
+// of groups in the grid).  Per row:
+//   * one elected thread issues two bulk-TMA copies (cp.async.bulk, 16 KiB each for K = 4096) of the
+//     conditional / unconditional logit rows into the group's shared-memory stage, completion signalled
+//     on an mbarrier; the copy of row r+1 flies while row r is being computed from registers;
+//   * the 128 threads pull the row into registers (32 class pairs per thread), and run the softmax
+//     statistics, the guidance combine and the posterior entirely in registers with thread-local maxima,
+//     so that only two 128-thread named barriers per row are needed;
+//   * sampling is the thinned exponential race (see ThinRule): 16 Philox bits per class decide whether the
+//     class can still win; the ~8 survivors per row are appended to a small shared-memory list and scored
+//     exactly by one warp (rotating) while the other warps already work on the next row;
+//   * rows whose best survivor does not clear the acceptance bound (probability e^-c) are queued and redone
+//     by the same group with exhaustive scoring after its main loop.
+// HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
 #pragma once
 
 #include "d3pm_step_rows.cuh"
 
 namespace d3pm {
 
-inline bool stream_kernel_eligible(const StepParams&) { return false; }
-inline int launch_step_stream(const StepParams&, cudaStream_t) { return D3PM_ERR_UNSUPPORTED; }
+constexpr int kGroupThreads = 128;
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kGroupsPerCta = 4;
+constexpr int kStreamThreads = kGroupThreads * kGroupsPerCta;
+constexpr int kCandCap = 64;     // survivors kept per row (Poisson(c) of them; more -> the row is redone)
+constexpr int kRedoCap = 4096;   // rows a group can queue for exhaustive rescoring (= max rows per group)
+
+struct RowInfo {  // what the scoring warp needs to finish a row after the others have moved on
+  float A, Bc, Pj, PK, accept;
+  uint32_t j;
+  int32_t masked;
+  int32_t pad;
+  long long row;
+};
+
+template <int NP>
+struct __align__(128) GroupSmem {
+  float c[1024 * NP];  // conditional logits of the row in flight
+  float u[1024 * NP];  // unconditional logits
+  unsigned long long full;  // mbarrier: TMA bytes landed
+  unsigned long long keys[kGroupWarps];
+  float red[2][4 * kGroupWarps];
+  RowInfo info[2];
+  uint32_t cand_cnt[2];
+  uint32_t redo_cnt;
+  uint32_t pad;
+  uint32_t cand_k[2][kCandCap];
+  float cand_p[2][kCandCap];
+  int32_t redo[kRedoCap];  // row indices relative to the group's first row, in units of G
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// bulk TMA (1-D): global -> shared, completion bytes counted on the mbarrier; L2 evict-first (read once)
+__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, unsigned long long* bar,
+                                             unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void group_bar(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroupThreads) : "memory");
+}
+struct GroupSync {
+  int id;
+  __device__ __forceinline__ void operator()() const { group_bar(id); }
+};
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// One warp finishes a row from its survivor list: exact scores, argmax, accept or queue for redo.
+template <int NP>
+__device__ __forceinline__ void score_survivors(GroupSmem<NP>& S, int buf, const NoiseStream& rng, const StepParams& p,
+                                                int lane, long long G_rows, long long first_row) {
+  const RowInfo ri = S.info[buf];
+  const uint32_t cnt = S.cand_cnt[buf];
+  const uint32_t n = cnt < static_cast<uint32_t>(kCandCap) ? cnt : static_cast<uint32_t>(kCandCap);
+  const uint64_t grow = static_cast<uint64_t>(p.row_offset + ri.row);
+  const int K = 1024 * NP;
+  unsigned long long best = 0ull;
+  for (uint32_t c = lane; c < n; c += 32) {
+    const uint32_t k = S.cand_k[buf][c];
+    const float pe = S.cand_p[buf][c];
+    const float pcl = fminf(fmaxf(pe, kPFloor), 1.0f);
+    const float P = (k == ri.j) ? ri.Pj : fmaf(pcl, ri.A, ri.Bc);
+    const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+    const unsigned long long key = pack_key(sc, k);
+    best = key > best ? key : best;
+  }
+  if (lane == 0) {  // the [MASK] class is always scored ...
+    const unsigned long long key =
+        pack_key(log_prob_clamped(ri.PK) + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
+    best = key > best ? key : best;
+  } else if (lane == 1 && !ri.masked) {  // ... and so is the row's own class, which has its own coefficients
+    const unsigned long long key =
+        pack_key(log_prob_clamped(ri.Pj) + gumbel_from_uniform(uniform_from_draw(rng.draw(ri.j, grow))), ri.j);
+    best = key > best ? key : best;
+  }
+  best = warp_max_u64(best);
+  if (lane == 0) {
+    if (cnt <= static_cast<uint32_t>(kCandCap) && key_score(best) >= ri.accept) {
+      p.x_prev[ri.row] = key_class(best);
+    } else {
+      const uint32_t slot = S.redo_cnt;
+      S.redo[slot] = static_cast<int32_t>((ri.row - first_row) / G_rows);
+      S.redo_cnt = slot + 1;
+    }
+    S.cand_cnt[buf] = 0;
+  }
+  __syncwarp();
+}
+
+template <int NP, bool HAS_U>
+__global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const StepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int K = 1024 * NP;
+  constexpr int NC = 2 * NP;  // float4 chunks per thread per tensor
+  constexpr uint32_t kRowBytes = K * sizeof(float);
+  const int g = threadIdx.x / kGroupThreads;
+  const int tg = threadIdx.x % kGroupThreads;
+  const int wg = tg >> 5, lane = tg & 31;
+  GroupSmem<NP>& S = reinterpret_cast<GroupSmem<NP>*>(smem_raw)[g];
+  const GroupSync sync{g + 1};
+  const long long G = static_cast<long long>(gridDim.x) * kGroupsPerCta;
+  const long long first_row = static_cast<long long>(g) * gridDim.x + blockIdx.x;  // neighbouring rows -> different SMs
+  const long long rows = p.rows;
+  const NoiseStream rng(p.seed, p.offset);
+  const unsigned long long policy = l2_evict_first_policy();
+
+  if (tg == 0) {
+    mbar_init(&S.full, 1);
+    S.cand_cnt[0] = S.cand_cnt[1] = 0;
+    S.redo_cnt = 0;
+  }
+  sync();
+
+  auto issue_row = [&](long long row) {  // elected thread: arm the barrier and launch both row copies
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&S.full, HAS_U ? 2 * kRowBytes : kRowBytes);
+    tma_load_row(S.c, p.logits_c + row * p.pitch_logits, kRowBytes, &S.full, policy);
+    if (HAS_U) tma_load_row(S.u, p.logits_u + row * p.pitch_logits, kRowBytes, &S.full, policy);
+  };
+
+  uint32_t phase = 0;
+  uint32_t status_bits = 0;
+
+  // ------------------------------------------------------------------------------------------------
+  // process one row; `exact` = exhaustive log-space scoring (PHILOX_EXACT mode and redone rows)
+  // `pending` >= 0: survivor buffer of the previous row, to be scored by warp `pending_warp`
+  // ------------------------------------------------------------------------------------------------
+  auto process_row = [&](long long row, long long next_row, long long jj_in, long long tt_in, bool exact, int it,
+                         int pending) {
+    long long tt = tt_in, jj = jj_in;
+    if (tt < 0 || tt >= p.T) {
+      status_bits |= D3PM_STATUS_BAD_T;
+      tt = tt < 0 ? 0 : p.T - 1;
+    }
+    if (jj < 0 || jj > K) {
+      status_bits |= D3PM_STATUS_BAD_TOKEN;
+      jj = K;
+    }
+    const bool masked = (jj == K);
+    const uint32_t j = static_cast<uint32_t>(jj);
+    const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
+
+    mbar_wait(&S.full, phase);
+    phase ^= 1u;
+
+    // ---- shared -> registers: chunk pair (256*i + tg, 256*i + 128 + tg), conflict-free 128-bit reads ----
+    float x[NC][4], z[NC][4];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int q = 128 * i + tg;
+      const float4 a = lds4(S.c + 4 * q);
+      x[i][0] = a.x, x[i][1] = a.y, x[i][2] = a.z, x[i][3] = a.w;
+      if (HAS_U) {
+        const float4 b = lds4(S.u + 4 * q);
+        z[i][0] = b.x, z[i][1] = b.y, z[i][2] = b.z, z[i][3] = b.w;
+      }
+    }
+    const float xj = masked ? 0.f : S.c[j];
+    const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
+
+    // ---- softmax statistics with thread-local maxima (:231) ----
+    float m[2], s[2] = {0.f, 0.f};
+    m[0] = fmaxf(fmaxf(x[0][0], x[0][1]), fmaxf(x[0][2], x[0][3]));
+    m[1] = HAS_U ? fmaxf(fmaxf(z[0][0], z[0][1]), fmaxf(z[0][2], z[0][3])) : 0.f;
+#pragma unroll
+    for (int i = 1; i < NC; ++i) {
+      m[0] = fmaxf(fmaxf(m[0], x[i][0]), fmaxf(x[i][1], fmaxf(x[i][2], x[i][3])));
+      if (HAS_U) m[1] = fmaxf(fmaxf(m[1], z[i][0]), fmaxf(z[i][1], fmaxf(z[i][2], z[i][3])));
+    }
+    const float mc2 = to_log2_units(m[0]), mu2 = to_log2_units(m[1]);
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float ec = ex2(fmaf(x[i][e], kLog2e, -mc2));
+        s[0] += ec;
+        if (HAS_U) s[1] += ex2(fmaf(z[i][e], kLog2e, -mu2));
+        else z[i][e] = ec;
+      }
+    if (HAS_U) {
+      group_max_sum_n<2, kGroupWarps>(m, s, S.red[0], sync);  // barrier 1: every thread is done with the stage
+    } else {
+      float m1[1] = {m[0]}, s1[1] = {s[0]};
+      group_max_sum_n<1, kGroupWarps>(m1, s1, S.red[0], sync);
+      m[0] = m1[0], s[0] = s1[0];
+    }
+    if (tg == 0 && next_row >= 0) issue_row(next_row);  // the stage is free: prefetch the next row now
+    if (pending >= 0 && wg == ((it + 3) & 3)) score_survivors<NP>(S, pending, rng, p, lane, G, first_row);
+
+    // ---- guidance combine + renormalisation (:245-247) ----
+    float My, Sy, r, yj;
+    if (HAS_U) {
+      const float lnSc = ln_rel_sum(m[0], s[0]), lnSu = ln_rel_sum(m[1], s[1]);
+      const float gs = p.guidance_scale;
+      float my = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lc = fmaxf((x[i][e] - m[0]) - lnSc, kClampLo);
+          const float lu = fmaxf((z[i][e] - m[1]) - lnSu, kClampLo);
+          const float y = fmaf(gs, lc - lu, lu);
+          x[i][e] = y;
+          my = fmaxf(my, y);
+        }
+      {
+        const float lc = fmaxf((xj - m[0]) - lnSc, kClampLo), lu = fmaxf((zj - m[1]) - lnSu, kClampLo);
+        yj = fmaf(gs, lc - lu, lu);
+      }
+      const float my2 = to_log2_units(my);
+      float sy = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ey = ex2(fmaf(x[i][e], kLog2e, -my2));
+          z[i][e] = ey;
+          sy += ey;
+        }
+      float mm[1] = {my}, ss[1] = {sy};
+      group_max_sum_n<1, kGroupWarps>(mm, ss, S.red[1], sync);  // barrier 2
+      My = mm[0], Sy = ss[0];
+      r = ex2(my2 - to_log2_units(My)) / Sy;
+    } else {
+      My = m[0], Sy = s[0];
+      yj = xj;
+      r = ex2(mc2 - to_log2_units(My)) / Sy;
+    }
+    const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -to_log2_units(My))) / Sy, kPFloor), 1.0f);
+    RowMath rm;
+    rm.init(cf, masked, pj, j, K);
+    const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
+
+    if (!exact) {
+      // ---- thinned race: 16 noise bits per class, survivors go to the list of this row's parity ----
+      const ThinRule thin(rm, p.thin_factor);
+      const float thrA = r * thin.scaleA;
+      const int buf = it & 1;
+      if (tg == 0) {
+        RowInfo ri;
+        ri.A = rm.A, ri.Bc = rm.Bc, ri.Pj = rm.Pj, ri.PK = rm.PK, ri.accept = thin.accept;
+        ri.j = j, ri.masked = masked ? 1 : 0, ri.pad = 0, ri.row = row;
+        S.info[buf] = ri;
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const uint4 cw = rng.coarse((i << 7) | tg, grow);
+        float f[8];
+        f[0] = __uint_as_float(__byte_perm(cw.x, 0x3f80u, 0x5410)), f[1] = __uint_as_float(__byte_perm(cw.x, 0x3f80u, 0x5432));
+        f[2] = __uint_as_float(__byte_perm(cw.y, 0x3f80u, 0x5410)), f[3] = __uint_as_float(__byte_perm(cw.y, 0x3f80u, 0x5432));
+        f[4] = __uint_as_float(__byte_perm(cw.z, 0x3f80u, 0x5410)), f[5] = __uint_as_float(__byte_perm(cw.z, 0x3f80u, 0x5432));
+        f[6] = __uint_as_float(__byte_perm(cw.w, 0x3f80u, 0x5410)), f[7] = __uint_as_float(__byte_perm(cw.w, 0x3f80u, 0x5432));
+        float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
+#pragma unroll
+        for (int h = 0; h < 8; ++h) slack = fmaxf(slack, fmaf(z[2 * i + (h >> 2)][h & 3], thrA, thin.thrB) - f[h]);
+        if (slack >= 0.0f) {
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const float e = z[2 * i + (h >> 2)][h & 3];
+            if (f[h] <= fmaf(e, thrA, thin.thrB)) {
+              const uint32_t pos = atomicAdd(&S.cand_cnt[buf], 1u);
+              if (pos < static_cast<uint32_t>(kCandCap)) {
+                S.cand_k[buf][pos] = 4u * (256u * i + 128u * (h >> 2) + tg) + (h & 3);
+                S.cand_p[buf][pos] = e * r;
+              }
+            }
+          }
+        }
+      }
+      return;
+    }
+
+    // ---- exhaustive scoring (PHILOX_EXACT, or a redone row) ----
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const uint4 cw = rng.coarse((i << 7) | tg, grow);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t q = 256u * i + 128u * half + tg;
+        const uint4 fw = rng.fine(q >> 2, grow);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t k = 4u * q + e;
+          const uint32_t mdraw = (NoiseStream::half_of(cw, 4 * half + e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
+          const float sc = rm.post_of(k, z[2 * i + half][e], r) + gumbel_from_uniform(uniform_from_draw(mdraw));
+          const unsigned long long key = pack_key(sc, k);
+          best = key > best ? key : best;
+        }
+      }
+    }
+    if (tg == 0) {
+      const unsigned long long key =
+          pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
+      best = key > best ? key : best;
+    }
+    best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3 (exact rows only)
+    if (tg == 0) p.x_prev[row] = key_class(best);
+  };
+
+  // ---- main loop over this group's rows -------------------------------------------------------------
+  const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
+  long long row = first_row;
+  long long jj = 0, tt = 0;
+  if (row < rows) {
+    if (tg == 0) issue_row(row);
+    jj = p.x_t[row];
+    tt = p.t[row / p.N];
+  }
+  int it = 0;
+  for (; row < rows; row += G, ++it) {
+    const long long next = row + G < rows ? row + G : -1;
+    long long jj_next = 0, tt_next = 0;
+    if (next >= 0) {  // software prefetch of the next row's scalars
+      jj_next = p.x_t[next];
+      tt_next = p.t[next / p.N];
+    }
+    process_row(row, next, jj, tt, exact_mode, it, (!exact_mode && it > 0) ? ((it - 1) & 1) : -1);
+    jj = jj_next, tt = tt_next;
+  }
+  sync();
+  if (!exact_mode && it > 0 && wg == ((it + 3) & 3)) score_survivors<NP>(S, (it - 1) & 1, rng, p, lane, G, first_row);
+  sync();
+
+  // ---- rows whose survivors did not clear the bound: redo them exhaustively ----------------------------
+  const uint32_t n_redo = S.redo_cnt;
+  if (n_redo > 0) {
+    status_bits |= D3PM_STATUS_FALLBACK;
+    long long r0 = first_row + static_cast<long long>(S.redo[0]) * G;
+    if (tg == 0) issue_row(r0);
+    for (uint32_t i = 0; i < n_redo; ++i) {
+      const long long rr = first_row + static_cast<long long>(S.redo[i]) * G;
+      const long long nx = (i + 1 < n_redo) ? first_row + static_cast<long long>(S.redo[i + 1]) * G : -1;
+      process_row(rr, nx, p.x_t[rr], p.t[rr / p.N], true, 0, -1);
+    }
+  }
+  if (status_bits != 0 && tg == 0 && p.status != nullptr) atomicOr(p.status, status_bits);
+}
+
+constexpr long long kStreamMinRows = 2048;  // below this the one-CTA-per-row kernel has less latency
+
+inline bool stream_kernel_supports(const StepParams& p) {
+  if (p.sample_mode != D3PM_SAMPLE_PHILOX && p.sample_mode != D3PM_SAMPLE_PHILOX_EXACT) return false;
+  if (p.post != nullptr || p.recon != nullptr || p.gap != nullptr || p.x_prev == nullptr) return false;
+  if (p.K != 1024 && p.K != 2048 && p.K != 4096) return false;
+  return true;
+}
+
+template <int NP, bool HAS_U>
+int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
+  const size_t smem = sizeof(GroupSmem<NP>) * kGroupsPerCta;
+  auto kern = step_stream_kernel<NP, HAS_U>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return D3PM_ERR_CUDA;
+  long long ctas = sms;
+  const long long groups_needed = (p.rows + kRedoCap - 1) / kRedoCap;  // every group must be able to queue all its rows
+  if (ctas * kGroupsPerCta < groups_needed) ctas = (groups_needed + kGroupsPerCta - 1) / kGroupsPerCta;
+  kern<<<static_cast<unsigned>(ctas), kStreamThreads, smem, s>>>(p);
+  return D3PM_OK;
+}
+
+inline int launch_step_stream(const StepParams& p, cudaStream_t s) {
+  const bool has_u = p.logits_u != nullptr;
+  switch (p.K) {
+    case 1024: return has_u ? launch_step_stream_t<1, true>(p, s) : launch_step_stream_t<1, false>(p, s);
+    case 2048: return has_u ? launch_step_stream_t<2, true>(p, s) : launch_step_stream_t<2, false>(p, s);
+    case 4096: return has_u ? launch_step_stream_t<4, true>(p, s) : launch_step_stream_t<4, false>(p, s);
+    default: return D3PM_ERR_UNSUPPORTED;
+  }
+}
 
 }  // namespace d3pm

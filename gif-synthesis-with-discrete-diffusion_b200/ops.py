@@ -107,7 +107,7 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
                gumbel: Optional[torch.Tensor] = None, gumbel_is_uniform: bool = False, seed: int = 0, offset: int = 0, row_offset: int = 0,
                want_post: bool = False, want_recon: bool = False, want_gap: bool = False,
                status: Optional[torch.Tensor] = None, thin_factor: float = 0.0,
-               x_prev_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+               x_prev_out: Optional[torch.Tensor] = None, kernel: int = 0) -> Dict[str, torch.Tensor]:
     """One fused reverse step over token-major logits `[B, N, K]` (d3pm_fused_step).
 
     `logits_u=None` is guidance off.  `gumbel` is `[B, N, >=K+1]` rows (entry K = [MASK]).
@@ -164,6 +164,7 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
     d.guidance_scale, d.sample_mode = float(guidance_scale), int(sample_mode)
     d.seed, d.offset, d.row_offset = seed & (2**64 - 1), offset & (2**64 - 1), int(row_offset)
     d.thin_factor = float(thin_factor)
+    d.kernel = int(kernel)
     d.stream = _stream(dev)
     lib = _lib.load_library()
     _lib.check(lib.d3pm_fused_step(ctypes.byref(d)), "d3pm_fused_step")

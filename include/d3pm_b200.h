@@ -65,6 +65,10 @@ int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_s
 #define D3PM_SAMPLE_PHILOX 2       /* in-kernel Philox4x32-10 noise, thinned exponential race (production) */
 #define D3PM_SAMPLE_PHILOX_EXACT 3 /* same noise, every class scored in log space (verification) */
 
+#define D3PM_KERNEL_AUTO 0
+#define D3PM_KERNEL_ROWS 1   /* one CTA per token row, every shape and mode */
+#define D3PM_KERNEL_STREAM 2 /* persistent TMA-pipelined kernel: PHILOX / PHILOX_EXACT, no outputs, K in {1024,2048,4096} */
+
 typedef struct d3pm_step_desc {
   /* inputs */
   const float* logits_c;   /* [B*N][pitch_logits] conditional denoiser logits (first K valid) */
@@ -88,7 +92,8 @@ typedef struct d3pm_step_desc {
   int32_t gumbel_is_uniform; /* 1: `gumbel` holds uniforms u (torch.rand_like's tensor); g = -log(-log(u+1e-30)+1e-30) in-kernel */
   uint64_t seed, offset; /* Philox key / per-call stream offset */
   int64_t row_offset;    /* global index of local row 0 (b_global*N + n): shards reproduce the 1-GPU stream */
-  float thin_factor;     /* PHILOX thinning constant c (0 = default 16); smaller forces the exhaustive fallback */
+  float thin_factor;     /* PHILOX thinning constant c (0 = default 8); smaller forces the exhaustive fallback */
+  int32_t kernel;        /* D3PM_KERNEL_*: which implementation runs (AUTO picks by shape and mode) */
   d3pm_stream_t stream;
 } d3pm_step_desc;
 

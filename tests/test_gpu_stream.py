@@ -1,0 +1,124 @@
+"""The persistent TMA-pipelined production kernel (D3PM_KERNEL_STREAM) against its own exhaustive mode,
+the one-CTA-per-row kernel and the oracle fed the very noise the kernel drew.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from d3pm_b200 import _lib, ops
+from oracle import d3pm_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+T = 100
+
+
+def _table(K):
+    return ops.build_coef_table(O.pack_schedule(O.make_schedule(T, K)).to(DEV), T, K)
+
+
+def _run(lc, lu, x_t, t, K, mode, kernel, s=2.0, **kw):
+    out = ops.fused_step(lc, lu, x_t, t, _table(K), guidance_scale=s, sample_mode=mode, kernel=kernel, **kw)
+    torch.cuda.synchronize()
+    return out["x_prev"]
+
+
+CASES = [
+    # B, N, K, t, guidance, logit scale
+    (2, 1024, 4096, 50, 2.0, 1.0),
+    (2, 1024, 4096, 0, 2.0, 1.0),
+    (2, 1024, 4096, 99, 2.0, 1.0),
+    (3, 700, 4096, [0, 42, 99], 3.0, 4.0),   # ragged row count, per-video t, peaked logits
+    (2, 1500, 2048, 25, None, 1.0),          # guidance off, the UCF job's 2048-code book
+    (1, 2100, 1024, 60, 2.0, 1.0),
+    (1, 37, 4096, 50, 2.0, 1.0),             # fewer rows than groups
+]
+
+
+@pytest.mark.parametrize("B,N,K,tval,s,scale", CASES)
+def test_stream_kernel_parity(B, N, K, tval, s, scale):
+    sched = O.make_schedule(T, K)
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + N)
+    lc = torch.randn(B, N, K, device=DEV, generator=g) * scale
+    lu = None if s is None else torch.randn(B, N, K, device=DEV, generator=g) * scale
+    t = (torch.tensor(tval) if isinstance(tval, list) else torch.full((B,), tval)).long().to(DEV)
+    p_mask = sched["log_cumprod_ct"][t.cpu()].exp().view(B, 1).to(DEV)
+    x_t = torch.where(torch.rand(B, N, device=DEV, generator=g) < p_mask, torch.full((B, N), K, device=DEV),
+                      torch.randint(0, K, (B, N), device=DEV, generator=g))
+    kw = dict(s=0.0 if s is None else s, seed=99, offset=3, row_offset=12345)
+    status = ops.new_status(DEV)
+    thin = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, status=status, **kw)
+    assert int(status.item()) & (_lib.STATUS_BAD_T | _lib.STATUS_BAD_TOKEN) == 0
+    exact = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX_EXACT, _lib.KERNEL_STREAM, **kw)
+    assert torch.equal(thin, exact)                       # thinning never changes the draw
+    forced = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, thin_factor=1e-3, status=status, **kw)
+    assert torch.equal(forced, thin) and int(status.item()) & _lib.STATUS_FALLBACK
+    tiny = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, thin_factor=1.0, **kw)  # many redone rows
+    assert torch.equal(tiny, thin)
+    assert int(thin.min()) >= 0 and int(thin.max()) <= K
+
+    # against the oracle with the dumped uniforms (a sample of rows: the CPU oracle is slow)
+    rows = torch.arange(0, N, max(1, N // 24))
+    u = ops.philox_uniform(B, N, K, seed=99, offset=3, row_offset=12345, device=DEV)[:, rows, :K + 1].cpu().permute(0, 2, 1)
+    lc_s = lc[:, rows].cpu().permute(0, 2, 1)
+    lu_s = None if lu is None else lu[:, rows].cpu().permute(0, 2, 1)
+    out_o, post_o, _ = O.p_sample_step(sched, lc_s, lu_s, O.index_to_log_onehot(x_t[:, rows].cpu(), K + 1), t.cpu(),
+                                       0.0 if s is None else s, u)
+    ties = O.near_ties(post_o, u).numpy()
+    H.assert_tokens_match(thin[:, rows].cpu().numpy(), out_o.argmax(1).numpy(), ties, "stream vs oracle")
+    # and against the other kernel (same noise definition; p may differ in the last bit)
+    rowsk = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_ROWS, **kw)
+    H.assert_tokens_match(rowsk[:, rows].cpu().numpy(), out_o.argmax(1).numpy(), ties, "rows vs oracle")
+    assert (rowsk != thin).float().mean() < 1e-3
+
+
+def test_stream_kernel_shards_and_status():
+    K, B, N = 4096, 4, 600
+    g = torch.Generator(device=DEV).manual_seed(5)
+    lc, lu = torch.randn(B, N, K, device=DEV, generator=g), torch.randn(B, N, K, device=DEV, generator=g)
+    t = torch.tensor([3, 50, 70, 99], device=DEV)
+    x_t = torch.randint(0, K + 1, (B, N), device=DEV, generator=g)
+    whole = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, seed=9, offset=5)
+    parts = [_run(lc[b:e], lu[b:e], x_t[b:e].contiguous(), t[b:e].contiguous(), K, _lib.SAMPLE_PHILOX,
+                  _lib.KERNEL_STREAM, seed=9, offset=5, row_offset=b * N) for b, e in ((0, 1), (1, 4))]
+    assert torch.equal(torch.cat(parts), whole)
+    status = ops.new_status(DEV)
+    x_bad = x_t.clone()
+    x_bad[2, 17] = -1
+    _run(lc, lu, x_bad, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, status=status)
+    assert int(status.item()) & _lib.STATUS_BAD_TOKEN
+    status.zero_()
+    _run(lc, lu, x_t, torch.tensor([3, 50, 700, 99], device=DEV), K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, status=status)
+    assert int(status.item()) & _lib.STATUS_BAD_T
+    with pytest.raises(Exception):  # outputs are not something the stream kernel produces
+        ops.fused_step(lc, lu, x_t, t, _table(K), guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX,
+                       kernel=_lib.KERNEL_STREAM, want_post=True)
+
+
+def test_stream_sampling_statistics():
+    """Chi-square of 40k production draws of one row against exp(posterior)."""
+    K, R = 1024, 40000
+    sched = O.make_schedule(T, K)
+    lc1, lu1, _, _, _ = O.synth_inputs(1, 1, K, 50, sched, seed=800, scale=3.0)
+    lc, lu = lc1.expand(1, R, K).contiguous().to(DEV), lu1.expand(1, R, K).contiguous().to(DEV)
+    t = torch.full((1,), 50, dtype=torch.long, device=DEV)
+    for token in (K, 7):
+        x_t = torch.full((1, R), token, dtype=torch.long, device=DEV)
+        draws = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, seed=31, offset=token)
+        post = ops.fused_step(lc[:, :1], lu[:, :1], x_t[:, :1].contiguous(), t, _table(K), guidance_scale=2.0,
+                              sample_mode=_lib.SAMPLE_NONE, want_post=True)["post"][0, 0, :K + 1]
+        p = post.double().exp().cpu()
+        p = p / p.sum()
+        counts = torch.bincount(draws.flatten().cpu(), minlength=K + 1).double()
+        order = torch.argsort(p)
+        be, bc, ae, ac = [], [], 0.0, 0.0
+        for e_, c_ in zip((p[order] * R).numpy(), counts[order].numpy()):
+            ae, ac = ae + e_, ac + c_
+            if ae >= 5:
+                be.append(ae), bc.append(ac)
+                ae = ac = 0.0
+        be[-1] += ae
+        bc[-1] += ac
+        chi2 = float((((np.array(bc) - np.array(be)) ** 2) / np.array(be)).sum())
+        dof = len(be) - 1
+        assert chi2 < dof + 5 * np.sqrt(2 * dof) + 10, (chi2, dof)
