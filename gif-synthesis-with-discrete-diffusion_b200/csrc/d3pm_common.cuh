@@ -141,12 +141,12 @@ struct NoiseStream {
   __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
 #pragma unroll
     for (int r = 0; r < kPhiloxRounds; ++r) {
-      const uint32_t lo0 = kPhiloxM0 * c0, hi0 = __umulhi(kPhiloxM0, c0);
-      const uint32_t lo1 = kPhiloxM1 * c2, hi1 = __umulhi(kPhiloxM1, c2);
-      c0 = hi1 ^ c1 ^ rk0[r];
-      c2 = hi0 ^ c3 ^ rk1[r];
-      c1 = lo1;
-      c3 = lo0;
+      const unsigned long long p0 = static_cast<unsigned long long>(kPhiloxM0) * c0;  // one IMAD.WIDE each
+      const unsigned long long p1 = static_cast<unsigned long long>(kPhiloxM1) * c2;
+      c0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk0[r];
+      c2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk1[r];
+      c1 = static_cast<uint32_t>(p1);
+      c3 = static_cast<uint32_t>(p0);
     }
     return make_uint4(c0, c1, c2, c3);
   }

@@ -107,11 +107,13 @@ __device__ __forceinline__ void score_survivors(GroupSmem<NP>& S, int buf, const
   const int K = 1024 * NP;
   unsigned long long best = 0ull;
   for (uint32_t c = lane; c < n; c += 32) {
-    const uint32_t k = S.cand_k[buf][c];
+    const uint32_t packed = S.cand_k[buf][c];
+    const uint32_t k = packed & 0xffffu, h16 = packed >> 16;  // class and the 16 coarse noise bits it survived with
     const float pe = S.cand_p[buf][c];
     const float pcl = fminf(fmaxf(pe, kPFloor), 1.0f);
     const float P = (k == ri.j) ? ri.Pj : fmaf(pcl, ri.A, ri.Bc);
-    const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+    const uint32_t mdraw = (h16 << 7) | NoiseStream::low7_of(rng.fine(k >> 4, grow), k & 15u);
+    const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(mdraw));
     const unsigned long long key = pack_key(sc, k);
     best = key > best ? key : best;
   }
@@ -136,6 +138,13 @@ __device__ __forceinline__ void score_survivors(GroupSmem<NP>& S, int buf, const
     S.cand_cnt[buf] = 0;
   }
   __syncwarp();
+}
+
+// out-of-line copy for the (cold) call after a group's last row
+template <int NP>
+__device__ __noinline__ void score_survivors_cold(GroupSmem<NP>& S, int buf, const NoiseStream& rng, const StepParams& p,
+                                                  int lane, long long G_rows, long long first_row) {
+  score_survivors<NP>(S, buf, rng, p, lane, G_rows, first_row);
 }
 
 template <int NP, bool HAS_U>
@@ -194,40 +203,53 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
     mbar_wait(&S.full, phase);
     phase ^= 1u;
 
-    // ---- shared -> registers: chunk pair (256*i + tg, 256*i + 128 + tg), conflict-free 128-bit reads ----
-    float x[NC][4], z[NC][4];
+    // ---- shared -> registers: chunk i of this thread is float4 number 128*i + tg (conflict-free 128-bit
+    //      reads); x[i][0] = classes (0,1) of the chunk, x[i][1] = classes (2,3), packed for the f32x2 pipe ----
+    float2 x[NC][2], z[NC][2];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int q = 128 * i + tg;
       const float4 a = lds4(S.c + 4 * q);
-      x[i][0] = a.x, x[i][1] = a.y, x[i][2] = a.z, x[i][3] = a.w;
+      x[i][0] = make_float2(a.x, a.y), x[i][1] = make_float2(a.z, a.w);
       if (HAS_U) {
         const float4 b = lds4(S.u + 4 * q);
-        z[i][0] = b.x, z[i][1] = b.y, z[i][2] = b.z, z[i][3] = b.w;
+        z[i][0] = make_float2(b.x, b.y), z[i][1] = make_float2(b.z, b.w);
       }
     }
     const float xj = masked ? 0.f : S.c[j];
     const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
 
     // ---- softmax statistics with thread-local maxima (:231) ----
-    float m[2], s[2] = {0.f, 0.f};
-    m[0] = fmaxf(fmaxf(x[0][0], x[0][1]), fmaxf(x[0][2], x[0][3]));
-    m[1] = HAS_U ? fmaxf(fmaxf(z[0][0], z[0][1]), fmaxf(z[0][2], z[0][3])) : 0.f;
+    float m[2], s[2];
+    m[0] = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
+    m[1] = HAS_U ? fmaxf(fmaxf(z[0][0].x, z[0][0].y), fmaxf(z[0][1].x, z[0][1].y)) : 0.f;
 #pragma unroll
     for (int i = 1; i < NC; ++i) {
-      m[0] = fmaxf(fmaxf(m[0], x[i][0]), fmaxf(x[i][1], fmaxf(x[i][2], x[i][3])));
-      if (HAS_U) m[1] = fmaxf(fmaxf(m[1], z[i][0]), fmaxf(z[i][1], fmaxf(z[i][2], z[i][3])));
+      m[0] = fmaxf(fmaxf(m[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
+      if (HAS_U) m[1] = fmaxf(fmaxf(m[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
     }
+    m[0] = fmaxf(m[0], -3.0e38f), m[1] = fmaxf(m[1], -3.0e38f);  // keep -inf rows finite (no inf - inf)
     const float mc2 = to_log2_units(m[0]), mu2 = to_log2_units(m[1]);
+    {
+      const float2 l2e = make_float2(kLog2e, kLog2e), nmc = make_float2(-mc2, -mc2), nmu = make_float2(-mu2, -mu2);
+      float2 sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, su[2] = {sc[0], sc[0]};
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
+      for (int i = 0; i < NC; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float ec = ex2(fmaf(x[i][e], kLog2e, -mc2));
-        s[0] += ec;
-        if (HAS_U) s[1] += ex2(fmaf(z[i][e], kLog2e, -mu2));
-        else z[i][e] = ec;
-      }
+        for (int h = 0; h < 2; ++h) {
+          const float2 ac = __ffma2_rn(x[i][h], l2e, nmc);
+          const float2 ec = make_float2(ex2(ac.x), ex2(ac.y));
+          sc[h] = __fadd2_rn(sc[h], ec);
+          if (HAS_U) {
+            const float2 au = __ffma2_rn(z[i][h], l2e, nmu);
+            su[h] = __fadd2_rn(su[h], make_float2(ex2(au.x), ex2(au.y)));
+          } else {
+            z[i][h] = ec;
+          }
+        }
+      s[0] = (sc[0].x + sc[0].y) + (sc[1].x + sc[1].y);
+      s[1] = (su[0].x + su[0].y) + (su[1].x + su[1].y);
+    }
     if (HAS_U) {
       group_max_sum_n<2, kGroupWarps>(m, s, S.red[0], sync);  // barrier 1: every thread is done with the stage
     } else {
@@ -235,42 +257,51 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       group_max_sum_n<1, kGroupWarps>(m1, s1, S.red[0], sync);
       m[0] = m1[0], s[0] = s1[0];
     }
-    if (tg == 0 && next_row >= 0) issue_row(next_row);  // the stage is free: prefetch the next row now
+    // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
+    if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
     if (pending >= 0 && wg == ((it + 3) & 3)) score_survivors<NP>(S, pending, rng, p, lane, G, first_row);
 
     // ---- guidance combine + renormalisation (:245-247) ----
+    // With a = x - max, log-softmax clamped at -70 is max(a, -70 + lnS) - lnS, so
+    //   y = lu + s (lc - lu) = s a' + (1 - s) b' + C,  C = -s lnSc - (1 - s) lnSu
     float My, Sy, r, yj;
     if (HAS_U) {
       const float lnSc = ln_rel_sum(m[0], s[0]), lnSu = ln_rel_sum(m[1], s[1]);
-      const float gs = p.guidance_scale;
+      const float gs = p.guidance_scale, og = 1.0f - gs;
+      const float ta = kClampLo + lnSc, tb = kClampLo + lnSu;
+      const float C = fmaf(-gs, lnSc, -og * lnSu);
+      const float2 nMc = make_float2(-m[0], -m[0]), nMu = make_float2(-m[1], -m[1]);
+      const float2 gs2 = make_float2(gs, gs), og2 = make_float2(og, og), C2 = make_float2(C, C);
       float my = -CUDART_INF_F;
 #pragma unroll
       for (int i = 0; i < NC; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float lc = fmaxf((x[i][e] - m[0]) - lnSc, kClampLo);
-          const float lu = fmaxf((z[i][e] - m[1]) - lnSu, kClampLo);
-          const float y = fmaf(gs, lc - lu, lu);
-          x[i][e] = y;
-          my = fmaxf(my, y);
+        for (int h = 0; h < 2; ++h) {
+          float2 a = __fadd2_rn(x[i][h], nMc), b = __fadd2_rn(z[i][h], nMu);
+          a.x = fmaxf(a.x, ta), a.y = fmaxf(a.y, ta);
+          b.x = fmaxf(b.x, tb), b.y = fmaxf(b.y, tb);
+          const float2 y = __ffma2_rn(gs2, a, __ffma2_rn(og2, b, C2));
+          x[i][h] = y;
+          my = fmaxf(my, fmaxf(y.x, y.y));
         }
-      {
-        const float lc = fmaxf((xj - m[0]) - lnSc, kClampLo), lu = fmaxf((zj - m[1]) - lnSu, kClampLo);
-        yj = fmaf(gs, lc - lu, lu);
-      }
+      yj = fmaf(gs, fmaxf(xj - m[0], ta), fmaf(og, fmaxf(zj - m[1], tb), C));
       const float my2 = to_log2_units(my);
-      float sy = 0.f;
+      {
+        const float2 l2e = make_float2(kLog2e, kLog2e), nmy = make_float2(-my2, -my2);
+        float2 sy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
+        for (int i = 0; i < NC; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float ey = ex2(fmaf(x[i][e], kLog2e, -my2));
-          z[i][e] = ey;
-          sy += ey;
-        }
-      float mm[1] = {my}, ss[1] = {sy};
-      group_max_sum_n<1, kGroupWarps>(mm, ss, S.red[1], sync);  // barrier 2
-      My = mm[0], Sy = ss[0];
+          for (int h = 0; h < 2; ++h) {
+            const float2 ay = __ffma2_rn(x[i][h], l2e, nmy);
+            const float2 ey = make_float2(ex2(ay.x), ex2(ay.y));
+            z[i][h] = ey;
+            sy[h] = __fadd2_rn(sy[h], ey);
+          }
+        float mm[1] = {my}, ss[1] = {(sy[0].x + sy[0].y) + (sy[1].x + sy[1].y)};
+        group_max_sum_n<1, kGroupWarps>(mm, ss, S.red[1], sync);  // barrier 2
+        My = mm[0], Sy = ss[0];
+      }
       r = ex2(my2 - to_log2_units(My)) / Sy;
     } else {
       My = m[0], Sy = s[0];
@@ -286,6 +317,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       // ---- thinned race: 16 noise bits per class, survivors go to the list of this row's parity ----
       const ThinRule thin(rm, p.thin_factor);
       const float thrA = r * thin.scaleA;
+      const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
       const int buf = it & 1;
       if (tg == 0) {
         RowInfo ri;
@@ -295,49 +327,61 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       }
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
+        // one Philox call = 8 x 16 bits: word w serves classes (2w, 2w+1) of the chunk pair (2i, 2i+1);
+        // the halves are spliced under the exponent of 1.0f so that -(1 + h 2^-23) comes out of one PRMT
         const uint4 cw = rng.coarse((i << 7) | tg, grow);
-        float f[8];
-        f[0] = __uint_as_float(__byte_perm(cw.x, 0x3f80u, 0x5410)), f[1] = __uint_as_float(__byte_perm(cw.x, 0x3f80u, 0x5432));
-        f[2] = __uint_as_float(__byte_perm(cw.y, 0x3f80u, 0x5410)), f[3] = __uint_as_float(__byte_perm(cw.y, 0x3f80u, 0x5432));
-        f[4] = __uint_as_float(__byte_perm(cw.z, 0x3f80u, 0x5410)), f[5] = __uint_as_float(__byte_perm(cw.z, 0x3f80u, 0x5432));
-        f[6] = __uint_as_float(__byte_perm(cw.w, 0x3f80u, 0x5410)), f[7] = __uint_as_float(__byte_perm(cw.w, 0x3f80u, 0x5432));
+        const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
         float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
 #pragma unroll
-        for (int h = 0; h < 8; ++h) slack = fmaxf(slack, fmaf(z[2 * i + (h >> 2)][h & 3], thrA, thin.thrB) - f[h]);
+        for (int w = 0; w < 4; ++w) {
+          const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
+                                        __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
+          const float2 d = __ffma2_rn(z[2 * i + (w >> 1)][w & 1], tA2, __fadd2_rn(tB2, nf));
+          slack = fmaxf(slack, fmaxf(d.x, d.y));
+        }
         if (slack >= 0.0f) {
 #pragma unroll
-          for (int h = 0; h < 8; ++h) {
-            const float e = z[2 * i + (h >> 2)][h & 3];
-            if (f[h] <= fmaf(e, thrA, thin.thrB)) {
-              const uint32_t pos = atomicAdd(&S.cand_cnt[buf], 1u);
-              if (pos < static_cast<uint32_t>(kCandCap)) {
-                S.cand_k[buf][pos] = 4u * (256u * i + 128u * (h >> 2) + tg) + (h & 3);
-                S.cand_p[buf][pos] = e * r;
+          for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int hl = 0; hl < 2; ++hl) {
+              const float e = hl ? z[2 * i + (w >> 1)][w & 1].y : z[2 * i + (w >> 1)][w & 1].x;
+              const uint32_t h16 = hl ? (w4[w] >> 16) : (w4[w] & 0xffffu);
+              const float nf = __uint_as_float(0xbf800000u | h16);
+              if (fmaf(e, thrA, thin.thrB + nf) >= 0.0f) {
+                const uint32_t pos = atomicAdd(&S.cand_cnt[buf], 1u);
+                if (pos < static_cast<uint32_t>(kCandCap)) {
+                  const uint32_t k = 4u * (128u * (2 * i + (w >> 1)) + tg) + 2u * (w & 1) + hl;
+                  S.cand_k[buf][pos] = (h16 << 16) | k;
+                  S.cand_p[buf][pos] = e * r;
+                }
               }
             }
-          }
         }
       }
       return;
     }
 
-    // ---- exhaustive scoring (PHILOX_EXACT, or a redone row) ----
+    // ---- exhaustive scoring (PHILOX_EXACT, or a redone row): rare, so it is kept small rather than fast.
+    //      The softmax numerators are parked in the idle unconditional stage and scored in a rolled loop. ----
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      *reinterpret_cast<float4*>(S.u + 4 * (128 * i + tg)) = make_float4(z[i][0].x, z[i][0].y, z[i][1].x, z[i][1].y);
     unsigned long long best = 0ull;
+#pragma unroll 1
+    for (int i = 0; i < NC; ++i) {
+      const uint32_t q = 128u * i + tg;
+      const float4 e4 = lds4(S.u + 4 * q);
+      const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+      const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
+      const uint4 fw = rng.fine(q >> 2, grow);
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const uint4 cw = rng.coarse((i << 7) | tg, grow);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t q = 256u * i + 128u * half + tg;
-        const uint4 fw = rng.fine(q >> 2, grow);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t k = 4u * q + e;
-          const uint32_t mdraw = (NoiseStream::half_of(cw, 4 * half + e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
-          const float sc = rm.post_of(k, z[2 * i + half][e], r) + gumbel_from_uniform(uniform_from_draw(mdraw));
-          const unsigned long long key = pack_key(sc, k);
-          best = key > best ? key : best;
-        }
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t k = 4u * q + e;
+        const uint32_t mdraw =
+            (NoiseStream::half_of(cw, (((q >> 7) & 1u) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
+        const float sc = rm.post_of(k, ev[e], r) + gumbel_from_uniform(uniform_from_draw(mdraw));
+        const unsigned long long key = pack_key(sc, k);
+        best = key > best ? key : best;
       }
     }
     if (tg == 0) {
@@ -346,44 +390,52 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       best = key > best ? key : best;
     }
     best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3 (exact rows only)
-    if (tg == 0) p.x_prev[row] = key_class(best);
+    if (tg == 0) {
+      p.x_prev[row] = key_class(best);
+      if (next_row >= 0) issue_row(next_row);
+    }
   };
 
-  // ---- main loop over this group's rows -------------------------------------------------------------
+  // ---- one loop over this group's rows, then over the rows it queued for exhaustive rescoring ----------
   const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
-  long long row = first_row;
+  bool redo_phase = false;
+  uint32_t redo_i = 0, n_redo = 0;
+  long long row = first_row < rows ? first_row : -1;
   long long jj = 0, tt = 0;
-  if (row < rows) {
+  if (row >= 0) {
     if (tg == 0) issue_row(row);
     jj = p.x_t[row];
     tt = p.t[row / p.N];
   }
   int it = 0;
-  for (; row < rows; row += G, ++it) {
-    const long long next = row + G < rows ? row + G : -1;
+  for (;;) {
+    if (row < 0) {
+      if (redo_phase) break;
+      sync();  // every thread has finished appending survivors of the last row
+      if (!exact_mode && it > 0 && wg == ((it + 3) & 3)) score_survivors_cold<NP>(S, (it - 1) & 1, rng, p, lane, G, first_row);
+      sync();
+      redo_phase = true;
+      n_redo = S.redo_cnt;
+      if (n_redo == 0) break;
+      status_bits |= D3PM_STATUS_FALLBACK;
+      row = first_row + static_cast<long long>(S.redo[0]) * G;
+      if (tg == 0) issue_row(row);
+      jj = p.x_t[row];
+      tt = p.t[row / p.N];
+    }
+    long long next;
+    if (!redo_phase) next = row + G < rows ? row + G : -1;
+    else next = (redo_i + 1 < n_redo) ? first_row + static_cast<long long>(S.redo[redo_i + 1]) * G : -1;
     long long jj_next = 0, tt_next = 0;
     if (next >= 0) {  // software prefetch of the next row's scalars
       jj_next = p.x_t[next];
       tt_next = p.t[next / p.N];
     }
-    process_row(row, next, jj, tt, exact_mode, it, (!exact_mode && it > 0) ? ((it - 1) & 1) : -1);
-    jj = jj_next, tt = tt_next;
-  }
-  sync();
-  if (!exact_mode && it > 0 && wg == ((it + 3) & 3)) score_survivors<NP>(S, (it - 1) & 1, rng, p, lane, G, first_row);
-  sync();
-
-  // ---- rows whose survivors did not clear the bound: redo them exhaustively ----------------------------
-  const uint32_t n_redo = S.redo_cnt;
-  if (n_redo > 0) {
-    status_bits |= D3PM_STATUS_FALLBACK;
-    long long r0 = first_row + static_cast<long long>(S.redo[0]) * G;
-    if (tg == 0) issue_row(r0);
-    for (uint32_t i = 0; i < n_redo; ++i) {
-      const long long rr = first_row + static_cast<long long>(S.redo[i]) * G;
-      const long long nx = (i + 1 < n_redo) ? first_row + static_cast<long long>(S.redo[i + 1]) * G : -1;
-      process_row(rr, nx, p.x_t[rr], p.t[rr / p.N], true, 0, -1);
-    }
+    const bool exact = exact_mode || redo_phase;
+    process_row(row, next, jj, tt, exact, it, (!exact && it > 0) ? ((it - 1) & 1) : -1);
+    row = next, jj = jj_next, tt = tt_next;
+    ++it;
+    if (redo_phase) ++redo_i;
   }
   if (status_bits != 0 && tg == 0 && p.status != nullptr) atomicOr(p.status, status_bits);
 }
