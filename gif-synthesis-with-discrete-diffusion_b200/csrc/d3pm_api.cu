@@ -108,7 +108,7 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
 
   if (d->kernel < D3PM_KERNEL_AUTO || d->kernel > D3PM_KERNEL_STREAM)
     return fail(D3PM_ERR_INVALID, "fused_step: unknown kernel selector %d", d->kernel);
-  const bool can_stream = d3pm::stream_kernel_supports(p);
+  const bool can_stream = d3pm::stream_kernel_supports(p) && rows <= d3pm::stream_kernel_max_rows();
   if (d->kernel == D3PM_KERNEL_STREAM && !can_stream)
     return fail(D3PM_ERR_UNSUPPORTED, "fused_step: the stream kernel needs PHILOX sampling, no outputs and K in {1024,2048,4096}");
   if (d->kernel == D3PM_KERNEL_STREAM || (d->kernel == D3PM_KERNEL_AUTO && can_stream && rows >= d3pm::kStreamMinRows)) {

@@ -84,7 +84,7 @@ struct ThinRule {
     const float inv = c / rm.Ptot;
     scaleA = rm.A * inv * 0.0078125f;                                  // * 2^-7: h sits in the low mantissa bits
     thrB = fmaf(rm.Bc * inv, 0.0078125f, 1.0f) + 2.384185791015625e-7f;  // + 2 ulps of slack
-    accept = -logf(inv) + 0.02f;
+    accept = -lg2(inv) * kLn2 + 0.02f;
   }
 };
 

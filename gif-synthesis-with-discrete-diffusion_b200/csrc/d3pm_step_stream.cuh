@@ -5,13 +5,14 @@
 //   * one elected thread issues two bulk-TMA copies (cp.async.bulk, 16 KiB each for K = 4096) of the
 //     conditional / unconditional logit rows into the group's shared-memory stage, completion signalled
 //     on an mbarrier; the copy of row r+1 flies while row r is being computed from registers;
-//   * the 128 threads pull the row into registers (32 class pairs per thread), and run the softmax
-//     statistics, the guidance combine and the posterior entirely in registers with thread-local maxima,
-//     so that only two 128-thread named barriers per row are needed;
+//   * the 128 threads pull the row into registers (32 class pairs per thread, packed for the f32x2 pipe)
+//     and run the softmax statistics, the guidance combine and the posterior entirely in registers with
+//     thread-local maxima, so that only two 128-thread named barriers per row are needed;
 //   * sampling is the thinned exponential race (see ThinRule): 16 Philox bits per class decide whether the
-//     class can still win; the ~8 survivors per row are appended to a small shared-memory list and scored
-//     exactly by one warp (rotating) while the other warps already work on the next row;
-//   * rows whose best survivor does not clear the acceptance bound (probability e^-c) are queued and redone
+//     class can still win; the ~6 survivors per row are appended to a per-row list in shared memory;
+//   * every kScoreBatch rows the group scores the survivors of the whole batch exactly (Gumbel score in
+//     accurate fp32, argmax with first-index ties), two rows per warp pass, and writes the tokens;
+//   * rows whose best survivor does not clear the acceptance bound (probability ~e^-c) are queued and redone
 //     by the same group with exhaustive scoring after its main loop.
 // HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
 #pragma once
@@ -24,31 +25,32 @@ constexpr int kGroupThreads = 128;
 constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kGroupsPerCta = 4;
 constexpr int kStreamThreads = kGroupThreads * kGroupsPerCta;
-constexpr int kCandCap = 64;     // survivors kept per row (Poisson(c) of them; more -> the row is redone)
-constexpr int kRedoCap = 4096;   // rows a group can queue for exhaustive rescoring (= max rows per group)
+constexpr int kScoreBatch = 64;   // rows whose survivors are scored together
+constexpr int kCandPerRow = 14;   // survivors kept per row (a row with more is redone); +2 lanes: [MASK] and x_t
+constexpr int kRedoCap = 2048;    // rows a group can queue for exhaustive rescoring (= max rows per group)
+constexpr float kStreamThin = 6.0f;
 
-struct RowInfo {  // what the scoring warp needs to finish a row after the others have moved on
+struct RowInfo {  // what the scoring pass needs to finish a row
   float A, Bc, Pj, PK, accept;
-  uint32_t j;
-  int32_t masked;
+  uint32_t j;      // x_t, == K when masked
+  int32_t rel;     // row index relative to the group's first row, in units of G
   int32_t pad;
-  long long row;
 };
 
 template <int NP>
 struct __align__(128) GroupSmem {
   float c[1024 * NP];  // conditional logits of the row in flight
   float u[1024 * NP];  // unconditional logits
-  unsigned long long full;  // mbarrier: TMA bytes landed
+  alignas(16) float red[2][6 * kGroupWarps];  // reduction scratch, read back with 128-bit loads
+  unsigned long long full;                    // mbarrier: TMA bytes landed
   unsigned long long keys[kGroupWarps];
-  float red[2][4 * kGroupWarps];
-  RowInfo info[2];
-  uint32_t cand_cnt[2];
   uint32_t redo_cnt;
   uint32_t pad;
-  uint32_t cand_k[2][kCandCap];
-  float cand_p[2][kCandCap];
-  int32_t redo[kRedoCap];  // row indices relative to the group's first row, in units of G
+  RowInfo info[kScoreBatch];
+  uint32_t cand_cnt[kScoreBatch];
+  uint32_t cand_k[kScoreBatch][kCandPerRow];
+  float cand_p[kScoreBatch][kCandPerRow];
+  int32_t redo[kRedoCap];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -96,55 +98,87 @@ struct GroupSync {
 };
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// One warp finishes a row from its survivor list: exact scores, argmax, accept or queue for redo.
-template <int NP>
-__device__ __forceinline__ void score_survivors(GroupSmem<NP>& S, int buf, const NoiseStream& rng, const StepParams& p,
-                                                int lane, long long G_rows, long long first_row) {
-  const RowInfo ri = S.info[buf];
-  const uint32_t cnt = S.cand_cnt[buf];
-  const uint32_t n = cnt < static_cast<uint32_t>(kCandCap) ? cnt : static_cast<uint32_t>(kCandCap);
-  const uint64_t grow = static_cast<uint64_t>(p.row_offset + ri.row);
-  const int K = 1024 * NP;
-  unsigned long long best = 0ull;
-  for (uint32_t c = lane; c < n; c += 32) {
-    const uint32_t packed = S.cand_k[buf][c];
-    const uint32_t k = packed & 0xffffu, h16 = packed >> 16;  // class and the 16 coarse noise bits it survived with
-    const float pe = S.cand_p[buf][c];
-    const float pcl = fminf(fmaxf(pe, kPFloor), 1.0f);
-    const float P = (k == ri.j) ? ri.Pj : fmaf(pcl, ri.A, ri.Bc);
-    const uint32_t mdraw = (h16 << 7) | NoiseStream::low7_of(rng.fine(k >> 4, grow), k & 15u);
-    const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(mdraw));
-    const unsigned long long key = pack_key(sc, k);
-    best = key > best ? key : best;
-  }
-  if (lane == 0) {  // the [MASK] class is always scored ...
-    const unsigned long long key =
-        pack_key(log_prob_clamped(ri.PK) + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
-    best = key > best ? key : best;
-  } else if (lane == 1 && !ri.masked) {  // ... and so is the row's own class, which has its own coefficients
-    const unsigned long long key =
-        pack_key(log_prob_clamped(ri.Pj) + gumbel_from_uniform(uniform_from_draw(rng.draw(ri.j, grow))), ri.j);
-    best = key > best ? key : best;
-  }
-  best = warp_max_u64(best);
-  if (lane == 0) {
-    if (cnt <= static_cast<uint32_t>(kCandCap) && key_score(best) >= ri.accept) {
-      p.x_prev[ri.row] = key_class(best);
-    } else {
-      const uint32_t slot = S.redo_cnt;
-      S.redo[slot] = static_cast<int32_t>((ri.row - first_row) / G_rows);
-      S.redo_cnt = slot + 1;
+// Group-wide (max, sum) of per-thread softmax partials, one barrier.  m: thread-local max (natural units),
+// s: sum of 2^(x*log2e - fl(m*log2e)).  Returns the group max and the sum relative to it.
+template <int NV, typename Sync>
+__device__ __forceinline__ void stream_max_sum(float (&m)[NV], float (&s)[NV], float* scratch, Sync sync) {
+  constexpr int NW = kGroupWarps;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float mw = warp_max(m[v]);
+    const float mw2 = to_log2_units(mw);
+    const float sw = warp_sum(s[v] * ex2(to_log2_units(m[v]) - mw2));
+    if (lane == 0) {
+      scratch[(3 * v) * NW + warp] = mw;
+      scratch[(3 * v + 1) * NW + warp] = mw2;
+      scratch[(3 * v + 2) * NW + warp] = sw;
     }
-    S.cand_cnt[buf] = 0;
   }
-  __syncwarp();
+  sync();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 mw = lds4(scratch + (3 * v) * NW), mw2 = lds4(scratch + (3 * v + 1) * NW);
+    const float4 sw = lds4(scratch + (3 * v + 2) * NW);
+    const float M = fmaxf(fmaxf(mw.x, mw.y), fmaxf(mw.z, mw.w));
+    const float M2 = to_log2_units(M);
+    m[v] = M;
+    s[v] = fmaf(sw.x, ex2(mw2.x - M2), fmaf(sw.y, ex2(mw2.y - M2), fmaf(sw.z, ex2(mw2.z - M2), sw.w * ex2(mw2.w - M2))));
+  }
 }
 
-// out-of-line copy for the (cold) call after a group's last row
+// Exact finish of a batch of rows from their survivor lists: 16 lanes per row (14 survivors, the [MASK] class,
+// the row's own class), every lane scores one class exactly as the log-domain kernel does, a 16-lane
+// segmented argmax picks the winner, which is accepted if it clears the row's bound and queued otherwise.
 template <int NP>
-__device__ __noinline__ void score_survivors_cold(GroupSmem<NP>& S, int buf, const NoiseStream& rng, const StepParams& p,
-                                                  int lane, long long G_rows, long long first_row) {
-  score_survivors<NP>(S, buf, rng, p, lane, G_rows, first_row);
+__device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const NoiseStream& rng, const StepParams& p,
+                                         long long G, long long first_row) {
+  constexpr uint32_t K = 1024u * NP;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (kGroupWarps - 1);
+  const int sub = lane & 15;
+  for (int slot = 2 * warp + (lane >> 4); slot - (lane >> 4) < nslots; slot += 2 * kGroupWarps) {
+    unsigned long long key = 0ull;
+    const bool live = slot < nslots;
+    RowInfo ri;
+    ri.accept = 0.f, ri.rel = 0;
+    uint32_t cnt = 0;
+    if (live) {
+      ri = S.info[slot];
+      cnt = S.cand_cnt[slot];
+      const uint32_t n = cnt < static_cast<uint32_t>(kCandPerRow) ? cnt : static_cast<uint32_t>(kCandPerRow);
+      uint32_t k = 0;
+      float P = 0.f;
+      bool have = false;
+      if (static_cast<uint32_t>(sub) < n) {
+        k = S.cand_k[slot][sub];
+        const float pe = fminf(fmaxf(S.cand_p[slot][sub], kPFloor), 1.0f);
+        P = fmaf(pe, ri.A, ri.Bc);
+        have = (k != ri.j);  // the row's own class has its own coefficients and its own lane
+      } else if (sub == 14) {
+        k = K, P = ri.PK, have = true;
+      } else if (sub == 15 && ri.j != K) {
+        k = ri.j, P = ri.Pj, have = true;
+      }
+      if (have) {
+        const uint64_t grow = static_cast<uint64_t>(p.row_offset + first_row + static_cast<long long>(ri.rel) * G);
+        const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+        key = pack_key(sc, k);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {  // argmax within each 16-lane half
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other > key ? other : key;
+    }
+    if (live && sub == 0) {
+      if (cnt <= static_cast<uint32_t>(kCandPerRow) && key_score(key) >= ri.accept) {
+        p.x_prev[first_row + static_cast<long long>(ri.rel) * G] = key_class(key);
+      } else {
+        S.redo[atomicAdd(&S.redo_cnt, 1u)] = ri.rel;
+      }
+      S.cand_cnt[slot] = 0;
+    }
+  }
 }
 
 template <int NP, bool HAS_U>
@@ -155,7 +189,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   constexpr uint32_t kRowBytes = K * sizeof(float);
   const int g = threadIdx.x / kGroupThreads;
   const int tg = threadIdx.x % kGroupThreads;
-  const int wg = tg >> 5, lane = tg & 31;
   GroupSmem<NP>& S = reinterpret_cast<GroupSmem<NP>*>(smem_raw)[g];
   const GroupSync sync{g + 1};
   const long long G = static_cast<long long>(gridDim.x) * kGroupsPerCta;
@@ -163,12 +196,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   const long long rows = p.rows;
   const NoiseStream rng(p.seed, p.offset);
   const unsigned long long policy = l2_evict_first_policy();
+  const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kStreamThin;
 
   if (tg == 0) {
     mbar_init(&S.full, 1);
-    S.cand_cnt[0] = S.cand_cnt[1] = 0;
     S.redo_cnt = 0;
   }
+  if (tg < kScoreBatch) S.cand_cnt[tg] = 0;
   sync();
 
   auto issue_row = [&](long long row) {  // elected thread: arm the barrier and launch both row copies
@@ -182,12 +216,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   uint32_t status_bits = 0;
 
   // ------------------------------------------------------------------------------------------------
-  // process one row; `exact` = exhaustive log-space scoring (PHILOX_EXACT mode and redone rows)
-  // `pending` >= 0: survivor buffer of the previous row, to be scored by warp `pending_warp`
+  // one row.  `exact`: exhaustive log-space scoring (PHILOX_EXACT mode and redone rows); otherwise the
+  // row's survivors are left in slot `slot` for the next score_batch.
   // ------------------------------------------------------------------------------------------------
-  auto process_row = [&](long long row, long long next_row, long long jj_in, long long tt_in, bool exact, int it,
-                         int pending) {
-    long long tt = tt_in, jj = jj_in;
+  auto process_row = [&](long long row, long long next_row, int jj_in, int tt_in, bool exact, int slot, int rel) {
+    int tt = tt_in, jj = jj_in;
     if (tt < 0 || tt >= p.T) {
       status_bits |= D3PM_STATUS_BAD_T;
       tt = tt < 0 ? 0 : p.T - 1;
@@ -198,7 +231,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
     }
     const bool masked = (jj == K);
     const uint32_t j = static_cast<uint32_t>(jj);
-    const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
+    const RowCoef cf = load_row_coef(p.coef_table, tt, masked);
 
     mbar_wait(&S.full, phase);
     phase ^= 1u;
@@ -228,7 +261,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       m[0] = fmaxf(fmaxf(m[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
       if (HAS_U) m[1] = fmaxf(fmaxf(m[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
     }
-    m[0] = fmaxf(m[0], -3.0e38f), m[1] = fmaxf(m[1], -3.0e38f);  // keep -inf rows finite (no inf - inf)
+    m[0] = fmaxf(m[0], -3.0e38f), m[1] = fmaxf(m[1], -3.0e38f);  // keep all--inf chunks finite (no inf - inf)
     const float mc2 = to_log2_units(m[0]), mu2 = to_log2_units(m[1]);
     {
       const float2 l2e = make_float2(kLog2e, kLog2e), nmc = make_float2(-mc2, -mc2), nmu = make_float2(-mu2, -mu2);
@@ -251,20 +284,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       s[1] = (su[0].x + su[0].y) + (su[1].x + su[1].y);
     }
     if (HAS_U) {
-      group_max_sum_n<2, kGroupWarps>(m, s, S.red[0], sync);  // barrier 1: every thread is done with the stage
+      stream_max_sum<2>(m, s, S.red[0], sync);  // barrier 1: every thread is done with the stage
     } else {
       float m1[1] = {m[0]}, s1[1] = {s[0]};
-      group_max_sum_n<1, kGroupWarps>(m1, s1, S.red[0], sync);
+      stream_max_sum<1>(m1, s1, S.red[0], sync);
       m[0] = m1[0], s[0] = s1[0];
     }
     // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
     if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
-    if (pending >= 0 && wg == ((it + 3) & 3)) score_survivors<NP>(S, pending, rng, p, lane, G, first_row);
 
     // ---- guidance combine + renormalisation (:245-247) ----
     // With a = x - max, log-softmax clamped at -70 is max(a, -70 + lnS) - lnS, so
     //   y = lu + s (lc - lu) = s a' + (1 - s) b' + C,  C = -s lnSc - (1 - s) lnSu
-    float My, Sy, r, yj;
+    float My2, rSy, r, yj;
     if (HAS_U) {
       const float lnSc = ln_rel_sum(m[0], s[0]), lnSu = ln_rel_sum(m[1], s[1]);
       const float gs = p.guidance_scale, og = 1.0f - gs;
@@ -299,36 +331,37 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
             sy[h] = __fadd2_rn(sy[h], ey);
           }
         float mm[1] = {my}, ss[1] = {(sy[0].x + sy[0].y) + (sy[1].x + sy[1].y)};
-        group_max_sum_n<1, kGroupWarps>(mm, ss, S.red[1], sync);  // barrier 2
-        My = mm[0], Sy = ss[0];
+        stream_max_sum<1>(mm, ss, S.red[1], sync);  // barrier 2
+        My2 = to_log2_units(mm[0]);
+        rSy = __frcp_rn(ss[0]);
       }
-      r = ex2(my2 - to_log2_units(My)) / Sy;
+      r = ex2(my2 - My2) * rSy;
     } else {
-      My = m[0], Sy = s[0];
+      My2 = to_log2_units(m[0]);
+      rSy = __frcp_rn(s[0]);
       yj = xj;
-      r = ex2(mc2 - to_log2_units(My)) / Sy;
+      r = ex2(mc2 - My2) * rSy;
     }
-    const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -to_log2_units(My))) / Sy, kPFloor), 1.0f);
+    const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -My2)) * rSy, kPFloor), 1.0f);
     RowMath rm;
     rm.init(cf, masked, pj, j, K);
     const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
 
     if (!exact) {
-      // ---- thinned race: 16 noise bits per class, survivors go to the list of this row's parity ----
-      const ThinRule thin(rm, p.thin_factor);
+      // ---- thinned race: 16 noise bits per class, survivors go to this row's slot ----
+      const ThinRule thin(rm, thin_c);
       const float thrA = r * thin.scaleA;
       const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
-      const int buf = it & 1;
       if (tg == 0) {
         RowInfo ri;
         ri.A = rm.A, ri.Bc = rm.Bc, ri.Pj = rm.Pj, ri.PK = rm.PK, ri.accept = thin.accept;
-        ri.j = j, ri.masked = masked ? 1 : 0, ri.pad = 0, ri.row = row;
-        S.info[buf] = ri;
+        ri.j = j, ri.rel = rel, ri.pad = 0;
+        S.info[slot] = ri;
       }
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         // one Philox call = 8 x 16 bits: word w serves classes (2w, 2w+1) of the chunk pair (2i, 2i+1);
-        // the halves are spliced under the exponent of 1.0f so that -(1 + h 2^-23) comes out of one PRMT
+        // the halves are spliced under the exponent of -1.0f so that -(1 + h 2^-23) comes out of one PRMT
         const uint4 cw = rng.coarse((i << 7) | tg, grow);
         const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
         float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
@@ -348,11 +381,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
               const uint32_t h16 = hl ? (w4[w] >> 16) : (w4[w] & 0xffffu);
               const float nf = __uint_as_float(0xbf800000u | h16);
               if (fmaf(e, thrA, thin.thrB + nf) >= 0.0f) {
-                const uint32_t pos = atomicAdd(&S.cand_cnt[buf], 1u);
-                if (pos < static_cast<uint32_t>(kCandCap)) {
-                  const uint32_t k = 4u * (128u * (2 * i + (w >> 1)) + tg) + 2u * (w & 1) + hl;
-                  S.cand_k[buf][pos] = (h16 << 16) | k;
-                  S.cand_p[buf][pos] = e * r;
+                const uint32_t pos = atomicAdd(&S.cand_cnt[slot], 1u);
+                if (pos < static_cast<uint32_t>(kCandPerRow)) {
+                  S.cand_k[slot][pos] = 4u * (128u * (2 * i + (w >> 1)) + tg) + 2u * (w & 1) + hl;
+                  S.cand_p[slot][pos] = e * r;
                 }
               }
             }
@@ -397,42 +429,69 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   };
 
   // ---- one loop over this group's rows, then over the rows it queued for exhaustive rescoring ----------
+  // video index b = row / N is tracked incrementally (row advances by G per iteration)
   const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
+  const long long N = p.N;
+  const long long stepB = G / N, stepR = G % N;
+  auto token_of = [&](long long r_) {  // int64 token -> int, out-of-range folded to -1
+    const long long v = p.x_t[r_];
+    return (v < 0 || v > K) ? -1 : static_cast<int>(v);
+  };
+  auto time_of = [&](long long b_) {
+    const long long v = p.t[b_];
+    return (v < 0 || v >= p.T) ? -1 : static_cast<int>(v);
+  };
   bool redo_phase = false;
   uint32_t redo_i = 0, n_redo = 0;
   long long row = first_row < rows ? first_row : -1;
-  long long jj = 0, tt = 0;
+  long long vb = first_row / N, vr = first_row % N;  // video index and position of `row`
+  int jj = 0, tt = 0;
   if (row >= 0) {
     if (tg == 0) issue_row(row);
-    jj = p.x_t[row];
-    tt = p.t[row / p.N];
+    jj = token_of(row);
+    tt = time_of(vb);
   }
-  int it = 0;
+  int it = 0, in_batch = 0;
   for (;;) {
-    if (row < 0) {
-      if (redo_phase) break;
-      sync();  // every thread has finished appending survivors of the last row
-      if (!exact_mode && it > 0 && wg == ((it + 3) & 3)) score_survivors_cold<NP>(S, (it - 1) & 1, rng, p, lane, G, first_row);
-      sync();
-      redo_phase = true;
-      n_redo = S.redo_cnt;
-      if (n_redo == 0) break;
-      status_bits |= D3PM_STATUS_FALLBACK;
-      row = first_row + static_cast<long long>(S.redo[0]) * G;
-      if (tg == 0) issue_row(row);
-      jj = p.x_t[row];
-      tt = p.t[row / p.N];
+    if (row < 0 || in_batch == kScoreBatch) {  // finish the rows accumulated so far
+      if (in_batch > 0) {
+        sync();  // every thread has finished appending survivors
+        score_batch<NP>(S, in_batch, rng, p, G, first_row);
+        sync();  // slots may be reused, redo_cnt is final for this batch
+        in_batch = 0;
+      }
+      if (row < 0) {
+        if (redo_phase) break;
+        redo_phase = true;
+        n_redo = S.redo_cnt;
+        if (n_redo == 0) break;
+        status_bits |= D3PM_STATUS_FALLBACK;
+        row = first_row + static_cast<long long>(S.redo[0]) * G;
+        if (tg == 0) issue_row(row);
+        jj = token_of(row);
+        tt = time_of(row / N);
+      }
     }
     long long next;
-    if (!redo_phase) next = row + G < rows ? row + G : -1;
-    else next = (redo_i + 1 < n_redo) ? first_row + static_cast<long long>(S.redo[redo_i + 1]) * G : -1;
-    long long jj_next = 0, tt_next = 0;
-    if (next >= 0) {  // software prefetch of the next row's scalars
-      jj_next = p.x_t[next];
-      tt_next = p.t[next / p.N];
+    int jj_next = 0, tt_next = 0;
+    if (!redo_phase) {
+      next = row + G < rows ? row + G : -1;
+      vb += stepB, vr += stepR;
+      if (vr >= N) vr -= N, ++vb;
+      if (next >= 0) {  // software prefetch of the next row's scalars
+        jj_next = token_of(next);
+        tt_next = time_of(vb);
+      }
+    } else {
+      next = (redo_i + 1 < n_redo) ? first_row + static_cast<long long>(S.redo[redo_i + 1]) * G : -1;
+      if (next >= 0) {
+        jj_next = token_of(next);
+        tt_next = time_of(next / N);
+      }
     }
     const bool exact = exact_mode || redo_phase;
-    process_row(row, next, jj, tt, exact, it, (!exact && it > 0) ? ((it - 1) & 1) : -1);
+    process_row(row, next, jj, tt, exact, in_batch, it);
+    if (!exact) ++in_batch;
     row = next, jj = jj_next, tt = tt_next;
     ++it;
     if (redo_phase) ++redo_i;
@@ -449,6 +508,14 @@ inline bool stream_kernel_supports(const StepParams& p) {
   return true;
 }
 
+// every group must be able to queue all of its rows for rescoring
+inline long long stream_kernel_max_rows() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return static_cast<long long>(kRedoCap) * kGroupsPerCta * sms;
+}
+
 template <int NP, bool HAS_U>
 int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
   int dev = 0, sms = 0;
@@ -458,10 +525,7 @@ int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
   auto kern = step_stream_kernel<NP, HAS_U>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
-  long long ctas = sms;
-  const long long groups_needed = (p.rows + kRedoCap - 1) / kRedoCap;  // every group must be able to queue all its rows
-  if (ctas * kGroupsPerCta < groups_needed) ctas = (groups_needed + kGroupsPerCta - 1) / kGroupsPerCta;
-  kern<<<static_cast<unsigned>(ctas), kStreamThreads, smem, s>>>(p);
+  kern<<<static_cast<unsigned>(sms), kStreamThreads, smem, s>>>(p);
   return D3PM_OK;
 }
 
