@@ -41,7 +41,7 @@ template <int NP>
 struct __align__(128) GroupSmem {
   float c[1024 * NP];  // conditional logits of the row in flight
   float u[1024 * NP];  // unconditional logits
-  alignas(16) float red[2][6 * kGroupWarps];  // reduction scratch, read back with 128-bit loads
+  alignas(16) float red[3][6 * kGroupWarps];  // reduction scratch, read back with 128-bit loads
   unsigned long long full;                    // mbarrier: TMA bytes landed
   unsigned long long keys[kGroupWarps];
   uint32_t redo_cnt;
@@ -124,6 +124,52 @@ __device__ __forceinline__ void stream_max_sum(float (&m)[NV], float (&s)[NV], f
     const float M2 = to_log2_units(M);
     m[v] = M;
     s[v] = fmaf(sw.x, ex2(mw2.x - M2), fmaf(sw.y, ex2(mw2.y - M2), fmaf(sw.z, ex2(mw2.z - M2), sw.w * ex2(mw2.w - M2))));
+  }
+}
+
+__device__ __forceinline__ float warp_min(float x) {
+  float m;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(x));
+  return m;
+}
+
+// Group-wide max and min of NV values each (two CREDUX per value, one barrier).
+template <int NV, typename Sync>
+__device__ __forceinline__ void stream_min_max(float (&mx)[2], float (&mn)[2], float* scratch, Sync sync) {
+  constexpr int NW = kGroupWarps;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float a = warp_max(mx[v]), b = warp_min(mn[v]);
+    if (lane == 0) {
+      scratch[(2 * v) * NW + warp] = a;
+      scratch[(2 * v + 1) * NW + warp] = b;
+    }
+  }
+  sync();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 a = lds4(scratch + (2 * v) * NW), b = lds4(scratch + (2 * v + 1) * NW);
+    mx[v] = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+    mn[v] = fminf(fminf(b.x, b.y), fminf(b.z, b.w));
+  }
+}
+
+// Group-wide sums (all relative to the same, already global, maximum).
+template <int NV, typename Sync>
+__device__ __forceinline__ void stream_sum(float (&s)[NV], float* scratch, Sync sync) {
+  constexpr int NW = kGroupWarps;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float sw = warp_sum(s[v]);
+    if (lane == 0) scratch[v * NW + warp] = sw;
+  }
+  sync();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 a = lds4(scratch + v * NW);
+    s[v] = (a.x + a.y) + (a.z + a.w);
   }
 }
 
@@ -219,18 +265,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   // one row.  `exact`: exhaustive log-space scoring (PHILOX_EXACT mode and redone rows); otherwise the
   // row's survivors are left in slot `slot` for the next score_batch.
   // ------------------------------------------------------------------------------------------------
-  auto process_row = [&](long long row, long long next_row, int jj_in, int tt_in, bool exact, int slot, int rel) {
-    int tt = tt_in, jj = jj_in;
-    if (tt < 0 || tt >= p.T) {
+  auto process_row = [&](long long row, long long next_row, long long jj_in, long long tt_in, bool exact, int slot,
+                         int rel) {
+    long long tt64 = tt_in, jj64 = jj_in;  // prefetched one row ahead; first touched here
+    if (tt64 < 0 || tt64 >= p.T) {
       status_bits |= D3PM_STATUS_BAD_T;
-      tt = tt < 0 ? 0 : p.T - 1;
+      tt64 = tt64 < 0 ? 0 : p.T - 1;
     }
-    if (jj < 0 || jj > K) {
+    if (jj64 < 0 || jj64 > K) {
       status_bits |= D3PM_STATUS_BAD_TOKEN;
-      jj = K;
+      jj64 = K;
     }
-    const bool masked = (jj == K);
-    const uint32_t j = static_cast<uint32_t>(jj);
+    const int tt = static_cast<int>(tt64);
+    const bool masked = (jj64 == K);
+    const uint32_t j = static_cast<uint32_t>(jj64);
     const RowCoef cf = load_row_coef(p.coef_table, tt, masked);
 
     mbar_wait(&S.full, phase);
@@ -252,74 +300,103 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
     const float xj = masked ? 0.f : S.c[j];
     const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
 
-    // ---- softmax statistics with thread-local maxima (:231) ----
-    float m[2], s[2];
-    m[0] = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
-    m[1] = HAS_U ? fmaxf(fmaxf(z[0][0].x, z[0][0].y), fmaxf(z[0][1].x, z[0][1].y)) : 0.f;
+    // ---- range of the raw logits: thread-local max / min, then one cheap group reduction ----
+    float mx[2], mn[2];
+    mx[0] = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
+    mn[0] = fminf(fminf(x[0][0].x, x[0][0].y), fminf(x[0][1].x, x[0][1].y));
+    mx[1] = HAS_U ? fmaxf(fmaxf(z[0][0].x, z[0][0].y), fmaxf(z[0][1].x, z[0][1].y)) : 0.f;
+    mn[1] = HAS_U ? fminf(fminf(z[0][0].x, z[0][0].y), fminf(z[0][1].x, z[0][1].y)) : 0.f;
 #pragma unroll
     for (int i = 1; i < NC; ++i) {
-      m[0] = fmaxf(fmaxf(m[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
-      if (HAS_U) m[1] = fmaxf(fmaxf(m[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
+      mx[0] = fmaxf(fmaxf(mx[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
+      mn[0] = fminf(fminf(mn[0], x[i][0].x), fminf(x[i][0].y, fminf(x[i][1].x, x[i][1].y)));
+      if (HAS_U) {
+        mx[1] = fmaxf(fmaxf(mx[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
+        mn[1] = fminf(fminf(mn[1], z[i][0].x), fminf(z[i][0].y, fminf(z[i][1].x, z[i][1].y)));
+      }
     }
-    m[0] = fmaxf(m[0], -3.0e38f), m[1] = fmaxf(m[1], -3.0e38f);  // keep all--inf chunks finite (no inf - inf)
-    const float mc2 = to_log2_units(m[0]), mu2 = to_log2_units(m[1]);
-    {
-      const float2 l2e = make_float2(kLog2e, kLog2e), nmc = make_float2(-mc2, -mc2), nmu = make_float2(-mu2, -mu2);
-      float2 sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, su[2] = {sc[0], sc[0]};
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 ac = __ffma2_rn(x[i][h], l2e, nmc);
-          const float2 ec = make_float2(ex2(ac.x), ex2(ac.y));
-          sc[h] = __fadd2_rn(sc[h], ec);
-          if (HAS_U) {
-            const float2 au = __ffma2_rn(z[i][h], l2e, nmu);
-            su[h] = __fadd2_rn(su[h], make_float2(ex2(au.x), ex2(au.y)));
-          } else {
-            z[i][h] = ec;
-          }
-        }
-      s[0] = (sc[0].x + sc[0].y) + (sc[1].x + sc[1].y);
-      s[1] = (su[0].x + su[0].y) + (su[1].x + su[1].y);
-    }
-    if (HAS_U) {
-      stream_max_sum<2>(m, s, S.red[0], sync);  // barrier 1: every thread is done with the stage
-    } else {
-      float m1[1] = {m[0]}, s1[1] = {s[0]};
-      stream_max_sum<1>(m1, s1, S.red[0], sync);
-      m[0] = m1[0], s[0] = s1[0];
-    }
+    stream_min_max<HAS_U ? 2 : 1>(mx, mn, S.red[0], sync);  // barrier 1: every thread is done with the stage
+    mx[0] = fmaxf(mx[0], -3.0e38f), mx[1] = fmaxf(mx[1], -3.0e38f);  // an all--inf row stays finite (no inf - inf)
     // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
     if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
 
-    // ---- guidance combine + renormalisation (:245-247) ----
-    // With a = x - max, log-softmax clamped at -70 is max(a, -70 + lnS) - lnS, so
-    //   y = lu + s (lc - lu) = s a' + (1 - s) b' + C,  C = -s lnSc - (1 - s) lnSu
+    // the row's coarse noise: one Philox call = 8 x 16 bits, word w of call i serves classes (2w, 2w+1) of the
+    // chunk pair (2i, 2i+1)
+    const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
+    uint4 cws[NP];
+    auto draw_coarse = [&]() {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) cws[i] = rng.coarse((i << 7) | tg, grow);
+    };
+
     float My2, rSy, r, yj;
+    const float2 l2e = make_float2(kLog2e, kLog2e);
     if (HAS_U) {
-      const float lnSc = ln_rel_sum(m[0], s[0]), lnSu = ln_rel_sum(m[1], s[1]);
+      // ---- guidance combine (:245) ----
       const float gs = p.guidance_scale, og = 1.0f - gs;
-      const float ta = kClampLo + lnSc, tb = kClampLo + lnSu;
-      const float C = fmaf(-gs, lnSc, -og * lnSu);
-      const float2 nMc = make_float2(-m[0], -m[0]), nMu = make_float2(-m[1], -m[1]);
-      const float2 gs2 = make_float2(gs, gs), og2 = make_float2(og, og), C2 = make_float2(C, C);
+      const float2 gs2 = make_float2(gs, gs), og2 = make_float2(og, og);
       float my = -CUDART_INF_F;
+      // log-softmax can only reach the -70 clamp of :236 if some logit lies more than 70 - ln K below the row
+      // maximum (lse <= max + ln K).  When neither tensor does, both normalisers are constants that cancel in
+      // the renormalisation of :246, so  y = s c + (1 - s) u  up to a constant and no exponential of the raw
+      // logits is needed.  The magnitude guard keeps the two fused roundings below ~3e-5 in the worst case.
+      constexpr float kLnK = NP == 4 ? 8.3178f : (NP == 2 ? 7.6247f : 6.9315f);
+      const float big = fabsf(gs) * fmaxf(fabsf(mx[0]), fabsf(mn[0])) + fabsf(og) * fmaxf(fabsf(mx[1]), fabsf(mn[1]));
+      const bool no_clamp = (mx[0] - mn[0] <= 69.99f - kLnK) && (mx[1] - mn[1] <= 69.99f - kLnK) && (big <= 160.0f);
+      if (no_clamp) {
+        const float C = -fmaf(gs, mx[0], og * mx[1]);
+        const float2 C2 = make_float2(C, C);
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
+        for (int i = 0; i < NC; ++i)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float2 a = __fadd2_rn(x[i][h], nMc), b = __fadd2_rn(z[i][h], nMu);
-          a.x = fmaxf(a.x, ta), a.y = fmaxf(a.y, ta);
-          b.x = fmaxf(b.x, tb), b.y = fmaxf(b.y, tb);
-          const float2 y = __ffma2_rn(gs2, a, __ffma2_rn(og2, b, C2));
-          x[i][h] = y;
-          my = fmaxf(my, fmaxf(y.x, y.y));
+          for (int h = 0; h < 2; ++h) {
+            const float2 y = __ffma2_rn(gs2, x[i][h], __ffma2_rn(og2, z[i][h], C2));
+            x[i][h] = y;
+            my = fmaxf(my, fmaxf(y.x, y.y));
+          }
+        yj = fmaf(gs, xj, fmaf(og, zj, C));
+      } else {
+        // general path: softmax normalisers of both tensors (:231), clamps of :236 applied as thresholds.
+        // With a = x - max, log-softmax clamped at -70 is max(a, -70 + lnS) - lnS, so
+        //   y = lu + s (lc - lu) = s a' + (1 - s) b' + C,  C = -s lnSc - (1 - s) lnSu
+        float s[2];
+        {
+          const float mc2 = to_log2_units(mx[0]), mu2 = to_log2_units(mx[1]);
+          const float2 nmc = make_float2(-mc2, -mc2), nmu = make_float2(-mu2, -mu2);
+          float2 sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, su[2] = {sc[0], sc[0]};
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float2 ac = __ffma2_rn(x[i][h], l2e, nmc), au = __ffma2_rn(z[i][h], l2e, nmu);
+              sc[h] = __fadd2_rn(sc[h], make_float2(ex2(ac.x), ex2(ac.y)));
+              su[h] = __fadd2_rn(su[h], make_float2(ex2(au.x), ex2(au.y)));
+            }
+          s[0] = (sc[0].x + sc[0].y) + (sc[1].x + sc[1].y);
+          s[1] = (su[0].x + su[0].y) + (su[1].x + su[1].y);
         }
-      yj = fmaf(gs, fmaxf(xj - m[0], ta), fmaf(og, fmaxf(zj - m[1], tb), C));
+        stream_sum<2>(s, S.red[2], sync);  // extra barrier, general path only
+        const float lnSc = ln_rel_sum(mx[0], s[0]), lnSu = ln_rel_sum(mx[1], s[1]);
+        const float ta = kClampLo + lnSc, tb = kClampLo + lnSu;
+        const float C = fmaf(-gs, lnSc, -og * lnSu);
+        const float2 nMc = make_float2(-mx[0], -mx[0]), nMu = make_float2(-mx[1], -mx[1]), C2 = make_float2(C, C);
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float2 a = __fadd2_rn(x[i][h], nMc), b = __fadd2_rn(z[i][h], nMu);
+            a.x = fmaxf(a.x, ta), a.y = fmaxf(a.y, ta);
+            b.x = fmaxf(b.x, tb), b.y = fmaxf(b.y, tb);
+            const float2 y = __ffma2_rn(gs2, a, __ffma2_rn(og2, b, C2));
+            x[i][h] = y;
+            my = fmaxf(my, fmaxf(y.x, y.y));
+          }
+        yj = fmaf(gs, fmaxf(xj - mx[0], ta), fmaf(og, fmaxf(zj - mx[1], tb), C));
+      }
+      // ---- renormalisation (:246): numerators relative to the thread-local max, one reduction ----
       const float my2 = to_log2_units(my);
       {
-        const float2 l2e = make_float2(kLog2e, kLog2e), nmy = make_float2(-my2, -my2);
+        const float2 nmy = make_float2(-my2, -my2);
         float2 sy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int i = 0; i < NC; ++i)
@@ -337,18 +414,32 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       }
       r = ex2(my2 - My2) * rSy;
     } else {
-      My2 = to_log2_units(m[0]);
-      rSy = __frcp_rn(s[0]);
+      // ---- guidance off: p(x0) is the softmax of the conditional logits alone (predict_start, :231-236) ----
+      My2 = to_log2_units(mx[0]);
+      const float2 nmc = make_float2(-My2, -My2);
+      float2 sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 ac = __ffma2_rn(x[i][h], l2e, nmc);
+          const float2 ec = make_float2(ex2(ac.x), ex2(ac.y));
+          z[i][h] = ec;
+          sc[h] = __fadd2_rn(sc[h], ec);
+        }
+      float ss[1] = {(sc[0].x + sc[0].y) + (sc[1].x + sc[1].y)};
+      stream_sum<1>(ss, S.red[1], sync);  // barrier 2
+      rSy = __frcp_rn(ss[0]);
+      r = rSy;
       yj = xj;
-      r = ex2(mc2 - My2) * rSy;
     }
     const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -My2)) * rSy, kPFloor), 1.0f);
     RowMath rm;
     rm.init(cf, masked, pj, j, K);
-    const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
 
     if (!exact) {
       // ---- thinned race: 16 noise bits per class, survivors go to this row's slot ----
+      draw_coarse();  // all calls of the row up front: four independent Philox chains to interleave
       const ThinRule thin(rm, thin_c);
       const float thrA = r * thin.scaleA;
       const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
@@ -360,10 +451,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       }
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        // one Philox call = 8 x 16 bits: word w serves classes (2w, 2w+1) of the chunk pair (2i, 2i+1);
         // the halves are spliced under the exponent of -1.0f so that -(1 + h 2^-23) comes out of one PRMT
-        const uint4 cw = rng.coarse((i << 7) | tg, grow);
-        const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+        const uint32_t w4[4] = {cws[i].x, cws[i].y, cws[i].z, cws[i].w};
         float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -433,19 +522,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
   const long long N = p.N;
   const long long stepB = G / N, stepR = G % N;
-  auto token_of = [&](long long r_) {  // int64 token -> int, out-of-range folded to -1
-    const long long v = p.x_t[r_];
-    return (v < 0 || v > K) ? -1 : static_cast<int>(v);
-  };
-  auto time_of = [&](long long b_) {
-    const long long v = p.t[b_];
-    return (v < 0 || v >= p.T) ? -1 : static_cast<int>(v);
-  };
+  auto token_of = [&](long long r_) { return static_cast<long long>(p.x_t[r_]); };
+  auto time_of = [&](long long b_) { return static_cast<long long>(p.t[b_]); };
   bool redo_phase = false;
   uint32_t redo_i = 0, n_redo = 0;
   long long row = first_row < rows ? first_row : -1;
   long long vb = first_row / N, vr = first_row % N;  // video index and position of `row`
-  int jj = 0, tt = 0;
+  long long jj = 0, tt = 0;
   if (row >= 0) {
     if (tg == 0) issue_row(row);
     jj = token_of(row);
@@ -473,7 +556,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       }
     }
     long long next;
-    int jj_next = 0, tt_next = 0;
+    long long jj_next = 0, tt_next = 0;
     if (!redo_phase) {
       next = row + G < rows ? row + G : -1;
       vb += stepB, vr += stepR;

@@ -32,6 +32,8 @@ CASES = [
     (2, 1500, 2048, 25, None, 1.0),          # guidance off, the UCF job's 2048-code book
     (1, 2100, 1024, 60, 2.0, 1.0),
     (1, 37, 4096, 50, 2.0, 1.0),             # fewer rows than groups
+    (2, 900, 4096, 30, 2.0, 12.0),           # logit range > 70 - ln K: every row takes the general (clamping) path
+    (2, 900, 4096, 0, 2.0, -1.0),            # scale < 0: a few rows spiked by +150 / +90 (mixed fast / general rows)
 ]
 
 
@@ -39,8 +41,13 @@ CASES = [
 def test_stream_kernel_parity(B, N, K, tval, s, scale):
     sched = O.make_schedule(T, K)
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + N)
+    spiked = scale < 0
+    scale = abs(scale)
     lc = torch.randn(B, N, K, device=DEV, generator=g) * scale
     lu = None if s is None else torch.randn(B, N, K, device=DEV, generator=g) * scale
+    if spiked:  # every 7th row gets a dominant class in each tensor (different classes)
+        lc[:, ::7, 5] += 150.0
+        lu[:, ::7, 9] += 90.0
     t = (torch.tensor(tval) if isinstance(tval, list) else torch.full((B,), tval)).long().to(DEV)
     p_mask = sched["log_cumprod_ct"][t.cpu()].exp().view(B, 1).to(DEV)
     x_t = torch.where(torch.rand(B, N, device=DEV, generator=g) < p_mask, torch.full((B, N), K, device=DEV),
