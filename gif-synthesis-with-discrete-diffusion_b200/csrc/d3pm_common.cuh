@@ -110,7 +110,7 @@ __device__ __forceinline__ float key_score(unsigned long long key) {
   return __uint_as_float(b);
 }
 
-// ---- noise: Philox4x32-10 (Salmon et al. 2011) -----------------------------------------------------
+// ---- noise: Philox4x32-7 (Salmon et al. 2011) -----------------------------------------------------
 // Every class k of every global token row draws a 23-bit integer m from a counter-based stream, so a
 // row's noise does not depend on which GPU, CTA or kernel variant processes it:
 //   * 16 high bits h from a COARSE call, counter (coarse_call(k), row, offset), eight 16-bit halves per
@@ -123,7 +123,7 @@ __device__ __forceinline__ float key_score(unsigned long long key) {
 // 128-thread group owns): coarse_call = (c / 256) * 128 + c % 128, half = 4 * ((c / 128) % 2) + k % 4.
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
-constexpr int kPhiloxRounds = 10;
+constexpr int kPhiloxRounds = 7;  // Philox4x32-7: the fewest rounds that pass BigCrush (Salmon et al., Table 2)
 
 struct NoiseStream {
   uint32_t rk0[kPhiloxRounds], rk1[kPhiloxRounds];  // round keys (uniform across the grid)

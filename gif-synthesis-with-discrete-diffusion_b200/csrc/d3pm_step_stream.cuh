@@ -133,25 +133,21 @@ __device__ __forceinline__ float warp_min(float x) {
   return m;
 }
 
-// Group-wide max and min of NV values each (two CREDUX per value, one barrier).
+// Group-wide max of NV values (one CREDUX per value, one barrier).
 template <int NV, typename Sync>
-__device__ __forceinline__ void stream_min_max(float (&mx)[2], float (&mn)[2], float* scratch, Sync sync) {
+__device__ __forceinline__ void stream_max(float* mx, float* scratch, Sync sync) {
   constexpr int NW = kGroupWarps;
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float a = warp_max(mx[v]), b = warp_min(mn[v]);
-    if (lane == 0) {
-      scratch[(2 * v) * NW + warp] = a;
-      scratch[(2 * v + 1) * NW + warp] = b;
-    }
+    const float a = warp_max(mx[v]);
+    if (lane == 0) scratch[v * NW + warp] = a;
   }
   sync();
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float4 a = lds4(scratch + (2 * v) * NW), b = lds4(scratch + (2 * v + 1) * NW);
+    const float4 a = lds4(scratch + v * NW);
     mx[v] = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
-    mn[v] = fminf(fminf(b.x, b.y), fminf(b.z, b.w));
   }
 }
 
@@ -267,7 +263,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   // ------------------------------------------------------------------------------------------------
   auto process_row = [&](long long row, long long next_row, long long jj_in, long long tt_in, bool exact, int slot,
                          int rel) {
-    long long tt64 = tt_in, jj64 = jj_in;  // prefetched one row ahead; first touched here
+    mbar_wait(&S.full, phase);
+    phase ^= 1u;
+    long long tt64 = tt_in, jj64 = jj_in;  // loaded one row ahead
+    // opaque use point: keeps the compiler from hoisting the range checks up to the prefetching loads
+    asm volatile("" : "+l"(tt64), "+l"(jj64));
     if (tt64 < 0 || tt64 >= p.T) {
       status_bits |= D3PM_STATUS_BAD_T;
       tt64 = tt64 < 0 ? 0 : p.T - 1;
@@ -280,9 +280,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
     const bool masked = (jj64 == K);
     const uint32_t j = static_cast<uint32_t>(jj64);
     const RowCoef cf = load_row_coef(p.coef_table, tt, masked);
-
-    mbar_wait(&S.full, phase);
-    phase ^= 1u;
 
     // ---- shared -> registers: chunk i of this thread is float4 number 128*i + tg (conflict-free 128-bit
     //      reads); x[i][0] = classes (0,1) of the chunk, x[i][1] = classes (2,3), packed for the f32x2 pipe ----
@@ -300,23 +297,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
     const float xj = masked ? 0.f : S.c[j];
     const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
 
-    // ---- range of the raw logits: thread-local max / min, then one cheap group reduction ----
-    float mx[2], mn[2];
-    mx[0] = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
-    mn[0] = fminf(fminf(x[0][0].x, x[0][0].y), fminf(x[0][1].x, x[0][1].y));
-    mx[1] = HAS_U ? fmaxf(fmaxf(z[0][0].x, z[0][0].y), fmaxf(z[0][1].x, z[0][1].y)) : 0.f;
-    mn[1] = HAS_U ? fminf(fminf(z[0][0].x, z[0][0].y), fminf(z[0][1].x, z[0][1].y)) : 0.f;
+    // ---- largest |logit| of each tensor: thread-local, then one cheap group reduction ----
+    float am[2];
+    am[0] = fmaxf(fmaxf(fabsf(x[0][0].x), fabsf(x[0][0].y)), fmaxf(fabsf(x[0][1].x), fabsf(x[0][1].y)));
+    am[1] = HAS_U ? fmaxf(fmaxf(fabsf(z[0][0].x), fabsf(z[0][0].y)), fmaxf(fabsf(z[0][1].x), fabsf(z[0][1].y))) : 0.f;
 #pragma unroll
     for (int i = 1; i < NC; ++i) {
-      mx[0] = fmaxf(fmaxf(mx[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
-      mn[0] = fminf(fminf(mn[0], x[i][0].x), fminf(x[i][0].y, fminf(x[i][1].x, x[i][1].y)));
-      if (HAS_U) {
-        mx[1] = fmaxf(fmaxf(mx[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
-        mn[1] = fminf(fminf(mn[1], z[i][0].x), fminf(z[i][0].y, fminf(z[i][1].x, z[i][1].y)));
-      }
+      am[0] = fmaxf(fmaxf(am[0], fabsf(x[i][0].x)), fmaxf(fabsf(x[i][0].y), fmaxf(fabsf(x[i][1].x), fabsf(x[i][1].y))));
+      if (HAS_U)
+        am[1] = fmaxf(fmaxf(am[1], fabsf(z[i][0].x)), fmaxf(fabsf(z[i][0].y), fmaxf(fabsf(z[i][1].x), fabsf(z[i][1].y))));
     }
-    stream_min_max<HAS_U ? 2 : 1>(mx, mn, S.red[0], sync);  // barrier 1: every thread is done with the stage
-    mx[0] = fmaxf(mx[0], -3.0e38f), mx[1] = fmaxf(mx[1], -3.0e38f);  // an all--inf row stays finite (no inf - inf)
+    stream_max<HAS_U ? 2 : 1>(am, S.red[0], sync);  // barrier 1: every thread is done with the stage
     // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
     if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
 
@@ -337,29 +328,36 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       const float2 gs2 = make_float2(gs, gs), og2 = make_float2(og, og);
       float my = -CUDART_INF_F;
       // log-softmax can only reach the -70 clamp of :236 if some logit lies more than 70 - ln K below the row
-      // maximum (lse <= max + ln K).  When neither tensor does, both normalisers are constants that cancel in
-      // the renormalisation of :246, so  y = s c + (1 - s) u  up to a constant and no exponential of the raw
-      // logits is needed.  The magnitude guard keeps the two fused roundings below ~3e-5 in the worst case.
+      // maximum (lse <= max + ln K).  When |logit| <= (70 - ln K) / 2 throughout neither tensor can, both
+      // normalisers are constants that cancel in the renormalisation of :246, so  y = s c + (1 - s) u  up to a
+      // constant: no exponential of the raw logits is needed.  (|y| stays below ~100, two fused roundings.)
       constexpr float kLnK = NP == 4 ? 8.3178f : (NP == 2 ? 7.6247f : 6.9315f);
-      const float big = fabsf(gs) * fmaxf(fabsf(mx[0]), fabsf(mn[0])) + fabsf(og) * fmaxf(fabsf(mx[1]), fabsf(mn[1]));
-      const bool no_clamp = (mx[0] - mn[0] <= 69.99f - kLnK) && (mx[1] - mn[1] <= 69.99f - kLnK) && (big <= 160.0f);
+      constexpr float kSafeAbs = 0.5f * (69.99f - kLnK);
+      const bool no_clamp = (am[0] <= kSafeAbs) && (am[1] <= kSafeAbs) && (fabsf(gs) * am[0] + fabsf(og) * am[1] <= 160.0f);
       if (no_clamp) {
-        const float C = -fmaf(gs, mx[0], og * mx[1]);
-        const float2 C2 = make_float2(C, C);
 #pragma unroll
         for (int i = 0; i < NC; ++i)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const float2 y = __ffma2_rn(gs2, x[i][h], __ffma2_rn(og2, z[i][h], C2));
+            const float2 y = __ffma2_rn(gs2, x[i][h], __fmul2_rn(og2, z[i][h]));
             x[i][h] = y;
             my = fmaxf(my, fmaxf(y.x, y.y));
           }
-        yj = fmaf(gs, xj, fmaf(og, zj, C));
+        yj = fmaf(gs, xj, og * zj);
       } else {
         // general path: softmax normalisers of both tensors (:231), clamps of :236 applied as thresholds.
         // With a = x - max, log-softmax clamped at -70 is max(a, -70 + lnS) - lnS, so
         //   y = lu + s (lc - lu) = s a' + (1 - s) b' + C,  C = -s lnSc - (1 - s) lnSu
-        float s[2];
+        float mx[2], s[2];
+        mx[0] = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
+        mx[1] = fmaxf(fmaxf(z[0][0].x, z[0][0].y), fmaxf(z[0][1].x, z[0][1].y));
+#pragma unroll
+        for (int i = 1; i < NC; ++i) {
+          mx[0] = fmaxf(fmaxf(mx[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
+          mx[1] = fmaxf(fmaxf(mx[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
+        }
+        stream_max<2>(mx, S.red[2], sync);  // extra barriers, general path only
+        mx[0] = fmaxf(mx[0], -3.0e38f), mx[1] = fmaxf(mx[1], -3.0e38f);  // an all--inf row stays finite
         {
           const float mc2 = to_log2_units(mx[0]), mu2 = to_log2_units(mx[1]);
           const float2 nmc = make_float2(-mc2, -mc2), nmu = make_float2(-mu2, -mu2);
@@ -375,7 +373,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
           s[0] = (sc[0].x + sc[0].y) + (sc[1].x + sc[1].y);
           s[1] = (su[0].x + su[0].y) + (su[1].x + su[1].y);
         }
-        stream_sum<2>(s, S.red[2], sync);  // extra barrier, general path only
+        stream_sum<2>(s, S.red[2] + 2 * kGroupWarps, sync);
         const float lnSc = ln_rel_sum(mx[0], s[0]), lnSu = ln_rel_sum(mx[1], s[1]);
         const float ta = kClampLo + lnSc, tb = kClampLo + lnSu;
         const float C = fmaf(-gs, lnSc, -og * lnSu);
@@ -415,8 +413,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       r = ex2(my2 - My2) * rSy;
     } else {
       // ---- guidance off: p(x0) is the softmax of the conditional logits alone (predict_start, :231-236) ----
-      My2 = to_log2_units(mx[0]);
-      const float2 nmc = make_float2(-My2, -My2);
+      float mx[1];
+      mx[0] = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
+#pragma unroll
+      for (int i = 1; i < NC; ++i) mx[0] = fmaxf(fmaxf(mx[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
+      mx[0] = fmaxf(mx[0], -3.0e38f);
+      const float mc2 = to_log2_units(mx[0]);  // thread-local max: one reduction yields both max and sum
+      const float2 nmc = make_float2(-mc2, -mc2);
       float2 sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int i = 0; i < NC; ++i)
@@ -428,9 +431,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
           sc[h] = __fadd2_rn(sc[h], ec);
         }
       float ss[1] = {(sc[0].x + sc[0].y) + (sc[1].x + sc[1].y)};
-      stream_sum<1>(ss, S.red[1], sync);  // barrier 2
+      stream_max_sum<1>(mx, ss, S.red[1], sync);  // barrier 2
+      My2 = to_log2_units(mx[0]);
       rSy = __frcp_rn(ss[0]);
-      r = rSy;
+      r = ex2(mc2 - My2) * rSy;
       yj = xj;
     }
     const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -My2)) * rSy, kPFloor), 1.0f);

@@ -164,7 +164,10 @@ def test_philox_thinned_equals_exact_equals_reference_formula(B, N, K, tval, s):
     H.assert_tokens_match(thin.numpy(), out_o.argmax(1).numpy(), O.near_ties(post_o, u.permute(0, 2, 1)).numpy(), "philox")
     # different offset -> different noise; different shard offset -> different rows
     other = _cuda_step(lc, lu_in, x_t, t, T, mode=_lib.SAMPLE_PHILOX, **{**kw, "offset": offset + 1})["x_prev"]
-    assert not torch.equal(other, thin)
+    if not bool((thin == K).all()):  # (at t = 99 nearly every token stays [MASK] whatever the noise)
+        assert not torch.equal(other, thin)
+    u2 = ops.philox_uniform(B, N, K, seed=seed, offset=offset + 1, row_offset=row_offset, device=DEV)[:, :, :K + 1].cpu()
+    assert (u2 != u).float().mean() > 0.99
 
 
 def test_sharded_rows_reproduce_the_single_gpu_stream():
