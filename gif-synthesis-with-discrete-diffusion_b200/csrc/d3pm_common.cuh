@@ -248,31 +248,34 @@ __device__ __forceinline__ float group_max_f32(float x, float* scratch, Sync syn
   return best;
 }
 
-// Per-row coefficients from the table row of timestep t.
-__device__ __forceinline__ RowCoef load_row_coef(const float* __restrict__ table, int t, bool masked) {
-  const float4* row = reinterpret_cast<const float4*>(table + static_cast<size_t>(t) * D3PM_COEF_STRIDE);
-  const float4 a = __ldg(row + 0), b = __ldg(row + 1), c = __ldg(row + 2), d = __ldg(row + 3);
+// Per-row coefficients from the table row of timestep t: the first 8 floats of a row serve masked tokens, floats
+// 8..15 unmasked ones.  `lo`, `hi` are the two float4 of the half that applies.
+__device__ __forceinline__ RowCoef row_coef_from(const float4& lo, const float4& hi, bool masked) {
   RowCoef r;
   if (masked) {
-    r.A = a.x;      // AM
-    r.BO = a.y;     // BOM
+    r.A = lo.x;      // AM
+    r.BO = lo.y;     // BOM
     r.AS = 0.f;
     r.BOS = 0.f;
-    r.W = a.z;      // WM
-    r.WS = a.z;
-    r.PK0 = a.w;    // C1
-    r.PK1 = b.x;    // CP
+    r.W = lo.z;      // WM
+    r.WS = lo.z;
+    r.PK0 = lo.w;    // C1
+    r.PK1 = hi.x;    // CP
   } else {
-    r.A = c.x;      // AO
-    r.AS = c.y;     // AS
-    r.BO = c.z;     // BOO
-    r.BOS = c.w;    // BOS
-    r.W = d.x;      // WO
-    r.WS = d.y;     // WS
+    r.A = lo.x;      // AO
+    r.AS = lo.y;     // AS
+    r.BO = lo.z;     // BOO
+    r.BOS = lo.w;    // BOS
+    r.W = hi.x;      // WO
+    r.WS = hi.y;     // WS
     r.PK0 = 0.f;
-    r.PK1 = d.z;    // PK1
+    r.PK1 = hi.z;    // PK1
   }
   return r;
+}
+__device__ __forceinline__ RowCoef load_row_coef(const float* __restrict__ table, int t, bool masked) {
+  const float4* row = reinterpret_cast<const float4*>(table + static_cast<size_t>(t) * D3PM_COEF_STRIDE) + (masked ? 0 : 2);
+  return row_coef_from(__ldg(row), __ldg(row + 1), masked);
 }
 
 }  // namespace d3pm

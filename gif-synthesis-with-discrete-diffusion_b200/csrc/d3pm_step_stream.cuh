@@ -29,6 +29,7 @@ constexpr int kScoreBatch = 64;   // rows whose survivors are scored together
 constexpr int kCandPerRow = 14;   // survivors kept per row (a row with more is redone); +2 lanes: [MASK] and x_t
 constexpr int kRedoCap = 2048;    // rows a group can queue for exhaustive rescoring (= max rows per group)
 constexpr float kStreamThin = 6.0f;
+constexpr int kCoefSmemRows = 256;  // timesteps whose coefficients are staged in shared memory (16 KiB)
 
 struct RowInfo {  // what the scoring pass needs to finish a row
   float A, Bc, Pj, PK, accept;
@@ -229,9 +230,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   constexpr int K = 1024 * NP;
   constexpr int NC = 2 * NP;  // float4 chunks per thread per tensor
   constexpr uint32_t kRowBytes = K * sizeof(float);
-  const int g = threadIdx.x / kGroupThreads;
-  const int tg = threadIdx.x % kGroupThreads;
+  uint32_t tid;  // read once: a volatile read cannot be rematerialised as an S2R in every row
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  const int g = tid / kGroupThreads;
+  const int tg = tid % kGroupThreads;
   GroupSmem<NP>& S = reinterpret_cast<GroupSmem<NP>*>(smem_raw)[g];
+  // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits: per-row lookups become LDS
+  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(GroupSmem<NP>) * kGroupsPerCta);
+  const bool coef_in_smem = p.T <= kCoefSmemRows;
+  if (coef_in_smem) {
+    for (int i = tid; i < p.T * 16; i += kStreamThreads)
+      coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
+    __syncthreads();
+  }
   const GroupSync sync{g + 1};
   const long long G = static_cast<long long>(gridDim.x) * kGroupsPerCta;
   const long long first_row = static_cast<long long>(g) * gridDim.x + blockIdx.x;  // neighbouring rows -> different SMs
@@ -261,25 +272,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   // one row.  `exact`: exhaustive log-space scoring (PHILOX_EXACT mode and redone rows); otherwise the
   // row's survivors are left in slot `slot` for the next score_batch.
   // ------------------------------------------------------------------------------------------------
-  auto process_row = [&](long long row, long long next_row, long long jj_in, long long tt_in, bool exact, int slot,
-                         int rel) {
+  auto process_row = [&](long long row, long long next_row, uint32_t j, int tt, bool exact, int slot, int rel) {
+    const bool masked = (j == static_cast<uint32_t>(K));
     mbar_wait(&S.full, phase);
     phase ^= 1u;
-    long long tt64 = tt_in, jj64 = jj_in;  // loaded one row ahead
-    // opaque use point: keeps the compiler from hoisting the range checks up to the prefetching loads
-    asm volatile("" : "+l"(tt64), "+l"(jj64));
-    if (tt64 < 0 || tt64 >= p.T) {
-      status_bits |= D3PM_STATUS_BAD_T;
-      tt64 = tt64 < 0 ? 0 : p.T - 1;
-    }
-    if (jj64 < 0 || jj64 > K) {
-      status_bits |= D3PM_STATUS_BAD_TOKEN;
-      jj64 = K;
-    }
-    const int tt = static_cast<int>(tt64);
-    const bool masked = (jj64 == K);
-    const uint32_t j = static_cast<uint32_t>(jj64);
-    const RowCoef cf = load_row_coef(p.coef_table, tt, masked);
 
     // ---- shared -> registers: chunk i of this thread is float4 number 128*i + tg (conflict-free 128-bit
     //      reads); x[i][0] = classes (0,1) of the chunk, x[i][1] = classes (2,3), packed for the f32x2 pipe ----
@@ -438,6 +434,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       yj = xj;
     }
     const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -My2)) * rSy, kPFloor), 1.0f);
+    RowCoef cf;
+    if (coef_in_smem) {
+      const float* crow = coef_s + tt * 16 + (masked ? 0 : 8);
+      cf = row_coef_from(lds4(crow), lds4(crow + 4), masked);
+    } else {
+      cf = load_row_coef(p.coef_table, tt, masked);
+    }
     RowMath rm;
     rm.init(cf, masked, pj, j, K);
 
@@ -559,6 +562,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
         tt = time_of(row / N);
       }
     }
+    // Consume this row's scalars (loaded one row ahead) BEFORE issuing the next prefetch: the consumer waits on
+    // the scoreboard slot the loads share, so the other order would stall on the loads just issued.
+    if (tt < 0 || tt >= p.T) {
+      status_bits |= D3PM_STATUS_BAD_T;
+      tt = tt < 0 ? 0 : p.T - 1;
+    }
+    if (jj < 0 || jj > K) {
+      status_bits |= D3PM_STATUS_BAD_TOKEN;
+      jj = K;
+    }
+    int t_cur = static_cast<int>(tt);
+    uint32_t j_cur = static_cast<uint32_t>(jj);
+    asm volatile("" : "+r"(t_cur), "+r"(j_cur) : : "memory");
     long long next;
     long long jj_next = 0, tt_next = 0;
     if (!redo_phase) {
@@ -577,7 +593,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       }
     }
     const bool exact = exact_mode || redo_phase;
-    process_row(row, next, jj, tt, exact, in_batch, it);
+    process_row(row, next, j_cur, t_cur, exact, in_batch, it);
     if (!exact) ++in_batch;
     row = next, jj = jj_next, tt = tt_next;
     ++it;
@@ -608,7 +624,7 @@ int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
-  const size_t smem = sizeof(GroupSmem<NP>) * kGroupsPerCta;
+  const size_t smem = sizeof(GroupSmem<NP>) * kGroupsPerCta + kCoefSmemRows * 16 * sizeof(float);
   auto kern = step_stream_kernel<NP, HAS_U>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
