@@ -244,6 +244,11 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = B * N * BYTES_PER_TOKEN / (ms_per_step * 1e-3) / 1e9  # per GPU: one launch per step per rank
+        traffic, traffic_src = None, None  # dram bytes per launch of the same kernel/workload, from the committed ncu capture
+        summ = os.path.join(ROOT, "profiles", "r01_summary.json")
+        if os.path.isfile(summ):
+            sj = json.load(open(summ))
+            traffic, traffic_src = sj.get("traffic_bytes_per_launch"), sj.get("source")
         cpu_base, _ = cpu_reference(steps=3, warmup=1) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -253,7 +258,7 @@ def run_ours(args):
                        "classes": K + 1, "cache": "inputs 2.15 GB per GPU >> 126 MB L2, re-read every step (no flush needed)",
                        "parallelism": f"batch of videos partitioned over {world} GPU(s), no collective in the step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "d3pm fused step (one launch per step)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "d3pm fused step (one launch per step)",
                          "algorithmic_bytes_per_launch": B * N * BYTES_PER_TOKEN,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": tokens_global / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT,

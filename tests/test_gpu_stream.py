@@ -129,3 +129,29 @@ def test_stream_sampling_statistics():
         chi2 = float((((np.array(bc) - np.array(be)) ** 2) / np.array(be)).sum())
         dof = len(be) - 1
         assert chi2 < dof + 5 * np.sqrt(2 * dof) + 10, (chi2, dof)
+
+
+@pytest.mark.parametrize("kernel", [_lib.KERNEL_STREAM, _lib.KERNEL_ROWS])
+def test_no_access_outside_the_row_windows(kernel):
+    """compute-sanitizer is not available on the pool, so fence the buffers instead: NaN guard bands around
+    pitched input rows (an out-of-window read would poison the softmax and change tokens) and sentinels around the
+    token output (an out-of-window write would clobber them)."""
+    K, B, N, PITCH, PAD = 4096, 2, 600, 4096 + 64, 1024
+    g = torch.Generator(device=DEV).manual_seed(17)
+    buf_c = torch.full((PAD + B * N * PITCH + PAD,), float("nan"), device=DEV)
+    buf_u = torch.full_like(buf_c, float("nan"))
+    lc = buf_c[PAD:PAD + B * N * PITCH].view(B, N, PITCH)[:, :, :K]
+    lu = buf_u[PAD:PAD + B * N * PITCH].view(B, N, PITCH)[:, :, :K]
+    lc.copy_(torch.randn(B, N, K, device=DEV, generator=g))
+    lu.copy_(torch.randn(B, N, K, device=DEV, generator=g))
+    x_t = torch.randint(0, K + 1, (B, N), device=DEV, generator=g)
+    t = torch.tensor([10, 90], device=DEV)
+    out_buf = torch.full((64 + B * N + 64,), -7, dtype=torch.int64, device=DEV)
+    x_prev = out_buf[64:64 + B * N].view(B, N)
+    ops.fused_step(lc, lu, x_t, t, _table(K), guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX, seed=3, offset=1,
+                   kernel=kernel, x_prev_out=x_prev)
+    torch.cuda.synchronize()
+    assert (out_buf[:64] == -7).all() and (out_buf[-64:] == -7).all()
+    dense = _run(lc.contiguous(), lu.contiguous(), x_t, t, K, _lib.SAMPLE_PHILOX, kernel, seed=3, offset=1)
+    assert torch.equal(dense, x_prev)          # pitched rows == dense rows: nothing outside [0, K) was read
+    assert int(x_prev.min()) >= 0 and int(x_prev.max()) <= K
