@@ -118,7 +118,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((sm, reasons, power))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def summary(self):
         if not self.ok:
@@ -278,8 +278,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

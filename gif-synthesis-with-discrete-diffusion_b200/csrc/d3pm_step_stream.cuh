@@ -77,18 +77,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "memory");
   } while (!done);
 }
-// bulk TMA (1-D): global -> shared, completion bytes counted on the mbarrier; L2 evict-first (read once)
-__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, unsigned long long* bar,
-                                             unsigned long long policy) {
+// bulk TMA (1-D): global -> shared, completion bytes counted on the mbarrier.  (An L2 evict-first hint was
+// measured ~4 % slower on B200 for this read-once stream, so the copies carry no cache hint.)
+__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
-}
-__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
 }
 __device__ __forceinline__ void group_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroupThreads) : "memory");
@@ -248,7 +243,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   const long long first_row = static_cast<long long>(g) * gridDim.x + blockIdx.x;  // neighbouring rows -> different SMs
   const long long rows = p.rows;
   const NoiseStream rng(p.seed, p.offset);
-  const unsigned long long policy = l2_evict_first_policy();
   const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kStreamThin;
 
   if (tg == 0) {
@@ -261,8 +255,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
   auto issue_row = [&](long long row) {  // elected thread: arm the barrier and launch both row copies
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&S.full, HAS_U ? 2 * kRowBytes : kRowBytes);
-    tma_load_row(S.c, p.logits_c + row * p.pitch_logits, kRowBytes, &S.full, policy);
-    if (HAS_U) tma_load_row(S.u, p.logits_u + row * p.pitch_logits, kRowBytes, &S.full, policy);
+    tma_load_row(S.c, p.logits_c + row * p.pitch_logits, kRowBytes, &S.full);
+    if (HAS_U) tma_load_row(S.u, p.logits_u + row * p.pitch_logits, kRowBytes, &S.full);
   };
 
   uint32_t phase = 0;
