@@ -337,3 +337,55 @@ def closed_form_rows(sched, logits_c: np.ndarray, logits_u: Optional[np.ndarray]
                 post[b, n, :K] = np.log(p * W * Ap + Bp * eL) + one
                 post[b, n, K] = np.log(1e-30 * omCp + Cp * eL) + oneK
     return recon, np.clip(post, CLAMP_LO, 0)
+
+
+# --------------------------------------------------------------------------- training side
+def q_sample(sched, log_x_start: torch.Tensor, t: torch.Tensor, uniform: torch.Tensor) -> torch.Tensor:
+    """Forward noising draw x_t ~ q(x_t | x_0) (:361-366): q_pred then the Gumbel-max sampler, noise injected."""
+    return log_sample_categorical(q_pred(sched, log_x_start, t), uniform)
+
+
+def multinomial_kl(log_p: torch.Tensor, log_q: torch.Tensor) -> torch.Tensor:
+    """(:181-183)"""
+    return (log_p.exp() * (log_p - log_q)).sum(dim=1)
+
+
+def train_loss(sched, logits: torch.Tensor, x0: torch.Tensor, t: torch.Tensor, pt: torch.Tensor,
+               uniform: torch.Tensor, *, auxiliary_loss_weight: float = 0.0, adaptive_auxiliary_loss: bool = False,
+               mask_weight=(1, 1), is_train: bool = True):
+    """The variational-bound training loss of `_train_loss` (:391-457) for given timesteps `t` (with their
+    sampling probabilities `pt`), injected forward-noising noise and denoiser logits `[B, K, N]` (a leaf
+    that may require grad; in the reference they are `transformer(x_t, cond, t)`).
+
+    Returns (log_model_prob [B,K+1,N], vb_loss [B], x0_recon [B,N], x_t [B,N], kl_loss [B]).
+    The running-average bookkeeping (`Lt_history`, `Lt_count`, acc lists; :407-417, :434-438) is the caller's.
+    """
+    T = sched["log_at"].numel()
+    B, K, N = logits.shape
+    C = K + 1
+    log_x_start = index_to_log_onehot(x0, C)
+    log_xt = q_sample(sched, log_x_start, t, uniform)
+    xt = log_onehot_to_index(log_xt)
+
+    log_x0_recon = predict_start_from_logits(logits)                      # P_theta(x0 | xt)        (:404)
+    log_model_prob = q_posterior(sched, log_x0_recon, log_xt, t)          # through q(xt-1 | xt, x0) (:405)
+    x0_recon = log_onehot_to_index(log_x0_recon)
+
+    log_true_prob = q_posterior(sched, log_x_start, log_xt, t)            # (:420)
+    kl = multinomial_kl(log_true_prob, log_model_prob)
+    mask_region = (xt == C - 1).float()
+    w = mask_region * mask_weight[0] + (1.0 - mask_region) * mask_weight[1]
+    kl = (kl * w).reshape(B, -1).sum(-1)
+
+    decoder_nll = -(log_x_start.exp() * log_model_prob).sum(dim=1)        # log_categorical (:41-42, :427)
+    decoder_nll = decoder_nll.reshape(B, -1).sum(-1)
+    at_zero = (t == torch.zeros_like(t)).float()
+    kl_loss = at_zero * decoder_nll + (1.0 - at_zero) * kl
+    vb_loss = kl_loss / pt
+    if auxiliary_loss_weight != 0 and is_train:
+        kl_aux = multinomial_kl(log_x_start[:, :-1, :], log_x0_recon[:, :-1, :])
+        kl_aux = (kl_aux * w).reshape(B, -1).sum(-1)
+        kl_aux_loss = at_zero * decoder_nll + (1.0 - at_zero) * kl_aux
+        extra = (1 - t / T) + 1.0 if adaptive_auxiliary_loss else 1.0
+        vb_loss = vb_loss + extra * auxiliary_loss_weight * kl_aux_loss / pt
+    return log_model_prob, vb_loss, x0_recon, xt, kl_loss
