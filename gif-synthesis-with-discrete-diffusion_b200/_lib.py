@@ -15,7 +15,7 @@ _LIB_NAME = "libd3pm_b200.so"
 EXPORTED_SYMBOLS = (
     "d3pm_version", "d3pm_last_error", "d3pm_build_coef_table", "d3pm_fused_step", "d3pm_philox_uniform",
     "d3pm_q_posterior", "d3pm_gumbel_argmax", "d3pm_tokens_to_log_onehot", "d3pm_argmax_classes",
-    "d3pm_to_token_major",
+    "d3pm_to_token_major", "d3pm_q_pred", "d3pm_train_rows",
 )
 
 COEF_STRIDE = 32
@@ -39,6 +39,19 @@ class StepDesc(ctypes.Structure):
         ("guidance_scale", c_float), ("sample_mode", c_int32), ("gumbel_is_uniform", c_int32),
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64),
         ("thin_factor", c_float), ("kernel", c_int32), ("stream", c_void_p),
+    ]
+
+
+class TrainDesc(ctypes.Structure):
+    """Mirror of `d3pm_train_desc`."""
+    _fields_ = [
+        ("logits", c_void_p), ("x0", c_void_p), ("x_t", c_void_p), ("t", c_void_p), ("coef_table", c_void_p),
+        ("w_main", c_void_p), ("w_aux", c_void_p), ("tok_main", c_void_p), ("tok_aux", c_void_p),
+        ("x0_recon", c_void_p), ("xtm1_recon", c_void_p), ("grad", c_void_p), ("status", c_void_p),
+        ("B", c_int32), ("N", c_int32), ("K", c_int32), ("T", c_int32),
+        ("pitch", c_int64), ("pitch_grad", c_int64),
+        ("mask_weight_masked", c_float), ("mask_weight_unmasked", c_float),
+        ("backward", c_int32), ("stream", c_void_p),
     ]
 
 
@@ -88,6 +101,11 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_argmax_classes.restype = c_int
     lib.d3pm_argmax_classes.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                         c_void_p]
+    lib.d3pm_q_pred.restype = c_int
+    lib.d3pm_q_pred.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int,
+                                c_int, c_void_p]
+    lib.d3pm_train_rows.restype = c_int
+    lib.d3pm_train_rows.argtypes = [POINTER(TrainDesc)]
     lib.d3pm_to_token_major.restype = c_int
     lib.d3pm_to_token_major.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     _lib = lib

@@ -7,6 +7,7 @@
 #include "d3pm_ops.cuh"
 #include "d3pm_step_rows.cuh"
 #include "d3pm_step_stream.cuh"
+#include "d3pm_train_rows.cuh"
 
 namespace {
 
@@ -43,6 +44,13 @@ template <int V>
 void launch_rows_u(const d3pm::StepParams& p, cudaStream_t s) {
   if (p.logits_u != nullptr) launch_rows<V, true>(p, s);
   else launch_rows<V, false>(p, s);
+}
+
+template <int V>
+void launch_train(const d3pm::TrainParams& p, bool backward, cudaStream_t s) {
+  const dim3 grid(static_cast<unsigned>(p.rows)), block(d3pm::kRowThreads);
+  if (backward) d3pm::train_rows_kernel<V, true><<<grid, block, 0, s>>>(p);
+  else d3pm::train_rows_kernel<V, false><<<grid, block, 0, s>>>(p);
 }
 
 }  // namespace
@@ -191,6 +199,52 @@ int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stri
     d3pm::argmax_strided_kernel<<<grid, d3pm::kOpThreads, 0, s>>>(x, batch_stride, class_stride, token_stride, idx, C, N);
   }
   return check_launch("argmax_classes");
+}
+
+int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float* sched, int cumulative, float* out,
+                int64_t pitch_out, int B, int N, int K, int T, d3pm_stream_t stream) {
+  if (in == nullptr || t == nullptr || sched == nullptr || out == nullptr) return fail(D3PM_ERR_INVALID, "q_pred: null pointer");
+  if (B <= 0 || N <= 0 || K <= 0 || T <= 0 || pitch_in < K + 1 || pitch_out < K + 1)
+    return fail(D3PM_ERR_INVALID, "q_pred: bad sizes (rows need K+1 entries)");
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "q_pred: B*N too large");
+  d3pm::q_pred_rows_kernel<<<static_cast<unsigned>(rows), d3pm::kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, pitch_in, t, 0, sched, T, K, N, cumulative ? 1 : 0, out, pitch_out);
+  return check_launch("q_pred");
+}
+
+int d3pm_train_rows(const d3pm_train_desc* d) {
+  if (d == nullptr) return fail(D3PM_ERR_INVALID, "train_rows: null descriptor");
+  if (d->logits == nullptr || d->x0 == nullptr || d->x_t == nullptr || d->t == nullptr || d->coef_table == nullptr)
+    return fail(D3PM_ERR_INVALID, "train_rows: logits, x0, x_t, t and coef_table are required");
+  if (d->B <= 0 || d->N <= 0 || d->K <= 0 || d->T <= 0) return fail(D3PM_ERR_INVALID, "train_rows: sizes must be positive");
+  if (d->K % 4 != 0 || d->K > 8192) return fail(D3PM_ERR_UNSUPPORTED, "train_rows: K=%d must be a multiple of 4 and <= 8192", d->K);
+  if (d->pitch < d->K || d->pitch % 4 != 0 || !aligned16(d->logits) || !aligned16(d->coef_table))
+    return fail(D3PM_ERR_ALIGN, "train_rows: logits rows need pitch >= K, pitch %% 4 == 0, 16-byte base");
+  const int64_t rows = static_cast<int64_t>(d->B) * d->N;
+  if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "train_rows: B*N too large");
+  if (d->backward) {
+    if (d->grad == nullptr || d->w_main == nullptr || d->w_aux == nullptr)
+      return fail(D3PM_ERR_INVALID, "train_rows: backward needs grad, w_main and w_aux");
+    if (d->pitch_grad < d->K || d->pitch_grad % 4 != 0 || !aligned16(d->grad))
+      return fail(D3PM_ERR_ALIGN, "train_rows: grad rows need pitch >= K, pitch %% 4 == 0, 16-byte base");
+  } else if (d->tok_main == nullptr || d->tok_aux == nullptr) {
+    return fail(D3PM_ERR_INVALID, "train_rows: forward needs tok_main and tok_aux");
+  }
+  d3pm::TrainParams p;
+  p.logits = d->logits, p.x0 = d->x0, p.x_t = d->x_t, p.t = d->t, p.coef_table = d->coef_table;
+  p.w_main = d->w_main, p.w_aux = d->w_aux, p.tok_main = d->tok_main, p.tok_aux = d->tok_aux;
+  p.x0_recon = d->x0_recon, p.xtm1_recon = d->xtm1_recon, p.grad = d->grad, p.status = d->status;
+  p.B = d->B, p.N = d->N, p.K = d->K, p.T = d->T, p.pitch = d->pitch, p.pitch_grad = d->pitch_grad;
+  p.mask_weight_masked = d->mask_weight_masked, p.mask_weight_unmasked = d->mask_weight_unmasked;
+  p.rows = rows;
+  const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+  const int chunks = (d->K / 4 + d3pm::kRowThreads - 1) / d3pm::kRowThreads;
+  if (chunks <= 1) launch_train<1>(p, d->backward != 0, s);
+  else if (chunks <= 2) launch_train<2>(p, d->backward != 0, s);
+  else if (chunks <= 4) launch_train<4>(p, d->backward != 0, s);
+  else launch_train<8>(p, d->backward != 0, s);
+  return check_launch("train_rows");
 }
 
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N, d3pm_stream_t stream) {

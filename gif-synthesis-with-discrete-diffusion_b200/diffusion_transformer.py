@@ -18,7 +18,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from d3pm_b200 import _lib, ops
+from d3pm_b200 import _lib, ops, train
 from d3pm_b200._lib import D3PMError
 
 _SCHEDULE_BUFFERS = ("log_at", "log_bt", "log_ct", "log_1_min_ct",
@@ -356,7 +356,137 @@ class FusedDiffusionTransformer(nn.Module):
             output["logits"] = torch.exp(log_z)
         return output
 
-    # ------------------------------------------------------------------ explicitly out of scope this round
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("training forward/_train_loss (:391-457, :520-565) is SURVEY §8 f1 (next); "
-                                  "this class accelerates the sampling path")
+    # ------------------------------------------------------------------ training side
+    def _sched8(self) -> torch.Tensor:
+        """The eight schedule buffers as one `[8, T+1]` device matrix (cached like the coefficient table)."""
+        self.coef_table()
+        key = self._coef_cache[0]
+        if getattr(self, "_sched_cache", None) is None or self._sched_cache[0] != key:
+            sched = torch.zeros(8, self.num_timesteps + 1, dtype=torch.float32, device=self.device)
+            for i, n in enumerate(_SCHEDULE_BUFFERS):
+                b = getattr(self, n)
+                sched[i, : b.numel()] = b
+            self._sched_cache = (key, sched)
+        return self._sched_cache[1]
+
+    @torch.no_grad()
+    def q_pred(self, log_x_start, t):
+        """q(x_t | x_0) in log space, t wrapped modulo T+1 (:201-218)."""
+        rows, pitch = ops.to_rows(log_x_start.float())
+        out = train.q_pred_rows(rows, pitch, t, self._sched8(), self.num_classes - 1, cumulative=True)
+        return ops.as_logical(out, self.num_classes)
+
+    @torch.no_grad()
+    def q_pred_one_timestep(self, log_x_t, t):
+        """q(x_t | x_{t-1}) in log space (:185-199)."""
+        rows, pitch = ops.to_rows(log_x_t.float())
+        out = train.q_pred_rows(rows, pitch, t, self._sched8(), self.num_classes - 1, cumulative=False)
+        return ops.as_logical(out, self.num_classes)
+
+    @torch.no_grad()
+    def q_sample(self, log_x_start, t):
+        """Forward noising draw x_t ~ q(x_t | x_0), returned as a log one-hot (:361-366)."""
+        return self.log_sample_categorical(self.q_pred(log_x_start, t))
+
+    @torch.no_grad()
+    def q_sample_tokens(self, x_start, t):
+        """The same on integer tokens: int64 `[B, N]` -> int64 `[B, N]`."""
+        C = self.num_classes
+        hot = ops.tokens_to_log_onehot_rows(x_start.contiguous(), C, self._status_word())
+        qrows = train.q_pred_rows(hot, hot.shape[2], t, self._sched8(), C - 1, cumulative=True)
+        B, N = x_start.shape
+        noise = self._noise_rows(B, N)
+        if noise is not None:
+            return ops.gumbel_argmax_rows(qrows, qrows.shape[2], C, noise_rows=noise[0], pitch_noise=noise[1], noise_kind=1)
+        return ops.gumbel_argmax_rows(qrows, qrows.shape[2], C, noise_kind=2, seed=self.rng_seed,
+                                      offset=self._next_offset(), row_offset=self.row_offset)
+
+    def sample_time(self, b, device, method="uniform"):
+        """Timestep sampler (:368-389): importance sampling on the running loss history once every step has
+        been visited more than 10 times, uniform before that.  T-sized host-side logic, plain torch."""
+        if method == "importance":
+            if not (self.Lt_count > 10).all():
+                return self.sample_time(b, device, method="uniform")
+            Lt_sqrt = torch.sqrt(self.Lt_history + 1e-10) + 0.0001
+            Lt_sqrt[0] = Lt_sqrt[1]  # overwrite the decoder term with L1
+            pt_all = Lt_sqrt / Lt_sqrt.sum()
+            t = torch.multinomial(pt_all, num_samples=b, replacement=True)
+            return t, pt_all.gather(dim=0, index=t)
+        if method == "uniform":
+            t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
+            return t, torch.ones_like(t).float() / self.num_timesteps
+        raise ValueError
+
+    def _train_loss(self, x, cond_emb, is_train=True, need_log_model_prob=True):
+        """The variational-bound loss (:391-457) -> (log_model_prob, vb_loss [B], x0_recon [B, N]).
+
+        One denoiser forward, then `d3pm_train_rows` (forward) under autograd; its backward is the same kernel in
+        gradient mode.  `log_model_prob` `[B, K+1, N]` is only materialised when asked for (the reference's
+        `forward` exponentiates it for `out['logits']`)."""
+        b, device = x.size(0), x.device
+        assert self.loss_type == "vb_stochastic"
+        x_start = x.contiguous()
+        t, pt = self.sample_time(b, device, "importance")
+        xt = self.q_sample_tokens(x_start, t)
+
+        if self.amp:
+            with torch.autocast("cuda"):
+                out = self.transformer(xt, cond_emb, t)
+        else:
+            out = self.transformer(xt, cond_emb, t)
+        assert out.size(0) == xt.size(0) and out.size(1) == self.num_classes - 1 and out.size()[2:] == xt.size()[1:]
+        out = out.float()
+
+        aux_on = self.auxiliary_loss_weight != 0 and is_train
+        if aux_on:
+            extra = (1 - t / self.num_timesteps) + 1.0 if self.adaptive_auxiliary_loss else torch.ones_like(pt)
+            aux_w = (extra * self.auxiliary_loss_weight).float()
+        else:
+            aux_w = torch.zeros_like(pt)
+        vb_loss, kl_loss, x0_recon, xt_1_recon = train.VBLoss.apply(
+            out, x_start, xt, t, pt.float(), aux_w, self.coef_table(), tuple(self.mask_weight), self._status_word())
+
+        # running accuracy lists (:407-417): one device->host copy instead of 2B `.item()` syncs
+        with torch.no_grad():
+            acc = (x0_recon == x_start).float().mean(1)
+            keep = (xt_1_recon == xt).float().mean(1)
+            for this_t, a_, k_ in zip(t.tolist(), acc.tolist(), keep.tolist()):
+                self.diffusion_acc_list[this_t] = a_ * 0.1 + self.diffusion_acc_list[this_t] * 0.9
+                self.diffusion_keep_list[this_t] = k_ * 0.1 + self.diffusion_keep_list[this_t] * 0.9
+            # loss history for the importance sampler (:434-438)
+            Lt2 = kl_loss.detach().pow(2)
+            Lt2_prev = self.Lt_history.gather(dim=0, index=t)
+            self.Lt_history.scatter_(dim=0, index=t, src=(0.1 * Lt2 + 0.9 * Lt2_prev))
+            self.Lt_count.scatter_add_(dim=0, index=t, src=torch.ones_like(Lt2))
+
+        log_model_prob = None
+        if need_log_model_prob:
+            with torch.no_grad():
+                rows, _ = train._logit_rows(out.detach())
+                post = ops.fused_step(rows, None, xt, t.contiguous(), self.coef_table(), guidance_scale=1.0,
+                                      sample_mode=_lib.SAMPLE_NONE, want_post=True, status=self._status_word())["post"]
+                log_model_prob = ops.as_logical(post, self.num_classes)
+        return log_model_prob, vb_loss, x0_recon
+
+    def forward(self, input, return_loss=False, return_logits=True, return_att_weight=False, is_train=True, **kwargs):
+        """Training entry point (:520-565): {'loss', 'logits', 'pred_data'} for a batch of clean tokens."""
+        if kwargs.get("autocast") is True:
+            self.amp = True
+        sample_image = input["content_token"].type_as(input["content_token"])
+        if input.get("condition_embed_token") is None:
+            cond_emb = None
+        else:
+            cond_emb = input["condition_embed_token"].float()
+        if not is_train:
+            raise NotImplementedError("forward(is_train=False) leaves every output undefined in the reference (:552-565)")
+        log_model_prob, loss, sample_image_recon = self._train_loss(sample_image, cond_emb,
+                                                                    need_log_model_prob=return_logits)
+        loss = loss.sum() / (sample_image.size()[0] * sample_image.size()[1])
+        out = {}
+        if return_logits:
+            out["logits"] = torch.exp(log_model_prob)
+        if return_loss:
+            out["loss"] = loss
+        self.amp = False
+        out["pred_data"] = sample_image_recon
+        return out

@@ -128,6 +128,40 @@ int d3pm_tokens_to_log_onehot(const int64_t* x, float* out, int64_t pitch, int64
 int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stride, int64_t token_stride,
                         int64_t* idx, int B, int C, int N, d3pm_stream_t stream);
 
+/* ---------------------------------------------------------------- training side
+ * q_pred (:201-218, cumulative = 1, t wrapped modulo T+1) and q_pred_one_timestep (:185-199, cumulative = 0) on
+ * rows of K+1 log-probabilities.  `sched` = the [8][T+1] schedule matrix of d3pm_build_coef_table.            */
+int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float* sched, int cumulative,
+                float* out, int64_t pitch_out, int B, int N, int K, int T, d3pm_stream_t stream);
+
+/* The variational-bound loss of _train_loss (:391-457) given the denoiser logits, the clean tokens x0, the noised
+ * tokens x_t (from q_sample, :361-366) and t; and its gradient with respect to the logits.
+ *   backward == 0: writes per-token tok_main / tok_aux (the caller sums them per video: kl_loss = sum tok_main,
+ *                  vb_loss = kl_loss / pt + aux_weight * sum tok_aux / pt) and, optionally, x0_recon / xtm1_recon.
+ *   backward == 1: recomputes the row and writes grad[row][k] = d( sum_b w_main[b] main_b + w_aux[b] auxc_b ) / d logits. */
+typedef struct d3pm_train_desc {
+  const float* logits;   /* [B*N][pitch] denoiser logits (first K valid) */
+  const int64_t* x0;     /* [B*N] in [0, K) */
+  const int64_t* x_t;    /* [B*N] in [0, K] */
+  const int64_t* t;      /* [B] */
+  const float* coef_table;
+  const float* w_main;   /* [B], backward only */
+  const float* w_aux;    /* [B], backward only */
+  float* tok_main;       /* [B*N], forward only */
+  float* tok_aux;        /* [B*N], forward only */
+  int64_t* x0_recon;     /* [B*N] arg-max of p(x0 | x_t), nullable (forward) */
+  int64_t* xtm1_recon;   /* [B*N] arg-max of the model posterior, nullable (forward) */
+  float* grad;           /* [B*N][pitch_grad], backward only */
+  uint32_t* status;
+  int32_t B, N, K, T;
+  int64_t pitch, pitch_grad;
+  float mask_weight_masked, mask_weight_unmasked; /* mask_weight[0], mask_weight[1] (:423) */
+  int32_t backward;
+  d3pm_stream_t stream;
+} d3pm_train_desc;
+
+int d3pm_train_rows(const d3pm_train_desc* desc);
+
 /* [B, C, N] contiguous (reference layout) -> token-major rows [B*N][pitch]. */
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N,
                         d3pm_stream_t stream);
