@@ -37,8 +37,8 @@ BYTES_PER_TOKEN = 2 * K_CODES * 4 + 8 + 8  # both logit rows + x_t + x_{t-1}
 METRIC, UNIT = "reverse_step_token_updates_per_sec", "token-updates/s"
 
 
-def workload_name(n_gpus):
-    return (f"config2 x{n_gpus}: {VIDEOS_PER_GPU} videos/GPU, 16x16x16 grid, {K_CODES}+1 classes, guidance {GUIDANCE:g}, "
+def workload_name(n_gpus, videos_per_gpu=VIDEOS_PER_GPU):
+    return (f"config2 x{n_gpus}: {videos_per_gpu} videos/GPU, 16x16x16 grid, {K_CODES}+1 classes, guidance {GUIDANCE:g}, "
             f"t={T_NOW}, fp32 logits, in-kernel Philox Gumbel-max")
 
 
@@ -159,7 +159,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, N, K = VIDEOS_PER_GPU, N_TOKENS, K_CODES
+    # default: weak scaling, config 2 per GPU.  --global-videos G (config 4: G = 128): the SAME G videos split over the
+    # ranks (strong scaling), G divisible by the world size
+    if args.global_videos:
+        if args.global_videos % world:
+            raise SystemExit(f"--global-videos {args.global_videos} is not divisible by {world} ranks")
+        B = args.global_videos // world
+    else:
+        B = VIDEOS_PER_GPU
+    N, K = N_TOKENS, K_CODES
     B_global = B * world
     b0, b1 = d3pm_b200.shard_range(B_global, world, rank)
     row_offset = b0 * N
@@ -252,10 +260,11 @@ def run_ours(args):
         cpu_base, _ = cpu_reference(steps=3, warmup=1) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_videos else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(world), "global_batch": B_global, "tokens_per_video": N,
-                       "classes": K + 1, "cache": "inputs 2.15 GB per GPU >> 126 MB L2, re-read every step (no flush needed)",
+            "config": {"workload": workload_name(world, B), "global_batch": B_global, "tokens_per_video": N,
+                       "classes": K + 1, "cache": f"inputs {B * N * BYTES_PER_TOKEN / 1e9:.2f} GB per GPU >> 126 MB L2, re-read every step (no flush needed)",
                        "parallelism": f"batch of videos partitioned over {world} GPU(s), no collective in the step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "d3pm fused step (one launch per step)",
@@ -281,6 +290,9 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--global-videos", type=int, default=0,
+                    help="strong scaling: this many videos in total, split over the ranks (config 4: 128); "
+                         "default 0 = weak scaling, 16 videos per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

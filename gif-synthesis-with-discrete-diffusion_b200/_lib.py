@@ -15,13 +15,14 @@ _LIB_NAME = "libd3pm_b200.so"
 EXPORTED_SYMBOLS = (
     "d3pm_version", "d3pm_last_error", "d3pm_build_coef_table", "d3pm_fused_step", "d3pm_philox_uniform",
     "d3pm_q_posterior", "d3pm_gumbel_argmax", "d3pm_tokens_to_log_onehot", "d3pm_argmax_classes",
-    "d3pm_to_token_major", "d3pm_q_pred", "d3pm_train_rows",
+    "d3pm_to_token_major", "d3pm_q_pred", "d3pm_train_rows", "d3pm_purity_select",
 )
 
 COEF_STRIDE = 32
 SAMPLE_NONE, SAMPLE_GUMBEL, SAMPLE_PHILOX, SAMPLE_PHILOX_EXACT = 0, 1, 2, 3
 STATUS_BAD_T, STATUS_BAD_TOKEN, STATUS_FALLBACK = 1, 2, 4
 KERNEL_AUTO, KERNEL_ROWS, KERNEL_STREAM = 0, 1, 2
+FROM_POSTERIOR, FROM_RECON = 0, 1
 
 
 class D3PMError(RuntimeError):
@@ -39,6 +40,7 @@ class StepDesc(ctypes.Structure):
         ("guidance_scale", c_float), ("sample_mode", c_int32), ("gumbel_is_uniform", c_int32),
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64),
         ("thin_factor", c_float), ("kernel", c_int32), ("stream", c_void_p),
+        ("sample_from", c_int32), ("reserved", c_int32), ("score", c_void_p), ("sharpen", c_void_p),
     ]
 
 
@@ -104,6 +106,9 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_q_pred.restype = c_int
     lib.d3pm_q_pred.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int,
                                 c_int, c_void_p]
+    lib.d3pm_purity_select.restype = c_int
+    lib.d3pm_purity_select.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_uint64, c_uint64, c_int64, c_void_p]
     lib.d3pm_train_rows.restype = c_int
     lib.d3pm_train_rows.argtypes = [POINTER(TrainDesc)]
     lib.d3pm_to_token_major.restype = c_int

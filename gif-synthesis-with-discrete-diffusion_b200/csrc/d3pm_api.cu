@@ -34,7 +34,7 @@ constexpr int64_t kMaxGrid = 2147483647LL;
 template <int V, bool HAS_U>
 void launch_rows(const d3pm::StepParams& p, cudaStream_t s) {
   const dim3 grid(static_cast<unsigned>(p.rows)), block(d3pm::kRowThreads);
-  if (p.sample_mode == D3PM_SAMPLE_PHILOX && p.post == nullptr && p.recon == nullptr)
+  if (p.sample_mode == D3PM_SAMPLE_PHILOX && p.post == nullptr && p.recon == nullptr && p.sharpen == nullptr)
     d3pm::step_rows_kernel<V, HAS_U, true><<<grid, block, 0, s>>>(p);
   else
     d3pm::step_rows_kernel<V, HAS_U, false><<<grid, block, 0, s>>>(p);
@@ -86,8 +86,14 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   const int mode = d->sample_mode;
   if (mode < D3PM_SAMPLE_NONE || mode > D3PM_SAMPLE_PHILOX_EXACT)
     return fail(D3PM_ERR_INVALID, "fused_step: unknown sample_mode %d", mode);
-  if (mode == D3PM_SAMPLE_NONE && d->post == nullptr && d->recon == nullptr)
+  if (mode == D3PM_SAMPLE_NONE && d->post == nullptr && d->recon == nullptr && d->score == nullptr)
     return fail(D3PM_ERR_INVALID, "fused_step: nothing to do (no sampling and no output requested)");
+  if (d->sample_from != D3PM_FROM_POSTERIOR && d->sample_from != D3PM_FROM_RECON)
+    return fail(D3PM_ERR_INVALID, "fused_step: unknown sample_from %d", d->sample_from);
+  if (d->sharpen != nullptr && (d->sample_from != D3PM_FROM_RECON || mode == D3PM_SAMPLE_PHILOX || mode == D3PM_SAMPLE_NONE))
+    return fail(D3PM_ERR_INVALID, "fused_step: sharpen needs D3PM_FROM_RECON with GUMBEL or PHILOX_EXACT sampling");
+  if (d->sample_from == D3PM_FROM_RECON && d->post != nullptr)
+    return fail(D3PM_ERR_INVALID, "fused_step: post is the q_posterior output; it cannot be combined with D3PM_FROM_RECON");
   if (mode != D3PM_SAMPLE_NONE && d->x_prev == nullptr)
     return fail(D3PM_ERR_INVALID, "fused_step: x_prev is required when sampling");
   if (mode == D3PM_SAMPLE_GUMBEL) {
@@ -112,6 +118,7 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   p.guidance_scale = d->guidance_scale, p.sample_mode = mode, p.gumbel_is_uniform = d->gumbel_is_uniform;
   p.seed = d->seed, p.offset = d->offset, p.row_offset = d->row_offset, p.thin_factor = d->thin_factor;
   p.rows = rows;
+  p.sample_from = d->sample_from, p.score = d->score, p.sharpen = d->sharpen;
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
 
   if (d->kernel < D3PM_KERNEL_AUTO || d->kernel > D3PM_KERNEL_STREAM)
@@ -199,6 +206,23 @@ int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stri
     d3pm::argmax_strided_kernel<<<grid, d3pm::kOpThreads, 0, s>>>(x, batch_stride, class_stride, token_stride, idx, C, N);
   }
   return check_launch("argmax_classes");
+}
+
+int d3pm_purity_select(const int64_t* x_t, const int64_t* x_cand, const float* score, const float* expo,
+                       const int32_t* n_reveal, int64_t* x_out, int32_t* revealed, int B, int N, int K, uint64_t seed,
+                       uint64_t offset, int64_t row_offset, d3pm_stream_t stream) {
+  if (x_t == nullptr || x_cand == nullptr || n_reveal == nullptr || x_out == nullptr)
+    return fail(D3PM_ERR_INVALID, "purity_select: x_t, x_cand, n_reveal and x_out are required");
+  if (B <= 0 || N <= 0 || K <= 0) return fail(D3PM_ERR_INVALID, "purity_select: sizes must be positive");
+  if (N > d3pm::kPurityMaxN) return fail(D3PM_ERR_UNSUPPORTED, "purity_select: N=%d exceeds %d", N, d3pm::kPurityMaxN);
+  int n2 = 1;
+  while (n2 < N) n2 <<= 1;
+  const size_t smem = static_cast<size_t>(n2) * sizeof(unsigned long long);
+  if (cudaFuncSetAttribute(d3pm::purity_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return fail(D3PM_ERR_CUDA, "purity_select: %s", cudaGetErrorString(cudaGetLastError()));
+  d3pm::purity_select_kernel<<<static_cast<unsigned>(B), d3pm::kPurityThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      x_t, x_cand, score, expo, n_reveal, x_out, revealed, N, n2, K, seed, offset, row_offset);
+  return check_launch("purity_select");
 }
 
 int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float* sched, int cumulative, float* out,

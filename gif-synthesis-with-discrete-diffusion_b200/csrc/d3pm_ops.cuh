@@ -233,4 +233,87 @@ __global__ void __launch_bounds__(256) to_token_major_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- purity-prior reveal (p_sample :331-343)
+// One CTA per video.  key_n = w_n / q_n with w_n the per-video-normalised purity of the [MASK] positions (0 for the
+// already revealed ones) and q_n ~ Exp(1): the n_reveal largest keys are what torch.multinomial(w, n_reveal) returns
+// (ATen draws exactly this race).  The keys are sorted with a shared-memory bitonic network as 64-bit words
+// (key bits, ~position) so that equal keys -- only the zero weights -- resolve to the lowest position.
+constexpr int kPurityThreads = 1024;
+constexpr int kPurityMaxN = 8192;
+
+__global__ void __launch_bounds__(kPurityThreads) purity_select_kernel(
+    const int64_t* __restrict__ x_t, const int64_t* __restrict__ x_cand, const float* __restrict__ score,
+    const float* __restrict__ expo, const int32_t* __restrict__ n_reveal, int64_t* __restrict__ x_out,
+    int32_t* __restrict__ revealed, int N, int n2, int K, uint64_t seed, uint64_t offset, int64_t row_offset) {
+  extern __shared__ unsigned long long skeys[];
+  __shared__ float sred[kPurityThreads / 32];
+  __shared__ int scount[kPurityThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t base = static_cast<int64_t>(b) * N;
+  const NoiseStream rng(seed, offset);
+
+  // per-video maximum of the raw purity (:319)
+  float mx = 0.f;
+  if (score != nullptr)
+    for (int n = tid; n < N; n += kPurityThreads) mx = fmaxf(mx, score[base + n]);
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) sred[tid >> 5] = mx;
+  __syncthreads();
+  mx = sred[0];
+  for (int w = 1; w < kPurityThreads / 32; ++w) mx = fmaxf(mx, sred[w]);
+  const float denom = mx + 1e-10f;
+
+  for (int n = tid; n < n2; n += kPurityThreads) {
+    unsigned long long key = 0ull;  // padding sorts last
+    if (n < N) {
+      const bool is_mask = (x_t[base + n] == K);
+      const float w = is_mask ? (score != nullptr ? score[base + n] / denom : 1.0f) : 0.0f;
+      float q;
+      if (expo != nullptr) {
+        q = expo[base + n];
+      } else {  // Exp(1) = -log(u), u from the stream's class-0 draw of this (global) row
+        q = -logf(uniform_from_draw(rng.draw(0u, static_cast<uint64_t>(row_offset + base + n))));
+      }
+      const float r = w / q;  // >= 0, so its bit pattern orders like the value
+      key = (static_cast<unsigned long long>(__float_as_uint(r)) << 32) | (0xffffffffu - static_cast<uint32_t>(n));
+      key |= 1ull << 63;      // every real position outranks the padding
+    }
+    skeys[n] = key;
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = tid; i < n2; i += kPurityThreads) {
+        const int l = i ^ jj;
+        if (l > i) {
+          const unsigned long long a = skeys[i], c = skeys[l];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < c) : (a > c)) skeys[i] = c, skeys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  int want = n_reveal[b];
+  want = want < 0 ? 0 : (want > N ? N : want);
+  // x_out = x_t, then the selected positions take the candidate tokens
+  int gained = 0;
+  for (int n = tid; n < N; n += kPurityThreads) x_out[base + n] = x_t[base + n];
+  __syncthreads();
+  for (int i = tid; i < want; i += kPurityThreads) {
+    const int n = static_cast<int>(0xffffffffu - static_cast<uint32_t>(skeys[i] & 0xffffffffu));
+    const int64_t before = x_t[base + n], after = x_cand[base + n];
+    x_out[base + n] = after;
+    gained += (after != K ? 1 : 0) - (before != K ? 1 : 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) gained += __shfl_xor_sync(0xffffffffu, gained, o);
+  if ((tid & 31) == 0) scount[tid >> 5] = gained;
+  __syncthreads();
+  if (tid == 0 && revealed != nullptr) {
+    int total = 0;
+    for (int w = 0; w < kPurityThreads / 32; ++w) total += scount[w];
+    revealed[b] = total;
+  }
+}
+
 }  // namespace d3pm

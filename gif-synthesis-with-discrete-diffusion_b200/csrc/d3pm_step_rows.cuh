@@ -31,6 +31,9 @@ struct StepParams {
   int64_t row_offset;
   float thin_factor;
   int64_t rows;
+  int32_t sample_from;   // D3PM_FROM_POSTERIOR / D3PM_FROM_RECON
+  float* score;          // [rows] out: max_k p(x0 = k | x_t)
+  const float* sharpen;  // [rows] in: draw from softmax(f * recon)
 };
 
 // exact residual of the fp32 product m*log2e (natural-log units -> log2 units)
@@ -61,6 +64,12 @@ struct RowMath {
     PK = fmaf(cf.PK1, eL, cf.PK0);
     Ptot = masked ? fmaf(static_cast<float>(K), Bc, A) + PK
                   : fmaf(static_cast<float>(K - 1), Bc, A * (1.0f - pj)) + Pj + PK;
+  }
+  // the distribution the purity-prior branch samples (:327-329): log_x_recon itself, i.e. P_k = p_k for the codes
+  // and exp(-70) for [MASK]; every sampling path below then works unchanged
+  __device__ __forceinline__ void init_recon(float pj, uint32_t jj) {
+    j = jj;
+    A = 1.0f, Bc = 0.0f, Pj = pj, PK = kPFloor, Ptot = 1.0f + kPFloor;
   }
   // posterior log-prob of class k (< K) given its softmax numerator e and the thread's scale r
   __device__ __forceinline__ float post_of(uint32_t k, float e, float r) const {
@@ -125,7 +134,7 @@ __device__ __forceinline__ void group_max_sum_n(float (&m)[NV], float (&s)[NV], 
 template <int V, bool HAS_U, bool THIN>
 __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams p) {
   constexpr int NW = kRowThreads / 32;
-  __shared__ float sred[2][4 * NW];
+  __shared__ float sred[3][4 * NW];
   __shared__ unsigned long long skey[2][NW];
   __shared__ float sgap[NW];
   const CtaSync sync;
@@ -260,7 +269,11 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
   // ---- per-row posterior coefficients (:251-283 collapsed, see d3pm_common.cuh) ------------------
   const float pj = masked ? 0.f : fminf(fmaxf(ex2(fmaf(yj, kLog2e, -to_log2_units(My))) / Sy, kPFloor), 1.0f);
   RowMath rm;
-  rm.init(cf, masked, pj, j, K);
+  const bool from_recon = (p.sample_from == D3PM_FROM_RECON);
+  if (from_recon) rm.init_recon(masked ? 0.f : pj, masked ? static_cast<uint32_t>(K) + 1u : j);
+  else rm.init(cf, masked, pj, j, K);
+  // purity (:318): max_k exp(log_x_recon_k).clamp(0, 1); the largest recon entry is clamp(-lnSy, -70, 0)
+  if (p.score != nullptr && tid == 0) p.score[row] = expf(fminf(fmaxf(-lnSy, kClampLo), 0.0f));
 
   const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
   const NoiseStream rng(p.seed, p.offset);
@@ -285,13 +298,41 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
     float* __restrict__ rpost = p.post ? p.post + row * p.pitch_out : nullptr;
     float* __restrict__ rrec = p.recon ? p.recon + row * p.pitch_out : nullptr;
     const float* __restrict__ rg = (mode == D3PM_SAMPLE_GUMBEL) ? p.gumbel + row * p.pitch_gumbel : nullptr;
+    // sharpened draw (:323-325): prob = log_softmax(f * log_x_recon) over all K+1 classes, clamp(-70, 0).
+    // f >= 1 and recon <= 0, so the largest entry is f * max(recon) = f * clamp(-lnSy, -70, 0).
+    const bool sharp = from_recon && p.sharpen != nullptr;
+    float fsh = 1.0f, sh_off = 0.0f;  // prob_k = f * recon_k - sh_off
+    if (sharp) {
+      fsh = __ldg(p.sharpen + row);
+      const float top = fsh * fminf(fmaxf(-lnSy, kClampLo), 0.0f);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (i < nvalid)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float rcv = fminf(fmaxf((x[i][e] - My) - lnSy, kClampLo), 0.0f);
+            acc += expf(fmaf(fsh, rcv, -top));
+          }
+      if (tid == 0) acc += expf(fmaf(fsh, kClampLo, -top));  // the [MASK] row of log_x_recon (-70)
+      float mm[1] = {0.f}, ss[1] = {acc};
+      group_max_sum_n<1, NW>(mm, ss, sred[2], sync);
+      sh_off = top + logf(ss[0]);
+    }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       if (i < nvalid) {
         const int q = tid + i * kRowThreads;
         float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rm.post_of(4 * q + e, z[i][e], r);
+        for (int e = 0; e < 4; ++e) {
+          if (sharp) {
+            const float rcv = fminf(fmaxf((x[i][e] - My) - lnSy, kClampLo), 0.0f);
+            o[e] = fminf(fmaxf(fmaf(fsh, rcv, -sh_off), kClampLo), 0.0f);
+          } else {
+            o[e] = rm.post_of(4 * q + e, z[i][e], r);
+          }
+        }
         if (rpost) st_stream4(rpost + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
         if (rrec) {
           float rc4[4];
@@ -326,7 +367,7 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
     }
     float scoreK = 0.f;
     if (tid == 0) {  // the [MASK] class
-      const float oK = rm.post_mask();
+      const float oK = sharp ? fminf(fmaxf(fmaf(fsh, kClampLo, -sh_off), kClampLo), 0.0f) : rm.post_mask();
       if (rpost) rpost[K] = oK;
       if (rrec) rrec[K] = kClampLo;  // constant -70 row of :235, :248
       if (mode != D3PM_SAMPLE_NONE) {

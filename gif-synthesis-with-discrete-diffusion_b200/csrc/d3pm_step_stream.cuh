@@ -601,6 +601,7 @@ constexpr long long kStreamMinRows = 2048;  // below this the one-CTA-per-row ke
 inline bool stream_kernel_supports(const StepParams& p) {
   if (p.sample_mode != D3PM_SAMPLE_PHILOX && p.sample_mode != D3PM_SAMPLE_PHILOX_EXACT) return false;
   if (p.post != nullptr || p.recon != nullptr || p.gap != nullptr || p.x_prev == nullptr) return false;
+  if (p.sample_from != D3PM_FROM_POSTERIOR || p.score != nullptr || p.sharpen != nullptr) return false;
   if (p.K != 1024 && p.K != 2048 && p.K != 4096) return false;
   return true;
 }

@@ -119,6 +119,8 @@ class FusedDiffusionTransformer(nn.Module):
         self.rng_offset = 0          # advanced by one per sampling call: every call draws fresh noise
         self.row_offset = 0          # global index of local row 0 when the batch is sharded across ranks
         self.inject_uniform: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
+        # tests inject the Exp(1) noise torch.multinomial draws inside the purity-prior branch (:340): (B, N) -> tensor
+        self.inject_exponential: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
         self._coef_cache = None
         self._status = None
 
@@ -219,7 +221,12 @@ class FusedDiffusionTransformer(nn.Module):
         return abs(self.guidance_scale - 1) < 1e-3
 
     def _step(self, x_t, cond_emb, cf_cond_emb, t, *, sample_mode, want_post=False, want_recon=False,
-              want_gap=False, guidance=True, x_prev_out=None, thin_factor=0.0):
+              want_gap=False, guidance=True, x_prev_out=None, thin_factor=0.0, sample_from=_lib.FROM_POSTERIOR,
+              want_score=False, sharpen=None, logits=None):
+        if logits is not None:  # reuse the logits of an earlier call of the same step (purity prior, second pass)
+            return self._step_on(logits[0], logits[1], x_t, t, sample_mode=sample_mode, want_post=want_post,
+                                 want_recon=want_recon, want_gap=want_gap, x_prev_out=x_prev_out, thin_factor=thin_factor,
+                                 sample_from=sample_from, want_score=want_score, sharpen=sharpen)
         logits_c = self._denoise_rows(x_t, cond_emb, t)
         logits_u = None
         if guidance and not self._guidance_off():
@@ -227,6 +234,14 @@ class FusedDiffusionTransformer(nn.Module):
             if logits_u.stride() != logits_c.stride():
                 logits_u = logits_u.contiguous()
                 logits_c = logits_c.contiguous()
+        out = self._step_on(logits_c, logits_u, x_t, t, sample_mode=sample_mode, want_post=want_post,
+                            want_recon=want_recon, want_gap=want_gap, x_prev_out=x_prev_out, thin_factor=thin_factor,
+                            sample_from=sample_from, want_score=want_score, sharpen=sharpen)
+        out["_logits"] = (logits_c, logits_u)
+        return out
+
+    def _step_on(self, logits_c, logits_u, x_t, t, *, sample_mode, want_post=False, want_recon=False, want_gap=False,
+                 x_prev_out=None, thin_factor=0.0, sample_from=_lib.FROM_POSTERIOR, want_score=False, sharpen=None):
         B, N = x_t.shape
         gumbel = None
         uniform_given = False
@@ -239,7 +254,8 @@ class FusedDiffusionTransformer(nn.Module):
             sample_mode=sample_mode, gumbel=gumbel, gumbel_is_uniform=uniform_given, seed=self.rng_seed,
             offset=self._next_offset() if sample_mode != _lib.SAMPLE_NONE else 0, row_offset=self.row_offset,
             want_post=want_post, want_recon=want_recon, want_gap=want_gap, status=self._status_word(),
-            x_prev_out=x_prev_out, thin_factor=thin_factor)
+            x_prev_out=x_prev_out, thin_factor=thin_factor, sample_from=sample_from, want_score=want_score,
+            sharpen=sharpen)
 
     # ------------------------------------------------------------------ reference method surface
     @torch.no_grad()
@@ -281,12 +297,56 @@ class FusedDiffusionTransformer(nn.Module):
 
     @torch.no_grad()
     def p_sample(self, log_x, cond_emb, cf_cond_emb, t, sampled, to_sample):
-        """One reverse step (:304-352): returns (log one-hot of x_{t-1} `[B, K+1, N]`, `[1024]*B`)."""
-        if self.prior_rule != 0:
-            raise NotImplementedError("purity-prior sampling (prior_rule 1/2, :309-346) is SURVEY §8 f2 (next)")
-        x_prev = self.p_sample_tokens(self._tokens_of(log_x), cond_emb, cf_cond_emb, t)
+        """One reverse step (:304-352): returns (log one-hot of x_{t-1} `[B, K+1, N]`, `sampled`).
+
+        `prior_rule == 0` (the only value the reference's constructor sets, :157): Gumbel draw from the posterior for
+        every token, `sampled = [1024] * B`.  `prior_rule` 1 / 2 with `t[0] > 0`: the purity-prior reveal of Improved
+        VQ-Diffusion (:309-346), see `p_sample_tokens_purity`."""
+        x_t = self._tokens_of(log_x)
+        if self.prior_rule > 0 and int(t[0]) > 0:  # the reference reads t[0] on the host as well (:309)
+            x_prev, sampled = self.p_sample_tokens_purity(x_t, cond_emb, cf_cond_emb, t, sampled, to_sample)
+        else:
+            x_prev, sampled = self.p_sample_tokens(x_t, cond_emb, cf_cond_emb, t), [1024] * log_x.shape[0]
         out = ops.tokens_to_log_onehot_rows(x_prev, self.num_classes, self._status_word())
-        return ops.as_logical(out, self.num_classes), [1024] * log_x.shape[0]
+        return ops.as_logical(out, self.num_classes), sampled
+
+    @torch.no_grad()
+    def p_sample_tokens_purity(self, x_t, cond_emb, cf_cond_emb, t, sampled, to_sample):
+        """The `prior_rule` 1 / 2 branch of `p_sample` (:309-346) on integer tokens -> (x_{t-1} `[B, N]`, sampled).
+
+        One fused pass gives every token a candidate x0 ~ p(x0 | x_t) (Gumbel-max on `log_x_recon`, :327-329) and its
+        purity max_k p(x0 = k | x_t) (:318); `d3pm_purity_select` then reveals, per video, `n_sample` of the [MASK]
+        positions drawn without replacement with probability proportional to the normalised purity (:331-341).  With
+        `prior_weight > 0` (:321-325) the candidates are drawn from softmax((1 + purity * r) * log_x_recon) instead, which
+        needs the per-video purity maximum first: a second pass over the same logits.  `sampled` advances exactly like
+        the reference's list (one device->host read of B integers)."""
+        B, N = x_t.shape
+        K = self.num_classes - 1
+        sharpened = self.prior_rule != 1 and self.prior_weight > 0
+        first = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_NONE if sharpened else _lib.SAMPLE_PHILOX_EXACT,
+                           sample_from=_lib.FROM_RECON, want_score=True)
+        score = first["score"]
+        if sharpened:
+            norm = score / (score.max(dim=1, keepdim=True).values + 1e-10)         # (:319)
+            f = (1 + norm * self.prior_weight).float().contiguous()                 # (:323)
+            cand = self._step(x_t, None, None, t, sample_mode=_lib.SAMPLE_PHILOX_EXACT, sample_from=_lib.FROM_RECON,
+                              sharpen=f, logits=first["_logits"])["x_prev"]
+        else:
+            cand = first["x_prev"]
+        n_reveal = []
+        for i in range(B):                                                           # (:331-336)
+            n = min(to_sample - sampled[i], self.prior_ps)
+            if to_sample - sampled[i] - n == 1:
+                n = to_sample - sampled[i]
+            n_reveal.append(max(int(n), 0))
+        expo = None
+        if self.inject_exponential is not None:
+            expo = self.inject_exponential((B, N), self.device).to(self.device, torch.float32).contiguous()
+        x_out, revealed = ops.purity_select(
+            x_t, cand, None if self.prior_rule == 1 else score, torch.tensor(n_reveal, dtype=torch.int32, device=self.device),
+            K, expo=expo, seed=self.rng_seed, offset=self._next_offset(), row_offset=self.row_offset)
+        sampled = [int(s) + int(r) for s, r in zip(sampled, revealed.tolist())]     # (:342-343)
+        return x_out, sampled
 
     @torch.no_grad()
     def p_sample_tokens(self, x_t, cond_emb, cf_cond_emb, t, x_prev_out=None):
@@ -346,6 +406,13 @@ class FusedDiffusionTransformer(nn.Module):
         x_next = torch.empty_like(x)
         for diffusion_index in range(self.num_timesteps - 1, -1, -1):
             t = torch.full((batch_size,), diffusion_index, device=device, dtype=torch.long)
+            if self.prior_rule > 0 and diffusion_index > 0:
+                # purity prior: reveal n_sample[t] tokens per video, repeating the step until every video got them (:623-626)
+                sampled = [0] * batch_size
+                while min(sampled) < self.n_sample[diffusion_index]:
+                    x, sampled = self.p_sample_tokens_purity(x, cond_emb, cf_cond_emb, t, sampled,
+                                                             self.n_sample[diffusion_index])
+                continue
             # with prior_rule == 0 the reference's `while min(sampled) < n_sample[...]` body runs once (:624-626)
             self.p_sample_tokens(x, cond_emb, cf_cond_emb, t, x_prev_out=x_next)
             x, x_next = x_next, x

@@ -107,12 +107,16 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
                gumbel: Optional[torch.Tensor] = None, gumbel_is_uniform: bool = False, seed: int = 0, offset: int = 0, row_offset: int = 0,
                want_post: bool = False, want_recon: bool = False, want_gap: bool = False,
                status: Optional[torch.Tensor] = None, thin_factor: float = 0.0,
-               x_prev_out: Optional[torch.Tensor] = None, kernel: int = 0) -> Dict[str, torch.Tensor]:
+               x_prev_out: Optional[torch.Tensor] = None, kernel: int = 0, sample_from: int = 0,
+               want_score: bool = False, sharpen: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """One fused reverse step over token-major logits `[B, N, K]` (d3pm_fused_step).
 
     `logits_u=None` is guidance off.  `gumbel` is `[B, N, >=K+1]` rows (entry K = [MASK]).
     Returns a dict with the requested tensors: `x_prev` int64 `[B, N]`, `post` / `recon` as
     `[B, N, pitch]` rows (use `as_logical(rows, K+1)` for the reference's `[B, K+1, N]`), `gap` `[B, N]`.
+    Purity-prior sampling (p_sample with prior_rule 1 / 2): `sample_from=_lib.FROM_RECON` draws from p(x0 | x_t),
+    `want_score` returns the per-token purity max_k p(x0 = k | x_t) as `score` `[B, N]`, `sharpen` `[B, N]` is the
+    factor f of softmax(f * log p(x0 | x_t)).
     """
     dev = _need_cuda(logits_c, logits_u, x_t, t, coef_table, gumbel, status)
     if logits_c.dim() != 3 or logits_c.dtype != torch.float32 or logits_c.stride(2) != 1:
@@ -158,6 +162,14 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
     if want_gap:
         out["gap"] = torch.empty(B, N, dtype=torch.float32, device=dev)
         d.gap = _ptr(out["gap"])
+    if want_score:
+        out["score"] = torch.empty(B, N, dtype=torch.float32, device=dev)
+        d.score = _ptr(out["score"])
+    if sharpen is not None:
+        if sharpen.shape != (B, N) or sharpen.dtype != torch.float32 or not sharpen.is_contiguous() or sharpen.device != dev:
+            raise D3PMError("sharpen must be a contiguous float32 [B, N] tensor on the logits' device")
+        d.sharpen = _ptr(sharpen)
+    d.sample_from = int(sample_from)
     d.status = _ptr(status)
     d.B, d.N, d.K, d.T = B, N, K, T
     d.pitch_logits, d.pitch_out = pitch, pitch_out
@@ -210,6 +222,28 @@ def gumbel_argmax_rows(logits_rows: torch.Tensor, pitch_logits: int, num_classes
                                       seed & (2**64 - 1), offset & (2**64 - 1), row_offset, _stream(dev)),
                "d3pm_gumbel_argmax")
     return (x, gap) if want_gap else x
+
+
+def purity_select(x_t: torch.Tensor, x_cand: torch.Tensor, score: Optional[torch.Tensor], n_reveal: torch.Tensor, K: int,
+                  *, expo: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0, row_offset: int = 0):
+    """The per-video reveal of the purity-prior branch (d3pm_purity_select): -> (x_out int64 `[B, N]`,
+    revealed int32 `[B]`).  `score=None` is prior_rule 1 (uniform weights over the [MASK] positions); `expo` injects
+    the Exp(1) noise of `torch.multinomial` (parity tests), otherwise it comes from the Philox stream."""
+    dev = _need_cuda(x_t, x_cand, score, n_reveal, expo)
+    B, N = x_t.shape
+    for name, ten, dt in (("x_t", x_t, torch.int64), ("x_cand", x_cand, torch.int64), ("score", score, torch.float32),
+                          ("expo", expo, torch.float32)):
+        if ten is not None and (ten.shape != (B, N) or ten.dtype != dt or not ten.is_contiguous()):
+            raise D3PMError(f"{name} must be a contiguous {dt} [B, N] tensor")
+    if n_reveal.shape != (B,) or n_reveal.dtype != torch.int32 or not n_reveal.is_contiguous():
+        raise D3PMError("n_reveal must be a contiguous int32 [B] tensor")
+    x_out = torch.empty_like(x_t)
+    revealed = torch.empty(B, dtype=torch.int32, device=dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_purity_select(x_t.data_ptr(), x_cand.data_ptr(), _ptr(score), _ptr(expo), n_reveal.data_ptr(),
+                                      x_out.data_ptr(), revealed.data_ptr(), B, N, K, seed & (2**64 - 1),
+                                      offset & (2**64 - 1), int(row_offset), _stream(dev)), "d3pm_purity_select")
+    return x_out, revealed
 
 
 def tokens_to_log_onehot_rows(x: torch.Tensor, num_classes: int, status: Optional[torch.Tensor] = None) -> torch.Tensor:

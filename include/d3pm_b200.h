@@ -65,6 +65,9 @@ int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_s
 #define D3PM_SAMPLE_PHILOX 2       /* in-kernel Philox4x32-10 noise, thinned exponential race (production) */
 #define D3PM_SAMPLE_PHILOX_EXACT 3 /* same noise, every class scored in log space (verification) */
 
+#define D3PM_FROM_POSTERIOR 0 /* sample x_{t-1} from q_posterior's result (prior_rule 0, :347-350) */
+#define D3PM_FROM_RECON 1     /* sample from log_x_recon = p(x0 | x_t) (prior_rule 1 / 2, :327-329) */
+
 #define D3PM_KERNEL_AUTO 0
 #define D3PM_KERNEL_ROWS 1   /* one CTA per token row, every shape and mode */
 #define D3PM_KERNEL_STREAM 2 /* persistent TMA-pipelined kernel: PHILOX / PHILOX_EXACT, no outputs, K in {1024,2048,4096} */
@@ -95,6 +98,12 @@ typedef struct d3pm_step_desc {
   float thin_factor;     /* PHILOX thinning constant c (0 = default 8); smaller forces the exhaustive fallback */
   int32_t kernel;        /* D3PM_KERNEL_*: which implementation runs (AUTO picks by shape and mode) */
   d3pm_stream_t stream;
+  /* purity-prior sampling (p_sample with prior_rule 1 / 2, :309-346); all optional, rows kernel only */
+  int32_t sample_from;   /* D3PM_FROM_POSTERIOR (default) or D3PM_FROM_RECON: draw x from p(x0 | x_t) (:327-329) */
+  int32_t reserved;
+  float* score;          /* [B*N] out: max_k p(x0 = k | x_t), the purity of :318 before its per-video normalisation */
+  const float* sharpen;  /* [B*N] in: f = 1 + score * prior_weight; the draw is from softmax(f * log p(x0 | x_t)) (:323-325);
+                            D3PM_FROM_RECON with GUMBEL / PHILOX_EXACT sampling only */
 } d3pm_step_desc;
 
 int d3pm_fused_step(const d3pm_step_desc* desc);
@@ -127,6 +136,18 @@ int d3pm_tokens_to_log_onehot(const int64_t* x, float* out, int64_t pitch, int64
  * token-major rows (class_stride 1) or the reference's contiguous layout (token_stride 1).        */
 int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stride, int64_t token_stride,
                         int64_t* idx, int B, int C, int N, d3pm_stream_t stream);
+
+/* Purity-prior reveal (the per-video loop of p_sample, :331-343).  Per video b: weights w_n = score[b][n] /
+ * (max_n score[b][n] + 1e-10) where x_t[b][n] is [MASK], 0 elsewhere (:318-319, :334-337; score == NULL means
+ * prior_rule 1, all ones); the n_reveal[b] positions with the largest w_n / q_n are revealed, x_out = x_t except
+ * x_out[sel] = x_cand[sel] (:340-341).  q ~ Exp(1) is what torch.multinomial draws internally: `expo` injects it
+ * ([B*N], parity tests), expo == NULL draws it from the Philox stream (seed, offset, row_offset).
+ * revealed[b] = (#non-[MASK] in x_out) - (#non-[MASK] in x_t), the increment of `sampled[b]` (:342-343).
+ * Ties (only the zero-weight positions, reached when a video holds fewer [MASK] tokens than n_reveal[b]) resolve
+ * to the lowest position.  N <= 8192.                                                                          */
+int d3pm_purity_select(const int64_t* x_t, const int64_t* x_cand, const float* score, const float* expo,
+                       const int32_t* n_reveal, int64_t* x_out, int32_t* revealed, int B, int N, int K,
+                       uint64_t seed, uint64_t offset, int64_t row_offset, d3pm_stream_t stream);
 
 /* ---------------------------------------------------------------- training side
  * q_pred (:201-218, cumulative = 1, t wrapped modulo T+1) and q_pred_one_timestep (:185-199, cumulative = 0) on

@@ -389,3 +389,56 @@ def train_loss(sched, logits: torch.Tensor, x0: torch.Tensor, t: torch.Tensor, p
         extra = (1 - t / T) + 1.0 if adaptive_auxiliary_loss else 1.0
         vb_loss = vb_loss + extra * auxiliary_loss_weight * kl_aux_loss / pt
     return log_model_prob, vb_loss, x0_recon, xt, kl_loss
+
+
+# --------------------------------------------------------------------------- purity-prior sampling
+def multinomial_without_replacement(weights: torch.Tensor, n: int, expo: torch.Tensor) -> torch.Tensor:
+    """`torch.multinomial(weights, n)` (no replacement) with its noise injected.
+
+    ATen draws `q ~ Exp(1)` per category and returns `topk(weights / q, n)` (argmax for n = 1)
+    (aten/src/ATen/native/Distributions.cpp, multinomial_out); `tests/golden/make_golden_purity.py` checks that
+    equivalence against the real op before generating fixtures.  `expo` is that `q`."""
+    return torch.topk(weights / expo, n).indices
+
+
+def p_sample_purity_step(sched, logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], log_x_t: torch.Tensor,
+                         t: torch.Tensor, guidance_scale: float, uniform: torch.Tensor, expo: torch.Tensor,
+                         sampled, to_sample: int, *, prior_rule: int, prior_weight: float = 0.0, prior_ps: int = 1024):
+    """`p_sample` with `prior_rule` 1 / 2 (:304-352): Improved-VQ-Diffusion "high-quality inference" / purity prior.
+
+    uniform: `[B,K+1,N]` (the `rand_like` of the Gumbel draw), expo: `[B,N]` (the Exp(1) of each video's
+    `torch.multinomial`).  Returns (x_{t-1} tokens `[B,N]`, updated `sampled` list).
+    """
+    recon = cf_predict_start_from_logits(logits_c, logits_u, guidance_scale)
+    B, C, N = recon.shape
+    sampled = list(sampled)
+    if int(t[0]) > 0 and prior_rule > 0:
+        x_idx = log_onehot_to_index(log_x_t)
+        if prior_rule == 1:
+            score = torch.ones(B, N)
+        else:
+            score = torch.exp(recon).max(dim=1).values.clamp(0, 1)
+            score = score / (score.max(dim=1, keepdim=True).values + 1e-10)
+        if prior_rule != 1 and prior_weight > 0:
+            prob = ((1 + score * prior_weight).unsqueeze(1) * recon).softmax(dim=1)
+            prob = prob.log().clamp(CLAMP_LO, 0)
+        else:
+            prob = recon
+        out_idx = log_sample_categorical(prob, uniform, return_index=True)
+        out2 = x_idx.clone()
+        pick = score.clone()
+        if pick.sum() < 1e-6:
+            pick += 1
+        pick[x_idx != C - 1] = 0
+        for i in range(B):
+            n_sample = min(to_sample - sampled[i], prior_ps)
+            if to_sample - sampled[i] - n_sample == 1:
+                n_sample = to_sample - sampled[i]
+            if n_sample <= 0:
+                continue
+            sel = multinomial_without_replacement(pick[i], n_sample, expo[i])
+            out2[i][sel] = out_idx[i][sel]
+            sampled[i] += int((out2[i] != C - 1).sum() - (x_idx[i] != C - 1).sum())
+        return out2, sampled
+    post = q_posterior(sched, recon, log_x_t, t)
+    return log_sample_categorical(post, uniform, return_index=True), [1024] * B

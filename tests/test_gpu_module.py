@@ -111,15 +111,11 @@ def test_unbuilt_paths_fail_loudly():
     K = int(fx["K"])
     x_t, t = torch.from_numpy(fx["x_t"]).to(DEV), torch.from_numpy(fx["t"]).to(DEV)
     log_x = ops.as_logical(ops.tokens_to_log_onehot_rows(x_t, K + 1), K + 1)
-    m.prior_rule = 2
-    with pytest.raises(NotImplementedError):
-        m.p_sample(log_x, cond, cf, t, [0, 0], 10)
     with pytest.raises(NotImplementedError):
         m.sample(["a", "b"], None, cond, cf, filter_ratio=0.5)
     with pytest.raises(NotImplementedError):
         m.q_posterior(log_x.clone().requires_grad_(True), log_x, t)
     bad_t = torch.full_like(t, 100)
-    m.prior_rule = 0
     m.p_sample_tokens(x_t, cond, cf, bad_t)
     with pytest.raises(AssertionError):
         m.check_status()

@@ -1,0 +1,92 @@
+"""BASELINE configs beyond the bench line, on one B200: the fused reverse step at
+
+  * config 5 — MSRVTT text-conditioned shape, 64 videos x 16x16x16 grid, 4096+1 classes, guidance ON (scale 2) and OFF
+    (guidance off = `predict_start` alone, diffusion_transformer.py:220-238, because the reference's own |s-1|<1e-3 branch
+    raises, :242-243),
+  * config 2 at t in {99, 50, 1, 0} (the coefficient row changes, the traffic does not),
+  * smaller codebooks K in {1024, 2048} at the config-2 grid.
+
+Each line: ms per step (CUDA events, inputs >> L2), token-updates/s and algorithmic GB/s against MEASURED_PEAKS.json.
+
+    python tools/config_sweep.py [--steps 200] [--json gpurun_out/sweep.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import d3pm_b200  # noqa: E402
+from d3pm_b200 import _lib, ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=200)
+ap.add_argument("--json", default=None)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+T = 100
+peak = 6650.0
+pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.isfile(pk):
+    peak = float(json.load(open(pk))["hbm_gbs"])
+
+
+class _Stub(torch.nn.Module):
+    def __init__(self, K):
+        super().__init__()
+        self.content_emb = type("E", (), {"num_embed": K + 1})()
+
+
+def run(name, B, N, K, t_now, guidance):
+    model = d3pm_b200.FusedDiffusionTransformer(transformer=_Stub(K), diffusion_step=T, alpha_init_type="alpha1",
+                                                guidance_scale=2.0, content_seq_len=N).to(dev)
+    table = model.coef_table()
+    gen = torch.Generator(device=dev).manual_seed(7)
+    lc = torch.randn(B, N, K, device=dev, generator=gen)
+    lu = torch.randn(B, N, K, device=dev, generator=gen) if guidance else None
+    p_mask = float(model.log_cumprod_ct[t_now].exp())
+    x_t = torch.where(torch.rand(B, N, device=dev, generator=gen) < p_mask, torch.full((B, N), K, device=dev),
+                      torch.randint(0, K, (B, N), device=dev, generator=gen))
+    t = torch.full((B,), t_now, dtype=torch.int64, device=dev)
+    xp = torch.empty_like(x_t)
+    status = ops.new_status(dev)
+
+    def step(i):
+        ops.fused_step(lc, lu, x_t, t, table, guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX, seed=11, offset=i,
+                       x_prev_out=xp, status=status)
+
+    for i in range(5):
+        step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(a.steps):
+        step(5 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    assert int(status.item()) & 3 == 0 and 0 <= int(xp.min()) and int(xp.max()) <= K
+    nbytes = B * N * ((2 if guidance else 1) * K * 4 + 16)
+    rec = {"case": name, "videos": B, "tokens_per_video": N, "classes": K + 1, "t": t_now, "guidance": guidance,
+           "ms_per_step": ms, "token_updates_per_s": B * N / (ms * 1e-3), "algorithmic_GBps": nbytes / ms / 1e6,
+           "frac_of_measured_peak": nbytes / ms / 1e6 / peak, "logits_bytes_resident": nbytes}
+    print(json.dumps(rec), flush=True)
+    del lc, lu
+    torch.cuda.empty_cache()
+    return rec
+
+
+out = []
+out.append(run("config5 guidance on", 64, 4096, 4096, 50, True))
+out.append(run("config5 guidance off", 64, 4096, 4096, 50, False))
+for t_now in (99, 50, 1, 0):
+    out.append(run(f"config2 t={t_now}", 16, 4096, 4096, t_now, True))
+out.append(run("config2 guidance off", 16, 4096, 4096, 50, False))
+for K in (2048, 1024):
+    out.append(run(f"config2 grid, K={K}", 16, 4096, K, 50, True))
+if a.json:
+    with open(a.json, "w") as f:
+        json.dump({"peak_GBps": peak, "cases": out}, f, indent=1)
