@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = (
     "d3pm_version", "d3pm_last_error", "d3pm_build_coef_table", "d3pm_fused_step", "d3pm_philox_uniform",
     "d3pm_q_posterior", "d3pm_gumbel_argmax", "d3pm_tokens_to_log_onehot", "d3pm_argmax_classes",
     "d3pm_to_token_major", "d3pm_q_pred", "d3pm_train_rows", "d3pm_purity_select",
+    "d3pm_head_image_floats", "d3pm_head_prepare", "d3pm_head_step",
 )
 
 COEF_STRIDE = 32
@@ -23,6 +24,7 @@ SAMPLE_NONE, SAMPLE_GUMBEL, SAMPLE_PHILOX, SAMPLE_PHILOX_EXACT = 0, 1, 2, 3
 STATUS_BAD_T, STATUS_BAD_TOKEN, STATUS_FALLBACK = 1, 2, 4
 KERNEL_AUTO, KERNEL_ROWS, KERNEL_STREAM = 0, 1, 2
 FROM_POSTERIOR, FROM_RECON = 0, 1
+HEAD_STEP, HEAD_LOGITS, HEAD_REFERENCE = 0, 1, 2
 
 
 class D3PMError(RuntimeError):
@@ -54,6 +56,19 @@ class TrainDesc(ctypes.Structure):
         ("pitch", c_int64), ("pitch_grad", c_int64),
         ("mask_weight_masked", c_float), ("mask_weight_unmasked", c_float),
         ("backward", c_int32), ("stream", c_void_p),
+    ]
+
+
+class HeadDesc(ctypes.Structure):
+    """Mirror of `d3pm_head_desc`."""
+    _fields_ = [
+        ("hidden_c", c_void_p), ("hidden_u", c_void_p), ("ln_weight", c_void_p), ("ln_bias", c_void_p),
+        ("w_image", c_void_p), ("bias2", c_void_p), ("x_t", c_void_p), ("t", c_void_p), ("coef_table", c_void_p),
+        ("x_prev", c_void_p), ("logits_out", c_void_p), ("status", c_void_p), ("redo_rows", c_void_p),
+        ("redo_count", c_void_p),
+        ("B", c_int32), ("N", c_int32), ("K", c_int32), ("T", c_int32), ("D", c_int32), ("mode", c_int32),
+        ("ln_eps", c_float), ("guidance_scale", c_float), ("thin_factor", c_float),
+        ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64), ("stream", c_void_p),
     ]
 
 
@@ -109,6 +124,12 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_purity_select.restype = c_int
     lib.d3pm_purity_select.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_int, c_uint64, c_uint64, c_int64, c_void_p]
+    lib.d3pm_head_image_floats.restype = c_int64
+    lib.d3pm_head_image_floats.argtypes = [c_int, c_int]
+    lib.d3pm_head_prepare.restype = c_int
+    lib.d3pm_head_prepare.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.d3pm_head_step.restype = c_int
+    lib.d3pm_head_step.argtypes = [POINTER(HeadDesc)]
     lib.d3pm_train_rows.restype = c_int
     lib.d3pm_train_rows.argtypes = [POINTER(TrainDesc)]
     lib.d3pm_to_token_major.restype = c_int

@@ -8,6 +8,7 @@
 #include "d3pm_step_rows.cuh"
 #include "d3pm_step_stream.cuh"
 #include "d3pm_train_rows.cuh"
+#include "d3pm_head_step.cuh"
 
 namespace {
 
@@ -269,6 +270,93 @@ int d3pm_train_rows(const d3pm_train_desc* d) {
   else if (chunks <= 4) launch_train<4>(p, d->backward != 0, s);
   else launch_train<8>(p, d->backward != 0, s);
   return check_launch("train_rows");
+}
+
+int64_t d3pm_head_image_floats(int K, int D) {
+  if (D != 64 || K <= 0 || K % 1024 != 0) return 0;
+  return static_cast<int64_t>(K / d3pm::head::kChunk) * d3pm::head::Geo<64>::kChunkFloats;
+}
+
+int d3pm_head_prepare(const float* weight, const float* bias, int K, int D, float* w_image, float* bias2, float* stats,
+                      d3pm_stream_t stream) {
+  if (weight == nullptr || w_image == nullptr || bias2 == nullptr || stats == nullptr)
+    return fail(D3PM_ERR_INVALID, "head_prepare: null pointer");
+  if (D != 64) return fail(D3PM_ERR_UNSUPPORTED, "head_prepare: n_embd D=%d (the fused head is built for D = 64)", D);
+  if (K != 1024 && K != 2048 && K != 4096) return fail(D3PM_ERR_UNSUPPORTED, "head_prepare: K=%d must be 1024, 2048 or 4096", K);
+  if (!aligned16(weight) || !aligned16(w_image) || !aligned16(bias2))
+    return fail(D3PM_ERR_ALIGN, "head_prepare: weight, w_image and bias2 must be 16-byte aligned");
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(stats, 0, 2 * sizeof(float), s) != cudaSuccess) return fail(D3PM_ERR_CUDA, "head_prepare: memset failed");
+  const int threads = K * (D / 4);
+  d3pm::head::head_prepare_kernel<64><<<(threads + 255) / 256, 256, 0, s>>>(weight, bias, K, w_image, bias2,
+                                                                            reinterpret_cast<uint32_t*>(stats));
+  return check_launch("head_prepare");
+}
+
+int d3pm_head_step(const d3pm_head_desc* d) {
+  namespace H = d3pm::head;
+  if (d == nullptr) return fail(D3PM_ERR_INVALID, "head_step: null descriptor");
+  if (d->hidden_c == nullptr || d->ln_weight == nullptr || d->ln_bias == nullptr || d->w_image == nullptr || d->bias2 == nullptr)
+    return fail(D3PM_ERR_INVALID, "head_step: hidden_c, ln_weight, ln_bias, w_image and bias2 are required");
+  if (d->D != 64) return fail(D3PM_ERR_UNSUPPORTED, "head_step: n_embd D=%d (built for D = 64)", d->D);
+  if (d->K != 1024 && d->K != 2048 && d->K != 4096) return fail(D3PM_ERR_UNSUPPORTED, "head_step: K=%d must be 1024, 2048 or 4096", d->K);
+  if (d->B <= 0 || d->N <= 0) return fail(D3PM_ERR_INVALID, "head_step: B and N must be positive");
+  if (d->mode < D3PM_HEAD_STEP || d->mode > D3PM_HEAD_REFERENCE) return fail(D3PM_ERR_INVALID, "head_step: unknown mode %d", d->mode);
+  if (!aligned16(d->hidden_c) || !aligned16(d->hidden_u) || !aligned16(d->w_image) || !aligned16(d->bias2) || !aligned16(d->logits_out))
+    return fail(D3PM_ERR_ALIGN, "head_step: hidden, w_image, bias2 and logits_out must be 16-byte aligned");
+  const int64_t rows = static_cast<int64_t>(d->B) * d->N;
+  if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "head_step: B*N too large");
+  if (d->mode == D3PM_HEAD_LOGITS) {
+    if (d->logits_out == nullptr) return fail(D3PM_ERR_INVALID, "head_step: LOGITS mode needs logits_out");
+  } else {
+    if (d->x_t == nullptr || d->t == nullptr || d->coef_table == nullptr || d->x_prev == nullptr || d->T <= 0)
+      return fail(D3PM_ERR_INVALID, "head_step: x_t, t, coef_table and x_prev are required");
+    if (d->mode == D3PM_HEAD_STEP && (d->redo_rows == nullptr || d->redo_count == nullptr))
+      return fail(D3PM_ERR_INVALID, "head_step: redo_rows [B*N] and redo_count scratch are required");
+    if (!aligned16(d->coef_table)) return fail(D3PM_ERR_ALIGN, "head_step: coef_table must be 16-byte aligned");
+  }
+  H::HeadParams p;
+  p.hidden_c = d->hidden_c, p.hidden_u = d->hidden_u, p.ln_weight = d->ln_weight, p.ln_bias = d->ln_bias;
+  p.w_image = d->w_image, p.bias2 = d->bias2, p.x_t = d->x_t, p.t = d->t, p.coef_table = d->coef_table;
+  p.x_prev = d->x_prev, p.logits_out = d->logits_out, p.status = d->status;
+  p.redo_rows = d->redo_rows, p.redo_count = d->redo_count;
+  p.N = d->N, p.K = d->K, p.T = d->T, p.rows = rows;
+  p.ln_eps = d->ln_eps, p.guidance_scale = d->guidance_scale, p.thin_factor = d->thin_factor;
+  p.seed = d->seed, p.offset = d->offset, p.row_offset = d->row_offset;
+  const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+  const bool has_u = d->hidden_u != nullptr;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return fail(D3PM_ERR_CUDA, "head_step: cannot query the device");
+  if (d->mode == D3PM_HEAD_REFERENCE) {
+    const unsigned grid = static_cast<unsigned>(rows < 8LL * sms ? rows : 8LL * sms);
+    if (has_u) H::head_redo_kernel<64, true><<<grid, 256, 0, s>>>(p, 1);
+    else H::head_redo_kernel<64, false><<<grid, 256, 0, s>>>(p, 1);
+    return check_launch("head_step(reference)");
+  }
+  const size_t smem = H::smem_bytes<64>();
+  const long long tiles = (rows + H::kTileM - 1) / H::kTileM;
+  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
+  auto launch = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return fail(D3PM_ERR_CUDA, "head_step: %s", cudaGetErrorString(cudaGetLastError()));
+    kern<<<grid, H::kThreads, smem, s>>>(p);
+    return D3PM_OK;
+  };
+  int rc;
+  if (d->mode == D3PM_HEAD_LOGITS) {
+    rc = has_u ? launch(H::head_step_kernel<64, true, true>) : launch(H::head_step_kernel<64, false, true>);
+    if (rc != D3PM_OK) return rc;
+    return check_launch("head_step(logits)");
+  }
+  if (cudaMemsetAsync(d->redo_count, 0, sizeof(uint32_t), s) != cudaSuccess) return fail(D3PM_ERR_CUDA, "head_step: memset failed");
+  rc = has_u ? launch(H::head_step_kernel<64, true, false>) : launch(H::head_step_kernel<64, false, false>);
+  if (rc != D3PM_OK) return rc;
+  rc = check_launch("head_step");
+  if (rc != D3PM_OK) return rc;
+  if (has_u) H::head_redo_kernel<64, true><<<sms, 256, 0, s>>>(p, 0);
+  else H::head_redo_kernel<64, false><<<sms, 256, 0, s>>>(p, 0);
+  return check_launch("head_step(redo)");
 }
 
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N, d3pm_stream_t stream) {

@@ -1,0 +1,688 @@
+// Fused denoiser head + reverse step: the [B, N, K] logits never touch HBM.
+//
+// Replaces, in one kernel, the reference's prediction head `to_logits = LayerNorm(D) + Linear(D -> K)`
+// (transformer_utils.py:352-356, applied at :441) for BOTH denoiser passes of a step, plus everything
+// d3pm_fused_step replaces (predict_start / cf_predict_start / q_posterior / log_sample_categorical,
+// diffusion_transformer.py:220-283, :354-359).  Inputs are the hidden states that feed the head.
+//
+// Mathematics.  Rows whose logits cannot reach the -70 clamps of :236 (|logit| <= (70 - ln K) / 2, guaranteed for ALL
+// rows by a bound on the weights that the host checks once, see d3pm_head_prepare) satisfy
+//     y = s * log_softmax(c) + (1 - s) * log_softmax(u) = W (s a_c + (1 - s) a_u) + b + const,
+// a_* = LayerNorm(h_*): the guidance combine moves in front of the GEMM, so ONE [128 x D] x [D x K] product per token
+// tile yields the combined logits.  The product runs on the 5th-gen tensor cores (tcgen05.mma, kind::tf32, M = 128,
+// N = 128, accumulators in TMEM) as a 3xTF32 split (a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32-grade accuracy).
+// A 128 x K fp32 tile of logits (2 MB) does not fit on chip, so the kernel makes two passes over the classes, recomputing
+// the product: pass 1 accumulates the softmax statistics (max, sum) of every row, pass 2 regenerates the logits and runs
+// the thinned exponential race of the stream kernel (same Philox stream, same ThinRule, same exact scoring of the
+// survivors), so a token differs from the unfused path only where the logits' last bits decide a near-tie.
+//
+// Roles (320 threads, one CTA per SM, persistent over 128-token tiles):
+//   warp 0      one lane issues tcgen05.mma and the tcgen05.commit's that drive the mbarrier pipeline
+//   warps 1-8   (a) produce the A operand of the tile: LayerNorm, guidance combine, hi/lo split, 128B-swizzled K-major
+//               canonical layout in shared memory; (b) epilogue: tcgen05.ld a TMEM lane (= token row) per thread, so all
+//               row reductions are thread-local (two threads per row, one per half of the columns)
+//   warp 9      one lane streams the pre-swizzled weight image (hi and lo, 64 KiB per 128 classes) through a two-stage
+//               shared-memory ring with 1-D bulk TMA
+// TMEM: 4 accumulators of 128 columns (all 512 columns); the epilogue consumes them in pairs 512 classes apart because one
+// Philox call serves classes (4c..4c+3) and (4c+512..4c+515).
+#pragma once
+
+#include "d3pm_step_stream.cuh"
+
+namespace d3pm {
+namespace head {
+
+constexpr int kTileM = 128;      // token rows per tile = TMEM lanes
+constexpr int kChunk = 128;      // classes per accumulator and per weight stage
+constexpr int kAccStages = 4;
+constexpr int kBStages = 2;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr int kCand = 14;
+constexpr float kThin = 6.0f;
+constexpr int kBlockBytes = kTileM * 128;  // one 128-byte k-block of a 128-row operand
+// instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kChunk >> 3) << 17) | ((kTileM >> 4) << 24);
+
+struct HeadParams {
+  const float* hidden_c;  // [rows][D]
+  const float* hidden_u;  // nullable (guidance off)
+  const float* ln_weight;
+  const float* ln_bias;
+  const float* w_image;   // [K/128][2 terms][D/32][128 rows x 128 B, swizzled], scaled by log2(e)
+  const float* bias2;     // [K], scaled by log2(e)
+  const int64_t* x_t;
+  const int64_t* t;
+  const float* coef_table;
+  int64_t* x_prev;
+  float* logits_out;      // dump mode: [rows][K] combined logits (natural units)
+  uint32_t* status;
+  int32_t* redo_rows;
+  uint32_t* redo_count;
+  int32_t N, K, T;
+  int64_t rows;
+  float ln_eps, guidance_scale, thin_factor;
+  uint64_t seed, offset;
+  int64_t row_offset;
+};
+
+template <int D>
+struct Geo {
+  static_assert(D == 64, "the fused head is built for n_embd = 64 (configs/model/motionencoder/transformer_utils.yaml)");
+  static constexpr int KB = D / 32;
+  static constexpr int kTermBytes = KB * kBlockBytes;  // hi (or lo) part of a 128-row operand
+  static constexpr int kABytes = 2 * kTermBytes;
+  static constexpr int kBStageBytes = 2 * kTermBytes;
+  static constexpr int kOperandBytes = kABytes + kBStages * kBStageBytes;
+  static constexpr int kChunkFloats = kBStageBytes / 4;  // floats of the weight image per 128 classes
+};
+
+struct Ctl {
+  unsigned long long b_full[kBStages], b_empty[kBStages], acc_full[kAccStages], acc_empty[kAccStages], a_ready, a_free;
+  uint32_t tmem_base, pad;
+  float stat_m[2][kTileM], stat_s[2][kTileM];
+  float yj2[kTileM];
+  RowInfo info[kTileM];
+  uint32_t cand_cnt[kTileM];
+  uint32_t cand_k[kTileM][kCand];
+  float cand_p[kTileM][kCand];
+};
+
+template <int D>
+constexpr size_t smem_bytes() {
+  return 1024 + Geo<D>::kOperandBytes + sizeof(Ctl);
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: rows at 128 B, 8-row groups at SBO = 1024 B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return static_cast<uint64_t>((addr >> 4) & 0x3fffu) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// class chunk processed at position `ci` of a pass: pairs (p, p + 4) inside every block of 8 chunks (1024 classes)
+__device__ __forceinline__ int chunk_of(int ci) { return (ci & ~7) + ((ci & 7) >> 1) + ((ci & 1) << 2); }
+
+// float offset, inside the weight image, of the 16-byte piece `piece` (4 floats of hidden dims 32 kb + 4 piece ..) of
+// class k: image[k / 128][term][kb][k % 128][(piece ^ (k % 8)) * 4 ..]
+template <int D>
+__device__ __host__ __forceinline__ size_t image_offset(int k, int term, int kb, int piece) {
+  const int r = k & 127;
+  return static_cast<size_t>(k >> 7) * Geo<D>::kChunkFloats + static_cast<size_t>(term * Geo<D>::KB + kb) * (kBlockBytes / 4) +
+         r * 32 + ((piece ^ (r & 7)) << 2);
+}
+
+// ---- weight preparation --------------------------------------------------------------------------------------
+// One thread per (class, 4 hidden dims).  w' = w * log2(e); hi = w' with the 13 low mantissa bits cleared (exactly a
+// tf32 number), lo = w' - hi (exact in fp32).  stats[0] = max_k ||w_k||_2, stats[1] = max_k |b_k| (as float bits).
+template <int D>
+__global__ void head_prepare_kernel(const float* __restrict__ weight, const float* __restrict__ bias, int K,
+                                    float* __restrict__ image, float* __restrict__ bias2, uint32_t* __restrict__ stats) {
+  constexpr int PPR = D / 4;  // 16-byte pieces per class
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = idx / PPR, pp = idx % PPR;
+  float ss = 0.f;
+  if (k < K) {
+    const float4 w = *reinterpret_cast<const float4*>(weight + static_cast<size_t>(k) * D + 4 * pp);
+    const float v[4] = {w.x, w.y, w.z, w.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float s = v[e] * kLog2e;
+      hi[e] = __uint_as_float(__float_as_uint(s) & 0xffffe000u);
+      lo[e] = s - hi[e];
+      ss = fmaf(v[e], v[e], ss);
+    }
+    const int kb = pp >> 3, piece = pp & 7;
+    *reinterpret_cast<float4*>(image + image_offset<D>(k, 0, kb, piece)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(image + image_offset<D>(k, 1, kb, piece)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    if (pp == 0) {
+      const float b = bias != nullptr ? bias[k] : 0.f;
+      bias2[k] = b * kLog2e;
+      atomicMax(stats + 1, __float_as_uint(fabsf(b)));
+    }
+  }
+  // the PPR threads of a class are adjacent lanes (PPR = 16 divides 32)
+#pragma unroll
+  for (int o = PPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (k < K && pp == 0) atomicMax(stats, __float_as_uint(sqrtf(ss)));
+}
+
+// LayerNorm of 32 of the 64 hidden values of a row held by this thread (its partner lane holds the other 32).
+__device__ __forceinline__ void layer_norm_half(float (&x)[32], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                int half, float eps) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sum += x[i];
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  const float mean = sum * (1.0f / 64.0f);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float d = x[i] - mean;
+    sq = fmaf(d, d, sq);
+  }
+  sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+  const float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = fmaf((x[i] - mean) * rstd, __ldg(gamma + 32 * half + i), __ldg(beta + 32 * half + i));
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------
+template <int D, bool HAS_U, bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams p) {
+  using G = Geo<D>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + G::kABytes;
+  Ctl& C = *reinterpret_cast<Ctl*>(smem + G::kOperandBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NCH = p.K / kChunk;                // chunks per pass
+  const int NIT = DUMP ? NCH : 2 * NCH;        // accumulator iterations per tile
+  const long long ntiles = (p.rows + kTileM - 1) / kTileM;
+
+  if (tid == 0) {
+    for (int i = 0; i < kBStages; ++i) mbar_init(&C.b_full[i], 1), mbar_init(&C.b_empty[i], 1);
+    for (int i = 0; i < kAccStages; ++i) mbar_init(&C.acc_full[i], 1), mbar_init(&C.acc_empty[i], kEpiWarps);
+    mbar_init(&C.a_ready, kEpiThreads);
+    mbar_init(&C.a_free, 1);
+  }
+  if (tid < kTileM) C.cand_cnt[tid] = 0;
+  if (warp == 0) {  // the whole tensor memory: 4 accumulators x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&C.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = C.tmem_base;
+
+  if (warp == kEpiWarps + 1) {
+    // =========================== weight stream (bulk TMA) ===========================
+    if (lane == 0) {
+      long long g = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int it = 0; it < NIT; ++it, ++g) {
+          const int st = static_cast<int>(g & 1);
+          mbar_wait(&C.b_empty[st], static_cast<uint32_t>(((g >> 1) & 1) ^ 1));
+          mbar_expect_tx(&C.b_full[st], G::kBStageBytes);
+          const float* src = p.w_image + static_cast<size_t>(chunk_of(it % NCH)) * G::kChunkFloats;
+          unsigned char* dst = sB + st * G::kBStageBytes;
+#pragma unroll
+          for (int q = 0; q < G::kBStageBytes / kBlockBytes; ++q)
+            tma_load_row(dst + q * kBlockBytes, src + q * (kBlockBytes / 4), kBlockBytes, &C.b_full[st]);
+        }
+    }
+  } else if (warp == 0) {
+    // =========================== MMA issue ===========================
+    if (lane == 0) {
+      long long g = 0;
+      uint32_t tcount = 0;
+      const uint32_t a_addr = smem_u32(sA);
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        mbar_wait(&C.a_ready, tcount & 1);
+        for (int it = 0; it < NIT; ++it, ++g) {
+          const int st = static_cast<int>(g & 1), acc = it & 3;
+          mbar_wait(&C.b_full[st], static_cast<uint32_t>((g >> 1) & 1));
+          mbar_wait(&C.acc_empty[acc], static_cast<uint32_t>(((g >> 2) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(sB + st * G::kBStageBytes);
+          const uint32_t d_tmem = tmem + acc * kChunk;
+          uint32_t accum = 0;
+          // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a_off = (term == 0) ? G::kTermBytes : 0;  // 0 = hi, 1 = lo
+            const uint32_t b_off = (term == 1) ? G::kTermBytes : 0;
+#pragma unroll
+            for (int kb = 0; kb < G::KB; ++kb)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // 4 MMAs of K = 8 per 128-byte k-block
+                const uint32_t off = kb * kBlockBytes + ks * 32;
+                tc_mma_tf32(d_tmem, smem_desc(a_addr + a_off + off), smem_desc(b_addr + b_off + off), accum);
+                accum = 1;
+              }
+          }
+          tc_commit(&C.b_empty[st]);
+          tc_commit(&C.acc_full[acc]);
+        }
+        tc_commit(&C.a_free);
+      }
+    }
+  } else {
+    // =========================== A producer + epilogue (warps 1..8) ===========================
+    const int et = tid - 32;            // 0..255
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int colh = (warp - 1) >> 2;   // which 64 of the 128 columns of a chunk
+    const int erow = 32 * q + lane;     // row (TMEM lane) of this thread in the epilogue
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(32 * q) << 16);
+    const NoiseStream rng(p.seed, p.offset);
+    const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kThin;
+    uint32_t status_bits = 0;
+    uint32_t tcount = 0;
+    long long prev_tile = -1;
+
+    // exact finish of the previous tile's rows from their survivor lists (16 lanes per row, as score_batch)
+    auto score_tile = [&](long long tile) {
+      const int sub = lane & 15;
+      for (int slot = 2 * (warp - 1) + (lane >> 4); slot < kTileM; slot += 2 * kEpiWarps) {
+        const long long lrow = tile * kTileM + slot;
+        const bool live = lrow < p.rows;
+        unsigned long long key = 0ull;
+        RowInfo ri;
+        ri.accept = 0.f;
+        uint32_t cnt = 0;
+        if (live) {
+          ri = C.info[slot];
+          cnt = C.cand_cnt[slot];
+          const uint32_t n = cnt < static_cast<uint32_t>(kCand) ? cnt : static_cast<uint32_t>(kCand);
+          uint32_t k = 0;
+          float P = 0.f;
+          bool have = false;
+          if (static_cast<uint32_t>(sub) < n) {
+            k = C.cand_k[slot][sub];
+            const float pe = fminf(fmaxf(C.cand_p[slot][sub], kPFloor), 1.0f);
+            P = fmaf(pe, ri.A, ri.Bc);
+            have = (k != ri.j);
+          } else if (sub == 14) {
+            k = static_cast<uint32_t>(p.K), P = ri.PK, have = true;
+          } else if (sub == 15 && ri.j != static_cast<uint32_t>(p.K)) {
+            k = ri.j, P = ri.Pj, have = true;
+          }
+          if (have) {
+            const float sc = log_prob_clamped(P) +
+                             gumbel_from_uniform(uniform_from_draw(rng.draw(k, static_cast<uint64_t>(p.row_offset + lrow))));
+            key = pack_key(sc, k);
+          }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other > key ? other : key;
+        }
+        if (live && sub == 0) {
+          if (cnt <= static_cast<uint32_t>(kCand) && key_score(key) >= ri.accept) {
+            p.x_prev[lrow] = key_class(key);
+          } else {
+            p.redo_rows[atomicAdd(p.redo_count, 1u)] = static_cast<int32_t>(lrow);
+          }
+          C.cand_cnt[slot] = 0;
+        }
+      }
+    };
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      // ---------------- A operand: LayerNorm, guidance combine, hi/lo split, swizzled store ----------------
+      {
+        const int arow = et >> 1, half = et & 1;
+        const long long lrow = tile * kTileM + arow;
+        const bool valid = lrow < p.rows;
+        float a[32];
+        if (valid) {
+          const float4* src = reinterpret_cast<const float4*>(p.hidden_c + lrow * D + 32 * half);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(src + i);
+            a[4 * i] = v.x, a[4 * i + 1] = v.y, a[4 * i + 2] = v.z, a[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = 0.f;
+        }
+        layer_norm_half(a, p.ln_weight, p.ln_bias, half, p.ln_eps);
+        if (HAS_U) {
+          float u[32];
+          if (valid) {
+            const float4* src = reinterpret_cast<const float4*>(p.hidden_u + lrow * D + 32 * half);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = __ldg(src + i);
+              u[4 * i] = v.x, u[4 * i + 1] = v.y, u[4 * i + 2] = v.z, u[4 * i + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = 0.f;
+          }
+          layer_norm_half(u, p.ln_weight, p.ln_bias, half, p.ln_eps);
+          const float gs = p.guidance_scale, og = 1.0f - gs;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = fmaf(gs, a[i], og * u[i]);
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = 0.f;
+        }
+        // logit (log2 units) of the row's current token, needed by the posterior of unmasked rows
+        if (!DUMP) {
+          long long jj = valid ? p.x_t[lrow] : p.K;
+          if (jj < 0 || jj > p.K) status_bits |= D3PM_STATUS_BAD_TOKEN, jj = p.K;
+          float dot = 0.f;
+          if (jj < p.K) {
+            const int j = static_cast<int>(jj);
+#pragma unroll
+            for (int piece = 0; piece < 8; ++piece) {
+              const float4 hi = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(j, 0, half, piece)));
+              const float4 lo = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(j, 1, half, piece)));
+              dot = fmaf(a[4 * piece], hi.x + lo.x, dot);
+              dot = fmaf(a[4 * piece + 1], hi.y + lo.y, dot);
+              dot = fmaf(a[4 * piece + 2], hi.z + lo.z, dot);
+              dot = fmaf(a[4 * piece + 3], hi.w + lo.w, dot);
+            }
+          }
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          if (half == 0) C.yj2[arow] = (jj < p.K) ? dot + __ldg(p.bias2 + jj) : 0.f;
+        }
+        if (tcount > 0) mbar_wait(&C.a_free, (tcount - 1) & 1);  // the previous tile's MMAs no longer read A
+        unsigned char* rowp = sA + half * kBlockBytes + arow * 128;
+#pragma unroll
+        for (int piece = 0; piece < 8; ++piece) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __uint_as_float(__float_as_uint(a[4 * piece + e]) & 0xffffe000u);
+            lo[e] = a[4 * piece + e] - hi[e];
+          }
+          const int sw = (piece ^ (arow & 7)) * 16;
+          *reinterpret_cast<float4*>(rowp + sw) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(rowp + G::kTermBytes + sw) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&C.a_ready);
+      }
+      // the tensor pipe is busy with this tile now: finish the previous one
+      if (!DUMP && prev_tile >= 0) score_tile(prev_tile);
+
+      const long long lrow = tile * kTileM + erow;
+      const bool live = lrow < p.rows;
+
+      if (DUMP) {
+        for (int it = 0; it < NIT; ++it) {
+          const int acc = it & 3;
+          mbar_wait(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
+          tc_fence_after();
+          const int k0 = chunk_of(it) * kChunk + 64 * colh;
+#pragma unroll
+          for (int sb = 0; sb < 2; ++sb) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + acc * kChunk + 64 * colh + 32 * sb, v);
+            tmem_ld_wait();
+            if (live) {
+              float* dst = p.logits_out + lrow * p.K + k0 + 32 * sb;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 32 * sb) + i);
+                *reinterpret_cast<float4*>(dst + 4 * i) =
+                    make_float4((__uint_as_float(v[4 * i]) + b.x) * kLn2, (__uint_as_float(v[4 * i + 1]) + b.y) * kLn2,
+                                (__uint_as_float(v[4 * i + 2]) + b.z) * kLn2, (__uint_as_float(v[4 * i + 3]) + b.w) * kLn2);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
+        }
+        continue;
+      }
+
+      // ---------------- pass 1: softmax statistics of the row (log2 units) ----------------
+      float m = -CUDART_INF_F, s = 0.f;
+      for (int it = 0; it < NCH; ++it) {
+        const int acc = it & 3;
+        mbar_wait(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
+        tc_fence_after();
+        const int k0 = chunk_of(it) * kChunk + 64 * colh;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_lane + acc * kChunk + 64 * colh, v0);
+        tmem_ld32(t_lane + acc * kChunk + 64 * colh + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
+        float y[64];
+        float cm = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + i);
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 32) + i);
+          y[4 * i] = __uint_as_float(v0[4 * i]) + b0.x, y[4 * i + 1] = __uint_as_float(v0[4 * i + 1]) + b0.y;
+          y[4 * i + 2] = __uint_as_float(v0[4 * i + 2]) + b0.z, y[4 * i + 3] = __uint_as_float(v0[4 * i + 3]) + b0.w;
+          y[32 + 4 * i] = __uint_as_float(v1[4 * i]) + b1.x, y[32 + 4 * i + 1] = __uint_as_float(v1[4 * i + 1]) + b1.y;
+          y[32 + 4 * i + 2] = __uint_as_float(v1[4 * i + 2]) + b1.z, y[32 + 4 * i + 3] = __uint_as_float(v1[4 * i + 3]) + b1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) cm = fmaxf(cm, y[i]);
+        const float mn = fmaxf(m, cm);
+        s *= ex2(m - mn);
+        m = mn;
+        float acc_s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc_s += ex2(y[i] - m);
+        s += acc_s;
+      }
+      C.stat_m[colh][erow] = m;
+      C.stat_s[colh][erow] = s;
+      epi_bar();  // both halves of every row are in; the previous tile's lists have been scored and reset
+      const float m0 = C.stat_m[0][erow], m1 = C.stat_m[1][erow];
+      const float M2 = fmaxf(m0, m1);
+      const float S = fmaf(C.stat_s[0][erow], ex2(m0 - M2), C.stat_s[1][erow] * ex2(m1 - M2));
+      const float rS = __frcp_rn(S);
+
+      // ---------------- per-row posterior coefficients and thinning thresholds ----------------
+      long long jj = live ? p.x_t[lrow] : p.K;
+      if (jj < 0 || jj > p.K) jj = p.K;  // flagged by the A producer
+      long long tt = live ? p.t[lrow / p.N] : 0;
+      if (tt < 0 || tt >= p.T) status_bits |= D3PM_STATUS_BAD_T, tt = tt < 0 ? 0 : p.T - 1;
+      const bool masked = (jj == p.K);
+      const uint32_t j = static_cast<uint32_t>(jj);
+      const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
+      const float pj = masked ? 0.f : fminf(fmaxf(ex2(C.yj2[erow] - M2) * rS, kPFloor), 1.0f);
+      RowMath rm;
+      rm.init(cf, masked, pj, j, p.K);
+      const ThinRule thin(rm, thin_c);
+      const float thrA = rS * thin.scaleA;
+      if (colh == 0) {
+        RowInfo ri;
+        ri.A = rm.A, ri.Bc = rm.Bc, ri.Pj = rm.Pj, ri.PK = rm.PK, ri.accept = thin.accept;
+        ri.j = j, ri.rel = 0, ri.pad = 0;
+        C.info[erow] = ri;
+      }
+      const uint64_t grow = static_cast<uint64_t>(p.row_offset + lrow);
+
+      // ---------------- pass 2: regenerate the logits, thinned race, survivors to the row's list ----------------
+      for (int pr = 0; pr < NCH / 2; ++pr) {
+        const int itA = NCH + 2 * pr, itB = itA + 1;
+        const int accA = itA & 3, accB = itB & 3;
+        mbar_wait(&C.acc_full[accA], static_cast<uint32_t>((itA >> 2) & 1));
+        mbar_wait(&C.acc_full[accB], static_cast<uint32_t>((itB >> 2) & 1));
+        tc_fence_after();
+        const int kA = chunk_of(2 * pr) * kChunk + 64 * colh;  // chunk_of(2 pr + 1) = chunk_of(2 pr) + 4: classes + 512
+#pragma unroll 1
+        for (int sb = 0; sb < 2; ++sb) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_lane + accA * kChunk + 64 * colh + 32 * sb, va);
+          tmem_ld32(t_lane + accB * kChunk + 64 * colh + 32 * sb, vb);
+          tmem_ld_wait();
+          if (sb == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&C.acc_empty[accA]), mbar_arrive(&C.acc_empty[accB]);
+          }
+          const int k0 = kA + 32 * sb;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint32_t cq = static_cast<uint32_t>(k0 >> 2) + c8;
+            const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(cq), grow);
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + c8);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 512) + c8);
+            const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float ea = ex2((__uint_as_float(va[4 * c8 + e]) + bav[e]) - M2);
+              const float eb = ex2((__uint_as_float(vb[4 * c8 + e]) + bbv[e]) - M2);
+              const uint32_t ha = NoiseStream::half_of(cw, e), hb = NoiseStream::half_of(cw, 4 + e);
+              if (live && __uint_as_float(0x3f800000u | ha) <= fmaf(ea, thrA, thin.thrB)) {
+                const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
+                if (pos < static_cast<uint32_t>(kCand)) C.cand_k[erow][pos] = k0 + 4 * c8 + e, C.cand_p[erow][pos] = ea * rS;
+              }
+              if (live && __uint_as_float(0x3f800000u | hb) <= fmaf(eb, thrA, thin.thrB)) {
+                const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
+                if (pos < static_cast<uint32_t>(kCand)) C.cand_k[erow][pos] = k0 + 512 + 4 * c8 + e, C.cand_p[erow][pos] = eb * rS;
+              }
+            }
+          }
+        }
+      }
+      epi_bar();  // every survivor of the tile is listed
+      prev_tile = tile;
+    }
+    if (!DUMP && prev_tile >= 0) score_tile(prev_tile);
+    if (status_bits != 0 && p.status != nullptr) atomicOr(p.status, status_bits);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---- rescoring of the rows the race could not decide (probability ~e^-c per row) and reference CUDA-core path ----------
+// One CTA per listed row: the combined logits of the row in plain fp32 FMAs, then exhaustive exact Gumbel scoring (the
+// same arithmetic as the exhaustive path of step_rows_kernel).
+template <int D, bool HAS_U>
+__global__ void __launch_bounds__(256) head_redo_kernel(const HeadParams p, int all_rows) {
+  constexpr int NW = 8;
+  __shared__ float sa[D];
+  __shared__ float sred[2][4 * NW];
+  __shared__ unsigned long long skey[NW];
+  __shared__ float syj;
+  const int tid = threadIdx.x;
+  const long long count = all_rows ? p.rows : static_cast<long long>(*p.redo_count);
+  const NoiseStream rng(p.seed, p.offset);
+  for (long long e = blockIdx.x; e < count; e += gridDim.x) {
+    const long long lrow = all_rows ? e : p.redo_rows[e];
+    __syncthreads();
+    if (tid < 32) {  // one warp: the combined, normalised hidden vector (2 values per lane)
+      float x[2] = {p.hidden_c[lrow * D + tid], p.hidden_c[lrow * D + 32 + tid]};
+      auto ln = [&](float (&v)[2]) {
+        const float mean = warp_sum(v[0] + v[1]) * (1.0f / D);
+        const float d0 = v[0] - mean, d1 = v[1] - mean;
+        const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / D) + p.ln_eps);
+        v[0] = fmaf(d0 * rstd, p.ln_weight[tid], p.ln_bias[tid]);
+        v[1] = fmaf(d1 * rstd, p.ln_weight[32 + tid], p.ln_bias[32 + tid]);
+      };
+      ln(x);
+      if (HAS_U) {
+        float u[2] = {p.hidden_u[lrow * D + tid], p.hidden_u[lrow * D + 32 + tid]};
+        ln(u);
+        const float gs = p.guidance_scale, og = 1.0f - gs;
+        x[0] = fmaf(gs, x[0], og * u[0]), x[1] = fmaf(gs, x[1], og * u[1]);
+      }
+      sa[tid] = x[0], sa[32 + tid] = x[1];
+    }
+    __syncthreads();
+    long long jj = p.x_t[lrow], tt = p.t[lrow / p.N];
+    if (jj < 0 || jj > p.K) jj = p.K;
+    if (tt < 0 || tt >= p.T) tt = tt < 0 ? 0 : p.T - 1;
+    const bool masked = (jj == p.K);
+    const uint32_t j = static_cast<uint32_t>(jj);
+    float y[32];  // K <= 8192: classes tid + 256 i
+    const int per = p.K / 256;
+    float m = -CUDART_INF_F;
+#pragma unroll 1
+    for (int i = 0; i < per; ++i) {
+      const int k = tid + 256 * i;
+      float dot = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < Geo<D>::KB; ++kb)
+#pragma unroll
+        for (int piece = 0; piece < 8; ++piece) {
+          const float4 hi = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(k, 0, kb, piece)));
+          const float4 lo = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(k, 1, kb, piece)));
+          const float* av = sa + 32 * kb + 4 * piece;
+          dot = fmaf(av[0], hi.x + lo.x, dot), dot = fmaf(av[1], hi.y + lo.y, dot);
+          dot = fmaf(av[2], hi.z + lo.z, dot), dot = fmaf(av[3], hi.w + lo.w, dot);
+        }
+      y[i] = dot + __ldg(p.bias2 + k);
+      if (static_cast<uint32_t>(k) == j) syj = y[i];
+      m = fmaxf(m, y[i]);
+    }
+    // softmax statistics in log2 units
+    m = warp_max(m);
+    if ((tid & 31) == 0) sred[0][tid >> 5] = m;
+    __syncthreads();
+    float M2 = sred[0][0];
+    for (int w = 1; w < NW; ++w) M2 = fmaxf(M2, sred[0][w]);
+    float s = 0.f;
+    for (int i = 0; i < per; ++i) {
+      y[i] = ex2(y[i] - M2);
+      s += y[i];
+    }
+    s = warp_sum(s);
+    if ((tid & 31) == 0) sred[1][tid >> 5] = s;
+    __syncthreads();
+    float S = 0.f;
+    for (int w = 0; w < NW; ++w) S += sred[1][w];
+    const float rS = __frcp_rn(S);
+    const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
+    const float pj = masked ? 0.f : fminf(fmaxf(ex2(syj - M2) * rS, kPFloor), 1.0f);
+    RowMath rm;
+    rm.init(cf, masked, pj, j, p.K);
+    const uint64_t grow = static_cast<uint64_t>(p.row_offset + lrow);
+    unsigned long long best = 0ull;
+    for (int i = 0; i < per; ++i) {
+      const uint32_t k = tid + 256 * i;
+      const float sc = rm.post_of(k, y[i], rS) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+      const unsigned long long key = pack_key(sc, k);
+      best = key > best ? key : best;
+    }
+    if (tid == 0) {
+      const unsigned long long key =
+          pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(p.K, grow))), p.K);
+      best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+    if ((tid & 31) == 0) skey[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 0; w < NW; ++w) best = skey[w] > best ? skey[w] : best;
+      p.x_prev[lrow] = key_class(best);
+    }
+  }
+}
+
+}  // namespace head
+}  // namespace d3pm

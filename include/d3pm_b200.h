@@ -183,6 +183,52 @@ typedef struct d3pm_train_desc {
 
 int d3pm_train_rows(const d3pm_train_desc* desc);
 
+/* ---------------------------------------------------------------- fused denoiser head + reverse step
+ * Replaces the reference's prediction head `to_logits = LayerNorm(n_embd) + Linear(n_embd -> K)`
+ * (transformer_utils.py:352-356, applied at :441) of BOTH denoiser passes of a step together with everything
+ * d3pm_fused_step replaces: the [B, N, K] logits are produced tile by tile on the tensor cores (tcgen05, 3xTF32) and
+ * consumed on chip; HBM sees the hidden states [B*N][D] and the tokens only.  n_embd D = 64 (the shipped config),
+ * K in {1024, 2048, 4096}.
+ *
+ * d3pm_head_prepare: weight [K][D] / bias [K] (nullable) of the Linear -> `w_image` (d3pm_head_image_floats(K, D)
+ * floats: per 128 classes the tf32 hi and lo parts of W * log2(e) in the 128-byte-swizzled K-major layout the tensor
+ * core reads), `bias2` [K] = b * log2(e), and `stats` (2 floats, device): max_k ||W_k||_2 and max_k |b_k|, from which
+ * the caller bounds |logit| <= stats[0] * (sqrt(D) * max|gamma| + ||beta||_2) + stats[1].  The fused kernel is valid
+ * when that bound is <= (70 - ln K) / 2 (no -70 clamp of diffusion_transformer.py:236 can fire, so classifier-free
+ * guidance commutes with the Linear); otherwise the caller must use the unfused path.                               */
+int64_t d3pm_head_image_floats(int K, int D);
+int d3pm_head_prepare(const float* weight, const float* bias, int K, int D, float* w_image, float* bias2, float* stats,
+                      d3pm_stream_t stream);
+
+#define D3PM_HEAD_STEP 0      /* sample x_{t-1} (production: Philox noise, thinned race, same stream as d3pm_fused_step) */
+#define D3PM_HEAD_LOGITS 1    /* write the guidance-combined logits W (s a_c + (1-s) a_u) + b to logits_out (verification) */
+#define D3PM_HEAD_REFERENCE 2 /* the same step on CUDA cores in plain fp32, exhaustive scoring (verification, slow) */
+
+typedef struct d3pm_head_desc {
+  const float* hidden_c;   /* [B*N][D] input of to_logits for the conditional pass (transformer_utils.py:441) */
+  const float* hidden_u;   /* same for the unconditional pass; NULL = guidance off */
+  const float* ln_weight;  /* [D] LayerNorm gamma, beta (to_logits[0]) */
+  const float* ln_bias;
+  const float* w_image;    /* from d3pm_head_prepare */
+  const float* bias2;
+  const int64_t* x_t;      /* [B*N] */
+  const int64_t* t;        /* [B] */
+  const float* coef_table;
+  int64_t* x_prev;         /* [B*N] out (STEP, REFERENCE) */
+  float* logits_out;       /* [B*N][K] out (LOGITS) */
+  uint32_t* status;
+  int32_t* redo_rows;      /* [B*N] scratch: rows the thinned race could not decide, rescored exhaustively */
+  uint32_t* redo_count;    /* one word of scratch */
+  int32_t B, N, K, T, D;
+  int32_t mode;            /* D3PM_HEAD_* */
+  float ln_eps, guidance_scale, thin_factor;
+  uint64_t seed, offset;
+  int64_t row_offset;
+  d3pm_stream_t stream;
+} d3pm_head_desc;
+
+int d3pm_head_step(const d3pm_head_desc* desc);
+
 /* [B, C, N] contiguous (reference layout) -> token-major rows [B*N][pitch]. */
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N,
                         d3pm_stream_t stream);
