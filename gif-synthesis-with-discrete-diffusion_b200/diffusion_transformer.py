@@ -18,7 +18,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from d3pm_b200 import _lib, ops, train
+from d3pm_b200 import _lib, head, ops, train
 from d3pm_b200._lib import D3PMError
 
 _SCHEDULE_BUFFERS = ("log_at", "log_bt", "log_ct", "log_1_min_ct",
@@ -44,6 +44,14 @@ def alpha_schedule(time_step, N=100, att_1=0.99999, att_T=0.000009, ctt_1=0.0000
     ctt = np.concatenate((mask_cum[1:], [0]))
     btt = (1 - att - ctt) / N
     return at, bt, ct, att, btt, ctt
+
+
+class _PassThrough(nn.Module):
+    """Stands in for `transformer.to_logits` while the fused head kernel is active: the denoiser then returns the
+    hidden states that feed its head, laid out exactly like its logits (`[B, D, N]` view of `[B, N, D]`)."""
+
+    def forward(self, x):
+        return x
 
 
 class FusedDiffusionTransformer(nn.Module):
@@ -123,6 +131,10 @@ class FusedDiffusionTransformer(nn.Module):
         self.inject_exponential: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
         self._coef_cache = None
         self._status = None
+        # fold the denoiser's `to_logits` head into the update kernel (see enable_fused_head)
+        self.fuse_head = False
+        self._head_cache = None
+        self._head_scratch = None
 
     # ------------------------------------------------------------------ bookkeeping
     def update_n_sample(self):
@@ -182,6 +194,45 @@ class FusedDiffusionTransformer(nn.Module):
             raise AssertionError("t outside [0, num_timesteps)")
         if word & _lib.STATUS_BAD_TOKEN:
             raise AssertionError(f"token index >= num_classes ({self.num_classes})")
+
+    # ------------------------------------------------------------------ fused denoiser head
+    def enable_fused_head(self, enable: bool = True):
+        """Let `p_sample_tokens` / `sample` run the denoiser's prediction head `to_logits = LayerNorm + Linear`
+        (transformer_utils.py:352-356, :441) inside the update kernel (`d3pm_head_step`), so the `[B, N, K]` logits
+        never exist in memory.  Needs `transformer.to_logits` to be exactly that Sequential with n_embd = 64 and K in
+        (1024, 2048, 4096); `fused_head_active` tells whether the weights also satisfy the kernel's no-clamp bound (if
+        not, the step keeps using the unfused CUDA path, which is exact for any weights)."""
+        if enable:
+            self._head_weights()  # raises D3PMError on an unsupported head
+        self.fuse_head = bool(enable)
+        return self
+
+    def _head_weights(self) -> "head.HeadWeights":
+        tl = self.transformer.to_logits
+        params = [q for q in (tl[0].weight, tl[0].bias, tl[-1].weight, tl[-1].bias) if q is not None]
+        key = tuple((q.data_ptr(), q._version, str(q.device)) for q in params)
+        if self._head_cache is None or self._head_cache[0] != key:
+            self._head_cache = (key, head.HeadWeights.from_module(tl))
+        return self._head_cache[1]
+
+    @property
+    def fused_head_active(self) -> bool:
+        return bool(self.fuse_head) and self._head_weights().valid
+
+    def _hidden_rows(self, x_t, cond_emb, t) -> torch.Tensor:
+        """The denoiser up to (not including) its head: `[B, N, D]` hidden states, contiguous."""
+        tl = self.transformer.to_logits
+        self.transformer.to_logits = _PassThrough()
+        try:
+            if self.amp:
+                with torch.autocast("cuda"):
+                    out = self.transformer(x_t, cond_emb, t)
+            else:
+                out = self.transformer(x_t, cond_emb, t)
+        finally:
+            self.transformer.to_logits = tl
+        assert out.size(0) == x_t.size(0) and out.size()[2:] == x_t.size()[1:]
+        return out.float().permute(0, 2, 1).contiguous()  # the denoiser hands back a permuted view: no copy
 
     # ------------------------------------------------------------------ helpers
     def _denoise_rows(self, x_t: torch.Tensor, cond_emb, t: torch.Tensor) -> torch.Tensor:
@@ -351,6 +402,19 @@ class FusedDiffusionTransformer(nn.Module):
     @torch.no_grad()
     def p_sample_tokens(self, x_t, cond_emb, cf_cond_emb, t, x_prev_out=None):
         """The same step on integer tokens: int64 `[B, N]` in, int64 `[B, N]` out (fast path of `sample`)."""
+        if self.fuse_head and self.inject_uniform is None and self._head_weights().valid:
+            hw = self._head_weights()
+            hidden_c = self._hidden_rows(x_t, cond_emb, t)
+            hidden_u = None
+            if not self._guidance_off():
+                hidden_u = self._hidden_rows(x_t, cf_cond_emb.type_as(cond_emb) if cond_emb is not None else cf_cond_emb, t)
+            B, N = x_t.shape
+            if self._head_scratch is None or self._head_scratch[0].numel() != B * N or self._head_scratch[0].device != x_t.device:
+                self._head_scratch = head.head_scratch(B, N, x_t.device)
+            return head.head_step(hw, hidden_c, hidden_u, x_t, t.contiguous(), self.coef_table(),
+                                  guidance_scale=self.guidance_scale, seed=self.rng_seed, offset=self._next_offset(),
+                                  row_offset=self.row_offset, status=self._status_word(), x_prev_out=x_prev_out,
+                                  scratch=self._head_scratch)
         out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_PHILOX, x_prev_out=x_prev_out)
         return out["x_prev"]
 
