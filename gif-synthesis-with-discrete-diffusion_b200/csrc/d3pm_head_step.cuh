@@ -16,12 +16,12 @@
 // the thinned exponential race of the stream kernel (same Philox stream, same ThinRule, same exact scoring of the
 // survivors), so a token differs from the unfused path only where the logits' last bits decide a near-tie.
 //
-// Roles (320 threads, one CTA per SM, persistent over 128-token tiles):
+// Roles (576 threads, one CTA per SM, persistent over 128-token tiles):
 //   warp 0      one lane issues tcgen05.mma and the tcgen05.commit's that drive the mbarrier pipeline
-//   warps 1-8   (a) produce the A operand of the tile: LayerNorm, guidance combine, hi/lo split, 128B-swizzled K-major
+//   warps 1-16  (a) produce the A operand of the tile: LayerNorm, guidance combine, hi/lo split, 128B-swizzled K-major
 //               canonical layout in shared memory; (b) epilogue: tcgen05.ld a TMEM lane (= token row) per thread, so all
-//               row reductions are thread-local (two threads per row, one per half of the columns)
-//   warp 9      one lane streams the pre-swizzled weight image (hi and lo, 64 KiB per 128 classes) through a two-stage
+//               row reductions are thread-local (four threads per row, one per quarter of the columns)
+//   warp 17     one lane streams the pre-swizzled weight image (hi and lo, 64 KiB per 128 classes) through a two-stage
 //               shared-memory ring with 1-D bulk TMA
 // TMEM: 4 accumulators of 128 columns (all 512 columns); the epilogue consumes them in pairs 512 classes apart because one
 // Philox call serves classes (4c..4c+3) and (4c+512..4c+515).
@@ -36,9 +36,13 @@ constexpr int kTileM = 128;      // token rows per tile = TMEM lanes
 constexpr int kChunk = 128;      // classes per accumulator and per weight stage
 constexpr int kAccStages = 4;
 constexpr int kBStages = 2;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;    // 4 per TMEM lane quarter: each thread owns one row and a quarter of the columns
+constexpr int kColSplit = kEpiWarps / 4;
+constexpr int kCols = kChunk / kColSplit;  // columns of a chunk per thread (32)
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr int kRowThreads4 = kEpiThreads / kTileM;  // threads that build one row of the A operand (4)
+static_assert(kCols == 32 && kRowThreads4 == 4, "the epilogue below is written for 16 epilogue warps");
 constexpr int kCand = 14;
 constexpr float kThin = 6.0f;
 constexpr int kBlockBytes = kTileM * 128;  // one 128-byte k-block of a 128-row operand
@@ -81,7 +85,7 @@ struct Geo {
 struct Ctl {
   unsigned long long b_full[kBStages], b_empty[kBStages], acc_full[kAccStages], acc_empty[kAccStages], a_ready, a_free;
   uint32_t tmem_base, pad;
-  float stat_m[2][kTileM], stat_s[2][kTileM];
+  float stat_m[kColSplit][kTileM], stat_s[kColSplit][kTileM];
   float yj2[kTileM];
   RowInfo info[kTileM];
   uint32_t cand_cnt[kTileM];
@@ -97,6 +101,19 @@ constexpr size_t smem_bytes() {
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait that lets the hardware suspend the thread until the phase completes (time-limit hint ~10 ms) instead of
+// polling: the single-lane control warps would otherwise burn issue slots the epilogue warps need
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -178,24 +195,26 @@ __global__ void head_prepare_kernel(const float* __restrict__ weight, const floa
   if (k < K && pp == 0) atomicMax(stats, __float_as_uint(sqrtf(ss)));
 }
 
-// LayerNorm of 32 of the 64 hidden values of a row held by this thread (its partner lane holds the other 32).
-__device__ __forceinline__ void layer_norm_half(float (&x)[32], const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                int half, float eps) {
+// LayerNorm of 16 of the 64 hidden values of a row held by this thread (4 adjacent lanes hold a row; part = which 16).
+__device__ __forceinline__ void layer_norm_part(float (&x)[16], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                int part, float eps) {
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) sum += x[i];
+  for (int i = 0; i < 16; ++i) sum += x[i];
   sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
   const float mean = sum * (1.0f / 64.0f);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const float d = x[i] - mean;
     sq = fmaf(d, d, sq);
   }
   sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+  sq += __shfl_xor_sync(0xffffffffu, sq, 2);
   const float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + eps);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] = fmaf((x[i] - mean) * rstd, __ldg(gamma + 32 * half + i), __ldg(beta + 32 * half + i));
+  for (int i = 0; i < 16; ++i) x[i] = fmaf((x[i] - mean) * rstd, __ldg(gamma + 16 * part + i), __ldg(beta + 16 * part + i));
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int it = 0; it < NIT; ++it, ++g) {
           const int st = static_cast<int>(g & 1);
-          mbar_wait(&C.b_empty[st], static_cast<uint32_t>(((g >> 1) & 1) ^ 1));
+          mbar_wait_sleep(&C.b_empty[st], static_cast<uint32_t>(((g >> 1) & 1) ^ 1));
           mbar_expect_tx(&C.b_full[st], G::kBStageBytes);
           const float* src = p.w_image + static_cast<size_t>(chunk_of(it % NCH)) * G::kChunkFloats;
           unsigned char* dst = sB + st * G::kBStageBytes;
@@ -252,11 +271,11 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       uint32_t tcount = 0;
       const uint32_t a_addr = smem_u32(sA);
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        mbar_wait(&C.a_ready, tcount & 1);
+        mbar_wait_sleep(&C.a_ready, tcount & 1);
         for (int it = 0; it < NIT; ++it, ++g) {
           const int st = static_cast<int>(g & 1), acc = it & 3;
-          mbar_wait(&C.b_full[st], static_cast<uint32_t>((g >> 1) & 1));
-          mbar_wait(&C.acc_empty[acc], static_cast<uint32_t>(((g >> 2) & 1) ^ 1));
+          mbar_wait_sleep(&C.b_full[st], static_cast<uint32_t>((g >> 1) & 1));
+          mbar_wait_sleep(&C.acc_empty[acc], static_cast<uint32_t>(((g >> 2) & 1) ^ 1));
           tc_fence_after();
           const uint32_t b_addr = smem_u32(sB + st * G::kBStageBytes);
           const uint32_t d_tmem = tmem + acc * kChunk;
@@ -282,12 +301,12 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       }
     }
   } else {
-    // =========================== A producer + epilogue (warps 1..8) ===========================
-    const int et = tid - 32;            // 0..255
+    // =========================== A producer + epilogue (warps 1..16) ===========================
+    const int et = tid - 32;            // 0..511
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int colh = (warp - 1) >> 2;   // which 64 of the 128 columns of a chunk
+    const int cs = (warp - 1) >> 2;     // which 32 of the 128 columns of a chunk
     const int erow = 32 * q + lane;     // row (TMEM lane) of this thread in the epilogue
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(32 * q) << 16);
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(32 * q) << 16) + kCols * cs;
     const NoiseStream rng(p.seed, p.offset);
     const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kThin;
     uint32_t status_bits = 0;
@@ -346,44 +365,45 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       // ---------------- A operand: LayerNorm, guidance combine, hi/lo split, swizzled store ----------------
       {
-        const int arow = et >> 1, half = et & 1;
+        const int arow = et >> 2, part = et & 3;  // 4 adjacent lanes per row, 16 hidden values each
         const long long lrow = tile * kTileM + arow;
         const bool valid = lrow < p.rows;
-        float a[32];
+        float a[16];
         if (valid) {
-          const float4* src = reinterpret_cast<const float4*>(p.hidden_c + lrow * D + 32 * half);
+          const float4* src = reinterpret_cast<const float4*>(p.hidden_c + lrow * D + 16 * part);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const float4 v = __ldg(src + i);
             a[4 * i] = v.x, a[4 * i + 1] = v.y, a[4 * i + 2] = v.z, a[4 * i + 3] = v.w;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = 0.f;
+          for (int i = 0; i < 16; ++i) a[i] = 0.f;
         }
-        layer_norm_half(a, p.ln_weight, p.ln_bias, half, p.ln_eps);
+        layer_norm_part(a, p.ln_weight, p.ln_bias, part, p.ln_eps);
         if (HAS_U) {
-          float u[32];
+          float u[16];
           if (valid) {
-            const float4* src = reinterpret_cast<const float4*>(p.hidden_u + lrow * D + 32 * half);
+            const float4* src = reinterpret_cast<const float4*>(p.hidden_u + lrow * D + 16 * part);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
               const float4 v = __ldg(src + i);
               u[4 * i] = v.x, u[4 * i + 1] = v.y, u[4 * i + 2] = v.z, u[4 * i + 3] = v.w;
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) u[i] = 0.f;
+            for (int i = 0; i < 16; ++i) u[i] = 0.f;
           }
-          layer_norm_half(u, p.ln_weight, p.ln_bias, half, p.ln_eps);
+          layer_norm_part(u, p.ln_weight, p.ln_bias, part, p.ln_eps);
           const float gs = p.guidance_scale, og = 1.0f - gs;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = fmaf(gs, a[i], og * u[i]);
+          for (int i = 0; i < 16; ++i) a[i] = fmaf(gs, a[i], og * u[i]);
         }
         if (!valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = 0.f;
+          for (int i = 0; i < 16; ++i) a[i] = 0.f;
         }
+        const int kb = part >> 1, piece0 = 4 * (part & 1);  // k-block and first 16-byte piece of this thread's values
         // logit (log2 units) of the row's current token, needed by the posterior of unmasked rows
         if (!DUMP) {
           long long jj = valid ? p.x_t[lrow] : p.K;
@@ -392,29 +412,30 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
           if (jj < p.K) {
             const int j = static_cast<int>(jj);
 #pragma unroll
-            for (int piece = 0; piece < 8; ++piece) {
-              const float4 hi = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(j, 0, half, piece)));
-              const float4 lo = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(j, 1, half, piece)));
-              dot = fmaf(a[4 * piece], hi.x + lo.x, dot);
-              dot = fmaf(a[4 * piece + 1], hi.y + lo.y, dot);
-              dot = fmaf(a[4 * piece + 2], hi.z + lo.z, dot);
-              dot = fmaf(a[4 * piece + 3], hi.w + lo.w, dot);
+            for (int i = 0; i < 4; ++i) {
+              const float4 hi = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(j, 0, kb, piece0 + i)));
+              const float4 lo = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(j, 1, kb, piece0 + i)));
+              dot = fmaf(a[4 * i], hi.x + lo.x, dot);
+              dot = fmaf(a[4 * i + 1], hi.y + lo.y, dot);
+              dot = fmaf(a[4 * i + 2], hi.z + lo.z, dot);
+              dot = fmaf(a[4 * i + 3], hi.w + lo.w, dot);
             }
           }
           dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          if (half == 0) C.yj2[arow] = (jj < p.K) ? dot + __ldg(p.bias2 + jj) : 0.f;
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          if (part == 0) C.yj2[arow] = (jj < p.K) ? dot + __ldg(p.bias2 + jj) : 0.f;
         }
-        if (tcount > 0) mbar_wait(&C.a_free, (tcount - 1) & 1);  // the previous tile's MMAs no longer read A
-        unsigned char* rowp = sA + half * kBlockBytes + arow * 128;
+        if (tcount > 0) mbar_wait_sleep(&C.a_free, (tcount - 1) & 1);  // the previous tile's MMAs no longer read A
+        unsigned char* rowp = sA + kb * kBlockBytes + arow * 128;
 #pragma unroll
-        for (int piece = 0; piece < 8; ++piece) {
+        for (int i = 0; i < 4; ++i) {
           float hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            hi[e] = __uint_as_float(__float_as_uint(a[4 * piece + e]) & 0xffffe000u);
-            lo[e] = a[4 * piece + e] - hi[e];
+            hi[e] = __uint_as_float(__float_as_uint(a[4 * i + e]) & 0xffffe000u);
+            lo[e] = a[4 * i + e] - hi[e];
           }
-          const int sw = (piece ^ (arow & 7)) * 16;
+          const int sw = ((piece0 + i) ^ (arow & 7)) * 16;
           *reinterpret_cast<float4*>(rowp + sw) = make_float4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<float4*>(rowp + G::kTermBytes + sw) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -430,28 +451,25 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       if (DUMP) {
         for (int it = 0; it < NIT; ++it) {
           const int acc = it & 3;
-          mbar_wait(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
+          mbar_wait_sleep(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
           tc_fence_after();
-          const int k0 = chunk_of(it) * kChunk + 64 * colh;
-#pragma unroll
-          for (int sb = 0; sb < 2; ++sb) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + acc * kChunk + 64 * colh + 32 * sb, v);
-            tmem_ld_wait();
-            if (live) {
-              float* dst = p.logits_out + lrow * p.K + k0 + 32 * sb;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 32 * sb) + i);
-                *reinterpret_cast<float4*>(dst + 4 * i) =
-                    make_float4((__uint_as_float(v[4 * i]) + b.x) * kLn2, (__uint_as_float(v[4 * i + 1]) + b.y) * kLn2,
-                                (__uint_as_float(v[4 * i + 2]) + b.z) * kLn2, (__uint_as_float(v[4 * i + 3]) + b.w) * kLn2);
-              }
-            }
-          }
+          const int k0 = chunk_of(it) * kChunk + kCols * cs;
+          uint32_t v[32];
+          tmem_ld32(t_lane + acc * kChunk, v);
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
+          if (live) {
+            float* dst = p.logits_out + lrow * p.K + k0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + i);
+              *reinterpret_cast<float4*>(dst + 4 * i) =
+                  make_float4((__uint_as_float(v[4 * i]) + b.x) * kLn2, (__uint_as_float(v[4 * i + 1]) + b.y) * kLn2,
+                              (__uint_as_float(v[4 * i + 2]) + b.z) * kLn2, (__uint_as_float(v[4 * i + 3]) + b.w) * kLn2);
+            }
+          }
         }
         continue;
       }
@@ -460,43 +478,49 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       float m = -CUDART_INF_F, s = 0.f;
       for (int it = 0; it < NCH; ++it) {
         const int acc = it & 3;
-        mbar_wait(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
+        mbar_wait_sleep(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
         tc_fence_after();
-        const int k0 = chunk_of(it) * kChunk + 64 * colh;
-        uint32_t v0[32], v1[32];
-        tmem_ld32(t_lane + acc * kChunk + 64 * colh, v0);
-        tmem_ld32(t_lane + acc * kChunk + 64 * colh + 32, v1);
+        const int k0 = chunk_of(it) * kChunk + kCols * cs;
+        uint32_t v[32];
+        tmem_ld32(t_lane + acc * kChunk, v);
+        // the bias of these 32 classes while the TMEM load is in flight
+        float4 b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + i);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
-        float y[64];
-        float cm = -CUDART_INF_F;
+        float2 y[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + i);
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 32) + i);
-          y[4 * i] = __uint_as_float(v0[4 * i]) + b0.x, y[4 * i + 1] = __uint_as_float(v0[4 * i + 1]) + b0.y;
-          y[4 * i + 2] = __uint_as_float(v0[4 * i + 2]) + b0.z, y[4 * i + 3] = __uint_as_float(v0[4 * i + 3]) + b0.w;
-          y[32 + 4 * i] = __uint_as_float(v1[4 * i]) + b1.x, y[32 + 4 * i + 1] = __uint_as_float(v1[4 * i + 1]) + b1.y;
-          y[32 + 4 * i + 2] = __uint_as_float(v1[4 * i + 2]) + b1.z, y[32 + 4 * i + 3] = __uint_as_float(v1[4 * i + 3]) + b1.w;
+          y[2 * i] = __fadd2_rn(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), make_float2(b[i].x, b[i].y));
+          y[2 * i + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), make_float2(b[i].z, b[i].w));
         }
+        float cm = fmaxf(y[0].x, y[0].y);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) cm = fmaxf(cm, y[i]);
+        for (int i = 1; i < 16; ++i) cm = fmaxf(cm, fmaxf(y[i].x, y[i].y));
         const float mn = fmaxf(m, cm);
         s *= ex2(m - mn);
         m = mn;
-        float acc_s = 0.f;
+        const float2 nm = make_float2(-m, -m);
+        float2 part[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int i = 0; i < 64; ++i) acc_s += ex2(y[i] - m);
-        s += acc_s;
+        for (int i = 0; i < 16; ++i) {
+          const float2 d = __fadd2_rn(y[i], nm);
+          part[i & 1] = __fadd2_rn(part[i & 1], make_float2(ex2(d.x), ex2(d.y)));
+        }
+        s += (part[0].x + part[0].y) + (part[1].x + part[1].y);
       }
-      C.stat_m[colh][erow] = m;
-      C.stat_s[colh][erow] = s;
-      epi_bar();  // both halves of every row are in; the previous tile's lists have been scored and reset
-      const float m0 = C.stat_m[0][erow], m1 = C.stat_m[1][erow];
-      const float M2 = fmaxf(m0, m1);
-      const float S = fmaf(C.stat_s[0][erow], ex2(m0 - M2), C.stat_s[1][erow] * ex2(m1 - M2));
+      C.stat_m[cs][erow] = m;
+      C.stat_s[cs][erow] = s;
+      epi_bar();  // all parts of every row are in; the previous tile's lists have been scored and reset
+      float M2 = C.stat_m[0][erow];
+#pragma unroll
+      for (int c = 1; c < kColSplit; ++c) M2 = fmaxf(M2, C.stat_m[c][erow]);
+      float S = 0.f;
+#pragma unroll
+      for (int c = 0; c < kColSplit; ++c) S = fmaf(C.stat_s[c][erow], ex2(C.stat_m[c][erow] - M2), S);
       const float rS = __frcp_rn(S);
 
       // ---------------- per-row posterior coefficients and thinning thresholds ----------------
@@ -512,55 +536,74 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       rm.init(cf, masked, pj, j, p.K);
       const ThinRule thin(rm, thin_c);
       const float thrA = rS * thin.scaleA;
-      if (colh == 0) {
+      if (cs == 0) {
         RowInfo ri;
         ri.A = rm.A, ri.Bc = rm.Bc, ri.Pj = rm.Pj, ri.PK = rm.PK, ri.accept = thin.accept;
         ri.j = j, ri.rel = 0, ri.pad = 0;
         C.info[erow] = ri;
       }
       const uint64_t grow = static_cast<uint64_t>(p.row_offset + lrow);
+      const float2 nM2 = make_float2(-M2, -M2), tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
 
       // ---------------- pass 2: regenerate the logits, thinned race, survivors to the row's list ----------------
+      // The noise (integer pipe) is generated one group of eight classes AHEAD of the exponentials (MUFU pipe) that
+      // consume it, in the same basic block, so that the two pipes overlap inside every warp.
+      auto coarse_of = [&](int pr_, int c8_) {
+        const int kk = chunk_of(2 * pr_) * kChunk + kCols * cs;
+        return rng.coarse(NoiseStream::coarse_call_of_chunk(static_cast<uint32_t>(kk >> 2) + c8_), grow);
+      };
+      uint4 cw_next = coarse_of(0, 0);
       for (int pr = 0; pr < NCH / 2; ++pr) {
         const int itA = NCH + 2 * pr, itB = itA + 1;
         const int accA = itA & 3, accB = itB & 3;
-        mbar_wait(&C.acc_full[accA], static_cast<uint32_t>((itA >> 2) & 1));
-        mbar_wait(&C.acc_full[accB], static_cast<uint32_t>((itB >> 2) & 1));
+        // classes k0 .. k0+31 from the first chunk of the pair and the same + 512 from the second (chunk_of(2 pr + 1) =
+        // chunk_of(2 pr) + 4): one Philox call serves four classes of each
+        const int k0 = chunk_of(2 * pr) * kChunk + kCols * cs;
+        mbar_wait_sleep(&C.acc_full[accA], static_cast<uint32_t>((itA >> 2) & 1));
+        mbar_wait_sleep(&C.acc_full[accB], static_cast<uint32_t>((itB >> 2) & 1));
         tc_fence_after();
-        const int kA = chunk_of(2 * pr) * kChunk + 64 * colh;  // chunk_of(2 pr + 1) = chunk_of(2 pr) + 4: classes + 512
-#pragma unroll 1
-        for (int sb = 0; sb < 2; ++sb) {
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_lane + accA * kChunk + 64 * colh + 32 * sb, va);
-          tmem_ld32(t_lane + accB * kChunk + 64 * colh + 32 * sb, vb);
-          tmem_ld_wait();
-          if (sb == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&C.acc_empty[accA]), mbar_arrive(&C.acc_empty[accB]);
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_lane + accA * kChunk, va);
+        tmem_ld32(t_lane + accB * kChunk, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&C.acc_empty[accA]), mbar_arrive(&C.acc_empty[accB]);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint4 cw = cw_next;
+          if (c8 < 7) cw_next = coarse_of(pr, c8 + 1);
+          else if (pr + 1 < NCH / 2) cw_next = coarse_of(pr + 1, 0);
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + c8);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 512) + c8);
+          float2 e[4], d[4];
+          e[0] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(va[4 * c8]), __uint_as_float(va[4 * c8 + 1])), make_float2(ba.x, ba.y)), nM2);
+          e[1] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(va[4 * c8 + 2]), __uint_as_float(va[4 * c8 + 3])), make_float2(ba.z, ba.w)), nM2);
+          e[2] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vb[4 * c8]), __uint_as_float(vb[4 * c8 + 1])), make_float2(bb.x, bb.y)), nM2);
+          e[3] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vb[4 * c8 + 2]), __uint_as_float(vb[4 * c8 + 3])), make_float2(bb.z, bb.w)), nM2);
+          const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+          float slack = -1.0f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            e[w] = make_float2(ex2(e[w].x), ex2(e[w].y));
+            // the 16-bit halves spliced under the exponent of -1.0f: -(1 + h 2^-23)
+            const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
+                                          __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
+            d[w] = __ffma2_rn(e[w], tA2, __fadd2_rn(tB2, nf));
+            slack = fmaxf(slack, fmaxf(d[w].x, d[w].y));
           }
-          const int k0 = kA + 32 * sb;
+          if (slack >= 0.0f && live) {  // ~1 % of the lanes: some class of the eight survives
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const uint32_t cq = static_cast<uint32_t>(k0 >> 2) + c8;
-            const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(cq), grow);
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + c8);
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 512) + c8);
-            const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+            for (int w = 0; w < 4; ++w)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float ea = ex2((__uint_as_float(va[4 * c8 + e]) + bav[e]) - M2);
-              const float eb = ex2((__uint_as_float(vb[4 * c8 + e]) + bbv[e]) - M2);
-              const uint32_t ha = NoiseStream::half_of(cw, e), hb = NoiseStream::half_of(cw, 4 + e);
-              if (live && __uint_as_float(0x3f800000u | ha) <= fmaf(ea, thrA, thin.thrB)) {
-                const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
-                if (pos < static_cast<uint32_t>(kCand)) C.cand_k[erow][pos] = k0 + 4 * c8 + e, C.cand_p[erow][pos] = ea * rS;
-              }
-              if (live && __uint_as_float(0x3f800000u | hb) <= fmaf(eb, thrA, thin.thrB)) {
-                const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
-                if (pos < static_cast<uint32_t>(kCand)) C.cand_k[erow][pos] = k0 + 512 + 4 * c8 + e, C.cand_p[erow][pos] = eb * rS;
-              }
-            }
+              for (int hl = 0; hl < 2; ++hl)
+                if ((hl ? d[w].y : d[w].x) >= 0.0f) {
+                  const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
+                  if (pos < static_cast<uint32_t>(kCand)) {
+                    C.cand_k[erow][pos] = k0 + 4 * c8 + (w >> 1) * 512 + 2 * (w & 1) + hl;
+                    C.cand_p[erow][pos] = (hl ? e[w].y : e[w].x) * rS;
+                  }
+                }
           }
         }
       }

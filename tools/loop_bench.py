@@ -51,13 +51,26 @@ model = d3pm_b200.FusedDiffusionTransformer(transformer=den, diffusion_step=T, a
                                             guidance_scale=2.0, content_seq_len=N).to(dev)
 cond, cf = torch.randn(B, 1, 512, device=dev), torch.zeros(B, 1, 512, device=dev)
 
-model.manual_seed(1).sample(["x"] * B, None, cond, cf, filter_ratio=0)  # warm-up (allocator, table)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-out = model.manual_seed(2).sample(["x"] * B, None, cond, cf, filter_ratio=0)["content_token"]
-torch.cuda.synchronize()
-total = time.perf_counter() - t0
-assert out.shape == (B, N) and int(out.max()) < K, "a finished chain holds no [MASK]"
+def chain():
+    model.manual_seed(1).sample(["x"] * B, None, cond, cf, filter_ratio=0)  # warm-up (allocator, table)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = model.manual_seed(2).sample(["x"] * B, None, cond, cf, filter_ratio=0)["content_token"]
+    torch.cuda.synchronize()
+    total = time.perf_counter() - t0
+    assert out.shape == (B, N) and int(out.max()) < K, "a finished chain holds no [MASK]"
+    return total, out
+
+
+total, out = chain()
+if K in (1024, 2048, 4096):  # the head folded into the update kernel (logits never written)
+    model.enable_fused_head()
+    assert model.fused_head_active
+    total_f, out_f = chain()
+    model.enable_fused_head(False)
+    print(f"chain with the fused head (d3pm_head_step): {total_f * 1e3:.1f} ms total, {total_f / T * 1e3:.3f} ms/step, "
+          f"{B * N * T / total_f / 1e6:.1f} M token-updates/s through sample(); first-step agreement with the unfused chain "
+          f"is covered by tests/test_gpu_head.py (chains diverge after the first near-tie)")
 
 # the update alone on the same shapes, for the split
 x = torch.full((B, N), K, dtype=torch.int64, device=dev)
