@@ -8,6 +8,7 @@
 #include "d3pm_step_rows.cuh"
 #include "d3pm_step_stream.cuh"
 #include "d3pm_train_rows.cuh"
+#include "d3pm_train_stream.cuh"
 #include "d3pm_head_step.cuh"
 
 namespace {
@@ -248,14 +249,15 @@ int d3pm_train_rows(const d3pm_train_desc* d) {
     return fail(D3PM_ERR_ALIGN, "train_rows: logits rows need pitch >= K, pitch %% 4 == 0, 16-byte base");
   const int64_t rows = static_cast<int64_t>(d->B) * d->N;
   if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "train_rows: B*N too large");
-  if (d->backward) {
+  if (d->backward < 0 || d->backward > 2) return fail(D3PM_ERR_INVALID, "train_rows: backward must be 0, 1 or 2");
+  if (d->backward != 0) {
     if (d->grad == nullptr || d->w_main == nullptr || d->w_aux == nullptr)
-      return fail(D3PM_ERR_INVALID, "train_rows: backward needs grad, w_main and w_aux");
+      return fail(D3PM_ERR_INVALID, "train_rows: the gradient needs grad, w_main and w_aux");
     if (d->pitch_grad < d->K || d->pitch_grad % 4 != 0 || !aligned16(d->grad))
       return fail(D3PM_ERR_ALIGN, "train_rows: grad rows need pitch >= K, pitch %% 4 == 0, 16-byte base");
-  } else if (d->tok_main == nullptr || d->tok_aux == nullptr) {
-    return fail(D3PM_ERR_INVALID, "train_rows: forward needs tok_main and tok_aux");
   }
+  if (d->backward != 1 && (d->tok_main == nullptr || d->tok_aux == nullptr))
+    return fail(D3PM_ERR_INVALID, "train_rows: the forward outputs need tok_main and tok_aux");
   d3pm::TrainParams p;
   p.logits = d->logits, p.x0 = d->x0, p.x_t = d->x_t, p.t = d->t, p.coef_table = d->coef_table;
   p.w_main = d->w_main, p.w_aux = d->w_aux, p.tok_main = d->tok_main, p.tok_aux = d->tok_aux;
@@ -264,12 +266,31 @@ int d3pm_train_rows(const d3pm_train_desc* d) {
   p.mask_weight_masked = d->mask_weight_masked, p.mask_weight_unmasked = d->mask_weight_unmasked;
   p.rows = rows;
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+  if (d3pm::train_stream_supports(p) && (d->x0_recon == nullptr) == (d->xtm1_recon == nullptr)) {
+    if (d->backward == 1) p.tok_main = nullptr, p.tok_aux = nullptr, p.x0_recon = nullptr, p.xtm1_recon = nullptr;
+    const int rc = d3pm::launch_train_stream(p, d->backward != 0, s);
+    if (rc != D3PM_OK) return fail(rc, "train_rows: stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return check_launch("train_rows(stream)");
+  }
   const int chunks = (d->K / 4 + d3pm::kRowThreads - 1) / d3pm::kRowThreads;
-  if (chunks <= 1) launch_train<1>(p, d->backward != 0, s);
-  else if (chunks <= 2) launch_train<2>(p, d->backward != 0, s);
-  else if (chunks <= 4) launch_train<4>(p, d->backward != 0, s);
-  else launch_train<8>(p, d->backward != 0, s);
+  for (int pass = 0; pass < 2; ++pass) {  // one CTA per row: forward and gradient are separate launches
+    const bool bwd = pass == 1;
+    if ((bwd && d->backward == 0) || (!bwd && d->backward == 1)) continue;
+    if (chunks <= 1) launch_train<1>(p, bwd, s);
+    else if (chunks <= 2) launch_train<2>(p, bwd, s);
+    else if (chunks <= 4) launch_train<4>(p, bwd, s);
+    else launch_train<8>(p, bwd, s);
+  }
   return check_launch("train_rows");
+}
+
+int d3pm_scale_rows(float* rows, int64_t pitch, const float* factor, int B, int N, int K, d3pm_stream_t stream) {
+  if (rows == nullptr || factor == nullptr || B <= 0 || N <= 0 || K <= 0 || K % 4 != 0 || pitch < K || pitch % 4 != 0 || !aligned16(rows))
+    return fail(D3PM_ERR_INVALID, "scale_rows: bad arguments");
+  const int64_t n = static_cast<int64_t>(B) * N;
+  if (n > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "scale_rows: B*N too large");
+  d3pm::scale_rows_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, pitch, factor, N, K);
+  return check_launch("scale_rows");
 }
 
 int64_t d3pm_head_image_floats(int K, int D) {

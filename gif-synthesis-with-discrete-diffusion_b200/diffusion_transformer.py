@@ -574,8 +574,12 @@ class FusedDiffusionTransformer(nn.Module):
             aux_w = (extra * self.auxiliary_loss_weight).float()
         else:
             aux_w = torch.zeros_like(pt)
+        # d(final loss) / d(vb_loss[b]) as the caller will apply it (`forward` divides the sum by B N, :546): lets the
+        # kernel write the final gradient in the same pass as the loss
+        grad_scale, self._loss_grad_scale = getattr(self, "_loss_grad_scale", 1.0), 1.0
         vb_loss, kl_loss, x0_recon, xt_1_recon = train.VBLoss.apply(
-            out, x_start, xt, t, pt.float(), aux_w, self.coef_table(), tuple(self.mask_weight), self._status_word())
+            out, x_start, xt, t, pt.float(), aux_w, self.coef_table(), tuple(self.mask_weight), self._status_word(),
+            grad_scale)
 
         # running accuracy lists (:407-417): one device->host copy instead of 2B `.item()` syncs
         with torch.no_grad():
@@ -610,6 +614,7 @@ class FusedDiffusionTransformer(nn.Module):
             cond_emb = input["condition_embed_token"].float()
         if not is_train:
             raise NotImplementedError("forward(is_train=False) leaves every output undefined in the reference (:552-565)")
+        self._loss_grad_scale = 1.0 / (sample_image.size()[0] * sample_image.size()[1])
         log_model_prob, loss, sample_image_recon = self._train_loss(sample_image, cond_emb,
                                                                     need_log_model_prob=return_logits)
         loss = loss.sum() / (sample_image.size()[0] * sample_image.size()[1])

@@ -36,6 +36,8 @@ def _logit_rows(logits_bkn: torch.Tensor) -> Tuple[torch.Tensor, int]:
 
 def _train_rows(rows, pitch, x0, x_t, t, coef_table, mask_weight, *, backward, w_main=None, w_aux=None,
                 want_recon=False, status=None):
+    """`d3pm_train_rows`: backward False / 0 = losses, True / 1 = gradient, 2 = both in one pass over the logits."""
+    backward = int(backward)
     dev = ops._need_cuda(rows, x0, x_t, t, coef_table, w_main, w_aux, status)
     B, N, K = rows.shape
     d = _lib.TrainDesc()
@@ -46,11 +48,12 @@ def _train_rows(rows, pitch, x0, x_t, t, coef_table, mask_weight, *, backward, w
     d.status = ops._ptr(status)
     d.stream = ops._stream(dev)
     out = {}
+    d.backward = backward
     if backward:
         out["grad"] = torch.empty(B, N, K, dtype=torch.float32, device=dev)
-        d.grad, d.pitch_grad, d.backward = out["grad"].data_ptr(), K, 1
+        d.grad, d.pitch_grad = out["grad"].data_ptr(), K
         d.w_main, d.w_aux = w_main.data_ptr(), w_aux.data_ptr()
-    else:
+    if backward != 1:
         out["tok_main"] = torch.empty(B, N, dtype=torch.float32, device=dev)
         out["tok_aux"] = torch.empty(B, N, dtype=torch.float32, device=dev)
         d.tok_main, d.tok_aux = out["tok_main"].data_ptr(), out["tok_aux"].data_ptr()
@@ -63,20 +66,43 @@ def _train_rows(rows, pitch, x0, x_t, t, coef_table, mask_weight, *, backward, w
     return out
 
 
+def scale_rows(rows: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
+    """rows[b, n, :] *= factor[b] in place (d3pm_scale_rows); videos whose factor is exactly 1 cost nothing."""
+    dev = ops._need_cuda(rows, factor)
+    B, N, K = rows.shape
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_scale_rows(rows.data_ptr(), rows.stride(1), factor.contiguous().data_ptr(), B, N, K, ops._stream(dev)),
+               "d3pm_scale_rows")
+    return rows
+
+
 class VBLoss(torch.autograd.Function):
     """vb_loss[b] = kl_loss[b] / pt[b] + aux_w[b] * aux[b] / pt[b]   (:431-455), differentiable in the logits.
 
-    forward reads the logits once and returns (vb_loss [B], kl_loss [B], x0_recon [B,N], xtm1_recon [B,N]);
-    backward reads them once more and writes the gradient rows — no `[B, K+1, N]` intermediate is ever stored.
+    When the logits require grad, forward makes ONE pass over them that yields the losses AND the gradient rows for the
+    upstream gradient the caller announces (`grad_scale`: d(final loss)/d(vb_loss[b]), e.g. 1 / (B N) for the reference's
+    `loss.sum() / (B N)`, :546); backward then only rescales the videos whose true upstream gradient differs from it
+    (none in the reference's training loop).  No `[B, K+1, N]` intermediate is ever stored.  A gradient flowing into the
+    second output (kl_loss) takes the explicit recomputation path.
     """
 
     @staticmethod
-    def forward(ctx, logits_bkn, x0, x_t, t, pt, aux_w, coef_table, mask_weight, status):
+    def forward(ctx, logits_bkn, x0, x_t, t, pt, aux_w, coef_table, mask_weight, status, grad_scale=1.0):
         if logits_bkn.dim() != 3 or logits_bkn.dtype != torch.float32:
             raise D3PMError("logits must be float32 [B, K, N]")
         rows, pitch = _logit_rows(logits_bkn.detach())
         x0, x_t, t = x0.contiguous(), x_t.contiguous(), t.contiguous()
-        out = _train_rows(rows, pitch, x0, x_t, t, coef_table, mask_weight, backward=False, want_recon=True, status=status)
+        fused = bool(ctx.needs_input_grad[0])
+        ctx.set_materialize_grads(False)  # an unused output (kl_loss is only read detached) arrives as None in backward
+        ctx.grad_scale, ctx.grad = float(grad_scale), None
+        if fused:
+            w_main = (ctx.grad_scale / pt).float().contiguous()
+            w_aux = (ctx.grad_scale * aux_w / pt).float().contiguous()
+            out = _train_rows(rows, pitch, x0, x_t, t, coef_table, mask_weight, backward=2, w_main=w_main, w_aux=w_aux,
+                              want_recon=True, status=status)
+            ctx.grad = out["grad"]
+        else:
+            out = _train_rows(rows, pitch, x0, x_t, t, coef_table, mask_weight, backward=0, want_recon=True, status=status)
         kl_loss = out["tok_main"].sum(1)
         aux = out["tok_aux"].sum(1)
         vb = kl_loss / pt + aux_w * aux / pt
@@ -89,8 +115,12 @@ class VBLoss(torch.autograd.Function):
     def backward(ctx, g_vb, g_kl, _g0, _g1):
         rows, x0, x_t, t, pt, aux_w, coef_table = ctx.saved_tensors
         g_vb = torch.zeros_like(pt) if g_vb is None else g_vb
+        if ctx.grad is not None and g_kl is None:
+            grad, ctx.grad = ctx.grad, None  # consumed: a second backward would need retain_graph semantics anyway
+            scale_rows(grad, (g_vb / ctx.grad_scale).float())
+            return grad.permute(0, 2, 1), None, None, None, None, None, None, None, None, None
         w_main = (g_vb / pt + (0 if g_kl is None else g_kl)).float().contiguous()
         w_aux = (g_vb * aux_w / pt).float().contiguous()
-        out = _train_rows(rows, ctx.pitch, x0, x_t, t, coef_table, ctx.mask_weight, backward=True, w_main=w_main,
+        out = _train_rows(rows, ctx.pitch, x0, x_t, t, coef_table, ctx.mask_weight, backward=1, w_main=w_main,
                           w_aux=w_aux, status=ctx.status)
-        return out["grad"].permute(0, 2, 1), None, None, None, None, None, None, None, None
+        return out["grad"].permute(0, 2, 1), None, None, None, None, None, None, None, None, None

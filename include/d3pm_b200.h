@@ -159,7 +159,11 @@ int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float
  * tokens x_t (from q_sample, :361-366) and t; and its gradient with respect to the logits.
  *   backward == 0: writes per-token tok_main / tok_aux (the caller sums them per video: kl_loss = sum tok_main,
  *                  vb_loss = kl_loss / pt + aux_weight * sum tok_aux / pt) and, optionally, x0_recon / xtm1_recon.
- *   backward == 1: recomputes the row and writes grad[row][k] = d( sum_b w_main[b] main_b + w_aux[b] auxc_b ) / d logits. */
+ *   backward == 1: recomputes the row and writes grad[row][k] = d( sum_b w_main[b] main_b + w_aux[b] auxc_b ) / d logits.
+ *   backward == 2: both in ONE pass over the logits (forward outputs and the gradient for the given weights): the
+ *                  training step's minimum of 16 KiB read + 16 KiB written per token.  A caller that learns the true
+ *                  upstream gradient later rescales per video with d3pm_scale_rows (free when the factor is 1).
+ * K in {1024, 2048, 4096} with >= 2048 rows runs the persistent TMA-pipelined kernel, other shapes one CTA per row.  */
 typedef struct d3pm_train_desc {
   const float* logits;   /* [B*N][pitch] denoiser logits (first K valid) */
   const int64_t* x0;     /* [B*N] in [0, K) */
@@ -182,6 +186,9 @@ typedef struct d3pm_train_desc {
 } d3pm_train_desc;
 
 int d3pm_train_rows(const d3pm_train_desc* desc);
+
+/* rows[b*N + n][0..K) *= factor[b]; videos whose factor is exactly 1.0f are skipped without touching memory. */
+int d3pm_scale_rows(float* rows, int64_t pitch, const float* factor, int B, int N, int K, d3pm_stream_t stream);
 
 /* ---------------------------------------------------------------- fused denoiser head + reverse step
  * Replaces the reference's prediction head `to_logits = LayerNorm(n_embd) + Linear(n_embd -> K)`

@@ -133,3 +133,71 @@ def test_unsupported_training_inputs_fail_loudly():
     m({"content_token": bad}, return_loss=True, return_logits=False)
     with pytest.raises(AssertionError):
         m.check_status()
+
+
+@pytest.mark.parametrize("K,scale", [(4096, 1.0), (4096, 9.0), (1024, 3.0)])
+def test_stream_kernel_equals_row_kernel(K, scale):
+    """The persistent TMA-pipelined training kernel (>= 2048 rows, K in {1024, 2048, 4096}: losses and gradient in one
+    pass) against the one-CTA-per-row kernel (which the fixtures above pin to the reference), video by video."""
+    from d3pm_b200 import train
+    T, B, N = 100, 3, 1024
+    g = torch.Generator().manual_seed(K + int(scale))
+    logits = (torch.randn(B, N, K, generator=g) * scale)
+    if scale > 5:  # peaked rows: both clamps fire
+        logits[:, ::7, 5] += 200.0
+    logits = logits.to(DEV)
+    x0 = torch.randint(0, K, (B, N), generator=g).to(DEV)
+    t = torch.tensor([0, 37, 99]).to(DEV)
+    m = _model(K, T, N, logits)
+    x_t = m.q_sample_tokens(x0, t)
+    x_t[1, :50] = x0[1, :50]  # unmasked positions that kept their token
+    table = m.coef_table()
+    w_main = torch.tensor([0.7, 1.3, 0.01], device=DEV)
+    w_aux = torch.tensor([0.2, 0.0, 0.5], device=DEV)
+    both = train._train_rows(logits, K, x0, x_t, t, table, (1.0, 0.5), backward=2, w_main=w_main, w_aux=w_aux, want_recon=True)
+    for b in range(B):  # one video = 1024 rows: below the stream kernel's threshold, so these run the row kernel
+        sl = slice(b, b + 1)
+        f = train._train_rows(logits[sl].contiguous(), K, x0[sl].contiguous(), x_t[sl].contiguous(), t[sl].contiguous(), table,
+                              (1.0, 0.5), backward=0, want_recon=True)
+        gr = train._train_rows(logits[sl].contiguous(), K, x0[sl].contiguous(), x_t[sl].contiguous(), t[sl].contiguous(), table,
+                               (1.0, 0.5), backward=1, w_main=w_main[sl].contiguous(), w_aux=w_aux[sl].contiguous())
+        for name in ("tok_main", "tok_aux"):
+            a, w = both[name][sl], f[name]
+            assert (a - w).abs().max() <= 2e-5 * w.abs().max() + 1e-6, (name, b)
+        assert torch.equal(both["x0_recon"][sl], f["x0_recon"])
+        assert (both["xtm1_recon"][sl] != f["xtm1_recon"]).float().mean() <= 0.002  # exact ties of clamped classes aside
+        gw = gr["grad"]
+        assert (both["grad"][sl] - gw).abs().max() <= 3e-5 * gw.abs().max() + 1e-9, b
+    fwd = train._train_rows(logits, K, x0, x_t, t, table, (1.0, 0.5), backward=0, want_recon=True)
+    assert torch.equal(fwd["tok_main"], both["tok_main"]) and torch.equal(fwd["x0_recon"], both["x0_recon"])
+    only = train._train_rows(logits, K, x0, x_t, t, table, (1.0, 0.5), backward=1, w_main=w_main, w_aux=w_aux)
+    assert torch.equal(only["grad"], both["grad"])
+
+
+def test_upstream_gradient_other_than_announced():
+    """`forward` announces d loss / d vb = 1 / (B N); a caller that scales the loss afterwards still gets the right gradient
+    (d3pm_scale_rows), and one that uses vb_loss directly goes through the same route."""
+    T, K, B, N = 100, 1024, 2, 1024
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(B, N, K, generator=g).to(DEV)
+    x0 = torch.randint(0, K, (B, N), generator=g).to(DEV)
+    tt, pt = torch.tensor([20, 70], device=DEV), torch.tensor([0.01, 0.02], device=DEV)
+    grads = []
+    for factor in (1.0, 3.0):
+        logits = base.clone().requires_grad_(True)
+        m = _model(K, T, N, logits, aux=1e-3)
+        m.sample_time = lambda b, device, method="uniform": (tt, pt)
+        m.manual_seed(5)
+        out = m({"content_token": x0, "condition_embed_token": torch.ones(B, 1, 512, device=DEV)}, return_loss=True, return_logits=False)
+        (out["loss"] * factor).backward()
+        grads.append(logits.grad.clone())
+    assert (grads[1] - 3.0 * grads[0]).abs().max() <= 1e-6 * grads[0].abs().max()
+    logits = base.clone().requires_grad_(True)
+    m = _model(K, T, N, logits, aux=1e-3)
+    m.sample_time = lambda b, device, method="uniform": (tt, pt)
+    m.manual_seed(5)
+    _, vb, _ = m._train_loss(x0, torch.ones(B, 1, 512, device=DEV), need_log_model_prob=False)
+    (vb * torch.tensor([1.0, 0.25], device=DEV)).sum().backward()
+    want = grads[0] * (B * N)
+    want[1] *= 0.25
+    assert (logits.grad - want).abs().max() <= 2e-6 * want.abs().max()

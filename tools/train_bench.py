@@ -51,7 +51,12 @@ def bwd():
     return train._train_rows(logits, K, x0, x_t, t, table, (1, 1), backward=True, w_main=w, w_aux=w)
 
 
-for name, fn, nbytes in (("forward", fwd, B * N * K * 4), ("backward", bwd, 2 * B * N * K * 4)):
+def both():
+    return train._train_rows(logits, K, x0, x_t, t, table, (1, 1), backward=2, w_main=w, w_aux=w, want_recon=True)
+
+
+for name, fn, nbytes in (("forward (losses, arg-maxes)", fwd, B * N * K * 4), ("gradient only", bwd, 2 * B * N * K * 4),
+                         ("forward + gradient, one pass", both, 2 * B * N * K * 4)):
     for _ in range(3):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
