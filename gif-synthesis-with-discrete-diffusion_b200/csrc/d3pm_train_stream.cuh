@@ -92,20 +92,21 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     const float c_x0 = rowbuf[x0], c_j = masked ? 0.f : rowbuf[j];
 
     // ---- exchange 1: (max, sum of exponentials relative to the thread-local max) and the arg-max of the logits ----
-    float m = x[0][0];
+    float m = x[0][0], lo = x[0][0];
 #pragma unroll
     for (int i = 0; i < NC; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) m = fmaxf(m, x[i][c]);
+      for (int c = 0; c < 4; ++c) m = fmaxf(m, x[i][c]), lo = fminf(lo, x[i][c]);
     unsigned long long kbest = 0ull;
+    uint32_t idx = 0;
     if (want_arg) {  // first class (lowest index) that attains the thread-local maximum
-      uint32_t idx = 0;
 #pragma unroll
       for (int i = NC - 1; i >= 0; --i)
 #pragma unroll
         for (int c = 3; c >= 0; --c) idx = (x[i][c] == m) ? 4u * (128u * i + tg) + c : idx;
       kbest = pack_key(m, idx);
     }
+    const float e_top = ex2(fmaf(m, kLog2e, -to_log2_units(fmaxf(m, -3.0e38f))));  // numerator of the thread's best class
     m = fmaxf(m, -3.0e38f);
     const float m2 = to_log2_units(m);
     float e[NC][4];
@@ -121,17 +122,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       const float mw = warp_max(m);
       const float mw2 = to_log2_units(mw);
       const float sw = warp_sum(sloc * ex2(m2 - mw2));
+      const float lw = warp_min(lo);
       if (want_arg) kbest = warp_max_u64(kbest);
       if (lane == 0) {
-        S.red[0][warp] = mw, S.red[0][kGroupWarps + warp] = sw;
+        S.red[0][warp] = mw, S.red[0][kGroupWarps + warp] = sw, S.red[0][2 * kGroupWarps + warp] = lw;
         if (want_arg) S.keys[0][warp] = kbest;
       }
     }
     sync();  // everyone has drained the stage and published its partials
     if (tg == 0 && row + 2 * G < rows) issue_row(row + 2 * G, st);
-    float M, Ssum;
+    float M, Ssum, xmin;
     {
-      const float4 mw = lds4(S.red[0]), sw = lds4(S.red[0] + kGroupWarps);
+      const float4 mw = lds4(S.red[0]), sw = lds4(S.red[0] + kGroupWarps), lw = lds4(S.red[0] + 2 * kGroupWarps);
+      xmin = fminf(fminf(lw.x, lw.y), fminf(lw.z, lw.w));
       M = fmaxf(fmaxf(mw.x, mw.y), fmaxf(mw.z, mw.w));
       const float M2g = to_log2_units(M);
       Ssum = fmaf(sw.x, ex2(to_log2_units(mw.x) - M2g),
@@ -179,30 +182,55 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     // "open" <=> log-softmax_k >= -70 <=> softmax_k >= exp(-70): decided on the softmax value, so the logits themselves
     // are dead after the first sweep (registers: numerators e and reciprocals inv only)
     float inv[NC][4];
+    // Clamp-free fast path (row-uniform): when no log-softmax entry can reach -70 (smallest logit of the row) and every
+    // generic P_k = p_k A + Bc lies in [exp(-70), 1] (Bc and A + Bc say so), none of the clamps of :236 / :283 can fire for
+    // a generic class: the sweep needs no predicates, and the posterior arg-max is the logits' arg-max.
+    const bool fast = ((xmin - M) - lnS >= kClampLo + 1.0e-3f) && (Bc >= 1.01f * kPFloor) && (cf.A + Bc <= 0.9999f) &&
+                      (cf.A >= 0.f);
+    if (fast) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
+      for (int i = 0; i < NC; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float sm = e[i][c] * r;
-        const float pk = fminf(fmaxf(sm, kPFloor), 1.0f);
-        const float Pk = fmaf(pk, cf.A, Bc);
-        const float lp = lg2(Pk) * kLn2;
-        const float Mk = fminf(fmaxf(lp, kClampLo), 0.0f);
-        sumM += Mk;
-        if (WRITE_GRAD) {
-          const bool inside = (lp >= kClampLo) && (lp <= 0.0f), open = sm >= kPFloor;
-          const float iv = inside ? rcp_fast(Pk) : 0.f;
-          inv[i][c] = iv;
-          sInv += iv;
-          sPP += open ? pk * iv : 0.f;
-          sP += open ? pk : 0.f;
+        for (int c = 0; c < 4; ++c) {
+          const float sm = e[i][c] * r;
+          const float Pk = fmaf(sm, cf.A, Bc);
+          sumM = fmaf(lg2(Pk), kLn2, sumM);
+          if (WRITE_GRAD) {
+            const float iv = rcp_fast(Pk);
+            inv[i][c] = iv;
+            sInv += iv;
+            sPP = fmaf(sm, iv, sPP);
+            sP += sm;
+          }
         }
-        if (want_arg) {  // strict ">" keeps the lowest class of a tie inside the thread (classes ascend with i, c)
-          const bool better = Mk > post_best;
-          post_best = better ? Mk : post_best;
-          post_idx = better ? 4u * (128u * i + tg) + c : post_idx;
+      post_best = log_prob_clamped(fmaf(fminf(e_top * r, 1.0f), cf.A, Bc));
+      post_idx = idx;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float sm = e[i][c] * r;
+          const float pk = fminf(fmaxf(sm, kPFloor), 1.0f);
+          const float Pk = fmaf(pk, cf.A, Bc);
+          const float lp = lg2(Pk) * kLn2;
+          const float Mk = fminf(fmaxf(lp, kClampLo), 0.0f);
+          sumM += Mk;
+          if (WRITE_GRAD) {
+            const bool inside = (lp >= kClampLo) && (lp <= 0.0f), open = sm >= kPFloor;
+            const float iv = inside ? rcp_fast(Pk) : 0.f;
+            inv[i][c] = iv;
+            sInv += iv;
+            sPP += open ? pk * iv : 0.f;
+            sP += open ? pk : 0.f;
+          }
+          if (want_arg) {  // strict ">" keeps the lowest class of a tie inside the thread (classes ascend with i, c)
+            const bool better = Mk > post_best;
+            post_best = better ? Mk : post_best;
+            post_idx = better ? 4u * (128u * i + tg) + c : post_idx;
+          }
         }
-      }
+    }
     if (want_arg) kpost = pack_key(post_best, post_idx);
     // the sweep scored x_t with the generic coefficients: the one thread that owns it redoes its 32 classes
     if (want_arg && !masked && tg == static_cast<int>((j >> 2) & 127u)) {
@@ -300,11 +328,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float sm = e[i][c] * r;
-        const float hk = (sm >= kPFloor) ? fmaf(gA, inv[i][c], WG) : 0.f;  // h_k / p_k, 0 where the recon clamp fired
-        o[c] = fminf(sm, 1.0f) * hk - sm * hsum;
+        if (fast) {
+          o[c] = sm * (fmaf(gA, inv[i][c], WG) - hsum);
+        } else {
+          const float hk = (sm >= kPFloor) ? fmaf(gA, inv[i][c], WG) : 0.f;  // h_k / p_k, 0 where the recon clamp fired
+          o[c] = fminf(sm, 1.0f) * hk - sm * hsum;
+        }
       }
-      if (q == q_x0) o[x0 & 3] = fmaf(-sm_x0, hsum, h_x0);
-      if (q == q_j) o[j & 3] = fmaf(-sm_j, hsum, h_j);
+      if (q == q_x0) {
+        const float v = fmaf(-sm_x0, hsum, h_x0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = ((x0 & 3u) == static_cast<uint32_t>(c)) ? v : o[c];
+      }
+      if (q == q_j) {
+        const float v = fmaf(-sm_j, hsum, h_j);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = ((j & 3u) == static_cast<uint32_t>(c)) ? v : o[c];
+      }
       st_stream4(rg + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
     }
   }
