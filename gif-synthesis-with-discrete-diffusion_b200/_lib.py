@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = (
     "d3pm_q_posterior", "d3pm_gumbel_argmax", "d3pm_tokens_to_log_onehot", "d3pm_argmax_classes",
     "d3pm_to_token_major", "d3pm_q_pred", "d3pm_train_rows", "d3pm_purity_select",
     "d3pm_head_image_floats", "d3pm_head_prepare", "d3pm_head_step", "d3pm_scale_rows",
+    "d3pm_decode_lut", "d3pm_tokens_to_features",
 )
 
 COEF_STRIDE = 32
@@ -130,6 +131,10 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_head_prepare.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.d3pm_head_step.restype = c_int
     lib.d3pm_head_step.argtypes = [POINTER(HeadDesc)]
+    lib.d3pm_decode_lut.restype = c_int
+    lib.d3pm_decode_lut.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.d3pm_tokens_to_features.restype = c_int
+    lib.d3pm_tokens_to_features.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.d3pm_scale_rows.restype = c_int
     lib.d3pm_scale_rows.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.d3pm_train_rows.restype = c_int

@@ -380,6 +380,24 @@ int d3pm_head_step(const d3pm_head_desc* d) {
   return check_launch("head_step(redo)");
 }
 
+int d3pm_decode_lut(const float* codebook, const float* conv_weight, const float* conv_bias, int K, int E, int C, float* lut,
+                    d3pm_stream_t stream) {
+  if (codebook == nullptr || conv_weight == nullptr || lut == nullptr || K <= 0 || E <= 0 || C <= 0 || E > 8192)
+    return fail(D3PM_ERR_INVALID, "decode_lut: bad arguments (K=%d E=%d C=%d)", K, E, C);
+  d3pm::decode_lut_kernel<<<static_cast<unsigned>(K), 256, static_cast<size_t>(E) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      codebook, conv_weight, conv_bias, E, C, lut);
+  return check_launch("decode_lut");
+}
+
+int d3pm_tokens_to_features(const int64_t* tokens, const float* lut, float* out, int B, int N, int K, int C, uint32_t* status,
+                            d3pm_stream_t stream) {
+  if (tokens == nullptr || lut == nullptr || out == nullptr || B <= 0 || N <= 0 || K <= 0 || C <= 0 || B > 65535)
+    return fail(D3PM_ERR_INVALID, "tokens_to_features: bad arguments");
+  const dim3 grid((N + 31) / 32, B);
+  d3pm::tokens_to_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, lut, out, N, K, C, status);
+  return check_launch("tokens_to_features");
+}
+
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N, d3pm_stream_t stream) {
   if (src == nullptr || dst == nullptr || B <= 0 || C <= 0 || N <= 0 || pitch < C || B > 65535)
     return fail(D3PM_ERR_INVALID, "to_token_major: bad arguments");

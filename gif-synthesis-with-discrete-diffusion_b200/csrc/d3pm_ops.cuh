@@ -316,4 +316,57 @@ __global__ void __launch_bounds__(kPurityThreads) purity_select_kernel(
   }
 }
 
+// ---------------------------------------------------------------- token -> video, first stage
+// VQVAE.decode (videogpt_vq_vae.py:53-56) starts with  h = post_vq_conv(shift_dim(F.embedding(tokens, codebook), -1, 1)):
+// a gather of E-dim codebook rows followed by a 1x1x1 convolution E -> C.  Both are per-token and the token takes K
+// values, so they collapse into ONE table  lut[k][c] = sum_e codebook[k][e] w[c][e] + b[c]  (built once per weight version)
+// and the stage becomes a gather that writes the channels-first [B, C, T*H*W] tensor the decoder's convolutions expect.
+__global__ void __launch_bounds__(256) decode_lut_kernel(const float* __restrict__ codebook, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int E, int C, float* __restrict__ lut) {
+  extern __shared__ float srow[];  // the code's embedding
+  const int k = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) srow[e] = codebook[static_cast<size_t>(k) * E + e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* wc = w + static_cast<size_t>(c) * E;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(srow[e], __ldg(wc + e), acc);
+    lut[static_cast<size_t>(k) * C + c] = acc + (b != nullptr ? b[c] : 0.f);
+  }
+}
+
+// out[b][c][n] = lut[tokens[b][n]][c].  One CTA per 32 consecutive positions of a video; 32 x 32 tiles are transposed
+// through shared memory so that both the table reads (along c) and the stores (along n) are coalesced.
+__global__ void __launch_bounds__(256) tokens_to_features_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ lut,
+                                                                 float* __restrict__ out, int N, int K, int C,
+                                                                 uint32_t* __restrict__ status) {
+  __shared__ float tile[32][33];
+  __shared__ int stok[32];
+  const int b = blockIdx.y, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (threadIdx.x < 32) {
+    const int n = n0 + threadIdx.x;
+    long long tk = n < N ? tokens[static_cast<size_t>(b) * N + n] : 0;
+    if (tk < 0 || tk >= K) {  // [MASK] (= K) has no codebook row either
+      if (status != nullptr) atomicOr(status, D3PM_STATUS_BAD_TOKEN);
+      tk = -1;
+    }
+    stok[threadIdx.x] = static_cast<int>(tk);
+  }
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {  // row r = position n0 + r, column tx = channel c0 + tx
+      const int tk = stok[r];
+      tile[r][tx] = (tk >= 0 && c0 + tx < C) ? __ldg(lut + static_cast<size_t>(tk) * C + c0 + tx) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {  // row r = channel c0 + r, column tx = position n0 + tx
+      if (c0 + r < C && n0 + tx < N) out[(static_cast<size_t>(b) * C + c0 + r) * N + n0 + tx] = tile[tx][r];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace d3pm

@@ -236,6 +236,17 @@ typedef struct d3pm_head_desc {
 
 int d3pm_head_step(const d3pm_head_desc* desc);
 
+/* ---------------------------------------------------------------- token -> video, first stage
+ * VQVAE.decode (videogpt_vq_vae.py:53-56): h = post_vq_conv(shift_dim(F.embedding(tokens, codebook.embeddings), -1, 1)).
+ * d3pm_decode_lut folds the codebook [K][E] and the 1x1x1 convolution (weight [C][E], bias [C] nullable) into
+ * lut[K][C] once per weight version; d3pm_tokens_to_features then produces h as [B][C][N] (channels first, N = T*H*W, the
+ * layout the decoder's Conv3d layers take) from the int64 [B][N] tokens this path samples.  Tokens outside [0, K) -- the
+ * [MASK] class included -- set D3PM_STATUS_BAD_TOKEN and give zeros.                                                   */
+int d3pm_decode_lut(const float* codebook, const float* conv_weight, const float* conv_bias, int K, int E, int C, float* lut,
+                    d3pm_stream_t stream);
+int d3pm_tokens_to_features(const int64_t* tokens, const float* lut, float* out, int B, int N, int K, int C,
+                            uint32_t* status, d3pm_stream_t stream);
+
 /* [B, C, N] contiguous (reference layout) -> token-major rows [B*N][pitch]. */
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N,
                         d3pm_stream_t stream);

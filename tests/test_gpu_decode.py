@@ -1,0 +1,62 @@
+"""Token -> video, first stage: the fused codebook gather + 1x1x1 convolution against the reference's op
+sequence `post_vq_conv(shift_dim(F.embedding(tokens, codebook), -1, 1))` (videogpt_vq_vae.py:53-56).  Needs a B200."""
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from d3pm_b200 import decode, ops
+from d3pm_b200._lib import D3PMError
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _autoencoder(K, E, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    conv = torch.nn.Conv3d(E, C, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(C, E, 1, 1, 1, generator=g) * 0.1)
+        conv.bias.copy_(torch.randn(C, generator=g))
+    ae = types.SimpleNamespace()
+    ae.codebook = types.SimpleNamespace(embeddings=torch.randn(K, E, generator=g))
+    ae.post_vq_conv = types.SimpleNamespace(conv=conv)
+    ae.decoder = torch.nn.Identity()
+    return ae
+
+
+def _reference(ae, tokens):  # the reference's own op sequence, on the CPU
+    h = F.embedding(tokens, ae.codebook.embeddings)
+    h = h.permute(0, 4, 1, 2, 3).contiguous()  # shift_dim(h, -1, 1)
+    return ae.post_vq_conv.conv(h)
+
+
+@pytest.mark.parametrize("K,E,C,B,grid", [(4096, 128, 256, 2, (4, 16, 16)), (4096, 128, 256, 1, (16, 16, 16)), (512, 64, 240, 3, (3, 5, 7))])
+def test_fused_gather_conv_matches_reference_ops(K, E, C, B, grid):
+    ae = _autoencoder(K, E, C, 1)
+    tokens = torch.randint(0, K, (B, *grid), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = _reference(ae, tokens)
+    ae_dev = types.SimpleNamespace(codebook=types.SimpleNamespace(embeddings=ae.codebook.embeddings.to(DEV)),
+                                   post_vq_conv=types.SimpleNamespace(conv=ae.post_vq_conv.conv.to(DEV)), decoder=torch.nn.Identity())
+    status = ops.new_status(DEV)
+    table = decode.DecodeTable.from_autoencoder(ae_dev)
+    got = decode.tokens_to_features(table, tokens.to(DEV), status)
+    assert got.shape == want.shape == (B, C, *grid)
+    assert (got.cpu() - want).abs().max() <= 1e-5 * want.abs().max()
+    assert int(status.item()) == 0
+    assert torch.equal(decode.decode(ae_dev, tokens.to(DEV), table), got)  # decoder = Identity here
+
+
+def test_mask_token_is_flagged():
+    ae = _autoencoder(64, 16, 32, 3)
+    ae.codebook.embeddings = ae.codebook.embeddings.to(DEV)
+    ae.post_vq_conv.conv.to(DEV)
+    table = decode.DecodeTable.from_autoencoder(ae)
+    tokens = torch.full((1, 2, 2, 2), 64, dtype=torch.int64, device=DEV)  # [MASK] left in the grid
+    status = ops.new_status(DEV)
+    out = decode.tokens_to_features(table, tokens, status)
+    assert int(status.item()) & 2 and float(out.abs().max()) == 0.0
+    with pytest.raises(D3PMError):
+        decode.DecodeTable(torch.zeros(64, 16, device=DEV), torch.zeros(32, 16, 3, 3, 3, device=DEV), None)
