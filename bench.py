@@ -235,6 +235,14 @@ def run_ours(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
 
+    # ---- beyond the bench line (rank 0, informational; the metric above is untouched): the rows SURVEY §8 marks "next"
+    extras = {}
+    if rank == 0:
+        try:
+            extras = measure_next_rows(dev, model, table, x_t, t, x_prev)
+        except Exception as exc:  # reported in the JSON line, never swallowed
+            extras = {"error": repr(exc)}
+
     times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)  # max over ranks, measured on the device
@@ -279,9 +287,65 @@ def run_ours(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        line["next_rows"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_next_rows(dev, model, table, x_t, t, x_prev, reps=20):
+    """CUDA-event timings of the SURVEY §8 (f) rows at the bench shape: the denoiser head folded into the update
+    (d3pm_head_step, hidden states in, tokens out) next to head-in-torch + d3pm_fused_step, and the training loss with its
+    gradient (d3pm_train_rows, one pass) at the shipped training shape (16 x 1024 tokens)."""
+    import torch
+
+    from d3pm_b200 import _lib, head, ops, train
+
+    B, N = x_t.shape
+    K, D = K_CODES, 64
+    gen = torch.Generator(device=dev).manual_seed(77)
+    to_logits = torch.nn.Sequential(torch.nn.LayerNorm(D), torch.nn.Linear(D, K)).to(dev)
+    hw = head.HeadWeights.from_module(to_logits)
+    hc = torch.randn(B, N, D, device=dev, generator=gen)
+    hu = torch.randn(B, N, D, device=dev, generator=gen)
+    scratch = head.head_scratch(B, N, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        for i in range(3):
+            fn(i)
+        e0.record()
+        for i in range(n):
+            fn(3 + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    fused = timed(lambda i: head.head_step(hw, hc, hu, x_t, t, table, guidance_scale=GUIDANCE, seed=5, offset=i,
+                                           x_prev_out=x_prev, scratch=scratch), reps)
+
+    def unfused(i):
+        with torch.no_grad():
+            lc, lu = to_logits(hc), to_logits(hu)
+        ops.fused_step(lc, lu, x_t, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX, seed=5, offset=i,
+                       x_prev_out=x_prev)
+
+    unf = timed(unfused, 5)
+    Bt, Nt = 16, 1024
+    logits = torch.randn(Bt, Nt, K, device=dev, generator=gen)
+    x0 = torch.randint(0, K, (Bt, Nt), device=dev, generator=gen)
+    tt = torch.randint(0, T_STEPS, (Bt,), device=dev, generator=gen)
+    xt = model.q_sample_tokens(x0, tt)
+    w = torch.ones(Bt, device=dev)
+    tr = timed(lambda i: train._train_rows(logits, K, x0, xt, tt, table, (1, 1), backward=2, w_main=w, w_aux=w, want_recon=True), reps)
+    return {
+        "head_fused_step": {"ms_per_step": fused, "token_updates_per_s": B * N / (fused * 1e-3), "valid_weight_bound": bool(hw.valid),
+                            "what": "d3pm_head_step: LayerNorm + Linear(64 -> 4096) of both denoiser passes + the whole update, "
+                                    "tcgen05 3xTF32, logits never in memory"},
+        "head_in_torch_then_fused_step": {"ms_per_step": unf, "what": "torch LayerNorm + Linear (fp32) x2, then d3pm_fused_step"},
+        "train_loss_and_gradient": {"ms_per_step": tr, "GBps_algorithmic": 2 * Bt * Nt * K * 4 / tr / 1e6,
+                                    "what": "d3pm_train_rows backward=2, 16 x 1024 tokens x 4096 codes, losses + logits gradient in one pass"},
+    }
 
 
 def main():
