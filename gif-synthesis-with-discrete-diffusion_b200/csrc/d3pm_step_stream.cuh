@@ -12,8 +12,10 @@
 //     class can still win; the ~6 survivors per row are appended to a per-row list in shared memory;
 //   * every kScoreBatch rows the group scores the survivors of the whole batch exactly (Gumbel score in
 //     accurate fp32, argmax with first-index ties), two rows per warp pass, and writes the tokens;
-//   * rows whose best survivor does not clear the acceptance bound (probability ~e^-c) are queued and redone
-//     by the same group with exhaustive scoring after its main loop.
+//   * rows whose best survivor does not clear the acceptance bound (probability ~e^-c, ~200 of 65 536 rows)
+//     are queued and redone by the same group after its main loop: the same race thinned at c = 16 with the
+//     survivors scored on the spot (4 us per row; exhaustive scoring, 10 us per row, made the unluckiest
+//     group - three such rows - lengthen the launch by 5 %), and exhaustively only if that fails too (e^-16).
 // HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
 #pragma once
 
@@ -29,8 +31,8 @@ constexpr int kScoreBatch = 64;   // rows whose survivors are scored together
 constexpr int kCandPerRow = 14;   // survivors kept per row (a row with more is redone); +2 lanes: [MASK] and x_t
 constexpr int kRedoCap = 2048;    // rows a group can queue for exhaustive rescoring (= max rows per group)
 constexpr float kStreamThin = 6.0f;
+constexpr float kRedoThin = 16.0f;  // bound of the second attempt at a row whose best survivor did not clear the first
 constexpr int kCoefSmemRows = 256;  // timesteps whose coefficients are staged in shared memory (16 KiB)
-
 struct RowInfo {  // what the scoring pass needs to finish a row
   float A, Bc, Pj, PK, accept;
   uint32_t j;      // x_t, == K when masked
@@ -93,7 +95,6 @@ struct GroupSync {
   __device__ __forceinline__ void operator()() const { group_bar(id); }
 };
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-
 // Group-wide (max, sum) of per-thread softmax partials, one barrier.  m: thread-local max (natural units),
 // s: sum of 2^(x*log2e - fl(m*log2e)).  Returns the group max and the sum relative to it.
 template <int NV, typename Sync>
@@ -220,7 +221,7 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
 }
 
 template <int NP, bool HAS_U>
-__global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int K = 1024 * NP;
   constexpr int NC = 2 * NP;  // float4 chunks per thread per tensor
@@ -261,6 +262,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
 
   uint32_t phase = 0;
   uint32_t status_bits = 0;
+  const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
+#ifdef D3PM_STREAM_TIMING  // debug build: p.status is a [groups][8] uint32 trace buffer (word 0 of the grid = origin)
+  auto now_ns = [] { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; };
+  const unsigned long long tm_start = now_ns();
+  unsigned long long tm_main = 0;
+  uint32_t tm_rows = 0, tm_redo = 0;
+#endif
 
   // ------------------------------------------------------------------------------------------------
   // one row.  `exact`: exhaustive log-space scoring (PHILOX_EXACT mode and redone rows); otherwise the
@@ -483,35 +491,94 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       return;
     }
 
-    // ---- exhaustive scoring (PHILOX_EXACT, or a redone row): rare, so it is kept small rather than fast.
-    //      The softmax numerators are parked in the idle unconditional stage and scored in a rolled loop. ----
-#pragma unroll
-    for (int i = 0; i < NC; ++i)
-      *reinterpret_cast<float4*>(S.u + 4 * (128 * i + tg)) = make_float4(z[i][0].x, z[i][0].y, z[i][1].x, z[i][1].y);
+    // ---- rows outside the batched path ----
     unsigned long long best = 0ull;
-#pragma unroll 1
-    for (int i = 0; i < NC; ++i) {
-      const uint32_t q = 128u * i + tg;
-      const float4 e4 = lds4(S.u + 4 * q);
-      const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-      const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
-      const uint4 fw = rng.fine(q >> 2, grow);
+    bool settled = false;
+    if (!exact_mode) {
+      // a row whose best survivor missed the acceptance bound: the same thinned race at a bound that fails with
+      // probability e^-16, survivors scored on the spot (exactly as score_batch scores them)
+      draw_coarse();
+      // (a test knob: thin_factor < 0.01 is used for this attempt too, which then fails and reaches the code below)
+      const ThinRule thin2(rm, (p.thin_factor > 0.f && p.thin_factor < 0.01f) ? p.thin_factor : kRedoThin);
+      const float thrA = r * thin2.scaleA;
+      const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin2.thrB, thin2.thrB);
+      uint32_t hits = 0;  // bit 8 i + 2 w + h: class h of word w of Philox call i passed the coarse test
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t k = 4u * q + e;
-        const uint32_t mdraw =
-            (NoiseStream::half_of(cw, (((q >> 7) & 1u) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
-        const float sc = rm.post_of(k, ev[e], r) + gumbel_from_uniform(uniform_from_draw(mdraw));
-        const unsigned long long key = pack_key(sc, k);
+      for (int i = 0; i < NP; ++i) {
+        const uint32_t w4[4] = {cws[i].x, cws[i].y, cws[i].z, cws[i].w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
+                                        __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
+          const float2 d = __ffma2_rn(z[2 * i + (w >> 1)][w & 1], tA2, __fadd2_rn(tB2, nf));
+          hits |= (d.x >= 0.0f ? 1u : 0u) << (8 * i + 2 * w);
+          hits |= (d.y >= 0.0f ? 1u : 0u) << (8 * i + 2 * w + 1);
+        }
+      }
+      while (hits != 0) {  // ~16 classes per row in all
+        const int b = __ffs(hits) - 1;
+        hits &= hits - 1;
+        float e = 0.f;  // z viewed as float[8 NP] is indexed by b; picked with selects, never through memory
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            e = (b == 4 * c + 2 * h) ? z[c][h].x : e;
+            e = (b == 4 * c + 2 * h + 1) ? z[c][h].y : e;
+          }
+        const uint32_t k = 4u * (128u * static_cast<uint32_t>(b >> 2) + tg) + static_cast<uint32_t>(b & 3);
+        if (k != j) {
+          const float sc = rm.post_of(k, e, r) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+          const unsigned long long key = pack_key(sc, k);
+          best = key > best ? key : best;
+        }
+      }
+      if (tg == 0) {
+        const unsigned long long key =
+            pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
         best = key > best ? key : best;
       }
+      if (tg == 32 && !masked) {  // the row's own class has its own coefficients
+        const unsigned long long key = pack_key(rm.post_self() + gumbel_from_uniform(uniform_from_draw(rng.draw(j, grow))), j);
+        best = key > best ? key : best;
+      }
+      best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3
+      settled = key_score(best) >= thin2.accept;
+      if (!settled) {
+        best = 0ull;
+        sync();  // S.keys is about to be reused
+      }
     }
-    if (tg == 0) {
-      const unsigned long long key =
-          pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
-      best = key > best ? key : best;
+    if (!settled) {
+      // ---- exhaustive scoring (PHILOX_EXACT mode, or the second attempt failed too): kept small rather than
+      //      fast.  The softmax numerators are parked in the idle unconditional stage and scored in a rolled loop.
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        *reinterpret_cast<float4*>(S.u + 4 * (128 * i + tg)) = make_float4(z[i][0].x, z[i][0].y, z[i][1].x, z[i][1].y);
+#pragma unroll 1
+      for (int i = 0; i < NC; ++i) {
+        const uint32_t q = 128u * i + tg;
+        const float4 e4 = lds4(S.u + 4 * q);
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
+        const uint4 fw = rng.fine(q >> 2, grow);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t k = 4u * q + e;
+          const uint32_t mdraw =
+              (NoiseStream::half_of(cw, (((q >> 7) & 1u) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
+          const float sc = rm.post_of(k, ev[e], r) + gumbel_from_uniform(uniform_from_draw(mdraw));
+          const unsigned long long key = pack_key(sc, k);
+          best = key > best ? key : best;
+        }
+      }
+      if (tg == 0) {
+        const unsigned long long key =
+            pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
+        best = key > best ? key : best;
+      }
+      best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3
     }
-    best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3 (exact rows only)
     if (tg == 0) {
       p.x_prev[row] = key_class(best);
       if (next_row >= 0) issue_row(next_row);
@@ -520,7 +587,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
 
   // ---- one loop over this group's rows, then over the rows it queued for exhaustive rescoring ----------
   // video index b = row / N is tracked incrementally (row advances by G per iteration)
-  const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
   const long long N = p.N;
   const long long stepB = G / N, stepR = G % N;
   auto token_of = [&](long long r_) { return static_cast<long long>(p.x_t[r_]); };
@@ -547,6 +613,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
       if (row < 0) {
         if (redo_phase) break;
         redo_phase = true;
+#ifdef D3PM_STREAM_TIMING
+        tm_main = now_ns();
+#endif
         n_redo = S.redo_cnt;
         if (n_redo == 0) break;
         status_bits |= D3PM_STATUS_FALLBACK;
@@ -588,12 +657,28 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const St
     }
     const bool exact = exact_mode || redo_phase;
     process_row(row, next, j_cur, t_cur, exact, in_batch, it);
+#ifdef D3PM_STREAM_TIMING
+    if (redo_phase) ++tm_redo; else ++tm_rows;
+#endif
     if (!exact) ++in_batch;
     row = next, jj = jj_next, tt = tt_next;
     ++it;
     if (redo_phase) ++redo_i;
   }
+#ifdef D3PM_STREAM_TIMING
+  if (tg == 0 && p.status != nullptr) {
+    const unsigned long long tm_end = now_ns();
+    uint32_t* o = p.status + 8 * (blockIdx.x * kGroupsPerCta + g);
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (tm_main == 0) tm_main = tm_end;
+    o[0] = static_cast<uint32_t>(tm_start), o[1] = static_cast<uint32_t>(tm_start >> 32);
+    o[2] = static_cast<uint32_t>(tm_main - tm_start), o[3] = static_cast<uint32_t>(tm_end - tm_start);
+    o[4] = tm_rows, o[5] = tm_redo, o[6] = smid, o[7] = 0;
+  }
+#else
   if (status_bits != 0 && tg == 0 && p.status != nullptr) atomicOr(p.status, status_bits);
+#endif
 }
 
 constexpr long long kStreamMinRows = 2048;  // below this the one-CTA-per-row kernel has less latency

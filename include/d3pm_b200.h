@@ -95,7 +95,8 @@ typedef struct d3pm_step_desc {
   int32_t gumbel_is_uniform; /* 1: `gumbel` holds uniforms u (torch.rand_like's tensor); g = -log(-log(u+1e-30)+1e-30) in-kernel */
   uint64_t seed, offset; /* Philox key / per-call stream offset */
   int64_t row_offset;    /* global index of local row 0 (b_global*N + n): shards reproduce the 1-GPU stream */
-  float thin_factor;     /* PHILOX thinning constant c (0 = default 8); smaller forces the exhaustive fallback */
+  float thin_factor;     /* PHILOX thinning constant c (0 = default); smaller values make more rows take the second
+                            attempt (stream kernel: c = 16), values < 0.01 force the exhaustive fallback */
   int32_t kernel;        /* D3PM_KERNEL_*: which implementation runs (AUTO picks by shape and mode) */
   d3pm_stream_t stream;
   /* purity-prior sampling (p_sample with prior_rule 1 / 2, :309-346); all optional, rows kernel only */

@@ -155,3 +155,23 @@ def test_no_access_outside_the_row_windows(kernel):
     dense = _run(lc.contiguous(), lu.contiguous(), x_t, t, K, _lib.SAMPLE_PHILOX, kernel, seed=3, offset=1)
     assert torch.equal(dense, x_prev)          # pitched rows == dense rows: nothing outside [0, K) was read
     assert int(x_prev.min()) >= 0 and int(x_prev.max()) <= K
+
+
+def test_stream_second_attempt_and_exhaustive_fallback_at_scale():
+    """Rows whose best survivor misses the acceptance bound get a second attempt (thinned at c = 16, survivors scored on
+    the spot) and, should that fail too, exhaustive scoring.  thin_factor 0.5 sends most rows to the second attempt,
+    1e-3 (the documented test knob) makes both attempts fail: the tokens never change.  Guidance off, K = 1024, more
+    than two score batches per group."""
+    K, B, N = 1024, 20, 4096
+    g = torch.Generator(device=DEV).manual_seed(77)
+    lc = torch.randn(B, N, K, device=DEV, generator=g)
+    x_t = torch.randint(0, K + 1, (B, N), device=DEV, generator=g)
+    t = torch.randint(0, T, (B,), device=DEV, generator=g)
+    kw = dict(s=0.0, seed=5, offset=8)
+    status = ops.new_status(DEV)
+    exact = _run(lc, None, x_t, t, K, _lib.SAMPLE_PHILOX_EXACT, _lib.KERNEL_STREAM, **kw)
+    for c in (1e-3, 0.5, 2.0, 0.0):
+        status.zero_()
+        got = _run(lc, None, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, thin_factor=c, status=status, **kw)
+        assert torch.equal(got, exact), c
+        assert int(status.item()) & _lib.STATUS_FALLBACK   # 80k rows: some are redone even at the default c

@@ -18,6 +18,7 @@ ap.add_argument("--videos", type=int, default=16)
 ap.add_argument("--t", type=int, default=50)
 ap.add_argument("--mode", default="philox")
 ap.add_argument("--no-guidance", action="store_true")
+ap.add_argument("--sleep-ms", type=float, default=0.0, help="idle gap before every launch (isolated launches)")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -45,6 +46,11 @@ kw = dict(guidance_scale=2.0, seed=1, x_prev_out=xp)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
 ev[0].record()
 for i in range(a.launches):
+    if a.sleep_ms > 0:
+        torch.cuda.synchronize()
+        import time
+        time.sleep(a.sleep_ms / 1e3)
+        ev[i].record()
     if a.mode == "philox":
         ops.fused_step(lc, lu, x_t, t, table, sample_mode=_lib.SAMPLE_PHILOX, offset=i, **kw)
     elif a.mode == "exact":
