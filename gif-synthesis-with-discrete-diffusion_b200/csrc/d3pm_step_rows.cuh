@@ -90,7 +90,7 @@ struct ThinRule {
   float scaleA, thrB, accept;
   __device__ __forceinline__ ThinRule(const RowMath& rm, float thin_factor) {
     const float c = thin_factor > 0.f ? thin_factor : kDefaultThin;
-    const float inv = c / rm.Ptot;
+    const float inv = __fdividef(c, rm.Ptot);  // approximate is fine: the filter and the bound use the same value
     scaleA = rm.A * inv * 0.0078125f;                                  // * 2^-7: h sits in the low mantissa bits
     thrB = fmaf(rm.Bc * inv, 0.0078125f, 1.0f) + 2.384185791015625e-7f;  // + 2 ulps of slack
     accept = -lg2(inv) * kLn2 + 0.02f;

@@ -170,8 +170,8 @@ __device__ __forceinline__ void stream_sum(float (&s)[NV], float* scratch, Sync 
 // the row's own class), every lane scores one class exactly as the log-domain kernel does, a 16-lane
 // segmented argmax picks the winner, which is accepted if it clears the row's bound and queued otherwise.
 template <int NP>
-__device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const NoiseStream& rng, const StepParams& p,
-                                         long long G, long long first_row) {
+__device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const NoiseStream& rng, const StepParams& p, int G,
+                                         int first_row) {
   constexpr uint32_t K = 1024u * NP;
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (kGroupWarps - 1);
   const int sub = lane & 15;
@@ -199,7 +199,7 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
         k = ri.j, P = ri.Pj, have = true;
       }
       if (have) {
-        const uint64_t grow = static_cast<uint64_t>(p.row_offset + first_row + static_cast<long long>(ri.rel) * G);
+        const uint64_t grow = static_cast<uint64_t>(p.row_offset + (first_row + ri.rel * G));
         const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
         key = pack_key(sc, k);
       }
@@ -211,7 +211,7 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
     }
     if (live && sub == 0) {
       if (cnt <= static_cast<uint32_t>(kCandPerRow) && key_score(key) >= ri.accept) {
-        p.x_prev[first_row + static_cast<long long>(ri.rel) * G] = key_class(key);
+        p.x_prev[first_row + ri.rel * G] = key_class(key);
       } else {
         S.redo[atomicAdd(&S.redo_cnt, 1u)] = ri.rel;
       }
@@ -240,9 +240,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     __syncthreads();
   }
   const GroupSync sync{g + 1};
-  const long long G = static_cast<long long>(gridDim.x) * kGroupsPerCta;
-  const long long first_row = static_cast<long long>(g) * gridDim.x + blockIdx.x;  // neighbouring rows -> different SMs
-  const long long rows = p.rows;
+  // row indices are 32-bit throughout (the launcher refuses more than 2^31 - 1 rows)
+  const int G = static_cast<int>(gridDim.x) * kGroupsPerCta;
+  const int first_row = g * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);  // neighbouring rows -> different SMs
+  const int rows = static_cast<int>(p.rows);
+  const uint32_t pitch = static_cast<uint32_t>(p.pitch_logits);
   const NoiseStream rng(p.seed, p.offset);
   const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kStreamThin;
 
@@ -253,11 +255,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
   if (tg < kScoreBatch) S.cand_cnt[tg] = 0;
   sync();
 
-  auto issue_row = [&](long long row) {  // elected thread: arm the barrier and launch both row copies
+  auto issue_row = [&](int row) {  // elected thread: arm the barrier and launch both row copies
+    const unsigned long long at = static_cast<unsigned long long>(static_cast<uint32_t>(row)) * pitch;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&S.full, HAS_U ? 2 * kRowBytes : kRowBytes);
-    tma_load_row(S.c, p.logits_c + row * p.pitch_logits, kRowBytes, &S.full);
-    if (HAS_U) tma_load_row(S.u, p.logits_u + row * p.pitch_logits, kRowBytes, &S.full);
+    tma_load_row(S.c, p.logits_c + at, kRowBytes, &S.full);
+    if (HAS_U) tma_load_row(S.u, p.logits_u + at, kRowBytes, &S.full);
   };
 
   uint32_t phase = 0;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
   // one row.  `exact`: exhaustive log-space scoring (PHILOX_EXACT mode and redone rows); otherwise the
   // row's survivors are left in slot `slot` for the next score_batch.
   // ------------------------------------------------------------------------------------------------
-  auto process_row = [&](long long row, long long next_row, uint32_t j, int tt, bool exact, int slot, int rel) {
+  auto process_row = [&](int row, int next_row, uint32_t j, int tt, bool exact, int slot, int rel) {
     const bool masked = (j == static_cast<uint32_t>(K));
     mbar_wait(&S.full, phase);
     phase ^= 1u;
@@ -296,16 +299,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
 
     // ---- largest |logit| of each tensor: thread-local, then one cheap group reduction ----
-    float am[2];
-    am[0] = fmaxf(fmaxf(fabsf(x[0][0].x), fabsf(x[0][0].y)), fmaxf(fabsf(x[0][1].x), fabsf(x[0][1].y)));
-    am[1] = HAS_U ? fmaxf(fmaxf(fabsf(z[0][0].x), fabsf(z[0][0].y)), fmaxf(fabsf(z[0][1].x), fabsf(z[0][1].y))) : 0.f;
+    float am[2] = {0.f, 0.f};
+    if (HAS_U) {
+      am[0] = fmaxf(fmaxf(fabsf(x[0][0].x), fabsf(x[0][0].y)), fmaxf(fabsf(x[0][1].x), fabsf(x[0][1].y)));
+      am[1] = fmaxf(fmaxf(fabsf(z[0][0].x), fabsf(z[0][0].y)), fmaxf(fabsf(z[0][1].x), fabsf(z[0][1].y)));
+    }
 #pragma unroll
     for (int i = 1; i < NC; ++i) {
-      am[0] = fmaxf(fmaxf(am[0], fabsf(x[i][0].x)), fmaxf(fabsf(x[i][0].y), fmaxf(fabsf(x[i][1].x), fabsf(x[i][1].y))));
+      if (HAS_U)
+        am[0] = fmaxf(fmaxf(am[0], fabsf(x[i][0].x)), fmaxf(fabsf(x[i][0].y), fmaxf(fabsf(x[i][1].x), fabsf(x[i][1].y))));
       if (HAS_U)
         am[1] = fmaxf(fmaxf(am[1], fabsf(z[i][0].x)), fmaxf(fabsf(z[i][0].y), fmaxf(fabsf(z[i][1].x), fabsf(z[i][1].y))));
     }
-    stream_max<HAS_U ? 2 : 1>(am, S.red[0], sync);  // barrier 1: every thread is done with the stage
+    if (HAS_U) stream_max<2>(am, S.red[0], sync);  // barrier 1: every thread is done with the stage
+    else sync();                                   // (without guidance nothing depends on the range of the logits)
     // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
     if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
 
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         float mm[1] = {my}, ss[1] = {(sy[0].x + sy[0].y) + (sy[1].x + sy[1].y)};
         stream_max_sum<1>(mm, ss, S.red[1], sync);  // barrier 2
         My2 = to_log2_units(mm[0]);
-        rSy = __frcp_rn(ss[0]);
+        rSy = __fdividef(1.0f, ss[0]);
       }
       r = ex2(my2 - My2) * rSy;
     } else {
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       float ss[1] = {(sc[0].x + sc[0].y) + (sc[1].x + sc[1].y)};
       stream_max_sum<1>(mx, ss, S.red[1], sync);  // barrier 2
       My2 = to_log2_units(mx[0]);
-      rSy = __frcp_rn(ss[0]);
+      rSy = __fdividef(1.0f, ss[0]);
       r = ex2(mc2 - My2) * rSy;
       yj = xj;
     }
@@ -587,14 +594,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 
   // ---- one loop over this group's rows, then over the rows it queued for exhaustive rescoring ----------
   // video index b = row / N is tracked incrementally (row advances by G per iteration)
-  const long long N = p.N;
-  const long long stepB = G / N, stepR = G % N;
-  auto token_of = [&](long long r_) { return static_cast<long long>(p.x_t[r_]); };
-  auto time_of = [&](long long b_) { return static_cast<long long>(p.t[b_]); };
+  const int N = p.N;
+  const int stepB = G / N, stepR = G % N;
+  auto token_of = [&](int r_) { return static_cast<long long>(p.x_t[r_]); };
+  auto time_of = [&](int b_) { return static_cast<long long>(p.t[b_]); };
   bool redo_phase = false;
   uint32_t redo_i = 0, n_redo = 0;
-  long long row = first_row < rows ? first_row : -1;
-  long long vb = first_row / N, vr = first_row % N;  // video index and position of `row`
+  int row = first_row < rows ? first_row : -1;
+  int vb = first_row / N, vr = first_row % N;  // video index and position of `row`
   long long jj = 0, tt = 0;
   if (row >= 0) {
     if (tg == 0) issue_row(row);
@@ -619,7 +626,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         n_redo = S.redo_cnt;
         if (n_redo == 0) break;
         status_bits |= D3PM_STATUS_FALLBACK;
-        row = first_row + static_cast<long long>(S.redo[0]) * G;
+        row = first_row + S.redo[0] * G;
         if (tg == 0) issue_row(row);
         jj = token_of(row);
         tt = time_of(row / N);
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     int t_cur = static_cast<int>(tt);
     uint32_t j_cur = static_cast<uint32_t>(jj);
     asm volatile("" : "+r"(t_cur), "+r"(j_cur) : : "memory");
-    long long next;
+    int next;
     long long jj_next = 0, tt_next = 0;
     if (!redo_phase) {
       next = row + G < rows ? row + G : -1;
@@ -649,7 +656,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         tt_next = time_of(vb);
       }
     } else {
-      next = (redo_i + 1 < n_redo) ? first_row + static_cast<long long>(S.redo[redo_i + 1]) * G : -1;
+      next = (redo_i + 1 < n_redo) ? first_row + S.redo[redo_i + 1] * G : -1;
       if (next >= 0) {
         jj_next = token_of(next);
         tt_next = time_of(next / N);
@@ -688,6 +695,7 @@ inline bool stream_kernel_supports(const StepParams& p) {
   if (p.post != nullptr || p.recon != nullptr || p.gap != nullptr || p.x_prev == nullptr) return false;
   if (p.sample_from != D3PM_FROM_POSTERIOR || p.score != nullptr || p.sharpen != nullptr) return false;
   if (p.K != 1024 && p.K != 2048 && p.K != 4096) return false;
+  if (p.pitch_logits >= (1LL << 32)) return false;  // row offsets are formed as 32 x 32 -> 64 bit products
   return true;
 }
 

@@ -1,5 +1,8 @@
-FAST=$PWD/tools/probes/libstep_fast.so; NEW=$PWD/gif-synthesis-with-discrete-diffusion_b200/csrc/libd3pm_b200.so
-for lib in $FAST $NEW; do
-echo "== $lib"
-D3PM_B200_STATIC_ROWS=1 D3PM_B200_LIB=$lib ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__warp_issue_stalled_barrier_per_warp_active.pct,smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct,smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct,smsp__warp_issue_stalled_wait_per_warp_active.pct,smsp__warp_issue_stalled_no_instruction_per_warp_active.pct,smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct,smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct,smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct,smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct --clock-control none -k regex:step_stream -s 2 -c 1 --csv python tools/prof_step.py --launches 4 --no-guidance --videos 32 2>/dev/null | grep step_stream | awk -F'","' '{print $(NF-2), $NF}'
-done
+stat() { python -c "
+import sys,re
+s=sys.stdin.read(); v=[float(x) for x in re.findall(r\"'([0-9.]+)'\", s)]; v=v[5:]; print('$1 mean %.4f min %.4f max %.4f'%(sum(v)/len(v), min(v), max(v)))"; }
+for i in 1 2; do
+for v in fast v1 v2 v3; do
+lib=$PWD/tools/probes/libstep_$v.so; [ -f $lib ] || lib=$PWD/tools/probes/lib$v.so
+echo "== $v"; D3PM_B200_LIB=$lib python tools/prof_step.py --launches 40 | stat on; D3PM_B200_LIB=$lib python tools/prof_step.py --launches 40 --no-guidance --videos 32 | stat off32
+done; done
