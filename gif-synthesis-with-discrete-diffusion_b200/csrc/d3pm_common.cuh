@@ -85,6 +85,15 @@ __device__ __forceinline__ float warp_sum(float x) {
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
+// Warp arg-max of (value, index) pairs with the first-index tie rule, as one orderable key: two CREDUX instead of a
+// five-step 64-bit butterfly.  Every lane returns the warp's key.
+__device__ __forceinline__ unsigned long long pack_key(float score, uint32_t k);
+__device__ __forceinline__ unsigned long long warp_argmax_key(float v, uint32_t idx) {
+  float vm;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(vm) : "f"(v));
+  const uint32_t im = __reduce_min_sync(0xffffffffu, v == vm ? idx : 0xffffffffu);
+  return pack_key(vm, im);
+}
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

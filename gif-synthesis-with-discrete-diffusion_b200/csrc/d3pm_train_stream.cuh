@@ -9,7 +9,10 @@
 //     compares;
 //   * the sum over classes of the gradient's softmax term is obtained in closed form from sums accumulated in the
 //     forward sweep, so a row needs two group exchanges (two 128-thread named barriers), not four;
-//   * the gradient row is written with streaming 128-bit stores straight from registers.
+//   * the gradient row is written with streaming 128-bit stores straight from registers;
+//   * a row's scalars (x_0, x_t, t of its video, the per-video gradient weights) are loaded one row ahead and the
+//     coefficient table is staged in shared memory: with ~28 rows per group at the shipped training shape the two
+//     dependent global loads at the top of every row (t, then the table row) were what the kernel waited for.
 // HBM traffic is the algorithmic minimum of a fused forward + backward: 16 KiB read and 16 KiB written per token.
 #pragma once
 
@@ -44,20 +47,29 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
   const int g = tid / kGroupThreads, tg = tid % kGroupThreads;
   const int lane = tid & 31, warp = (tid >> 5) & (kGroupWarps - 1);
   TrainGroupSmem<NP>& S = reinterpret_cast<TrainGroupSmem<NP>*>(smem_raw)[g];
+  // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits
+  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(TrainGroupSmem<NP>) * kGroupsPerCta);
+  const bool coef_in_smem = p.T <= kCoefSmemRows;
+  if (coef_in_smem) {
+    for (int i = tid; i < p.T * 16; i += kStreamThreads)
+      coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
+    __syncthreads();
+  }
   const GroupSync sync{g + 1};
-  const long long G = static_cast<long long>(gridDim.x) * kGroupsPerCta;
-  const long long first_row = static_cast<long long>(g) * gridDim.x + blockIdx.x;
-  const long long rows = p.rows;
+  // row indices are 32-bit (the launcher refuses more than 2^31 - 1 rows)
+  const int G = static_cast<int>(gridDim.x) * kGroupsPerCta;
+  const int first_row = g * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+  const int rows = static_cast<int>(p.rows);
 
   if (tg == 0) {
     mbar_init(&S.full[0], 1);
     mbar_init(&S.full[1], 1);
   }
   sync();
-  auto issue_row = [&](long long row, int st) {
+  auto issue_row = [&](int row, int st) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&S.full[st], kRowBytes);
-    tma_load_row(S.stage[st], p.logits + row * p.pitch, kRowBytes, &S.full[st]);
+    tma_load_row(S.stage[st], p.logits + static_cast<long long>(row) * p.pitch, kRowBytes, &S.full[st]);
   };
   if (tg == 0) {
     if (first_row < rows) issue_row(first_row, 0);
@@ -67,63 +79,89 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
   uint32_t status_bits = 0;
   const bool want_arg = (p.x0_recon != nullptr);
 
+  // scalars of a row, loaded one row ahead
+  long long tt_n = 0, jj_n = 0, x0_n = 0;
+  float am_n = 0.f, aa_n = 0.f;
+  auto load_scalars = [&](int r_) {
+    const int b_ = static_cast<int>(static_cast<uint32_t>(r_) / static_cast<uint32_t>(p.N));  // rows < 2^31 (launcher)
+    tt_n = p.t[b_], jj_n = p.x_t[r_], x0_n = p.x0[r_];
+    if (WRITE_GRAD) am_n = __ldg(p.w_main + b_), aa_n = __ldg(p.w_aux + b_);
+  };
+  if (first_row < rows) load_scalars(first_row);
   int it = 0;
-  for (long long row = first_row; row < rows; row += G, ++it) {
+  for (int row = first_row; row < rows; row += G, ++it) {
     const int st = it & 1;
-    const int b = static_cast<int>(row / p.N);
-    long long tt = p.t[b], jj = p.x_t[row], x0l = p.x0[row];
+    long long tt = tt_n, jj = jj_n, x0l = x0_n;
+    const float am = am_n, aa = aa_n;
+    asm volatile("" : "+l"(tt), "+l"(jj), "+l"(x0l) : : "memory");  // consume before the next loads are issued
+    if (row + G < rows) load_scalars(row + G);
     if (tt < 0 || tt >= p.T) status_bits |= D3PM_STATUS_BAD_T, tt = tt < 0 ? 0 : p.T - 1;
     if (jj < 0 || jj > K) status_bits |= D3PM_STATUS_BAD_TOKEN, jj = K;
     if (x0l < 0 || x0l >= K) status_bits |= D3PM_STATUS_BAD_TOKEN, x0l = 0;
     const bool masked = (jj == K), t0 = (tt == 0);
     const uint32_t j = static_cast<uint32_t>(jj), x0 = static_cast<uint32_t>(x0l);
-    const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
-    const float am = WRITE_GRAD ? __ldg(p.w_main + b) : 0.f, aa = WRITE_GRAD ? __ldg(p.w_aux + b) : 0.f;
+    RowCoef cf;
+    if (coef_in_smem) {
+      const float* crow = coef_s + static_cast<int>(tt) * 16 + (masked ? 0 : 8);
+      cf = row_coef_from(lds4(crow), lds4(crow + 4), masked);
+    } else {
+      cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
+    }
 
     mbar_wait(&S.full[st], phase[st]);
     phase[st] ^= 1u;
     const float* __restrict__ rowbuf = S.stage[st];
-    float x[NC][4];
+    float2 x[NC][2];  // class pairs (0,1) and (2,3) of chunk i, packed for the f32x2 pipe
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const float4 a = lds4(rowbuf + 4 * (128 * i + tg));
-      x[i][0] = a.x, x[i][1] = a.y, x[i][2] = a.z, x[i][3] = a.w;
+      x[i][0] = make_float2(a.x, a.y), x[i][1] = make_float2(a.z, a.w);
     }
     const float c_x0 = rowbuf[x0], c_j = masked ? 0.f : rowbuf[j];
 
     // ---- exchange 1: (max, sum of exponentials relative to the thread-local max) and the arg-max of the logits ----
-    float m = x[0][0], lo = x[0][0];
+    float m = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
+    float lo = fminf(fminf(x[0][0].x, x[0][0].y), fminf(x[0][1].x, x[0][1].y));
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) m = fmaxf(m, x[i][c]), lo = fminf(lo, x[i][c]);
+    for (int i = 1; i < NC; ++i) {  // 3-input min / max: two instructions per four classes each
+      m = fmaxf(fmaxf(m, x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
+      lo = fminf(fminf(lo, x[i][0].x), fminf(x[i][0].y, fminf(x[i][1].x, x[i][1].y)));
+    }
     unsigned long long kbest = 0ull;
     uint32_t idx = 0;
     if (want_arg) {  // first class (lowest index) that attains the thread-local maximum
 #pragma unroll
       for (int i = NC - 1; i >= 0; --i)
 #pragma unroll
-        for (int c = 3; c >= 0; --c) idx = (x[i][c] == m) ? 4u * (128u * i + tg) + c : idx;
-      kbest = pack_key(m, idx);
+        for (int c = 3; c >= 0; --c) {
+          const float xv = (c & 1) ? x[i][c >> 1].y : x[i][c >> 1].x;
+          idx = (xv == m) ? 4u * (128u * i + tg) + c : idx;
+        }
     }
     const float e_top = ex2(fmaf(m, kLog2e, -to_log2_units(fmaxf(m, -3.0e38f))));  // numerator of the thread's best class
     m = fmaxf(m, -3.0e38f);
     const float m2 = to_log2_units(m);
-    float e[NC][4];
-    float sloc = 0.f;
+    float2 e[NC][2];
+    float sloc;
+    {
+      const float2 l2e = make_float2(kLog2e, kLog2e), nm2 = make_float2(-m2, -m2);
+      float2 s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
+      for (int i = 0; i < NC; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        e[i][c] = ex2(fmaf(x[i][c], kLog2e, -m2));
-        sloc += e[i][c];
-      }
+        for (int h = 0; h < 2; ++h) {
+          const float2 a = __ffma2_rn(x[i][h], l2e, nm2);
+          e[i][h] = make_float2(ex2(a.x), ex2(a.y));
+          s2[h] = __fadd2_rn(s2[h], e[i][h]);
+        }
+      sloc = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y);
+    }
     {
       const float mw = warp_max(m);
       const float mw2 = to_log2_units(mw);
       const float sw = warp_sum(sloc * ex2(m2 - mw2));
       const float lw = warp_min(lo);
-      if (want_arg) kbest = warp_max_u64(kbest);
+      if (want_arg) kbest = warp_argmax_key(m, idx);
       if (lane == 0) {
         S.red[0][warp] = mw, S.red[0][kGroupWarps + warp] = sw, S.red[0][2 * kGroupWarps + warp] = lw;
         if (want_arg) S.keys[0][warp] = kbest;
@@ -181,28 +219,35 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     uint32_t post_idx = 0;
     // "open" <=> log-softmax_k >= -70 <=> softmax_k >= exp(-70): decided on the softmax value, so the logits themselves
     // are dead after the first sweep (registers: numerators e and reciprocals inv only)
-    float inv[NC][4];
+    float2 inv[NC][2];
     // Clamp-free fast path (row-uniform): when no log-softmax entry can reach -70 (smallest logit of the row) and every
     // generic P_k = p_k A + Bc lies in [exp(-70), 1] (Bc and A + Bc say so), none of the clamps of :236 / :283 can fire for
     // a generic class: the sweep needs no predicates, and the posterior arg-max is the logits' arg-max.
     const bool fast = ((xmin - M) - lnS >= kClampLo + 1.0e-3f) && (Bc >= 1.01f * kPFloor) && (cf.A + Bc <= 0.9999f) &&
                       (cf.A >= 0.f);
     if (fast) {
+      const float2 r2 = make_float2(r, r), A2 = make_float2(cf.A, cf.A), Bc2 = make_float2(Bc, Bc);
+      float2 sL[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sI[2] = {sL[0], sL[0]}, sQ[2] = {sL[0], sL[0]};
 #pragma unroll
       for (int i = 0; i < NC; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float sm = e[i][c] * r;
-          const float Pk = fmaf(sm, cf.A, Bc);
-          sumM = fmaf(lg2(Pk), kLn2, sumM);
+        for (int h = 0; h < 2; ++h) {
+          const float2 sm = __fmul2_rn(e[i][h], r2);
+          const float2 Pk = __ffma2_rn(sm, A2, Bc2);
+          sL[h] = __fadd2_rn(sL[h], make_float2(lg2(Pk.x), lg2(Pk.y)));
           if (WRITE_GRAD) {
-            const float iv = rcp_fast(Pk);
-            inv[i][c] = iv;
-            sInv += iv;
-            sPP = fmaf(sm, iv, sPP);
-            sP += sm;
+            const float2 iv = make_float2(rcp_fast(Pk.x), rcp_fast(Pk.y));
+            inv[i][h] = iv;
+            sI[h] = __fadd2_rn(sI[h], iv);
+            sQ[h] = __ffma2_rn(sm, iv, sQ[h]);
           }
         }
+      sumM = kLn2 * ((sL[0].x + sL[0].y) + (sL[1].x + sL[1].y));
+      if (WRITE_GRAD) {
+        sInv = (sI[0].x + sI[0].y) + (sI[1].x + sI[1].y);
+        sPP = (sQ[0].x + sQ[0].y) + (sQ[1].x + sQ[1].y);
+        sP = sloc * r;  // every class is "open" here
+      }
       post_best = log_prob_clamped(fmaf(fminf(e_top * r, 1.0f), cf.A, Bc));
       post_idx = idx;
     } else {
@@ -210,7 +255,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float sm = e[i][c] * r;
+          const float sm = ((c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x) * r;
           const float pk = fminf(fmaxf(sm, kPFloor), 1.0f);
           const float Pk = fmaf(pk, cf.A, Bc);
           const float lp = lg2(Pk) * kLn2;
@@ -219,7 +264,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
           if (WRITE_GRAD) {
             const bool inside = (lp >= kClampLo) && (lp <= 0.0f), open = sm >= kPFloor;
             const float iv = inside ? rcp_fast(Pk) : 0.f;
-            inv[i][c] = iv;
+            if (c & 1) inv[i][c >> 1].y = iv;
+            else inv[i][c >> 1].x = iv;
             sInv += iv;
             sPP += open ? pk * iv : 0.f;
             sP += open ? pk : 0.f;
@@ -231,26 +277,46 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
           }
         }
     }
-    if (want_arg) kpost = pack_key(post_best, post_idx);
-    // the sweep scored x_t with the generic coefficients: the one thread that owns it redoes its 32 classes
-    if (want_arg && !masked && tg == static_cast<int>((j >> 2) & 127u)) {
-      kpost = 0ull;
+    // The sweep scored x_t with the generic coefficients; its true term M_j joins at the end (first thread, with
+    // [MASK]), so the thread that owns class x_t must offer its best class OTHER than x_t.  Nothing to do unless
+    // x_t is that thread's best; then (fast rows) the runner-up among its softmax numerators, or (rows with clamps)
+    // a rescoring of its 32 classes.
+    if (want_arg && !masked && tg == static_cast<int>((j >> 2) & 127u) && post_idx == j) {
+      if (fast) {
+        float e2nd = -1.0f;
+        uint32_t i2nd = 0;
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
+        for (int i = 0; i < NC; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t k = 4u * (128u * i + tg) + c;
-          const float pk = fminf(fmaxf(e[i][c] * r, kPFloor), 1.0f);
-          const float Mk = (k == j) ? M_j : log_prob_clamped(fmaf(pk, cf.A, Bc));
-          const unsigned long long key = pack_key(Mk, k);
-          kpost = key > kpost ? key : kpost;
-        }
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t k = 4u * (128u * i + tg) + c;
+            const float ev = (c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x;
+            const bool better = (ev > e2nd) && (k != j);
+            e2nd = better ? ev : e2nd;
+            i2nd = better ? k : i2nd;
+          }
+        post_best = log_prob_clamped(fmaf(fminf(e2nd * r, 1.0f), cf.A, Bc));
+        post_idx = i2nd;
+      } else {
+        post_best = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t k = 4u * (128u * i + tg) + c;
+            const float pk = fminf(fmaxf(((c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x) * r, kPFloor), 1.0f);
+            const float Mk = log_prob_clamped(fmaf(pk, cf.A, Bc));
+            const bool better = (Mk > post_best) && (k != j);
+            post_best = better ? Mk : post_best;
+            post_idx = better ? k : post_idx;
+          }
+      }
     }
     // ---- exchange 2 ----
     {
       const float a0 = warp_sum(sumM), a1 = WRITE_GRAD ? warp_sum(sInv) : 0.f;
       const float a2 = WRITE_GRAD ? warp_sum(sPP) : 0.f, a3 = WRITE_GRAD ? warp_sum(sP) : 0.f;
-      if (want_arg) kpost = warp_max_u64(kpost);
+      if (want_arg) kpost = warp_argmax_key(post_best, post_idx);
       if (lane == 0) {
         S.red[1][warp] = a0, S.red[1][kGroupWarps + warp] = a1;
         S.red[1][2 * kGroupWarps + warp] = a2, S.red[1][3 * kGroupWarps + warp] = a3;
@@ -291,8 +357,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
         unsigned long long kb = S.keys[1][0];
 #pragma unroll
         for (int w = 1; w < kGroupWarps; ++w) kb = S.keys[1][w] > kb ? S.keys[1][w] : kb;
-        const unsigned long long kK = pack_key(M_K, K);
+        const unsigned long long kK = pack_key(M_K, K), kJ = masked ? 0ull : pack_key(M_j, j);
         kb = kK > kb ? kK : kb;
+        kb = kJ > kb ? kJ : kb;
         p.xtm1_recon[row] = key_class(kb);
       }
     }
@@ -319,34 +386,33 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     const float h_j = open_j ? p_j * fmaf(gP_j, cf.AS, cf.WS * Gs) : 0.f;
     const float gA = g_gen * cf.A, WG = cf.W * Gs;
     const float hsum = fmaf(gA, sPP - gpp_x0 - gpp_j, WG * (sP - gpo_x0 - gpo_j)) + h_x0 + h_j;
-    float* __restrict__ rg = p.grad + row * p.pitch_grad;
+    float* __restrict__ rg = p.grad + static_cast<long long>(row) * p.pitch_grad;
     const uint32_t q_x0 = x0 >> 2, q_j = j_other ? (j >> 2) : 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const uint32_t q = 128u * i + tg;
       float o[4];
+      if (fast) {
+        const float2 r2 = make_float2(r, r), gA2 = make_float2(gA, gA), wh2 = make_float2(WG - hsum, WG - hsum);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float sm = e[i][c] * r;
-        if (fast) {
-          o[c] = sm * (fmaf(gA, inv[i][c], WG) - hsum);
-        } else {
-          const float hk = (sm >= kPFloor) ? fmaf(gA, inv[i][c], WG) : 0.f;  // h_k / p_k, 0 where the recon clamp fired
+        for (int h = 0; h < 2; ++h) {
+          const float2 v = __fmul2_rn(__fmul2_rn(e[i][h], r2), __ffma2_rn(gA2, inv[i][h], wh2));
+          o[2 * h] = v.x, o[2 * h + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float sm = ((c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x) * r;
+          const float iv = (c & 1) ? inv[i][c >> 1].y : inv[i][c >> 1].x;
+          const float hk = (sm >= kPFloor) ? fmaf(gA, iv, WG) : 0.f;  // h_k / p_k, 0 where the recon clamp fired
           o[c] = fminf(sm, 1.0f) * hk - sm * hsum;
         }
       }
-      if (q == q_x0) {
-        const float v = fmaf(-sm_x0, hsum, h_x0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = ((x0 & 3u) == static_cast<uint32_t>(c)) ? v : o[c];
-      }
-      if (q == q_j) {
-        const float v = fmaf(-sm_j, hsum, h_j);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = ((j & 3u) == static_cast<uint32_t>(c)) ? v : o[c];
-      }
       st_stream4(rg + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
     }
+    // the two special classes: their owners overwrite the generic value (same thread, same address: program order)
+    if (tg == static_cast<int>(q_x0 & 127u)) rg[x0] = fmaf(-sm_x0, hsum, h_x0);
+    if (j_other && tg == static_cast<int>(q_j & 127u)) rg[j] = fmaf(-sm_j, hsum, h_j);
   }
   if (status_bits != 0 && tg == 0 && p.status != nullptr) atomicOr(p.status, status_bits);
 }
@@ -375,7 +441,7 @@ int launch_train_stream_t(const TrainParams& p, cudaStream_t s) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
-  const size_t smem = sizeof(TrainGroupSmem<NP>) * kGroupsPerCta;
+  const size_t smem = sizeof(TrainGroupSmem<NP>) * kGroupsPerCta + kCoefSmemRows * 16 * sizeof(float);
   auto kern = train_stream_kernel<NP, WRITE_GRAD>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
