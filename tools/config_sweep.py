@@ -4,7 +4,10 @@
     (guidance off = `predict_start` alone, diffusion_transformer.py:220-238, because the reference's own |s-1|<1e-3 branch
     raises, :242-243),
   * config 2 at t in {99, 50, 1, 0} (the coefficient row changes, the traffic does not),
-  * smaller codebooks K in {1024, 2048} at the config-2 grid.
+  * smaller codebooks K in {1024, 2048} at the config-2 grid,
+  * config 1 — ONE video on a 16x8x8 grid (1024 tokens): a latency case; its 33 MB of logits would sit in L2, so the
+    steps cycle through 8 input copies (268 MB > 126 MB L2).  Timed with the kernel the library picks (one CTA per
+    row below 2048 rows) and with the persistent stream kernel forced.
 
 Each line: ms per step (CUDA events, inputs >> L2), token-updates/s and algorithmic GB/s against MEASURED_PEAKS.json.
 
@@ -14,6 +17,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 import torch
 
@@ -40,13 +44,13 @@ class _Stub(torch.nn.Module):
         self.content_emb = type("E", (), {"num_embed": K + 1})()
 
 
-def run(name, B, N, K, t_now, guidance):
+def run(name, B, N, K, t_now, guidance, copies=1, kernel=_lib.KERNEL_AUTO):
     model = d3pm_b200.FusedDiffusionTransformer(transformer=_Stub(K), diffusion_step=T, alpha_init_type="alpha1",
                                                 guidance_scale=2.0, content_seq_len=N).to(dev)
     table = model.coef_table()
     gen = torch.Generator(device=dev).manual_seed(7)
-    lc = torch.randn(B, N, K, device=dev, generator=gen)
-    lu = torch.randn(B, N, K, device=dev, generator=gen) if guidance else None
+    lcs = [torch.randn(B, N, K, device=dev, generator=gen) for _ in range(copies)]
+    lus = [torch.randn(B, N, K, device=dev, generator=gen) if guidance else None for _ in range(copies)]
     p_mask = float(model.log_cumprod_ct[t_now].exp())
     x_t = torch.where(torch.rand(B, N, device=dev, generator=gen) < p_mask, torch.full((B, N), K, device=dev),
                       torch.randint(0, K, (B, N), device=dev, generator=gen))
@@ -55,11 +59,13 @@ def run(name, B, N, K, t_now, guidance):
     status = ops.new_status(dev)
 
     def step(i):
-        ops.fused_step(lc, lu, x_t, t, table, guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX, seed=11, offset=i,
-                       x_prev_out=xp, status=status)
+        ops.fused_step(lcs[i % copies], lus[i % copies], x_t, t, table, guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX,
+                       seed=11, offset=i, x_prev_out=xp, status=status, kernel=kernel)
 
     for i in range(5):
         step(i)
+    torch.cuda.synchronize()
+    time.sleep(2.0)  # let the board's power controller settle: back-to-back cases otherwise run power-capped
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -72,9 +78,10 @@ def run(name, B, N, K, t_now, guidance):
     nbytes = B * N * ((2 if guidance else 1) * K * 4 + 16)
     rec = {"case": name, "videos": B, "tokens_per_video": N, "classes": K + 1, "t": t_now, "guidance": guidance,
            "ms_per_step": ms, "token_updates_per_s": B * N / (ms * 1e-3), "algorithmic_GBps": nbytes / ms / 1e6,
-           "frac_of_measured_peak": nbytes / ms / 1e6 / peak, "logits_bytes_resident": nbytes}
+           "frac_of_measured_peak": nbytes / ms / 1e6 / peak, "logits_bytes_resident": nbytes * copies,
+           "kernel": {_lib.KERNEL_AUTO: "auto", _lib.KERNEL_STREAM: "stream", _lib.KERNEL_ROWS: "rows"}[kernel]}
     print(json.dumps(rec), flush=True)
-    del lc, lu
+    del lcs, lus
     torch.cuda.empty_cache()
     return rec
 
@@ -87,6 +94,8 @@ for t_now in (99, 50, 1, 0):
 out.append(run("config2 guidance off", 16, 4096, 4096, 50, False))
 for K in (2048, 1024):
     out.append(run(f"config2 grid, K={K}", 16, 4096, K, 50, True))
+out.append(run("config1 (1 video, 16x8x8 grid), library's choice", 1, 1024, 4096, 50, True, copies=8))
+out.append(run("config1, stream kernel forced", 1, 1024, 4096, 50, True, copies=8, kernel=_lib.KERNEL_STREAM))
 if a.json:
     with open(a.json, "w") as f:
         json.dump({"peak_GBps": peak, "cases": out}, f, indent=1)

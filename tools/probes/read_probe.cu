@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(512, 1) probe_tma(const float* __restrict__ a,
   if (acc == 12345.678f) out[0] = acc;
 }
 
-int main() {
+int main(int argc, char** argv) {
   const long long rows = 65536, K = 4096;
   const size_t n = (size_t)rows * K;
   float *a, *b, *out;
@@ -88,6 +88,25 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
     printf("%-44s %.3f ms  %.0f GB/s  (%s)\n", name, ms, 2.0 * n * 4 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
   };
+  if (argc > 1) {  // sustained mode: 30 chunks of 100 launches of the best plain-load configuration and of the TMA skeleton
+    auto kt = probe_tma<1, 4096>; const int smem_t = 4 * (1 * 2 * 4096 + 64) * 4;
+    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t);
+    for (int mode = 0; mode < 2; ++mode) {
+      printf("sustained %s:", mode ? "tma 1 stage" : "ldg.v4 grid=1184 block=512");
+      for (int c = 0; c < 30; ++c) {
+        cudaEventRecord(e0);
+        for (int i = 0; i < 100; ++i) {
+          if (mode) kt<<<148, 512, smem_t>>>(a, b, rows, out);
+          else probe_ldg<<<1184, 512>>>((const float4*)a, (const float4*)b, n / 4, out);
+        }
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf(" %.0f", 2.0 * n * 4 / (ms / 100) / 1e6);
+      }
+      printf(" GB/s\n");
+    }
+    return 0;
+  }
   for (int ctas : {148 * 4, 148 * 8, 148 * 16})
     for (int thr : {256, 512}) {
       char nm[64]; snprintf(nm, 64, "ldg.v4 grid=%d block=%d", ctas, thr);

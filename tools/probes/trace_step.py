@@ -11,8 +11,10 @@ T, K, N, B = 100, 4096, 4096, 16
 table = ops.build_coef_table(O.pack_schedule(O.make_schedule(T, K)).to(dev), T, K)
 g = torch.Generator(device=dev).manual_seed(0)
 lc = torch.randn(B, N, K, device=dev, generator=g); lu = torch.randn(B, N, K, device=dev, generator=g)
-x_t = torch.where(torch.rand(B, N, device=dev, generator=g) < 0.5, torch.full((B, N), K, device=dev), torch.randint(0, K, (B, N), device=dev, generator=g))
-t = torch.full((B,), 50, dtype=torch.int64, device=dev)
+PM = float(O.make_schedule(T, K)['log_cumprod_ct'][int(os.environ.get('T_NOW', '50'))].exp())
+x_t = torch.where(torch.rand(B, N, device=dev, generator=g) < PM, torch.full((B, N), K, device=dev), torch.randint(0, K, (B, N), device=dev, generator=g))
+TNOW = int(os.environ.get("T_NOW", "50"))
+t = torch.full((B,), TNOW, dtype=torch.int64, device=dev)
 xp = torch.empty_like(x_t)
 for it in range(6):
     st = torch.zeros(592 * 8, dtype=torch.int32, device=dev)
