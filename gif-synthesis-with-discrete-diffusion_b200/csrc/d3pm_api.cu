@@ -351,8 +351,8 @@ int d3pm_head_step(const d3pm_head_desc* d) {
     return fail(D3PM_ERR_CUDA, "head_step: cannot query the device");
   if (d->mode == D3PM_HEAD_REFERENCE) {
     const unsigned grid = static_cast<unsigned>(rows < 8LL * sms ? rows : 8LL * sms);
-    if (has_u) H::head_redo_kernel<64, true><<<grid, 256, 0, s>>>(p, 1);
-    else H::head_redo_kernel<64, false><<<grid, 256, 0, s>>>(p, 1);
+    if (has_u) H::head_redo_kernel<64, true><<<grid, H::kRedoThreads, 0, s>>>(p, 1);
+    else H::head_redo_kernel<64, false><<<grid, H::kRedoThreads, 0, s>>>(p, 1);
     return check_launch("head_step(reference)");
   }
   const size_t smem = H::smem_bytes<64>();
@@ -375,8 +375,8 @@ int d3pm_head_step(const d3pm_head_desc* d) {
   if (rc != D3PM_OK) return rc;
   rc = check_launch("head_step");
   if (rc != D3PM_OK) return rc;
-  if (has_u) H::head_redo_kernel<64, true><<<sms, 256, 0, s>>>(p, 0);
-  else H::head_redo_kernel<64, false><<<sms, 256, 0, s>>>(p, 0);
+  if (has_u) H::head_redo_kernel<64, true><<<sms, H::kRedoThreads, 0, s>>>(p, 0);
+  else H::head_redo_kernel<64, false><<<sms, H::kRedoThreads, 0, s>>>(p, 0);
   return check_launch("head_step(redo)");
 }
 

@@ -43,8 +43,11 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 32 * (kEpiWarps + 2);
 constexpr int kRowThreads4 = kEpiThreads / kTileM;  // threads that build one row of the A operand (4)
 static_assert(kCols == 32 && kRowThreads4 == 4, "the epilogue below is written for 16 epilogue warps");
-constexpr int kCand = 14;
-constexpr float kThin = 6.0f;
+// Survivor lists of 30 classes per row and a thinning constant of 8 (the unfused kernels: 14 and 6): a row the race
+// cannot decide costs a whole CTA of head_redo_kernel (2 MiB of weight image through L2, ~25 us), so they are made
+// rare - e^-8 of the rows, ~20 per 65 536 - at the price of 8 instead of 6 survivors per row to score.
+constexpr int kCand = 30;
+constexpr float kThin = 8.0f;
 constexpr int kBlockBytes = kTileM * 128;  // one 128-byte k-block of a 128-row operand
 // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kChunk >> 3) << 17) | ((kTileM >> 4) << 24);
@@ -89,8 +92,8 @@ struct Ctl {
   float yj2[kTileM];
   RowInfo info[kTileM];
   uint32_t cand_cnt[kTileM];
-  uint32_t cand_k[kTileM][kCand];
   float cand_p[kTileM][kCand];
+  uint16_t cand_k[kTileM][kCand];  // K <= 8192
 };
 
 template <int D>
@@ -327,23 +330,27 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
           ri = C.info[slot];
           cnt = C.cand_cnt[slot];
           const uint32_t n = cnt < static_cast<uint32_t>(kCand) ? cnt : static_cast<uint32_t>(kCand);
-          uint32_t k = 0;
-          float P = 0.f;
-          bool have = false;
-          if (static_cast<uint32_t>(sub) < n) {
-            k = C.cand_k[slot][sub];
-            const float pe = fminf(fmaxf(C.cand_p[slot][sub], kPFloor), 1.0f);
-            P = fmaf(pe, ri.A, ri.Bc);
-            have = (k != ri.j);
-          } else if (sub == 14) {
-            k = static_cast<uint32_t>(p.K), P = ri.PK, have = true;
-          } else if (sub == 15 && ri.j != static_cast<uint32_t>(p.K)) {
-            k = ri.j, P = ri.Pj, have = true;
-          }
-          if (have) {
-            const float sc = log_prob_clamped(P) +
-                             gumbel_from_uniform(uniform_from_draw(rng.draw(k, static_cast<uint64_t>(p.row_offset + lrow))));
-            key = pack_key(sc, k);
+          // items 0 .. n-1: the survivors, item n: [MASK], item n+1: the row's own class; one or two rounds of 16 lanes
+          for (uint32_t item = static_cast<uint32_t>(sub); item < n + 2u; item += 16u) {
+            uint32_t k = 0;
+            float P = 0.f;
+            bool have = false;
+            if (item < n) {
+              k = C.cand_k[slot][item];
+              const float pe = fminf(fmaxf(C.cand_p[slot][item], kPFloor), 1.0f);
+              P = fmaf(pe, ri.A, ri.Bc);
+              have = (k != ri.j);
+            } else if (item == n) {
+              k = static_cast<uint32_t>(p.K), P = ri.PK, have = true;
+            } else if (ri.j != static_cast<uint32_t>(p.K)) {
+              k = ri.j, P = ri.Pj, have = true;
+            }
+            if (have) {
+              const float sc = log_prob_clamped(P) +
+                               gumbel_from_uniform(uniform_from_draw(rng.draw(k, static_cast<uint64_t>(p.row_offset + lrow))));
+              const unsigned long long kk = pack_key(sc, k);
+              key = kk > key ? kk : key;
+            }
           }
         }
 #pragma unroll
@@ -600,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
                 if ((hl ? d[w].y : d[w].x) >= 0.0f) {
                   const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
                   if (pos < static_cast<uint32_t>(kCand)) {
-                    C.cand_k[erow][pos] = k0 + 4 * c8 + (w >> 1) * 512 + 2 * (w & 1) + hl;
+                    C.cand_k[erow][pos] = static_cast<uint16_t>(k0 + 4 * c8 + (w >> 1) * 512 + 2 * (w & 1) + hl);
                     C.cand_p[erow][pos] = (hl ? e[w].y : e[w].x) * rS;
                   }
                 }
@@ -625,11 +632,16 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
 // ---- rescoring of the rows the race could not decide (probability ~e^-c per row) and reference CUDA-core path ----------
 // One CTA per listed row: the combined logits of the row in plain fp32 FMAs, then exhaustive exact Gumbel scoring (the
 // same arithmetic as the exhaustive path of step_rows_kernel).
+// 1024 threads per row (at most 8 classes each, their weight loads all in flight at once): the launch lasts as long as
+// ONE row when few rows are listed, and that latency follows every fused step.
+constexpr int kRedoThreads = 1024;
 template <int D, bool HAS_U>
-__global__ void __launch_bounds__(256) head_redo_kernel(const HeadParams p, int all_rows) {
-  constexpr int NW = 8;
+__global__ void __launch_bounds__(kRedoThreads) head_redo_kernel(const HeadParams p, int all_rows) {
+  constexpr int NW = kRedoThreads / 32;
+  constexpr int kPer = 8;  // K <= 8192
   __shared__ float sa[D];
-  __shared__ float sred[2][4 * NW];
+  __shared__ float sred[2][NW];
+  __shared__ float ys[1024 * kPer];  // the row's logits (log2 units)
   __shared__ unsigned long long skey[NW];
   __shared__ float syj;
   const int tid = threadIdx.x;
@@ -662,27 +674,40 @@ __global__ void __launch_bounds__(256) head_redo_kernel(const HeadParams p, int 
     if (tt < 0 || tt >= p.T) tt = tt < 0 ? 0 : p.T - 1;
     const bool masked = (jj == p.K);
     const uint32_t j = static_cast<uint32_t>(jj);
-    float y[32];  // K <= 8192: classes tid + 256 i
-    const int per = p.K / 256;
-    float m = -CUDART_INF_F;
-#pragma unroll 1
-    for (int i = 0; i < per; ++i) {
-      const int k = tid + 256 * i;
-      float dot = 0.f;
+    // logits of the row: the eight lanes of a class read the eight 16-byte pieces of its 128-byte image rows (one
+    // coalesced line per class, term and k-block; one class per thread touched 32 lines per load instruction and the
+    // kernel spent its time in the load queue), four classes per warp pass, products summed across the eight lanes
+    {
+      const int piece = tid & 7, c4 = (tid >> 3) & 3, wrp = tid >> 5;
+      float4 av[Geo<D>::KB];
 #pragma unroll
-      for (int kb = 0; kb < Geo<D>::KB; ++kb)
+      for (int kb = 0; kb < Geo<D>::KB; ++kb) av[kb] = *reinterpret_cast<const float4*>(sa + 32 * kb + 4 * piece);
+#pragma unroll 4
+      for (int k = 4 * wrp + c4; k < p.K; k += 4 * NW) {
+        float dot = 0.f;
 #pragma unroll
-        for (int piece = 0; piece < 8; ++piece) {
+        for (int kb = 0; kb < Geo<D>::KB; ++kb) {
           const float4 hi = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(k, 0, kb, piece)));
           const float4 lo = __ldg(reinterpret_cast<const float4*>(p.w_image + image_offset<D>(k, 1, kb, piece)));
-          const float* av = sa + 32 * kb + 4 * piece;
-          dot = fmaf(av[0], hi.x + lo.x, dot), dot = fmaf(av[1], hi.y + lo.y, dot);
-          dot = fmaf(av[2], hi.z + lo.z, dot), dot = fmaf(av[3], hi.w + lo.w, dot);
+          dot = fmaf(av[kb].x, hi.x + lo.x, dot), dot = fmaf(av[kb].y, hi.y + lo.y, dot);
+          dot = fmaf(av[kb].z, hi.z + lo.z, dot), dot = fmaf(av[kb].w, hi.w + lo.w, dot);
         }
-      y[i] = dot + __ldg(p.bias2 + k);
-      if (static_cast<uint32_t>(k) == j) syj = y[i];
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        if (piece == 0) ys[k] = dot + __ldg(p.bias2 + k);
+      }
+    }
+    __syncthreads();
+    float y[kPer];  // classes tid + 1024 i
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int k = tid + kRedoThreads * i;
+      y[i] = k < p.K ? ys[k] : -CUDART_INF_F;
       m = fmaxf(m, y[i]);
     }
+    if (tid == 0 && !masked) syj = ys[j];
     // softmax statistics in log2 units
     m = warp_max(m);
     if ((tid & 31) == 0) sred[0][tid >> 5] = m;
@@ -690,8 +715,9 @@ __global__ void __launch_bounds__(256) head_redo_kernel(const HeadParams p, int 
     float M2 = sred[0][0];
     for (int w = 1; w < NW; ++w) M2 = fmaxf(M2, sred[0][w]);
     float s = 0.f;
-    for (int i = 0; i < per; ++i) {
-      y[i] = ex2(y[i] - M2);
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      y[i] = ex2(y[i] - M2);  // 0 for the slots beyond K
       s += y[i];
     }
     s = warp_sum(s);
@@ -706,8 +732,10 @@ __global__ void __launch_bounds__(256) head_redo_kernel(const HeadParams p, int 
     rm.init(cf, masked, pj, j, p.K);
     const uint64_t grow = static_cast<uint64_t>(p.row_offset + lrow);
     unsigned long long best = 0ull;
-    for (int i = 0; i < per; ++i) {
-      const uint32_t k = tid + 256 * i;
+#pragma unroll 2
+    for (int i = 0; i < kPer; ++i) {
+      const uint32_t k = tid + kRedoThreads * i;
+      if (k >= static_cast<uint32_t>(p.K)) break;
       const float sc = rm.post_of(k, y[i], rS) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
       const unsigned long long key = pack_key(sc, k);
       best = key > best ? key : best;
