@@ -220,7 +220,9 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
   }
 }
 
-template <int NP, bool HAS_U>
+// RECON: the purity-prior variant (draw from p(x0 | x_t), write the purity score); its own instantiation so that the
+// plain step's code is not perturbed
+template <int NP, bool HAS_U, bool RECON>
 __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int K = 1024 * NP;
@@ -451,7 +453,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       cf = load_row_coef(p.coef_table, tt, masked);
     }
     RowMath rm;
-    rm.init(cf, masked, pj, j, K);
+    if (RECON) {
+      // purity-prior sampling (:309-346) draws the candidate from p(x0 | x_t) itself and scores the token by its
+      // largest probability, 1 / (sum of the softmax numerators relative to the row maximum)
+      rm.init_recon(masked ? 0.f : pj, masked ? static_cast<uint32_t>(K) + 1u : j);
+      if (tg == 0 && p.score != nullptr) p.score[row] = fminf(fmaxf(rSy, kPFloor), 1.0f);
+    } else {
+      rm.init(cf, masked, pj, j, K);
+    }
 
     if (!exact) {
       // ---- thinned race: 16 noise bits per class, survivors go to this row's slot ----
@@ -694,7 +703,7 @@ constexpr long long kStreamMinRows = 1024;  // below this the one-CTA-per-row ke
 inline bool stream_kernel_supports(const StepParams& p) {
   if (p.sample_mode != D3PM_SAMPLE_PHILOX && p.sample_mode != D3PM_SAMPLE_PHILOX_EXACT) return false;
   if (p.post != nullptr || p.recon != nullptr || p.gap != nullptr || p.x_prev == nullptr) return false;
-  if (p.sample_from != D3PM_FROM_POSTERIOR || p.score != nullptr || p.sharpen != nullptr) return false;
+  if (p.sharpen != nullptr || (p.score != nullptr && p.sample_from != D3PM_FROM_RECON)) return false;
   if (p.K != 1024 && p.K != 2048 && p.K != 4096) return false;
   if (p.pitch_logits >= (1LL << 32)) return false;  // row offsets are formed as 32 x 32 -> 64 bit products
   return true;
@@ -708,17 +717,22 @@ inline long long stream_kernel_max_rows() {
   return static_cast<long long>(kRedoCap) * kGroupsPerCta * sms;
 }
 
-template <int NP, bool HAS_U>
-int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
+template <int NP, bool HAS_U, bool RECON>
+int launch_step_stream_r(const StepParams& p, cudaStream_t s) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
   const size_t smem = sizeof(GroupSmem<NP>) * kGroupsPerCta + kCoefSmemRows * 16 * sizeof(float);
-  auto kern = step_stream_kernel<NP, HAS_U>;
+  auto kern = step_stream_kernel<NP, HAS_U, RECON>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
   kern<<<static_cast<unsigned>(sms), kStreamThreads, smem, s>>>(p);
   return D3PM_OK;
+}
+
+template <int NP, bool HAS_U>
+int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
+  return p.sample_from == D3PM_FROM_RECON ? launch_step_stream_r<NP, HAS_U, true>(p, s) : launch_step_stream_r<NP, HAS_U, false>(p, s);
 }
 
 inline int launch_step_stream(const StepParams& p, cudaStream_t s) {

@@ -144,3 +144,29 @@ def test_sample_chain_with_purity_prior():
     t = torch.full((B,), 57, dtype=torch.int64, device=DEV)
     y, sampled = m.p_sample_tokens_purity(x, cond, cf, t, [0] * B, m.n_sample[57])
     assert sampled == [m.n_sample[57]] * B and ((y != K).sum(1) == m.n_sample[57]).all()
+
+
+def test_candidate_draw_and_purity_on_the_stream_kernel():
+    """The purity-prior candidate draw (x0 ~ p(x0 | x_t), D3PM_FROM_RECON) and the purity score on the persistent stream
+    kernel: same candidates as its exhaustive mode and as the one-CTA-per-row kernel, scores equal to 1e-5."""
+    from d3pm_b200 import _lib, ops
+    from oracle import d3pm_oracle as O
+    T, K, B, N = 100, 4096, 2, 1500
+    dev = "cuda:0"
+    table = ops.build_coef_table(O.pack_schedule(O.make_schedule(T, K)).to(dev), T, K)
+    g = torch.Generator(device=dev).manual_seed(2)
+    lc, lu = torch.randn(B, N, K, device=dev, generator=g) * 2, torch.randn(B, N, K, device=dev, generator=g) * 2
+    x_t = torch.where(torch.rand(B, N, device=dev, generator=g) < 0.6, torch.full((B, N), K, device=dev),
+                      torch.randint(0, K, (B, N), device=dev, generator=g))
+    t = torch.tensor([70, 20], device=dev)
+    kw = dict(guidance_scale=2.0, seed=8, offset=3, sample_from=_lib.FROM_RECON, want_score=True)
+    outs = {}
+    for name, mode, kern in (("stream", _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM), ("stream_exact", _lib.SAMPLE_PHILOX_EXACT, _lib.KERNEL_STREAM),
+                             ("rows", _lib.SAMPLE_PHILOX, _lib.KERNEL_ROWS), ("rows_exact", _lib.SAMPLE_PHILOX_EXACT, _lib.KERNEL_ROWS)):
+        outs[name] = ops.fused_step(lc, lu, x_t, t, table, sample_mode=mode, kernel=kern, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(outs["stream"]["x_prev"], outs["stream_exact"]["x_prev"])
+    assert torch.equal(outs["rows"]["x_prev"], outs["rows_exact"]["x_prev"])
+    assert (outs["stream"]["x_prev"] != outs["rows"]["x_prev"]).float().mean() < 1e-3   # p may differ in the last bit
+    torch.testing.assert_close(outs["stream"]["score"], outs["rows"]["score"], rtol=1e-5, atol=0)
+    assert int(outs["stream"]["x_prev"].max()) < K        # a candidate is never [MASK]
