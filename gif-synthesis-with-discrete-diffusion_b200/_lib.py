@@ -15,7 +15,7 @@ _LIB_NAME = "libd3pm_b200.so"
 EXPORTED_SYMBOLS = (
     "d3pm_version", "d3pm_last_error", "d3pm_build_coef_table", "d3pm_fused_step", "d3pm_philox_uniform",
     "d3pm_q_posterior", "d3pm_gumbel_argmax", "d3pm_tokens_to_log_onehot", "d3pm_argmax_classes",
-    "d3pm_to_token_major", "d3pm_q_pred", "d3pm_train_rows", "d3pm_purity_select",
+    "d3pm_to_token_major", "d3pm_q_pred", "d3pm_q_sample_tokens", "d3pm_train_rows", "d3pm_purity_select",
     "d3pm_head_image_floats", "d3pm_head_prepare", "d3pm_head_step", "d3pm_scale_rows",
     "d3pm_decode_lut", "d3pm_tokens_to_features",
 )
@@ -119,6 +119,9 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_argmax_classes.restype = c_int
     lib.d3pm_argmax_classes.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                         c_void_p]
+    lib.d3pm_q_sample_tokens.restype = c_int
+    lib.d3pm_q_sample_tokens.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_uint64, c_uint64, c_int64,
+                                         c_void_p, c_void_p, c_void_p]
     lib.d3pm_q_pred.restype = c_int
     lib.d3pm_q_pred.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int,
                                 c_int, c_void_p]

@@ -239,6 +239,19 @@ int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float
   return check_launch("q_pred");
 }
 
+int d3pm_q_sample_tokens(const int64_t* x0, const int64_t* t, const float* sched, int B, int N, int K, int T, uint64_t seed,
+                         uint64_t offset, int64_t row_offset, int64_t* x_t, uint32_t* status, d3pm_stream_t stream) {
+  if (x0 == nullptr || t == nullptr || sched == nullptr || x_t == nullptr) return fail(D3PM_ERR_INVALID, "q_sample_tokens: null pointer");
+  if (B <= 0 || N <= 0 || K <= 0 || T <= 0) return fail(D3PM_ERR_INVALID, "q_sample_tokens: sizes must be positive");
+  if (K % 4 != 0 || K > 8192) return fail(D3PM_ERR_UNSUPPORTED, "q_sample_tokens: K=%d must be a multiple of 4 and <= 8192", K);
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  const int64_t grid = (rows + d3pm::kQSampleWarps - 1) / d3pm::kQSampleWarps;
+  if (grid > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "q_sample_tokens: B*N too large");
+  d3pm::q_sample_tokens_kernel<<<static_cast<unsigned>(grid), 32 * d3pm::kQSampleWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+      x0, t, sched, T, K, N, rows, seed, offset, row_offset, x_t, status);
+  return check_launch("q_sample_tokens");
+}
+
 int d3pm_train_rows(const d3pm_train_desc* d) {
   if (d == nullptr) return fail(D3PM_ERR_INVALID, "train_rows: null descriptor");
   if (d->logits == nullptr || d->x0 == nullptr || d->x_t == nullptr || d->t == nullptr || d->coef_table == nullptr)

@@ -276,4 +276,97 @@ __global__ void __launch_bounds__(kRowThreads) q_pred_rows_kernel(const float* _
   if (threadIdx.x == 0) o[K] = lae32(r[K] + l1c, lc);
 }
 
+
+// ---------------------------------------------------------------- q_sample on integer tokens (:361-366), Philox noise
+// x_t ~ q(x_t | x_0) for a one-hot x_0.  The reference materialises the log one-hot, q_pred and the Gumbel tensor; the
+// row q_pred would produce takes three values only (x_0 itself, any other code, [MASK]), so this kernel forms them
+// with the SAME expressions as q_pred_rows_kernel on a log one-hot and runs the SAME race as gumbel_argmax_rows_kernel
+// in its Philox mode (score = q_k + Gumbel(u_k), u_k from NoiseStream::draw) - but thinned: a code other than x_0 can
+// only win if its 16 coarse noise bits are below c P_other / P_tot, one integer compare per class and no memory
+// traffic at all.  One warp per token; tokens identical to the three-kernel route (tested).
+constexpr int kQSampleWarps = 8;
+// exact score of one class (rare: ~6 codes + 2 special classes per token); a real call keeps the sweep below small
+__device__ __noinline__ unsigned long long q_sample_score(uint32_t k, uint64_t grow, uint64_t seed, uint64_t offset, float q) {
+  const NoiseStream rng(seed, offset);
+  return pack_key(gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow))) + q, k);
+}
+__global__ void __launch_bounds__(32 * kQSampleWarps) q_sample_tokens_kernel(
+    const int64_t* __restrict__ x0, const int64_t* __restrict__ t, const float* __restrict__ sched, int T, int K, int N,
+    int64_t rows, uint64_t seed, uint64_t offset, int64_t row_offset, int64_t* __restrict__ x_t, uint32_t* status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kQSampleWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int P = T + 1;
+  long long tt = t[row / N];
+  tt = ((tt % P) + P) % P;
+  const float la = sched[4 * P + tt], lb = sched[5 * P + tt], lc = sched[6 * P + tt], l1c = sched[7 * P + tt];
+  long long j64 = x0[row];
+  if (j64 < 0 || j64 > K) {  // the log one-hot of such a token has no 0 entry at all
+    if (lane == 0 && status != nullptr) atomicOr(status, D3PM_STATUS_BAD_TOKEN);
+    j64 = -1;
+  }
+  const uint32_t j = static_cast<uint32_t>(j64);  // 0xffffffff: no class is "self"
+  const float q_self = lae32(0.0f + la, lb), q_other = lae32(kLogTiny + la, lb);
+  const float q_mask = lae32((j64 == K ? 0.0f : kLogTiny) + l1c, lc);
+  const NoiseStream rng(seed, offset);
+  const uint64_t grow = static_cast<uint64_t>(row_offset + row);
+  auto score_of = [&](uint32_t k) {
+    const float q = (k == static_cast<uint32_t>(K)) ? q_mask : (k == j ? q_self : q_other);
+    return q_sample_score(k, grow, seed, offset, q);
+  };
+  // thinning: E_k >= h_k / 2^16, a code other than x_0 can only reach ln(P_tot / c) if E_k <= c P_other / P_tot
+  const float p_other = expf(q_other);
+  const float p_tot = fmaf(static_cast<float>(K - 1), p_other, expf(q_self) + expf(q_mask));
+  const float c = 12.0f;  // other codes carry almost no mass (b_t is tiny), so a wide bound costs nothing and the
+                          // score-everything fallback below (e^-c of the tokens) stays out of the launch's tail
+  const float hf = (c * p_other / p_tot) * 65536.0f * 1.001f + 2.0f;
+  const uint32_t hmax = hf >= 65535.0f ? 0xffffu : static_cast<uint32_t>(hf);
+  const float accept = logf(p_tot / c) + 0.02f;
+  unsigned long long best = 0ull;
+  const int nq = K >> 2;                               // float4 chunks of the codes
+  const int ncalls = ((nq + 255) >> 8) << 7;           // coarse calls that cover them
+  for (int call = lane; call < ncalls; call += 32) {
+    const uint4 cw = rng.coarse(static_cast<uint32_t>(call), grow);
+    const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+    const int chunk_lo = ((call >> 7) << 8) | (call & 127);
+    // smallest of the eight halves first: almost every call ends here
+    const uint32_t m01 = min(min(w4[0] & 0xffffu, w4[0] >> 16), min(w4[1] & 0xffffu, w4[1] >> 16));
+    const uint32_t m23 = min(min(w4[2] & 0xffffu, w4[2] >> 16), min(w4[3] & 0xffffu, w4[3] >> 16));
+    if (min(m01, m23) > hmax) continue;
+    uint32_t hits = 0;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const uint32_t half = (h & 1) ? (w4[h >> 1] >> 16) : (w4[h >> 1] & 0xffffu);
+      hits |= (half <= hmax ? 1u : 0u) << h;
+    }
+    while (hits != 0) {
+      const int h = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const uint32_t k = 4u * static_cast<uint32_t>(chunk_lo + 128 * (h >> 2)) + (h & 3);
+      if (k < static_cast<uint32_t>(K) && k != j) {
+        const unsigned long long key = score_of(k);
+        best = key > best ? key : best;
+      }
+    }
+  }
+  if (lane == 0) {
+    const unsigned long long key = score_of(static_cast<uint32_t>(K));
+    best = key > best ? key : best;
+  }
+  if (lane == 1 && j < static_cast<uint32_t>(K)) {
+    const unsigned long long key = score_of(j);
+    best = key > best ? key : best;
+  }
+  best = warp_max_u64(best);
+  if (!(key_score(best) >= accept)) {  // probability ~e^-c: score every class
+    best = 0ull;
+    for (uint32_t k = lane; k <= static_cast<uint32_t>(K); k += 32) {
+      const unsigned long long key = score_of(k);
+      best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+  }
+  if (lane == 0) x_t[row] = key_class(best);
+}
+
 }  // namespace d3pm

@@ -525,10 +525,14 @@ class FusedDiffusionTransformer(nn.Module):
     def q_sample_tokens(self, x_start, t):
         """The same on integer tokens: int64 `[B, N]` -> int64 `[B, N]`."""
         C = self.num_classes
-        hot = ops.tokens_to_log_onehot_rows(x_start.contiguous(), C, self._status_word())
-        qrows = train.q_pred_rows(hot, hot.shape[2], t, self._sched8(), C - 1, cumulative=True)
         B, N = x_start.shape
         noise = self._noise_rows(B, N)
+        if noise is None and (C - 1) % 4 == 0 and C - 1 <= 8192:
+            # own noise: one kernel, none of the three [B, K+1, N] tensors (same tokens as the route below, tested)
+            return train.q_sample_tokens(x_start, t, self._sched8(), C - 1, seed=self.rng_seed, offset=self._next_offset(),
+                                         row_offset=self.row_offset, status=self._status_word())
+        hot = ops.tokens_to_log_onehot_rows(x_start.contiguous(), C, self._status_word())
+        qrows = train.q_pred_rows(hot, hot.shape[2], t, self._sched8(), C - 1, cumulative=True)
         if noise is not None:
             return ops.gumbel_argmax_rows(qrows, qrows.shape[2], C, noise_rows=noise[0], pitch_noise=noise[1], noise_kind=1)
         return ops.gumbel_argmax_rows(qrows, qrows.shape[2], C, noise_kind=2, seed=self.rng_seed,

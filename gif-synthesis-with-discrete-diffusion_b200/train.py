@@ -25,6 +25,19 @@ def q_pred_rows(rows: torch.Tensor, pitch: int, t: torch.Tensor, sched8: torch.T
     return out
 
 
+def q_sample_tokens(x0: torch.Tensor, t: torch.Tensor, sched8: torch.Tensor, K: int, *, seed: int, offset: int,
+                    row_offset: int = 0, status=None) -> torch.Tensor:
+    """`d3pm_q_sample_tokens`: x_t ~ q(x_t | x_0) on int64 tokens `[B, N]` with the library's Philox noise (:361-366)."""
+    dev = ops._need_cuda(x0, t, sched8, status)
+    B, N = x0.shape
+    out = torch.empty_like(x0)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_q_sample_tokens(x0.contiguous().data_ptr(), t.contiguous().data_ptr(), sched8.data_ptr(), B, N, K,
+                                        sched8.shape[1] - 1, seed, offset, row_offset, out.data_ptr(), ops._ptr(status),
+                                        ops._stream(dev)), "d3pm_q_sample_tokens")
+    return out
+
+
 def _logit_rows(logits_bkn: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """Denoiser output, logically `[B, K, N]` -> token-major `[B, N, K]` rows (zero-copy for the reference's layout)."""
     got = ops.rows_of(logits_bkn)

@@ -156,6 +156,14 @@ int d3pm_purity_select(const int64_t* x_t, const int64_t* x_cand, const float* s
 int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float* sched, int cumulative,
                 float* out, int64_t pitch_out, int B, int N, int K, int T, d3pm_stream_t stream);
 
+/* q_sample (:361-366) on integer tokens with the library's Philox noise: x_t[b][n] ~ q(x_t | x_0 = x0[b][n]) at the
+ * per-video timestep t[b], i.e. index_to_log_onehot -> q_pred -> log_sample_categorical of the reference without any
+ * of the three [B, K+1, N] tensors.  Bit-identical to d3pm_tokens_to_log_onehot + d3pm_q_pred + d3pm_gumbel_argmax
+ * (Philox noise) with the same seed / offset / row_offset.  x0 in [0, K] (K = [MASK]); K % 4 == 0, K <= 8192.    */
+int d3pm_q_sample_tokens(const int64_t* x0, const int64_t* t, const float* sched, int B, int N, int K, int T,
+                         uint64_t seed, uint64_t offset, int64_t row_offset, int64_t* x_t, uint32_t* status,
+                         d3pm_stream_t stream);
+
 /* The variational-bound loss of _train_loss (:391-457) given the denoiser logits, the clean tokens x0, the noised
  * tokens x_t (from q_sample, :361-366) and t; and its gradient with respect to the logits.
  *   backward == 0: writes per-token tok_main / tok_aux (the caller sums them per video: kl_loss = sum tok_main,

@@ -201,3 +201,28 @@ def test_upstream_gradient_other_than_announced():
     want = grads[0] * (B * N)
     want[1] *= 0.25
     assert (logits.grad - want).abs().max() <= 2e-6 * want.abs().max()
+
+
+@pytest.mark.parametrize("K,N", [(4096, 1024), (2048, 700), (64, 333)])
+def test_fused_q_sample_tokens_equals_the_three_kernel_route(K, N):
+    """d3pm_q_sample_tokens (one kernel, thinned race, no [B, K+1, N] tensor) draws exactly the tokens of
+    tokens_to_log_onehot -> q_pred -> Gumbel-max with the same Philox stream, for every timestep incl. the wrap at
+    t = -1 and for x_0 = [MASK]; the [MASK] rate follows the schedule."""
+    from d3pm_b200 import _lib, ops, train
+    T, B = 100, 12
+    m = _model(K, T, N, torch.zeros(1, 1, K, device=DEV))
+    g = torch.Generator(device=DEV).manual_seed(K + N)
+    x0 = torch.randint(0, K, (B, N), device=DEV, generator=g)
+    x0[0, :7] = K                                            # a few [MASK] inputs
+    t = torch.tensor([0, 1, 5, 20, 37, 50, 63, 80, 95, 98, 99, -1], device=DEV)
+    sched8 = m._sched8()
+    kw = dict(seed=77, offset=5, row_offset=4321)
+    fused = train.q_sample_tokens(x0, t, sched8, K, **kw)
+    hot = ops.tokens_to_log_onehot_rows(x0, K + 1)
+    qrows = train.q_pred_rows(hot, hot.shape[2], t, sched8, K, cumulative=True)
+    ref = ops.gumbel_argmax_rows(qrows, qrows.shape[2], K + 1, noise_kind=2, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, ref)
+    ct = m.log_cumprod_ct[t[:-1]].exp().cpu()
+    rate = (fused[1:-1] == K).float().mean(1).cpu()
+    assert (rate - ct[1:]).abs().max() < 6.0 * (0.25 / N) ** 0.5
