@@ -260,6 +260,8 @@ def run_ours(args):
     extras = {}
     if rank == 0:
         try:
+            global _NEXT_ROWS_LOGITS
+            _NEXT_ROWS_LOGITS = (logits_c, logits_u)
             extras = measure_next_rows(dev, model, table, x_t, t, x_prev)
         except Exception as exc:  # reported in the JSON line, never swallowed
             extras = {"error": repr(exc)}
@@ -316,6 +318,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_NEXT_ROWS_LOGITS = None
+
+
 def measure_next_rows(dev, model, table, x_t, t, x_prev, reps=20):
     """CUDA-event timings of the SURVEY §8 (f) rows at the bench shape: the denoiser head folded into the update
     (d3pm_head_step, hidden states in, tokens out) next to head-in-torch + d3pm_fused_step, and the training loss with its
@@ -361,7 +366,22 @@ def measure_next_rows(dev, model, table, x_t, t, x_prev, reps=20):
     xt = model.q_sample_tokens(x0, tt)
     w = torch.ones(Bt, device=dev)
     tr = timed(lambda i: train._train_rows(logits, K, x0, xt, tt, table, (1, 1), backward=2, w_main=w, w_aux=w, want_recon=True), reps)
+    qs = timed(lambda i: train.q_sample_tokens(x0, tt, model._sched8(), K, seed=3, offset=i), reps)
+    # purity-prior step (prior_rule 2): candidate draw + purity on the bench's own logits, then the per-video reveal
+    lc, lu = _NEXT_ROWS_LOGITS
+    pur = {}
+
+    def purity(i):
+        pur["o"] = ops.fused_step(lc, lu, x_t, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX, seed=5, offset=i,
+                                  sample_from=_lib.FROM_RECON, want_score=True)
+
+    pd = timed(purity, reps)
+    n_reveal = torch.full((B,), 40, dtype=torch.int32, device=dev)
+    ps = timed(lambda i: ops.purity_select(x_t, pur["o"]["x_prev"], pur["o"]["score"], n_reveal, K, seed=1, offset=i), reps)
     return {
+        "purity_prior_step": {"ms_candidate_draw_and_purity": pd, "ms_reveal": ps,
+                              "what": "p_sample with prior_rule 2: d3pm_fused_step (D3PM_FROM_RECON + score, stream kernel) + d3pm_purity_select"},
+        "q_sample_tokens": {"ms_per_step": qs, "what": "d3pm_q_sample_tokens, 16 x 1024 tokens: forward noising of the training step, one kernel"},
         "head_fused_step": {"ms_per_step": fused, "token_updates_per_s": B * N / (fused * 1e-3), "valid_weight_bound": bool(hw.valid),
                             "what": "d3pm_head_step: LayerNorm + Linear(64 -> 4096) of both denoiser passes + the whole update, "
                                     "tcgen05 3xTF32, logits never in memory"},
