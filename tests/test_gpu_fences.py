@@ -102,3 +102,29 @@ def test_train_stream_stays_inside_its_buffers():
     assert int(out["x0_recon"].max()) < K and int(out["xtm1_recon"].max()) <= K
     dense = train._train_rows(logits.clone(), K, x0, x_t, t, _table(K), (1, 1), backward=2, w_main=w, w_aux=w, want_recon=True)
     assert torch.equal(dense["grad"], out["grad"]) and torch.equal(dense["tok_main"], out["tok_main"])
+
+
+def test_q_sample_tokens_kernel_stays_inside_its_buffers():
+    """d3pm_q_sample_tokens at a row count that leaves the last 8-warp CTA partly empty: sentinels around the token output,
+    out-of-range fences around x_0 / t (any use of them would flag the status word or change the [MASK] rate)."""
+    K, B, N = 1024, 3, 333            # 999 rows: 124 full CTAs + 7 warps
+    bx, x0 = _fenced((B, N), torch.int64, -5)
+    bt, t = _fenced((B,), torch.int64, 10 ** 9)
+    bo, out = _fenced((B, N), torch.int64, -7)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x0.copy_(torch.randint(0, K, (B, N), device=DEV, generator=g))
+    t.copy_(torch.tensor([99, 50, 0], device=DEV))
+    sched8 = torch.zeros(8, T + 1, device=DEV)
+    sched = O.make_schedule(T, K)
+    for i, n in enumerate(("log_at", "log_bt", "log_ct", "log_1_min_ct", "log_cumprod_at", "log_cumprod_bt", "log_cumprod_ct",
+                           "log_1_min_cumprod_ct")):
+        sched8[i, : sched[n].numel()] = sched[n].to(DEV)
+    status = ops.new_status(DEV)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_q_sample_tokens(x0.data_ptr(), t.data_ptr(), sched8.data_ptr(), B, N, K, T, 11, 2, 0, out.data_ptr(),
+                                        status.data_ptr(), torch.cuda.current_stream().cuda_stream), "d3pm_q_sample_tokens")
+    torch.cuda.synchronize()
+    assert _intact(bo, -7) and _intact(bx, -5) and _intact(bt, 10 ** 9)
+    assert int(status.item()) == 0
+    assert int(out.min()) >= 0 and int(out.max()) <= K
+    assert (out[0] == K).float().mean() > 0.97 and (out[2] == x0[2]).float().mean() > 0.99   # t = 99: masked, t = 0: kept
