@@ -179,6 +179,8 @@ int d3pm_gumbel_argmax(const float* logits, int64_t pitch_logits, const float* n
     d3pm::gumbel_argmax_rows_kernel<0><<<grid, block, 0, s>>>(logits, pitch_logits, noise, pitch_noise, x, gap, C, seed, offset, row_offset);
   else if (noise_kind == 1)
     d3pm::gumbel_argmax_rows_kernel<1><<<grid, block, 0, s>>>(logits, pitch_logits, noise, pitch_noise, x, gap, C, seed, offset, row_offset);
+  else if (gap == nullptr && C <= 8193)
+    d3pm::gumbel_argmax_thin_rows_kernel<<<grid, block, 0, s>>>(logits, pitch_logits, x, C, seed, offset, row_offset);
   else
     d3pm::gumbel_argmax_rows_kernel<2><<<grid, block, 0, s>>>(logits, pitch_logits, nullptr, 0, x, gap, C, seed, offset, row_offset);
   return check_launch("gumbel_argmax");

@@ -155,6 +155,108 @@ __global__ void __launch_bounds__(kOpThreads) gumbel_argmax_rows_kernel(
   }
 }
 
+// The same draw (Philox noise) with the race thinned: softmax statistics of the row first, then a class is scored only
+// if its 16 coarse noise bits h satisfy h / 2^16 <= c p_k (it cannot reach ln(sum exp) - ln c otherwise); the winner
+// is accepted when it does reach that bound (probability 1 - e^-c), else every class is scored as in the kernel above.
+// Identical tokens by construction (tested); ~60 instructions per class become ~12.  One CTA per row, a thread per
+// coarse Philox call (the classes of float4 chunks q and q + 128).
+constexpr float kOpThin = 8.0f;
+__device__ __noinline__ unsigned long long gumbel_key_of(float logit, uint32_t k, uint64_t grow, uint64_t seed, uint64_t offset) {
+  const NoiseStream rng(seed, offset);
+  return pack_key(gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow))) + logit, k);
+}
+__global__ void __launch_bounds__(kOpThreads) gumbel_argmax_thin_rows_kernel(const float* __restrict__ logits, int64_t pitch_logits,
+                                                                             int64_t* __restrict__ x, int C, uint64_t seed,
+                                                                             uint64_t offset, int64_t row_offset) {
+  constexpr int NW = kOpThreads / 32;
+  constexpr int kMaxCalls = 5;  // C <= 8193: 2049 chunks -> 1152 calls over 256 threads
+  __shared__ unsigned long long skey[NW];
+  __shared__ float sred[2][NW];
+  const int64_t row = blockIdx.x;
+  const float* __restrict__ lg = logits + row * pitch_logits;
+  const NoiseStream rng(seed, offset);
+  const uint64_t grow = static_cast<uint64_t>(row_offset + row);
+  const int nq = (C + 3) >> 2;
+  const int ncalls = ((nq + 255) >> 8) << 7;
+  const int tid = threadIdx.x;
+  // ---- the row: classes 4 chunk + e of chunks (lo, lo + 128) per call ----
+  float v[kMaxCalls][8];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int jc = 0; jc < kMaxCalls; ++jc) {
+    const int call = tid + kOpThreads * jc;
+    const int lo = ((call >> 7) << 8) | (call & 127);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int k = 4 * (lo + 128 * (h >> 2)) + (h & 3);
+      v[jc][h] = (call < ncalls && k < C) ? __ldg(lg + k) : -CUDART_INF_F;
+      m = fmaxf(m, v[jc][h]);
+    }
+  }
+  m = warp_max(m);
+  if ((tid & 31) == 0) sred[0][tid >> 5] = m;
+  __syncthreads();
+  float M = sred[0][0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) M = fmaxf(M, sred[0][w]);
+  unsigned long long best = 0ull;
+  bool settled = false;
+  if (M > -CUDART_INF_F && M < CUDART_INF_F) {
+    const float M2 = __fmul_rn(M, kLog2e);
+    float ssum = 0.f;
+#pragma unroll
+    for (int jc = 0; jc < kMaxCalls; ++jc)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        v[jc][h] = ex2(fmaf(v[jc][h], kLog2e, -M2));  // softmax numerators (0 beyond C and for -inf entries)
+        ssum += v[jc][h];
+      }
+    ssum = warp_sum(ssum);
+    if ((tid & 31) == 0) sred[1][tid >> 5] = ssum;
+    __syncthreads();
+    float S = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) S += sred[1][w];
+    const float scale = kOpThin / S * 65536.0f * 1.001f;  // h <= e_k * scale + 2
+    const float accept = M + logf(S / kOpThin) + 0.02f;
+#pragma unroll
+    for (int jc = 0; jc < kMaxCalls; ++jc) {
+      const int call = tid + kOpThreads * jc;
+      if (call >= ncalls) continue;
+      const uint4 cw = rng.coarse(static_cast<uint32_t>(call), grow);
+      const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+      const int lo = ((call >> 7) << 8) | (call & 127);
+      uint32_t hits = 0;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const uint32_t half = (h & 1) ? (w4[h >> 1] >> 16) : (w4[h >> 1] & 0xffffu);
+        hits |= (static_cast<float>(half) <= fmaf(v[jc][h], scale, 2.0f) ? 1u : 0u) << h;
+      }
+      while (hits != 0) {
+        const int h = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int k = 4 * (lo + 128 * (h >> 2)) + (h & 3);
+        if (k < C) {
+          const unsigned long long key = gumbel_key_of(__ldg(lg + k), static_cast<uint32_t>(k), grow, seed, offset);
+          best = key > best ? key : best;
+        }
+      }
+    }
+    best = group_max_u64<NW>(best, skey, CtaSync());
+    settled = key_score(best) >= accept;
+    __syncthreads();  // skey is reused below
+  }
+  if (!settled) {  // every class (probability ~e^-c, and rows without a finite maximum)
+    best = 0ull;
+    for (int k = tid; k < C; k += kOpThreads) {
+      const unsigned long long key = gumbel_key_of(__ldg(lg + k), static_cast<uint32_t>(k), grow, seed, offset);
+      best = key > best ? key : best;
+    }
+    best = group_max_u64<NW>(best, skey, CtaSync());
+  }
+  if (tid == 0) x[row] = key_class(best);
+}
+
 __global__ void __launch_bounds__(kOpThreads) philox_uniform_kernel(float* __restrict__ u, int K, int64_t pitch,
                                                                     uint64_t seed, uint64_t offset,
                                                                     int64_t row_offset) {

@@ -291,3 +291,28 @@ def test_full_size_properties_config2():
     out_o, post_o, _ = O.p_sample_step(sched, lc_s.permute(0, 2, 1), lu_s.permute(0, 2, 1),
                                        O.index_to_log_onehot(x_s, K + 1), t[:2].cpu(), 2.0, u_s)
     H.assert_tokens_match(thin[:2, rows].cpu().numpy(), out_o.argmax(1).numpy(), O.near_ties(post_o, u_s).numpy(), "config2")
+
+
+@pytest.mark.parametrize("C,N", [(4097, 700), (2049, 300), (65, 515), (8193, 40)])
+def test_thinned_gumbel_argmax_equals_the_exhaustive_one(C, N):
+    """log_sample_categorical with the library's own noise: the thinned race (softmax statistics, coarse noise filter,
+    exact scoring of the survivors) draws exactly the class the per-class kernel draws - which `want_gap` still selects -
+    for peaked, flat, clamped (-70) and partly -inf rows, a row of all -inf, and the reference's pitch C (no padding)."""
+    B = 2
+    g = torch.Generator(device=DEV).manual_seed(C + N)
+    rows = ops.alloc_rows(B, N, C, DEV)
+    lg = torch.randn(B, N, C, device=DEV, generator=g) * 3.0
+    lg = torch.log_softmax(lg, dim=-1).clamp(-70.0, 0.0)
+    lg[0, ::5] *= 0.01                                   # nearly flat rows
+    lg[1, ::7, : C // 2] = float("-inf")                 # half the classes impossible
+    lg[1, 3] = float("-inf")                             # nothing possible: falls back to scoring everything
+    lg[0, 11] = -70.0                                    # all clamped
+    rows[:, :, :C] = lg
+    kw = dict(noise_kind=2, seed=21, offset=4, row_offset=999)
+    thin = ops.gumbel_argmax_rows(rows, rows.shape[2], C, **kw)
+    full, _ = ops.gumbel_argmax_rows(rows, rows.shape[2], C, want_gap=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(thin, full)
+    dense = lg.contiguous()                              # pitch == C (4097 floats: unaligned rows)
+    assert torch.equal(ops.gumbel_argmax_rows(dense, C, C, **kw), full)
+    assert int(thin.min()) >= 0 and int(thin.max()) < C

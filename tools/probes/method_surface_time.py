@@ -1,11 +1,11 @@
-"""Every public method of the drop-in class once, at 4 videos x 4096 tokens x 4096 codes (268 MB per [B,K+1,N] tensor):
+"""Every public method of the drop-in class once, at the config-2 shape (16 videos x 4096 tokens x 4096 codes, 1.07 GB per [B,K+1,N] tensor; VIDEOS=4 for a smaller run):
 wall time per call (CUDA events) - and, under ncu, the kernels each one launches."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import d3pm_b200
 from d3pm_b200 import ops
 dev = torch.device("cuda", 0)
-T, K, N, B = 100, 4096, 4096, 4
+T, K, N, B = 100, 4096, 4096, int(os.environ.get('VIDEOS', '16'))
 g = torch.Generator(device=dev).manual_seed(0)
 LC = torch.randn(B, N, K, device=dev, generator=g); LU = torch.randn(B, N, K, device=dev, generator=g)
 class _Emb:
@@ -16,9 +16,10 @@ class _Stub(torch.nn.Module):
         self.content_emb = _Emb()
         self.to_logits = torch.nn.Sequential(torch.nn.LayerNorm(64), torch.nn.Linear(64, K))
     def forward(self, x_t, cond, t):
-        return (LC if float(cond.flatten()[0]) > 0 else LU).permute(0, 2, 1)
+        return (LC if cond is COND else LU).permute(0, 2, 1)  # no host sync: identity of the conditioning tensor
 m = d3pm_b200.FusedDiffusionTransformer(transformer=_Stub(), diffusion_step=T, alpha_init_type="alpha1", guidance_scale=2.0, content_seq_len=N).to(dev)
-cond, cf = torch.ones(B, 1, 512, device=dev), -torch.ones(B, 1, 512, device=dev)
+COND = torch.ones(B, 1, 512, device=dev)
+cond, cf = COND, -torch.ones(B, 1, 512, device=dev)
 t = torch.full((B,), 50, dtype=torch.int64, device=dev)
 x_t = torch.where(torch.rand(B, N, device=dev, generator=g) < 0.5, torch.full((B, N), K, device=dev), torch.randint(0, K, (B, N), device=dev, generator=g))
 log_x = m.index_to_log_onehot(x_t, K + 1) if hasattr(m, "index_to_log_onehot") else ops.as_logical(ops.tokens_to_log_onehot_rows(x_t, K + 1), K + 1)
