@@ -260,6 +260,7 @@ def run_ours(args):
     extras = {}
     if rank == 0:
         try:
+            time.sleep(2.0)  # let the power controller settle after the sustained block
             global _NEXT_ROWS_LOGITS
             _NEXT_ROWS_LOGITS = (logits_c, logits_u)
             extras = measure_next_rows(dev, model, table, x_t, t, x_prev)
