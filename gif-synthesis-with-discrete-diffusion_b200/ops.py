@@ -291,6 +291,8 @@ class HostStep:
         self.t = torch.empty(B, dtype=torch.int64, device=dev)
         self.x_prev = torch.empty(B, N, dtype=torch.int64, device=dev)
         self.x_prev_host = torch.empty(B, N, dtype=torch.int64).pin_memory()
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._events = [torch.cuda.Event() for _ in range(4)]
         self.h2d_bytes = (self.logits_c.numel() * 4 * (2 if guidance else 1) + self.x_t.numel() * 8 + self.t.numel() * 8)
         self.d2h_bytes = self.x_prev.numel() * 8
 
@@ -299,14 +301,27 @@ class HostStep:
         for src in (logits_c, logits_u, x_t, t):
             if src is not None and src.is_cuda:
                 raise D3PMError("HostStep takes host tensors; use fused_step for device-resident inputs")
-        self.logits_c.copy_(logits_c, non_blocking=True)
-        if self.guidance:
-            self.logits_u.copy_(logits_u, non_blocking=True)
+        dev = self.x_prev.device
+        main = torch.cuda.current_stream(dev)
         self.x_t.copy_(x_t, non_blocking=True)
         self.t.copy_(t, non_blocking=True)
-        fused_step(self.logits_c, self.logits_u, self.x_t, self.t, self.coef_table, guidance_scale=guidance_scale,
-                   sample_mode=_lib.SAMPLE_PHILOX, seed=seed, offset=offset, row_offset=row_offset,
-                   x_prev_out=self.x_prev)
+        # the logits travel in chunks of whole videos on a copy stream; the step of a chunk runs while the next one is on
+        # the bus (the noise is keyed by the global row, so the chunks reproduce the one-launch result)
+        B, N = self.x_t.shape
+        nchunk = 4 if B % 4 == 0 and B * N // 4 >= 1024 else 1
+        per = B // nchunk
+        self._copy_stream.wait_stream(main)
+        for c in range(nchunk):
+            b0, b1 = c * per, (c + 1) * per
+            with torch.cuda.stream(self._copy_stream):
+                self.logits_c[b0:b1].copy_(logits_c[b0:b1], non_blocking=True)
+                if self.guidance:
+                    self.logits_u[b0:b1].copy_(logits_u[b0:b1], non_blocking=True)
+                self._events[c].record(self._copy_stream)
+            main.wait_event(self._events[c])
+            fused_step(self.logits_c[b0:b1], self.logits_u[b0:b1] if self.guidance else None, self.x_t[b0:b1], self.t[b0:b1],
+                       self.coef_table, guidance_scale=guidance_scale, sample_mode=_lib.SAMPLE_PHILOX, seed=seed, offset=offset,
+                       row_offset=row_offset + b0 * N, x_prev_out=self.x_prev[b0:b1])
         self.x_prev_host.copy_(self.x_prev, non_blocking=True)
-        torch.cuda.current_stream(self.x_prev.device).synchronize()
+        main.synchronize()
         return self.x_prev_host

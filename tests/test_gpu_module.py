@@ -119,3 +119,27 @@ def test_unbuilt_paths_fail_loudly():
     m.p_sample_tokens(x_t, cond, cf, bad_t)
     with pytest.raises(AssertionError):
         m.check_status()
+
+
+@pytest.mark.parametrize("B,guidance", [(8, True), (3, True), (4, False)])
+def test_host_step_equals_the_device_resident_step(B, guidance):
+    """`ops.HostStep` (pinned host logits in, host tokens out - the call `bench.py` times as e2e) sends the videos in
+    chunks and runs the step of one chunk while the next is on the bus: the tokens are those of one launch over
+    device-resident inputs."""
+    from d3pm_b200 import _lib, ops
+    from oracle import d3pm_oracle as O
+    T, K, N = 100, 4096, 1024
+    dev = "cuda:0"
+    table = ops.build_coef_table(O.pack_schedule(O.make_schedule(T, K)).to(dev), T, K)
+    g = torch.Generator().manual_seed(B)
+    lc = torch.randn(B, N, K, generator=g).pin_memory()
+    lu = torch.randn(B, N, K, generator=g).pin_memory() if guidance else None
+    x_t = torch.randint(0, K + 1, (B, N), generator=g).pin_memory()
+    t = torch.randint(0, T, (B,), generator=g).pin_memory()
+    host = ops.HostStep(B, N, K, table, guidance=guidance)
+    got = host(lc, lu, x_t, t, guidance_scale=2.0, seed=5, offset=9, row_offset=77).clone()
+    want = ops.fused_step(lc.to(dev), lu.to(dev) if guidance else None, x_t.to(dev), t.to(dev), table, guidance_scale=2.0,
+                          sample_mode=_lib.SAMPLE_PHILOX, seed=5, offset=9, row_offset=77)["x_prev"]
+    assert torch.equal(got, want.cpu())
+    again = host(lc, lu, x_t, t, guidance_scale=2.0, seed=5, offset=9, row_offset=77)
+    assert torch.equal(again, got)
