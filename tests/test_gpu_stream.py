@@ -175,3 +175,40 @@ def test_stream_second_attempt_and_exhaustive_fallback_at_scale():
         got = _run(lc, None, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, thin_factor=c, status=status, **kw)
         assert torch.equal(got, exact), c
         assert int(status.item()) & _lib.STATUS_FALLBACK   # 80k rows: some are redone even at the default c
+
+
+def test_steps_can_be_captured_in_a_cuda_graph():
+    """The step allocates nothing and never synchronises, so a chain of steps (tokens fed back, one Philox offset per
+    step) can be captured once and replayed: same tokens as the eager chain."""
+    K, B, N, STEPS = 4096, 2, 1024, 4
+    g = torch.Generator(device=DEV).manual_seed(9)
+    lc, lu = torch.randn(B, N, K, device=DEV, generator=g), torch.randn(B, N, K, device=DEV, generator=g)
+    table = _table(K)
+    ts = [torch.full((B,), 99 - i, dtype=torch.long, device=DEV) for i in range(STEPS)]
+    x_a = torch.full((B, N), K, dtype=torch.long, device=DEV)
+    x_b = torch.empty_like(x_a)
+    status = ops.new_status(DEV)
+
+    def chain():
+        src, dst = x_a, x_b
+        for i in range(STEPS):
+            ops.fused_step(lc, lu, src, ts[i], table, guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX, seed=3, offset=i,
+                           kernel=_lib.KERNEL_STREAM, x_prev_out=dst, status=status)
+            src, dst = dst, src
+        return src
+
+    eager = chain().clone()
+    x_a.fill_(K)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            out = chain()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        x_a.fill_(K)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)
