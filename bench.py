@@ -42,45 +42,110 @@ def workload_name(n_gpus, videos_per_gpu=VIDEOS_PER_GPU):
             f"t={T_NOW}, fp32 logits, in-kernel Philox Gumbel-max")
 
 
+def config_dict(world, videos_per_gpu=VIDEOS_PER_GPU):
+    """The `config` object of the JSON line: the same for our arm and for `--impl reference`."""
+    return {"workload": workload_name(world, videos_per_gpu), "global_batch": videos_per_gpu * world, "tokens_per_video": N_TOKENS,
+            "classes": K_CODES + 1,
+            "cache": f"inputs {videos_per_gpu * N_TOKENS * BYTES_PER_TOKEN / 1e9:.2f} GB per GPU >> 126 MB L2, re-read every step (no flush needed)",
+            "parallelism": f"batch of videos partitioned over {world} GPU(s), no collective in the step"}
+
+
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(steps, warmup, sample_videos=1):
-    """Time the oracle's op-faithful p_sample_step on the host cores: a bounded sample of the workload
-    (`sample_videos` videos of the 16x16x16 grid per step)."""
+def _host_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 1e9
+    except Exception:
+        return 0.0
+
+
+def cpu_reference(steps, warmup, sample_videos=VIDEOS_PER_GPU):
+    """Time the reference's OWN `p_sample` (diffusion_transformer.py:304-352, unmodified module from
+    `baseline/reference_loader.py`: /root/reference here, the staged baseline/_ref on the GPU box) on the host cores, on
+    `sample_videos` videos of the workload per step; its denoiser is a stub that hands back pre-generated logits the way
+    `Text2ImageTransformer` does (a [B, K, N] view of [B, N, K]), so only the update is timed, as on the GPU arm.
+    Falls back to the oracle port (bit-for-bit pinned to the reference by tests/golden) only when no copy of the
+    reference is present, and says so in `kind`."""
     import torch
-    from oracle import d3pm_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sched = O.make_schedule(T_STEPS, K_CODES)
-    lc, lu, x_t, t, u = O.synth_inputs(sample_videos, N_TOKENS, K_CODES, T_NOW, sched, seed=0)
-    lc_l, lu_l = lc.permute(0, 2, 1), lu.permute(0, 2, 1)
-    log_x_t = O.index_to_log_onehot(x_t, K_CODES + 1)
+    B, N, K = sample_videos, N_TOKENS, K_CODES
+    g = torch.Generator().manual_seed(0)
+    lc = torch.randn(B, N, K, generator=g)
+    lu = torch.randn(B, N, K, generator=g)
+    t = torch.full((B,), T_NOW, dtype=torch.int64)
+
+    from baseline import reference_loader as RL
+    if RL.reference_available():
+        kind = "reference"
+
+        class Stub(torch.nn.Module):  # the three attributes DiffusionTransformer touches + the denoiser's output layout
+            def __init__(self):
+                super().__init__()
+                self.content_emb = type("E", (), {"num_embed": K + 1})()
+                self.to_logits = torch.nn.Sequential(torch.nn.Identity(), torch.nn.Linear(1, 1))
+
+            def forward(self, x_t, cond, t_):
+                return (lc if float(cond.flatten()[0]) > 0.5 else lu).permute(0, 2, 1)
+
+        model = RL.build_reference_model(Stub(), diffusion_step=T_STEPS, guidance_scale=GUIDANCE, content_seq_len=N)
+        p_mask = float(model.log_cumprod_ct[T_NOW].exp())
+        x_t = torch.where(torch.rand(B, N, generator=g) < p_mask, torch.full((B, N), K), torch.randint(0, K, (B, N), generator=g))
+        log_x_t = RL.load_diffusion_module().index_to_log_onehot(x_t, K + 1)
+        cond, cf = torch.ones(B, 1, 1), torch.zeros(B, 1, 1)
+
+        def step():
+            model.p_sample(log_x_t, cond, cf, t, [0] * B, model.n_sample[T_NOW])
+    else:
+        kind = "port"
+        from oracle import d3pm_oracle as O
+        sched = O.make_schedule(T_STEPS, K)
+        p_mask = float(sched["log_cumprod_ct"][T_NOW].exp())
+        x_t = torch.where(torch.rand(B, N, generator=g) < p_mask, torch.full((B, N), K), torch.randint(0, K, (B, N), generator=g))
+        log_x_t = O.index_to_log_onehot(x_t, K + 1)
+        u = torch.rand(B, K + 1, N, generator=g)
+        lc_l, lu_l = lc.permute(0, 2, 1), lu.permute(0, 2, 1)
+
+        def step():
+            O.p_sample_step(sched, lc_l, lu_l, log_x_t, t, GUIDANCE, u)
+
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.p_sample_step(sched, lc_l, lu_l, log_x_t, t, GUIDANCE, u)
+            step()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
-    tokens = sample_videos * N_TOKENS
-    return {"value": tokens / per_step, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_videos} video(s) x {N_TOKENS} tokens x {K_CODES + 1} classes per step, {len(times)} timed steps, "
-                      f"{per_step * 1e3:.0f} ms/step, torch {torch.__version__} CPU"}, per_step
+    tokens = B * N
+    what = ("the reference's own DiffusionTransformer.p_sample (unmodified module)" if kind == "reference"
+            else "oracle port of p_sample (no copy of the reference on this box)")
+    return {"value": tokens / per_step, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{what}: {B} video(s) x {N} tokens x {K + 1} classes per step, {len(times)} timed step(s) after {warmup} "
+                      f"warm-up, {per_step * 1e3:.0f} ms/step, torch {torch.__version__} CPU, {cores} threads"}, per_step
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores, on OUR arm's config
+    (config 2: 16 videos per step) whenever the host has the memory for it (peak ~25 GB of fp32/fp64 temporaries)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 40), min(args.warmup, 3)
-    base, per_step = cpu_reference(steps, max(warmup, 1))
+    ram = _host_ram_gb()
+    videos = VIDEOS_PER_GPU if ram >= 48 else (4 if ram >= 16 else 1)
+    # ~5-15 s of CPU work per 16-video step: bound the run to a few minutes whatever --steps says
+    steps, warmup = max(1, min(args.steps, 4)), 1
+    base, per_step = cpu_reference(steps, warmup, sample_videos=videos)
+    note = (f"each step is the full config-2 batch ({videos} videos)" if videos == VIDEOS_PER_GPU else
+            f"each step is a {videos}-video sample of the 16-video batch (host RAM available {ram:.0f} GB)")
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": max(warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "note": "CPU port of the reference's p_sample; each step is a "
-                   "1-video sample of the workload"},
+        "config": dict(config_dict(args.gpus), reference_sample=f"reference PyTorch p_sample on the host CPU, rank 0 only (the CPU "
+                       f"path does not use the GPUs): {note}; throughput per step does not depend on how many such batches the "
+                       f"job holds"),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -289,15 +354,13 @@ def run_ours(args):
         if os.path.isfile(summ):
             sj = json.load(open(summ))
             traffic, traffic_src = sj.get("traffic_bytes_per_launch"), sj.get("source")
-        cpu_base, _ = cpu_reference(steps=3, warmup=1) if world == 1 else (None, None)
+        cpu_base, _ = cpu_reference(steps=2, warmup=1, sample_videos=2) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.global_videos else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(world, B), "global_batch": B_global, "tokens_per_video": N,
-                       "classes": K + 1, "cache": f"inputs {B * N * BYTES_PER_TOKEN / 1e9:.2f} GB per GPU >> 126 MB L2, re-read every step (no flush needed)",
-                       "parallelism": f"batch of videos partitioned over {world} GPU(s), no collective in the step"},
+            "config": config_dict(world, B),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "d3pm fused step (one launch per step)",
                          "algorithmic_bytes_per_launch": B * N * BYTES_PER_TOKEN,

@@ -44,6 +44,7 @@ class StepDesc(ctypes.Structure):
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64),
         ("thin_factor", c_float), ("kernel", c_int32), ("stream", c_void_p),
         ("sample_from", c_int32), ("reserved", c_int32), ("score", c_void_p), ("sharpen", c_void_p),
+        ("winner_post", c_void_p),
     ]
 
 

@@ -33,6 +33,35 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 constexpr int64_t kMaxGrid = 2147483647LL;
 
+// The kernels launch on the CUDA *current* device; the caller's tensors (and stream) may live on another one
+// (model on cuda:1 while cuda:0 is current).  Every entry point therefore makes the device that owns its first
+// device pointer current for the duration of the call and restores the previous one on return.
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(const void* device_ptr) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    cudaPointerAttributes attr;
+    if (device_ptr == nullptr || cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess) {
+      cudaGetLastError();  // not a CUDA allocation: the launch itself will report it
+      return;
+    }
+    if ((attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.device != prev_)
+      switched_ = cudaSetDevice(attr.device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched_) cudaSetDevice(prev_);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+
+ private:
+  int prev_ = 0;
+  bool switched_ = false;
+};
+
 template <int V, bool HAS_U>
 void launch_rows(const d3pm::StepParams& p, cudaStream_t s) {
   const dim3 grid(static_cast<unsigned>(p.rows)), block(d3pm::kRowThreads);
@@ -65,6 +94,7 @@ const char* d3pm_last_error(void) { return g_err; }
 
 int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_stream_t stream) {
   if (sched == nullptr || table == nullptr) return fail(D3PM_ERR_INVALID, "coef_table: null pointer");
+  const DeviceGuard on_device(table);
   if (T <= 0 || K <= 0) return fail(D3PM_ERR_INVALID, "coef_table: T=%d K=%d must be positive", T, K);
   if (!aligned16(table)) return fail(D3PM_ERR_ALIGN, "coef_table: table must be 16-byte aligned");
   d3pm::coef_table_kernel<<<(T + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sched, T, K, table);
@@ -73,6 +103,7 @@ int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_s
 
 int d3pm_fused_step(const d3pm_step_desc* d) {
   if (d == nullptr) return fail(D3PM_ERR_INVALID, "fused_step: null descriptor");
+  const DeviceGuard on_device(d->logits_c);
   if (d->logits_c == nullptr || d->x_t == nullptr || d->t == nullptr || d->coef_table == nullptr)
     return fail(D3PM_ERR_INVALID, "fused_step: logits_c, x_t, t and coef_table are required");
   if (d->B <= 0 || d->N <= 0 || d->K <= 0 || d->T <= 0)
@@ -121,14 +152,18 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   p.seed = d->seed, p.offset = d->offset, p.row_offset = d->row_offset, p.thin_factor = d->thin_factor;
   p.rows = rows;
   p.sample_from = d->sample_from, p.score = d->score, p.sharpen = d->sharpen;
+  p.winner_post = d->winner_post;
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
 
   if (d->kernel < D3PM_KERNEL_AUTO || d->kernel > D3PM_KERNEL_STREAM)
     return fail(D3PM_ERR_INVALID, "fused_step: unknown kernel selector %d", d->kernel);
   const bool can_stream = d3pm::stream_kernel_supports(p) && rows <= d3pm::stream_kernel_max_rows();
+  if (d->winner_post != nullptr && !(can_stream && d->kernel != D3PM_KERNEL_ROWS))
+    return fail(D3PM_ERR_UNSUPPORTED, "fused_step: winner_post is an output of the stream kernel (PHILOX sampling, K in {1024,2048,4096}); "
+                                      "the rows kernel offers the whole posterior row (post) instead");
   if (d->kernel == D3PM_KERNEL_STREAM && !can_stream)
     return fail(D3PM_ERR_UNSUPPORTED, "fused_step: the stream kernel needs PHILOX sampling, no outputs and K in {1024,2048,4096}");
-  if (d->kernel == D3PM_KERNEL_STREAM || (d->kernel == D3PM_KERNEL_AUTO && can_stream && rows >= d3pm::kStreamMinRows)) {
+  if (d->kernel == D3PM_KERNEL_STREAM || (d->kernel == D3PM_KERNEL_AUTO && can_stream && (rows >= d3pm::kStreamMinRows || d->winner_post != nullptr))) {
     const int rc = d3pm::launch_step_stream(p, s);
     if (rc != D3PM_OK) return fail(rc, "fused_step: stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("fused_step(stream)");
@@ -145,6 +180,7 @@ int d3pm_philox_uniform(float* u, int64_t rows, int K, int64_t pitch, uint64_t s
                         int64_t row_offset, d3pm_stream_t stream) {
   if (u == nullptr || rows <= 0 || K <= 0 || pitch < K + 1 || rows > kMaxGrid)
     return fail(D3PM_ERR_INVALID, "philox_uniform: bad arguments (rows=%lld K=%d pitch=%lld)", (long long)rows, K, (long long)pitch);
+  const DeviceGuard on_device(u);
   d3pm::philox_uniform_kernel<<<static_cast<unsigned>(rows), d3pm::kOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       u, K, pitch, seed, offset, row_offset);
   return check_launch("philox_uniform");
@@ -155,6 +191,7 @@ int d3pm_q_posterior(const float* log_x_start, int64_t pitch_in, const int64_t* 
                      uint32_t* status, d3pm_stream_t stream) {
   if (log_x_start == nullptr || x_t == nullptr || t == nullptr || coef_table == nullptr || post == nullptr)
     return fail(D3PM_ERR_INVALID, "q_posterior: null pointer");
+  const DeviceGuard on_device(post);
   if (B <= 0 || N <= 0 || K <= 0 || T <= 0) return fail(D3PM_ERR_INVALID, "q_posterior: sizes must be positive");
   const int64_t rows = static_cast<int64_t>(B) * N;
   if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "q_posterior: B*N too large");
@@ -170,6 +207,7 @@ int d3pm_gumbel_argmax(const float* logits, int64_t pitch_logits, const float* n
                        uint64_t offset, int64_t row_offset, d3pm_stream_t stream) {
   if (logits == nullptr || x == nullptr || rows <= 0 || C <= 0 || pitch_logits < C || rows > kMaxGrid)
     return fail(D3PM_ERR_INVALID, "gumbel_argmax: bad arguments");
+  const DeviceGuard on_device(x);
   if (noise_kind < 0 || noise_kind > 2) return fail(D3PM_ERR_INVALID, "gumbel_argmax: noise_kind %d", noise_kind);
   if (noise_kind != 2 && (noise == nullptr || pitch_noise < C))
     return fail(D3PM_ERR_INVALID, "gumbel_argmax: noise tensor required for noise_kind %d", noise_kind);
@@ -190,6 +228,7 @@ int d3pm_tokens_to_log_onehot(const int64_t* x, float* out, int64_t pitch, int64
                               d3pm_stream_t stream) {
   if (x == nullptr || out == nullptr || rows <= 0 || C <= 0 || pitch < C || rows > kMaxGrid)
     return fail(D3PM_ERR_INVALID, "tokens_to_log_onehot: bad arguments");
+  const DeviceGuard on_device(out);
   d3pm::tokens_to_log_onehot_kernel<<<static_cast<unsigned>(rows), d3pm::kOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       x, out, pitch, C, status);
   return check_launch("tokens_to_log_onehot");
@@ -199,6 +238,7 @@ int d3pm_argmax_classes(const float* x, int64_t batch_stride, int64_t class_stri
                         int64_t* idx, int B, int C, int N, d3pm_stream_t stream) {
   if (x == nullptr || idx == nullptr || B <= 0 || C <= 0 || N <= 0)
     return fail(D3PM_ERR_INVALID, "argmax_classes: bad arguments");
+  const DeviceGuard on_device(idx);
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t rows = static_cast<int64_t>(B) * N;
   if (class_stride == 1) {
@@ -217,6 +257,7 @@ int d3pm_purity_select(const int64_t* x_t, const int64_t* x_cand, const float* s
                        uint64_t offset, int64_t row_offset, d3pm_stream_t stream) {
   if (x_t == nullptr || x_cand == nullptr || n_reveal == nullptr || x_out == nullptr)
     return fail(D3PM_ERR_INVALID, "purity_select: x_t, x_cand, n_reveal and x_out are required");
+  const DeviceGuard on_device(x_out);
   if (B <= 0 || N <= 0 || K <= 0) return fail(D3PM_ERR_INVALID, "purity_select: sizes must be positive");
   if (N > d3pm::kPurityMaxN) return fail(D3PM_ERR_UNSUPPORTED, "purity_select: N=%d exceeds %d", N, d3pm::kPurityMaxN);
   int n2 = 1;
@@ -232,6 +273,7 @@ int d3pm_purity_select(const int64_t* x_t, const int64_t* x_cand, const float* s
 int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float* sched, int cumulative, float* out,
                 int64_t pitch_out, int B, int N, int K, int T, d3pm_stream_t stream) {
   if (in == nullptr || t == nullptr || sched == nullptr || out == nullptr) return fail(D3PM_ERR_INVALID, "q_pred: null pointer");
+  const DeviceGuard on_device(out);
   if (B <= 0 || N <= 0 || K <= 0 || T <= 0 || pitch_in < K + 1 || pitch_out < K + 1)
     return fail(D3PM_ERR_INVALID, "q_pred: bad sizes (rows need K+1 entries)");
   const int64_t rows = static_cast<int64_t>(B) * N;
@@ -244,6 +286,7 @@ int d3pm_q_pred(const float* in, int64_t pitch_in, const int64_t* t, const float
 int d3pm_q_sample_tokens(const int64_t* x0, const int64_t* t, const float* sched, int B, int N, int K, int T, uint64_t seed,
                          uint64_t offset, int64_t row_offset, int64_t* x_t, uint32_t* status, d3pm_stream_t stream) {
   if (x0 == nullptr || t == nullptr || sched == nullptr || x_t == nullptr) return fail(D3PM_ERR_INVALID, "q_sample_tokens: null pointer");
+  const DeviceGuard on_device(x_t);
   if (B <= 0 || N <= 0 || K <= 0 || T <= 0) return fail(D3PM_ERR_INVALID, "q_sample_tokens: sizes must be positive");
   if (K % 4 != 0 || K > 8192) return fail(D3PM_ERR_UNSUPPORTED, "q_sample_tokens: K=%d must be a multiple of 4 and <= 8192", K);
   const int64_t rows = static_cast<int64_t>(B) * N;
@@ -256,6 +299,7 @@ int d3pm_q_sample_tokens(const int64_t* x0, const int64_t* t, const float* sched
 
 int d3pm_train_rows(const d3pm_train_desc* d) {
   if (d == nullptr) return fail(D3PM_ERR_INVALID, "train_rows: null descriptor");
+  const DeviceGuard on_device(d->logits);
   if (d->logits == nullptr || d->x0 == nullptr || d->x_t == nullptr || d->t == nullptr || d->coef_table == nullptr)
     return fail(D3PM_ERR_INVALID, "train_rows: logits, x0, x_t, t and coef_table are required");
   if (d->B <= 0 || d->N <= 0 || d->K <= 0 || d->T <= 0) return fail(D3PM_ERR_INVALID, "train_rows: sizes must be positive");
@@ -302,6 +346,7 @@ int d3pm_train_rows(const d3pm_train_desc* d) {
 int d3pm_scale_rows(float* rows, int64_t pitch, const float* factor, int B, int N, int K, d3pm_stream_t stream) {
   if (rows == nullptr || factor == nullptr || B <= 0 || N <= 0 || K <= 0 || K % 4 != 0 || pitch < K || pitch % 4 != 0 || !aligned16(rows))
     return fail(D3PM_ERR_INVALID, "scale_rows: bad arguments");
+  const DeviceGuard on_device(rows);
   const int64_t n = static_cast<int64_t>(B) * N;
   if (n > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "scale_rows: B*N too large");
   d3pm::scale_rows_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, pitch, factor, N, K);
@@ -317,6 +362,7 @@ int d3pm_head_prepare(const float* weight, const float* bias, int K, int D, floa
                       d3pm_stream_t stream) {
   if (weight == nullptr || w_image == nullptr || bias2 == nullptr || stats == nullptr)
     return fail(D3PM_ERR_INVALID, "head_prepare: null pointer");
+  const DeviceGuard on_device(w_image);
   if (D != 64) return fail(D3PM_ERR_UNSUPPORTED, "head_prepare: n_embd D=%d (the fused head is built for D = 64)", D);
   if (K != 1024 && K != 2048 && K != 4096) return fail(D3PM_ERR_UNSUPPORTED, "head_prepare: K=%d must be 1024, 2048 or 4096", K);
   if (!aligned16(weight) || !aligned16(w_image) || !aligned16(bias2))
@@ -332,6 +378,7 @@ int d3pm_head_prepare(const float* weight, const float* bias, int K, int D, floa
 int d3pm_head_step(const d3pm_head_desc* d) {
   namespace H = d3pm::head;
   if (d == nullptr) return fail(D3PM_ERR_INVALID, "head_step: null descriptor");
+  const DeviceGuard on_device(d->hidden_c);
   if (d->hidden_c == nullptr || d->ln_weight == nullptr || d->ln_bias == nullptr || d->w_image == nullptr || d->bias2 == nullptr)
     return fail(D3PM_ERR_INVALID, "head_step: hidden_c, ln_weight, ln_bias, w_image and bias2 are required");
   if (d->D != 64) return fail(D3PM_ERR_UNSUPPORTED, "head_step: n_embd D=%d (built for D = 64)", d->D);
@@ -399,6 +446,7 @@ int d3pm_decode_lut(const float* codebook, const float* conv_weight, const float
                     d3pm_stream_t stream) {
   if (codebook == nullptr || conv_weight == nullptr || lut == nullptr || K <= 0 || E <= 0 || C <= 0 || E > 8192)
     return fail(D3PM_ERR_INVALID, "decode_lut: bad arguments (K=%d E=%d C=%d)", K, E, C);
+  const DeviceGuard on_device(lut);
   d3pm::decode_lut_kernel<<<static_cast<unsigned>(K), 256, static_cast<size_t>(E) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       codebook, conv_weight, conv_bias, E, C, lut);
   return check_launch("decode_lut");
@@ -408,6 +456,7 @@ int d3pm_tokens_to_features(const int64_t* tokens, const float* lut, float* out,
                             d3pm_stream_t stream) {
   if (tokens == nullptr || lut == nullptr || out == nullptr || B <= 0 || N <= 0 || K <= 0 || C <= 0 || B > 65535)
     return fail(D3PM_ERR_INVALID, "tokens_to_features: bad arguments");
+  const DeviceGuard on_device(out);
   const dim3 grid((N + 31) / 32, B);
   d3pm::tokens_to_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, lut, out, N, K, C, status);
   return check_launch("tokens_to_features");
@@ -416,6 +465,7 @@ int d3pm_tokens_to_features(const int64_t* tokens, const float* lut, float* out,
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N, d3pm_stream_t stream) {
   if (src == nullptr || dst == nullptr || B <= 0 || C <= 0 || N <= 0 || pitch < C || B > 65535)
     return fail(D3PM_ERR_INVALID, "to_token_major: bad arguments");
+  const DeviceGuard on_device(dst);
   const dim3 grid((N + 31) / 32, (C + 31) / 32, B);
   d3pm::to_token_major_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, pitch, C, N);
   return check_launch("to_token_major");

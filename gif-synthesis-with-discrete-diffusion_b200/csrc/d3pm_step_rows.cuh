@@ -34,6 +34,7 @@ struct StepParams {
   int32_t sample_from;   // D3PM_FROM_POSTERIOR / D3PM_FROM_RECON
   float* score;          // [rows] out: max_k p(x0 = k | x_t)
   const float* sharpen;  // [rows] in: draw from softmax(f * recon)
+  float* winner_post;    // [rows] out (stream kernel): log-posterior of the sampled class as the kernel computed it
 };
 
 // exact residual of the fp32 product m*log2e (natural-log units -> log2 units)

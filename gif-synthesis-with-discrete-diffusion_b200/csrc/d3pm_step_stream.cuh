@@ -177,6 +177,7 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
   const int sub = lane & 15;
   for (int slot = 2 * warp + (lane >> 4); slot - (lane >> 4) < nslots; slot += 2 * kGroupWarps) {
     unsigned long long key = 0ull;
+    float lp = 0.f;  // log-posterior of this lane's class (kept for the optional winner_post output)
     const bool live = slot < nslots;
     RowInfo ri;
     ri.accept = 0.f, ri.rel = 0;
@@ -200,23 +201,28 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
       }
       if (have) {
         const uint64_t grow = static_cast<uint64_t>(p.row_offset + (first_row + ri.rel * G));
-        const float sc = log_prob_clamped(P) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+        lp = log_prob_clamped(P);
+        const float sc = lp + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
         key = pack_key(sc, k);
       }
     }
+    const unsigned long long mine = key;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {  // argmax within each 16-lane half
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
       key = other > key ? other : key;
     }
+    const bool accepted = live && cnt <= static_cast<uint32_t>(kCandPerRow) && key_score(key) >= ri.accept;
     if (live && sub == 0) {
-      if (cnt <= static_cast<uint32_t>(kCandPerRow) && key_score(key) >= ri.accept) {
+      if (accepted) {
         p.x_prev[first_row + ri.rel * G] = key_class(key);
       } else {
         S.redo[atomicAdd(&S.redo_cnt, 1u)] = ri.rel;
       }
       S.cand_cnt[slot] = 0;
     }
+    // verification output: what THIS kernel computed as the posterior log-prob of the class it sampled
+    if (p.winner_post != nullptr && accepted && mine == key && mine != 0ull) p.winner_post[first_row + ri.rel * G] = lp;
   }
 }
 
@@ -509,6 +515,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 
     // ---- rows outside the batched path ----
     unsigned long long best = 0ull;
+    float best_lp = 0.f;  // log-posterior of this thread's best class (winner_post output)
     bool settled = false;
     if (!exact_mode) {
       // a row whose best survivor missed the acceptance bound: the same thinned race at a bound that fails with
@@ -544,23 +551,27 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
           }
         const uint32_t k = 4u * (128u * static_cast<uint32_t>(b >> 2) + tg) + static_cast<uint32_t>(b & 3);
         if (k != j) {
-          const float sc = rm.post_of(k, e, r) + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
-          const unsigned long long key = pack_key(sc, k);
-          best = key > best ? key : best;
+          const float lpk = rm.post_of(k, e, r);
+          const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow))), k);
+          if (key > best) best = key, best_lp = lpk;
         }
       }
       if (tg == 0) {
-        const unsigned long long key =
-            pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
-        best = key > best ? key : best;
+        const float lpk = rm.post_mask();
+        const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
+        if (key > best) best = key, best_lp = lpk;
       }
       if (tg == 32 && !masked) {  // the row's own class has its own coefficients
-        const unsigned long long key = pack_key(rm.post_self() + gumbel_from_uniform(uniform_from_draw(rng.draw(j, grow))), j);
-        best = key > best ? key : best;
+        const float lpk = rm.post_self();
+        const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(j, grow))), j);
+        if (key > best) best = key, best_lp = lpk;
       }
+      const unsigned long long mine = best;
       best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3
       settled = key_score(best) >= thin2.accept;
-      if (!settled) {
+      if (settled) {
+        if (p.winner_post != nullptr && mine == best) p.winner_post[row] = best_lp;
+      } else {
         best = 0ull;
         sync();  // S.keys is about to be reused
       }
@@ -583,17 +594,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
           const uint32_t k = 4u * q + e;
           const uint32_t mdraw =
               (NoiseStream::half_of(cw, (((q >> 7) & 1u) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
-          const float sc = rm.post_of(k, ev[e], r) + gumbel_from_uniform(uniform_from_draw(mdraw));
-          const unsigned long long key = pack_key(sc, k);
-          best = key > best ? key : best;
+          const float lpk = rm.post_of(k, ev[e], r);
+          const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(mdraw)), k);
+          if (key > best) best = key, best_lp = lpk;
         }
       }
       if (tg == 0) {
-        const unsigned long long key =
-            pack_key(rm.post_mask() + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
-        best = key > best ? key : best;
+        const float lpk = rm.post_mask();
+        const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
+        if (key > best) best = key, best_lp = lpk;
       }
+      const unsigned long long mine = best;
       best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3
+      if (p.winner_post != nullptr && mine == best) p.winner_post[row] = best_lp;
     }
     if (tg == 0) {
       p.x_prev[row] = key_class(best);

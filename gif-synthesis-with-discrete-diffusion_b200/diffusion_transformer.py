@@ -46,14 +46,6 @@ def alpha_schedule(time_step, N=100, att_1=0.99999, att_T=0.000009, ctt_1=0.0000
     return at, bt, ct, att, btt, ctt
 
 
-class _PassThrough(nn.Module):
-    """Stands in for `transformer.to_logits` while the fused head kernel is active: the denoiser then returns the
-    hidden states that feed its head, laid out exactly like its logits (`[B, D, N]` view of `[B, N, D]`)."""
-
-    def forward(self, x):
-        return x
-
-
 class FusedDiffusionTransformer(nn.Module):
     """Drop-in for `DiffusionTransformer` (:71-164) whose reverse step runs as one CUDA kernel."""
 
@@ -123,9 +115,15 @@ class FusedDiffusionTransformer(nn.Module):
         self.guidance_scale = guidance_scale
 
         # --- state of the CUDA path (not part of the reference surface) ---
+        # Noise: a counter-based Philox stream keyed by (rng_seed, rng_offset, global row, class).  The key is taken
+        # from torch.initial_seed() HERE and later torch.manual_seed() calls do not re-key it: `manual_seed()` below is
+        # the re-keying path, `rng_state()` / `set_rng_state()` carry it across a checkpoint (it is deliberately NOT in
+        # state_dict(), whose key set stays the reference's so that checkpoints load strictly in both directions).
         self.rng_seed = int(torch.initial_seed()) & (2**63 - 1)
         self.rng_offset = 0          # advanced by one per sampling call: every call draws fresh noise
-        self.row_offset = 0          # global index of local row 0 when the batch is sharded across ranks
+        # global index of local row 0 when the batch is sharded across ranks.  None = derive it per call from the
+        # process group (rank * local rows: equal shards, the layout of `distributed.shard_range`), 0 without one.
+        self.row_offset = None
         self.inject_uniform: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
         # tests inject the Exp(1) noise torch.multinomial draws inside the purity-prior branch (:340): (B, N) -> tensor
         self.inject_exponential: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
@@ -160,10 +158,28 @@ class FusedDiffusionTransformer(nn.Module):
         self.rng_seed, self.rng_offset = int(seed) & (2**63 - 1), int(offset)
         return self
 
+    def rng_state(self) -> dict:
+        """The noise key as a picklable dict (store it next to the checkpoint; `set_rng_state` resumes the stream)."""
+        return {"rng_seed": self.rng_seed, "rng_offset": self.rng_offset}
+
+    def set_rng_state(self, state: dict):
+        self.rng_seed, self.rng_offset = int(state["rng_seed"]) & (2**63 - 1), int(state["rng_offset"])
+        return self
+
     def _next_offset(self) -> int:
         off = self.rng_offset
         self.rng_offset += 1
         return off
+
+    def _row_offset(self, local_rows: int) -> int:
+        """Global index of this rank's first token row: ranks of a data-parallel job must not noise different videos
+        with the same stream (the reference's per-process torch generators differ by seed_everything + rank)."""
+        if self.row_offset is not None:
+            return int(self.row_offset)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank() * int(local_rows)
+        return 0
 
     def coef_table(self) -> torch.Tensor:
         """Device coefficient table derived from the *registered buffers* (so a loaded checkpoint's
@@ -204,6 +220,11 @@ class FusedDiffusionTransformer(nn.Module):
         not, the step keeps using the unfused CUDA path, which is exact for any weights)."""
         if enable:
             self._head_weights()  # raises D3PMError on an unsupported head
+            tr = self.transformer
+            if not (callable(getattr(tr, "hidden_states", None)) or (hasattr(tr, "blocks") and callable(getattr(tr, "content_emb", None)))):
+                raise D3PMError("enable_fused_head: the denoiser must either be the reference's Text2ImageTransformer "
+                                "(content_emb + blocks + to_logits, transformer_utils.py:429-444) or offer "
+                                "hidden_states(x_t, cond_emb, t) -> [B, N, n_embd], the input of its to_logits head")
         self.fuse_head = bool(enable)
         return self
 
@@ -220,19 +241,29 @@ class FusedDiffusionTransformer(nn.Module):
         return bool(self.fuse_head) and self._head_weights().valid
 
     def _hidden_rows(self, x_t, cond_emb, t) -> torch.Tensor:
-        """The denoiser up to (not including) its head: `[B, N, D]` hidden states, contiguous."""
-        tl = self.transformer.to_logits
-        self.transformer.to_logits = _PassThrough()
-        try:
-            if self.amp:
-                with torch.autocast("cuda"):
-                    out = self.transformer(x_t, cond_emb, t)
-            else:
-                out = self.transformer(x_t, cond_emb, t)
-        finally:
-            self.transformer.to_logits = tl
-        assert out.size(0) == x_t.size(0) and out.size()[2:] == x_t.size()[1:]
-        return out.float().permute(0, 2, 1).contiguous()  # the denoiser hands back a permuted view: no copy
+        """The denoiser up to (not including) its head: `[B, N, D]` hidden states, contiguous.
+
+        Nothing is swapped or hooked (re-entrant, CUDA-graph / DDP safe): a denoiser that offers
+        `hidden_states(x_t, cond_emb, t)` is asked directly; the reference's `Text2ImageTransformer` is walked exactly as
+        its own `forward` does (transformer_utils.py:433-440: `content_emb`, then every block with the timestep), stopping
+        before `to_logits` (:441)."""
+        tr = self.transformer
+
+        def run():
+            if callable(getattr(tr, "hidden_states", None)):
+                return tr.hidden_states(x_t, cond_emb, t)
+            emb = tr.content_emb(x_t)
+            for block in tr.blocks:
+                emb, _ = block(emb, cond_emb, t)
+            return emb
+
+        if self.amp:
+            with torch.autocast("cuda"):
+                out = run()
+        else:
+            out = run()
+        assert out.dim() == 3 and out.size(0) == x_t.size(0) and out.size(1) == x_t.size(1)
+        return out.float().contiguous()
 
     # ------------------------------------------------------------------ helpers
     def _denoise_rows(self, x_t: torch.Tensor, cond_emb, t: torch.Tensor) -> torch.Tensor:
@@ -303,7 +334,7 @@ class FusedDiffusionTransformer(nn.Module):
         return ops.fused_step(
             logits_c, logits_u, x_t, t.contiguous(), self.coef_table(), guidance_scale=self.guidance_scale,
             sample_mode=sample_mode, gumbel=gumbel, gumbel_is_uniform=uniform_given, seed=self.rng_seed,
-            offset=self._next_offset() if sample_mode != _lib.SAMPLE_NONE else 0, row_offset=self.row_offset,
+            offset=self._next_offset() if sample_mode != _lib.SAMPLE_NONE else 0, row_offset=self._row_offset(B * N),
             want_post=want_post, want_recon=want_recon, want_gap=want_gap, status=self._status_word(),
             x_prev_out=x_prev_out, thin_factor=thin_factor, sample_from=sample_from, want_score=want_score,
             sharpen=sharpen)
@@ -314,6 +345,7 @@ class FusedDiffusionTransformer(nn.Module):
         """p(x0 | x_t): float64-accurate log-softmax of the denoiser logits, -70 [MASK] row, clamp (:220-238)."""
         x_t = self._tokens_of(log_x_t)
         out = self._step(x_t, cond_emb, None, t, sample_mode=_lib.SAMPLE_NONE, want_recon=True, guidance=False)
+        self.check_status()
         return ops.as_logical(out["recon"], self.num_classes)
 
     @torch.no_grad()
@@ -321,20 +353,23 @@ class FusedDiffusionTransformer(nn.Module):
         """Classifier-free guidance combine + renormalise + clamp (:240-249)."""
         x_t = self._tokens_of(log_x_t)
         out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_NONE, want_recon=True)
+        self.check_status()
         return ops.as_logical(out["recon"], self.num_classes)
 
     def q_posterior(self, log_x_start, log_x_t, t):
         """p_theta(x_{t-1} | x_t) from an arbitrary log p(x0) (:251-283), forward only.
 
-        The differentiable use inside `_train_loss` (:405) is SURVEY.md §8 f1 ("next"): it is refused
-        here rather than silently routed through a slow path."""
+        The differentiable use inside `_train_loss` (:405) does not go through this method: the training loss and
+        its gradient with respect to the logits are one kernel (`d3pm_train_rows`, `train.VBLoss`).  A direct call on
+        a tensor that requires grad is therefore refused rather than silently returning a result without a graph."""
         if torch.is_grad_enabled() and log_x_start.requires_grad:
-            raise NotImplementedError("q_posterior backward (training, SURVEY §8 f1) is not built yet; "
-                                      "call under torch.no_grad() or detach log_x_start")
+            raise NotImplementedError("q_posterior is forward-only here; the differentiable route is _train_loss / "
+                                      "train.VBLoss (d3pm_train_rows).  Call under torch.no_grad() or detach log_x_start")
         x_t = self._tokens_of(log_x_t)
         rows, pitch = ops.to_rows(log_x_start.detach().float())
         post = ops.q_posterior_rows(rows, pitch, x_t, t.contiguous(), self.coef_table(), self.num_classes - 1,
                                     self._status_word())
+        self.check_status()  # the reference asserts the token range right here (:253)
         return ops.as_logical(post, self.num_classes)
 
     @torch.no_grad()
@@ -344,6 +379,7 @@ class FusedDiffusionTransformer(nn.Module):
             raise ValueError
         x_t = self._tokens_of(log_x)
         out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_NONE, want_post=True, want_recon=True)
+        self.check_status()
         return ops.as_logical(out["post"], self.num_classes), ops.as_logical(out["recon"], self.num_classes)
 
     @torch.no_grad()
@@ -359,6 +395,7 @@ class FusedDiffusionTransformer(nn.Module):
         else:
             x_prev, sampled = self.p_sample_tokens(x_t, cond_emb, cf_cond_emb, t), [1024] * log_x.shape[0]
         out = ops.tokens_to_log_onehot_rows(x_prev, self.num_classes, self._status_word())
+        self.check_status()  # one host read per public call, where the reference syncs several times (:45-46, :253)
         return ops.as_logical(out, self.num_classes), sampled
 
     @torch.no_grad()
@@ -397,7 +434,7 @@ class FusedDiffusionTransformer(nn.Module):
             expo = self.inject_exponential((B, N), self.device).to(self.device, torch.float32).contiguous()
         x_out, revealed = ops.purity_select(
             x_t, cand, None if self.prior_rule == 1 else score, torch.tensor(n_reveal, dtype=torch.int32, device=self.device),
-            K, expo=expo, seed=self.rng_seed, offset=self._next_offset(), row_offset=self.row_offset)
+            K, expo=expo, seed=self.rng_seed, offset=self._next_offset(), row_offset=self._row_offset(B * N))
         sampled = [int(s) + int(r) for s, r in zip(sampled, revealed.tolist())]     # (:342-343)
         return x_out, sampled
 
@@ -415,7 +452,7 @@ class FusedDiffusionTransformer(nn.Module):
                 self._head_scratch = head.head_scratch(B, N, x_t.device)
             return head.head_step(hw, hidden_c, hidden_u, x_t, t.contiguous(), self.coef_table(),
                                   guidance_scale=self.guidance_scale, seed=self.rng_seed, offset=self._next_offset(),
-                                  row_offset=self.row_offset, status=self._status_word(), x_prev_out=x_prev_out,
+                                  row_offset=self._row_offset(B * N), status=self._status_word(), x_prev_out=x_prev_out,
                                   scratch=self._head_scratch)
         out = self._step(x_t, cond_emb, cf_cond_emb, t, sample_mode=_lib.SAMPLE_PHILOX, x_prev_out=x_prev_out)
         return out["x_prev"]
@@ -430,7 +467,7 @@ class FusedDiffusionTransformer(nn.Module):
             x = ops.gumbel_argmax_rows(rows, pitch, C, noise_rows=noise[0], pitch_noise=noise[1], noise_kind=1)
         else:
             x = ops.gumbel_argmax_rows(rows, pitch, C, noise_kind=2, seed=self.rng_seed, offset=self._next_offset(),
-                                       row_offset=self.row_offset)
+                                       row_offset=self._row_offset(B * N))
         return ops.as_logical(ops.tokens_to_log_onehot_rows(x, C, self._status_word()), C)
 
     @torch.no_grad()
@@ -468,6 +505,7 @@ class FusedDiffusionTransformer(nn.Module):
         cf_cond_emb = cf_condition_embed.float()
 
         N, K = self.shape, self.num_classes - 1
+        self._status_word().zero_()  # a stale bit of an earlier, unchecked call must not fail this chain (no sync)
         x = torch.full((batch_size, N), K, dtype=torch.int64, device=device)  # all [MASK] (:615-618)
         x_next = torch.empty_like(x)
         for diffusion_index in range(self.num_timesteps - 1, -1, -1):
@@ -530,13 +568,13 @@ class FusedDiffusionTransformer(nn.Module):
         if noise is None and (C - 1) % 4 == 0 and C - 1 <= 8192:
             # own noise: one kernel, none of the three [B, K+1, N] tensors (same tokens as the route below, tested)
             return train.q_sample_tokens(x_start, t, self._sched8(), C - 1, seed=self.rng_seed, offset=self._next_offset(),
-                                         row_offset=self.row_offset, status=self._status_word())
+                                         row_offset=self._row_offset(B * N), status=self._status_word())
         hot = ops.tokens_to_log_onehot_rows(x_start.contiguous(), C, self._status_word())
         qrows = train.q_pred_rows(hot, hot.shape[2], t, self._sched8(), C - 1, cumulative=True)
         if noise is not None:
             return ops.gumbel_argmax_rows(qrows, qrows.shape[2], C, noise_rows=noise[0], pitch_noise=noise[1], noise_kind=1)
         return ops.gumbel_argmax_rows(qrows, qrows.shape[2], C, noise_kind=2, seed=self.rng_seed,
-                                      offset=self._next_offset(), row_offset=self.row_offset)
+                                      offset=self._next_offset(), row_offset=self._row_offset(B * N))
 
     def sample_time(self, b, device, method="uniform"):
         """Timestep sampler (:368-389): importance sampling on the running loss history once every step has
@@ -591,6 +629,7 @@ class FusedDiffusionTransformer(nn.Module):
         with torch.no_grad():
             acc = (x0_recon == x_start).float().mean(1)
             keep = (xt_1_recon == xt).float().mean(1)
+            self.check_status()  # out-of-range tokens / timesteps: the reference asserts (:45-46, :253); free next to .tolist()
             for this_t, a_, k_ in zip(t.tolist(), acc.tolist(), keep.tolist()):
                 self.diffusion_acc_list[this_t] = a_ * 0.1 + self.diffusion_acc_list[this_t] * 0.9
                 self.diffusion_keep_list[this_t] = k_ * 0.1 + self.diffusion_keep_list[this_t] * 0.9

@@ -108,7 +108,8 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
                want_post: bool = False, want_recon: bool = False, want_gap: bool = False,
                status: Optional[torch.Tensor] = None, thin_factor: float = 0.0,
                x_prev_out: Optional[torch.Tensor] = None, kernel: int = 0, sample_from: int = 0,
-               want_score: bool = False, sharpen: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+               want_score: bool = False, sharpen: Optional[torch.Tensor] = None,
+               want_winner_post: bool = False) -> Dict[str, torch.Tensor]:
     """One fused reverse step over token-major logits `[B, N, K]` (d3pm_fused_step).
 
     `logits_u=None` is guidance off.  `gumbel` is `[B, N, >=K+1]` rows (entry K = [MASK]).
@@ -165,6 +166,9 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
     if want_score:
         out["score"] = torch.empty(B, N, dtype=torch.float32, device=dev)
         d.score = _ptr(out["score"])
+    if want_winner_post:  # stream kernel only: the log-posterior of the sampled class as that kernel computed it
+        out["winner_post"] = torch.empty(B, N, dtype=torch.float32, device=dev)
+        d.winner_post = _ptr(out["winner_post"])
     if sharpen is not None:
         if sharpen.shape != (B, N) or sharpen.dtype != torch.float32 or not sharpen.is_contiguous() or sharpen.device != dev:
             raise D3PMError("sharpen must be a contiguous float32 [B, N] tensor on the logits' device")

@@ -62,7 +62,7 @@ int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_s
  * (:44-54) — i.e. p_pred (:285-296) + the prior_rule==0 branch of p_sample (:304-352).        */
 #define D3PM_SAMPLE_NONE 0         /* outputs only (p_pred) */
 #define D3PM_SAMPLE_GUMBEL 1       /* argmax(gumbel + posterior), noise injected by the caller */
-#define D3PM_SAMPLE_PHILOX 2       /* in-kernel Philox4x32-10 noise, thinned exponential race (production) */
+#define D3PM_SAMPLE_PHILOX 2       /* in-kernel Philox4x32-7 noise (23-bit uniforms), thinned exponential race (production) */
 #define D3PM_SAMPLE_PHILOX_EXACT 3 /* same noise, every class scored in log space (verification) */
 
 #define D3PM_FROM_POSTERIOR 0 /* sample x_{t-1} from q_posterior's result (prior_rule 0, :347-350) */
@@ -99,12 +99,17 @@ typedef struct d3pm_step_desc {
                             attempt (stream kernel: c = 16), values < 0.01 force the exhaustive fallback */
   int32_t kernel;        /* D3PM_KERNEL_*: which implementation runs (AUTO picks by shape and mode) */
   d3pm_stream_t stream;
-  /* purity-prior sampling (p_sample with prior_rule 1 / 2, :309-346); all optional, rows kernel only */
+  /* purity-prior sampling (p_sample with prior_rule 1 / 2, :309-346); all optional.  D3PM_FROM_RECON + score with PHILOX
+   * sampling runs on the stream kernel (its RECON instantiation); `sharpen` and the other modes on the rows kernel */
   int32_t sample_from;   /* D3PM_FROM_POSTERIOR (default) or D3PM_FROM_RECON: draw x from p(x0 | x_t) (:327-329) */
   int32_t reserved;
   float* score;          /* [B*N] out: max_k p(x0 = k | x_t), the purity of :318 before its per-video normalisation */
   const float* sharpen;  /* [B*N] in: f = 1 + score * prior_weight; the draw is from softmax(f * log p(x0 | x_t)) (:323-325);
                             D3PM_FROM_RECON with GUMBEL / PHILOX_EXACT sampling only */
+  float* winner_post;    /* [B*N] out, optional, stream kernel only (forces it): the posterior log-prob (clamp(log P, -70, 0),
+                            :283; log p(x0 | x_t) with D3PM_FROM_RECON) of the class x_prev holds, exactly as the production
+                            kernel computed it.  Verification hook: lets a test measure the 1e-4 posterior tolerance on the
+                            kernel that is benchmarked, which otherwise outputs tokens only */
 } d3pm_step_desc;
 
 int d3pm_fused_step(const d3pm_step_desc* desc);

@@ -1,10 +1,10 @@
-"""Import the reference's own `diffusion_transformer.py` by path (build container only).
+"""Import the reference's own `diffusion_transformer.py` by path.
 
-TEST INFRASTRUCTURE.  `/root/reference` exists only in the build container, never on
-the GPU box, so nothing under `-m gpu`, `smoke()` or `bench.py` may call this.  It is
-used by `tests/golden/make_golden.py` (to generate the committed fixtures) and by the
-CPU-side cross-check `tests/test_oracle_vs_reference.py`, which skips when the
-reference tree is absent.
+TEST INFRASTRUCTURE.  `/root/reference` exists only in the build container; `build()` stages the
+few files of the path verbatim under the git-ignored `baseline/_ref/`, which travels to the GPU box
+(`baseline/reference_loader.py` finds whichever is present).  Used by `tests/golden/make_golden*.py`
+(to generate the committed fixtures) and by the cross-checks in `tests/`, which skip when neither
+copy of the reference is present.
 
 The reference module imports `hydra.utils.instantiate` (diffusion_transformer.py:16)
 without using it; hydra is not installed here, so a two-attribute stub module is
@@ -21,32 +21,15 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("D3PM_REFERENCE_ROOT", "/root/reference")
-_REL = "src/models/motionencoder/diffusion_transformer.py"
+from baseline import reference_loader as _RL  # noqa: E402  (locates /root/reference or the staged baseline/_ref copy)
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, _REL))
+    return _RL.reference_available()
 
 
 def load_reference_module():
-    if not reference_available():
-        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT}")
-    sys.dont_write_bytecode = True
-    if "hydra" not in sys.modules:
-        hydra = types.ModuleType("hydra")
-        hydra_utils = types.ModuleType("hydra.utils")
-        hydra_utils.instantiate = lambda *a, **k: None
-        hydra.utils = hydra_utils
-        sys.modules["hydra"], sys.modules["hydra.utils"] = hydra, hydra_utils
-    name = "_d3pm_reference_diffusion_transformer"
-    if name in sys.modules:
-        return sys.modules[name]
-    spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, _REL))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    return mod
+    return _RL.load_diffusion_module()
 
 
 class StubDenoiser(torch.nn.Module):

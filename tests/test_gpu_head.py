@@ -119,9 +119,11 @@ class HeadDenoiser(torch.nn.Module):
         self.pos = torch.nn.Parameter(torch.randn(N, D) * 0.5)
         self.to_logits = _head(K, 7)
 
+    def hidden_states(self, x_t, cond, t):
+        return self.content_emb(x_t) + self.pos + cond.mean(-1, keepdim=True) + 0.01 * t[:, None, None]
+
     def forward(self, x_t, cond, t):
-        hcur = self.content_emb(x_t) + self.pos + cond.mean(-1, keepdim=True) + 0.01 * t[:, None, None]
-        return self.to_logits(hcur).permute(0, 2, 1)
+        return self.to_logits(self.hidden_states(x_t, cond, t)).permute(0, 2, 1)
 
 
 def test_drop_in_class_with_fused_head():
@@ -138,7 +140,7 @@ def test_drop_in_class_with_fused_head():
     m.enable_fused_head()
     assert m.fused_head_active
     b = m.manual_seed(9).p_sample_tokens(x, cond, cf, t)
-    assert isinstance(m.transformer.to_logits, torch.nn.Sequential)  # restored after the bypass
+    assert isinstance(m.transformer.to_logits, torch.nn.Sequential)  # the module tree is never touched
     assert (a != b).float().mean().item() <= 0.01 and (a != x).any()
     out = m.manual_seed(1).sample(["x"] * B, None, cond, cf, filter_ratio=0)["content_token"]
     assert out.shape == (B, N) and not (out == K).any()

@@ -73,6 +73,14 @@ def test_stream_kernel_parity(B, N, K, tval, s, scale):
                                        0.0 if s is None else s, u)
     ties = O.near_ties(post_o, u).numpy()
     H.assert_tokens_match(thin[:, rows].cpu().numpy(), out_o.argmax(1).numpy(), ties, "stream vs oracle")
+    # the posterior log-prob of the drawn class as the stream kernel computed it, on each of its three scoring paths
+    # (batched survivor scoring, second thinned attempt, exhaustive), against the oracle's posterior row
+    for tf in (0.0, 1.0, 1e-3):
+        o = ops.fused_step(lc, lu, x_t, t, _table(K), guidance_scale=kw["s"], sample_mode=_lib.SAMPLE_PHILOX,
+                           kernel=_lib.KERNEL_STREAM, seed=99, offset=3, row_offset=12345, thin_factor=tf, want_winner_post=True)
+        assert torch.equal(o["x_prev"], thin)
+        want = post_o.gather(1, thin[:, rows].cpu().unsqueeze(1)).squeeze(1)
+        assert (o["winner_post"][:, rows].cpu() - want).abs().max().item() <= H.POST_TOL, f"thin_factor {tf}"
     # and against the other kernel (same noise definition; p may differ in the last bit)
     rowsk = _run(lc, lu, x_t, t, K, _lib.SAMPLE_PHILOX, _lib.KERNEL_ROWS, **kw)
     H.assert_tokens_match(rowsk[:, rows].cpu().numpy(), out_o.argmax(1).numpy(), ties, "rows vs oracle")
@@ -129,6 +137,96 @@ def test_stream_sampling_statistics():
         chi2 = float((((np.array(bc) - np.array(be)) ** 2) / np.array(be)).sum())
         dof = len(be) - 1
         assert chi2 < dof + 5 * np.sqrt(2 * dof) + 10, (chi2, dof)
+
+
+def test_philox7_uniforms_many_rows_and_offsets():
+    """The noise itself (Philox4x32-7, 23-bit draws): Kolmogorov-Smirnov against U(0,1) per row and pooled, over 96
+    distinct rows x 3 step offsets, moments, and the correlation between neighbouring classes, rows and offsets."""
+    from scipy import stats
+    K, R = 4096, 96
+    us = []
+    for off in (0, 1, 2**33 + 5):
+        u = ops.philox_uniform(1, R, K, seed=0xD3, offset=off, row_offset=7_000_000_000, device=DEV)[0, :, :K + 1].double().cpu().numpy()
+        us.append(u)
+        assert u.min() > 0.0 and u.max() < 1.0
+        worst_p = min(stats.kstest(u[r], "uniform").pvalue for r in range(R))
+        assert worst_p > 1e-4 / R, worst_p                      # Bonferroni over the rows
+        assert stats.kstest(u.ravel(), "uniform").pvalue > 1e-3  # ~4e5 draws pooled
+        n = u.size
+        assert abs(u.mean() - 0.5) < 5 * np.sqrt(1 / 12 / n) and abs(u.var() - 1 / 12) < 5 * np.sqrt(1 / 180 / n)
+        for a_, b_ in ((u[:, :-1], u[:, 1:]), (u[:-1], u[1:]), (u[:, :-4], u[:, 4:]), (u[:, :-512], u[:, 512:])):
+            r_ = np.corrcoef(a_.ravel(), b_.ravel())[0, 1]      # classes k / k+1, rows r / r+1, chunk and call partners
+            assert abs(r_) < 5 / np.sqrt(a_.size), r_
+    for a_, b_ in ((us[0], us[1]), (us[1], us[2])):             # consecutive steps of a chain
+        assert abs(np.corrcoef(a_.ravel(), b_.ravel())[0, 1]) < 5 / np.sqrt(a_.size)
+    # the 23-bit lattice: u = 1 - (2m+1)/2^24, every draw an odd multiple of 2^-24
+    m = np.round((1.0 - us[0]) * 2**24).astype(np.int64)
+    assert (m % 2 == 1).all()
+    expect_distinct = 2**23 * (1 - np.exp(-m.size / 2**23))       # birthday bound for 23-bit draws
+    assert abs(len(np.unique(m >> 1)) / expect_distinct - 1) < 0.01
+
+
+def test_sampler_statistics_many_rows_and_timesteps():
+    """Per-class counts of the production sampler over 64 DISTINCT rows (own logits, masked and unmasked x_t, four
+    timesteps), 3000 draws each, against exp(posterior) of the oracle: one pooled chi-square plus a bound on every row's
+    own statistic.  Each replica of a row sits at a different global row index, i.e. draws fresh noise."""
+    K, ROWS, R = 1024, 64, 3000
+    sched = O.make_schedule(T, K)
+    g = torch.Generator().manual_seed(4321)
+    base_c, base_u = torch.randn(4, ROWS // 4, K, generator=g) * 2.5, torch.randn(4, ROWS // 4, K, generator=g) * 2.5
+    t = torch.tensor([0, 30, 60, 99])
+    x_base = torch.randint(0, K, (4, ROWS // 4), generator=g)
+    x_base[:, ::2] = K                                           # half the rows masked
+    lc = base_c.repeat_interleave(R, dim=1).to(DEV)              # [4, 16 * R, K]: R replicas of each distinct row
+    lu = base_u.repeat_interleave(R, dim=1).to(DEV)
+    x_t = x_base.repeat_interleave(R, dim=1).to(DEV)
+    draws = _run(lc, lu, x_t, t.to(DEV), K, _lib.SAMPLE_PHILOX, _lib.KERNEL_STREAM, seed=77, offset=12).cpu()
+    del lc, lu
+    _, post, _ = O.p_sample_step(sched, base_c.permute(0, 2, 1), base_u.permute(0, 2, 1), O.index_to_log_onehot(x_base, K + 1),
+                                 t, 2.0, torch.rand(4, K + 1, ROWS // 4, generator=g))
+    p_all = post.double().exp().permute(0, 2, 1)                 # [4, 16, K+1]
+    total_chi2, total_dof = 0.0, 0
+    for b in range(4):
+        for r in range(ROWS // 4):
+            p = p_all[b, r] / p_all[b, r].sum()
+            counts = torch.bincount(draws[b, r * R:(r + 1) * R], minlength=K + 1).double()
+            order = torch.argsort(p)
+            be, bc, ae, ac = [], [], 0.0, 0.0
+            for e_, c_ in zip((p[order] * R).numpy(), counts[order].numpy()):
+                ae, ac = ae + e_, ac + c_
+                if ae >= 5:
+                    be.append(ae), bc.append(ac)
+                    ae = ac = 0.0
+            be[-1] += ae
+            bc[-1] += ac
+            chi2 = float((((np.array(bc) - np.array(be)) ** 2) / np.array(be)).sum())
+            dof = len(be) - 1
+            assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (b, r, chi2, dof)
+            total_chi2, total_dof = total_chi2 + chi2, total_dof + dof
+    z = (total_chi2 - total_dof) / np.sqrt(2 * total_dof)
+    print(f"[sampler statistics] 64 rows x {R} draws: pooled chi2 {total_chi2:.0f} on {total_dof} dof (z = {z:+.2f})")
+    assert abs(z) < 5
+
+
+def test_tensors_on_a_non_current_device():
+    """The C ABI makes the device that owns the tensors current for the call (and restores the caller's): a model on
+    cuda:1 while cuda:0 is current launches on cuda:1 with cuda:1's SM count."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    K, B, N = 4096, 2, 1024
+    other = torch.device("cuda", 1)
+    g = torch.Generator().manual_seed(3)
+    lc, lu = torch.randn(B, N, K, generator=g), torch.randn(B, N, K, generator=g)
+    x_t = torch.randint(0, K + 1, (B, N), generator=g)
+    t = torch.tensor([10, 90])
+    sched = O.pack_schedule(O.make_schedule(T, K))
+    torch.cuda.set_device(0)
+    want = ops.fused_step(lc.to(DEV), lu.to(DEV), x_t.to(DEV), t.to(DEV), ops.build_coef_table(sched.to(DEV), T, K),
+                          guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX, seed=1, offset=2)["x_prev"].cpu()
+    got = ops.fused_step(lc.to(other), lu.to(other), x_t.to(other), t.to(other), ops.build_coef_table(sched.to(other), T, K),
+                         guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX, seed=1, offset=2)["x_prev"]
+    assert got.device == other and torch.cuda.current_device() == 0
+    assert torch.equal(got.cpu(), want)
 
 
 @pytest.mark.parametrize("kernel", [_lib.KERNEL_STREAM, _lib.KERNEL_ROWS])

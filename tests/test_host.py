@@ -100,6 +100,28 @@ def test_module_surface_matches_reference():
         d3pm_b200.FusedDiffusionTransformer(transformer=_stub_transformer(K), alpha_init_type="cos")
 
 
+def test_reference_checkpoint_loads_strictly_both_ways():
+    """The reference `DiffusionTransformer` (real `Text2ImageTransformer` inside) -> `state_dict()` -> the drop-in, strict,
+    and back (diffusion_transformer.py:142-152 buffers + every denoiser parameter)."""
+    from baseline import reference_loader as RL
+    if not RL.reference_available():
+        pytest.skip("reference not present (neither /root/reference nor baseline/_ref)")
+    torch.manual_seed(0)
+    ref = RL.build_reference_model(RL.build_denoiser(1024, 64, [8, 8]), content_seq_len=64)
+    ours = d3pm_b200.FusedDiffusionTransformer(transformer=RL.build_denoiser(1024, 64, [8, 8]), diffusion_step=100,
+                                                alpha_init_type="alpha1", guidance_scale=2.0, content_seq_len=64)
+    sd = ref.state_dict()
+    assert set(sd) == set(ours.state_dict())
+    res = ours.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in ours.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    # the noise key is NOT part of the checkpoint contract; it has its own accessor
+    state = ours.manual_seed(77, offset=5).rng_state()
+    assert ours.manual_seed(1).set_rng_state(state).rng_state() == {"rng_seed": 77, "rng_offset": 5}
+
+
 def test_layout_helpers_round_trip():
     rows = torch.arange(2 * 3 * 8, dtype=torch.float32).reshape(2, 3, 8)
     logical = ops.as_logical(rows, 5)

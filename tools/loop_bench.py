@@ -40,9 +40,11 @@ class HeadDenoiser(torch.nn.Module):
         self.time = torch.nn.Embedding(T, n_embd)
         self.to_logits = torch.nn.Sequential(torch.nn.LayerNorm(n_embd), torch.nn.Linear(n_embd, K))
 
+    def hidden_states(self, x_t, cond, t):
+        return self.content_emb(x_t) + self.pos + self.time(t)[:, None, :] + cond.mean(-1, keepdim=True)
+
     def forward(self, x_t, cond, t):
-        h = self.content_emb(x_t) + self.pos + self.time(t)[:, None, :] + cond.mean(-1, keepdim=True)
-        return self.to_logits(h).permute(0, 2, 1)  # [B, K, N] view of [B, N, K]
+        return self.to_logits(self.hidden_states(x_t, cond, t)).permute(0, 2, 1)  # [B, K, N] view of [B, N, K]
 
 
 torch.manual_seed(0)
