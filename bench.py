@@ -10,12 +10,19 @@ partitioned across ranks with no data-path collective (weak scaling: 16 videos p
 is exactly config 4's B = 128).  Prints ONE JSON line on rank 0.
 
   value      token updates / s with the logits already resident in HBM (whole job, all ranks)
-  e2e        the same through `ops.HostStep` with pinned HOST logits: H2D + kernel + D2H every step
+  e2e        the same through the host-buffer C entry `d3pm_host_step_run` (`ops.HostStep`) with pinned HOST logits:
+             H2D + kernel + D2H every step; per-rank H2D GB/s and CPU affinity are reported next to it
   roofline   algorithmic bytes (32 784 B / token update) / kernel time vs the measured HBM peak
-  cpu_baseline  the oracle (a PyTorch-CPU port of the reference's p_sample) on a bounded sample, rank 0 only
+  cpu_baseline  the reference's own `p_sample` (unmodified module, staged under baseline/_ref) on the host cores, on a
+             bounded sample of the batch, rank 0 only (the oracle port only where no copy of the reference is present)
+  sustained  the same step, 1500 back to back (power-capped regime)
+  config4_gather_check  (N > 1) the token all-gather timed, and rank 0's recomputation of other ranks' videos: bit-identical
+  configs    config 4 as written (128 videos split over the ranks, strong scaling) and config 5 (64 videos, guidance on/off)
+  next_rows  config 3 with the reference's real denoiser (reference sample loop on the GPU vs the drop-in, same weights),
+             fused head, training loss + gradient, purity prior, q_sample, the host entry of the fused head
 
-`--impl reference` times that CPU port alone (the reference is pure Python and does not travel to the GPU
-box; oracle/d3pm_oracle.py is pinned bit-for-bit to it by tests/golden).
+`--impl reference` times the reference's own `p_sample` alone on the host cores at the full config-2 batch (16 videos per
+step) - the same `config` as our arm.
 """
 from __future__ import annotations
 
@@ -128,24 +135,24 @@ def cpu_reference(steps, warmup, sample_videos=VIDEOS_PER_GPU):
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path on this box's host cores, on OUR arm's config
-    (config 2: 16 videos per step) whenever the host has the memory for it (peak ~25 GB of fp32/fp64 temporaries)."""
+    (config 2: 16 videos per step) whenever the host has the memory for it (peak ~25 GB of fp32/fp64 temporaries).
+    `--steps` / `--warmup` are honoured up to 20 / 5 (a 16-video step takes ~7 s on 16 cores: the run ends within minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     ram = _host_ram_gb()
     videos = VIDEOS_PER_GPU if ram >= 48 else (4 if ram >= 16 else 1)
-    # ~5-15 s of CPU work per 16-video step: bound the run to a few minutes whatever --steps says
-    steps, warmup = max(1, min(args.steps, 4)), 1
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 5))
     base, per_step = cpu_reference(steps, warmup, sample_videos=videos)
     note = (f"each step is the full config-2 batch ({videos} videos)" if videos == VIDEOS_PER_GPU else
             f"each step is a {videos}-video sample of the 16-video batch (host RAM available {ram:.0f} GB)")
+    base["sample"] += (f"; {note}; rank 0 only (the CPU path does not use the GPUs; its throughput per step does not depend on how "
+                       f"many such batches the job holds)")
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(config_dict(args.gpus), reference_sample=f"reference PyTorch p_sample on the host CPU, rank 0 only (the CPU "
-                       f"path does not use the GPUs): {note}; throughput per step does not depend on how many such batches the "
-                       f"job holds"),
+        "config": config_dict(args.gpus),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,6 +214,32 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- our arm
+def _pin_to_gpu_numa_node(local_rank):
+    """Bind this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is
+    allocated, so that first-touch places the e2e staging memory on the GPU's NUMA node.  -> description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return {"cpus": f"{cpus[0]}-{cpus[-1]}" if cpus else "", "n_cpus": len(cpus), "n_cpus_before": before}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def _video_inputs(b_global, N, K, p_mask, dev):
+    """Synthetic inputs of ONE video, keyed by its GLOBAL index (any rank generates the same bits for the same video)."""
+    import torch
+    gen = torch.Generator(device=dev).manual_seed(1000 + b_global)
+    lc = torch.randn(N, K, device=dev, generator=gen)
+    lu = torch.randn(N, K, device=dev, generator=gen)
+    x = torch.where(torch.rand(N, device=dev, generator=gen) < p_mask, torch.full((N,), K, device=dev),
+                    torch.randint(0, K, (N,), device=dev, generator=gen))
+    return lc, lu, x
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -221,6 +254,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N>1")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    affinity = _pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -247,20 +281,23 @@ def run_ours(args):
                                                 guidance_scale=GUIDANCE, content_seq_len=N).to(dev)
     table = model.coef_table()
 
-    # synthetic inputs: N(0,1) logits, x_t masked with the schedule's probability at t (seeded per global video)
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    logits_c = torch.randn(B, N, K, device=dev, generator=gen)
-    logits_u = torch.randn(B, N, K, device=dev, generator=gen)
+    # synthetic inputs: N(0,1) logits, x_t masked with the schedule's probability at t; every video is generated from ITS
+    # GLOBAL index, so a rank's shard is a slice of the one global batch whatever the world size (config 4's premise)
     p_mask = float(model.log_cumprod_ct[T_NOW].exp())
-    x_t = torch.where(torch.rand(B, N, device=dev, generator=gen) < p_mask, torch.full((B, N), K, device=dev),
-                      torch.randint(0, K, (B, N), device=dev, generator=gen))
+    logits_c = torch.empty(B, N, K, device=dev)
+    logits_u = torch.empty(B, N, K, device=dev)
+    x_t = torch.empty(B, N, dtype=torch.int64, device=dev)
+    for i in range(B):
+        logits_c[i], logits_u[i], x_t[i] = _video_inputs(b0 + i, N, K, p_mask, dev)
     t = torch.full((B,), T_NOW, dtype=torch.int64, device=dev)
     x_prev = torch.empty_like(x_t)
     status = ops.new_status(dev)
+    launches = {"n": 0}
 
     def step(i):
         ops.fused_step(logits_c, logits_u, x_t, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX,
                        seed=2024, offset=i, row_offset=row_offset, x_prev_out=x_prev, status=status)
+        launches["n"] += 1
 
     def barrier():
         if world > 1:
@@ -273,19 +310,53 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches["n"] = 0
     ev0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     ev1.record()
     barrier()
+    timed_launches = launches["n"]
     sampler.stop_flag.set()
     sampler.join()
     elapsed_ms = ev0.elapsed_time(ev1)
     assert int(status.item()) & (_lib.STATUS_BAD_T | _lib.STATUS_BAD_TOKEN) == 0
     assert int(x_prev.min()) >= 0 and int(x_prev.max()) <= K
 
-    # ---- end to end through the host-buffer API (pinned host logits; copies inside the timed region)
-    host = ops.HostStep(B, N, K, table, guidance=True)
+    # ---- config 4's claim on hardware: the gathered tokens of the sharded job equal what ONE GPU computes for the same
+    # global videos.  One step at a fixed offset on every rank, the (timed) token all-gather, then rank 0 regenerates
+    # videos owned by OTHER ranks from their global seeds, runs them alone with their global row offset, and compares.
+    gather = None
+    if world > 1:
+        step(4242)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gathered = d3pm_b200.gather_tokens(x_prev, B_global)  # warm-up of the communicator
+        barrier()
+        reps = 20
+        g0.record()
+        for _ in range(reps):
+            gathered = d3pm_b200.gather_tokens(x_prev, B_global)
+        g1.record()
+        barrier()
+        assert gathered.shape == (B_global, N)
+        gather_us = g0.elapsed_time(g1) / reps * 1e3
+        checked, mismatches = [], 0
+        if rank == 0:
+            for bg in sorted({B_global - 1, B, B_global // 2}):  # first video of rank 1, one in the middle, the very last
+                lc1, lu1, x1 = _video_inputs(bg, N, K, p_mask, dev)
+                one = ops.fused_step(lc1.unsqueeze(0), lu1.unsqueeze(0), x1.unsqueeze(0), t[:1], table, guidance_scale=GUIDANCE,
+                                     sample_mode=_lib.SAMPLE_PHILOX, seed=2024, offset=4242, row_offset=bg * N)["x_prev"][0]
+                mismatches += int((one != gathered[bg]).sum())
+                checked.append(bg)
+            assert mismatches == 0, f"sharded result differs from the single-GPU result on {mismatches} tokens"
+        gather = {"all_gather_us": gather_us, "bytes_per_rank": B * N * 8, "collective": "all_gather_into_tensor (NCCL), int64 [B_local, N]",
+                  "timed_reps": reps, "recomputed_on_rank0_global_videos": checked, "token_mismatches": mismatches,
+                  "what": "one step on every rank, token all-gather timed on the device; rank 0 re-runs videos of other ranks from "
+                          "their global seeds with their global row offset: bit-identical"}
+
+    # ---- end to end through the host-buffer C entry (d3pm_host_step_run): pinned host logits, copies inside the timed region
+    host = ops.HostStep(B, N, K, table, guidance=True, T=T_STEPS)
     h_c, h_u = logits_c.cpu().pin_memory(), logits_u.cpu().pin_memory()
     h_x, h_t = x_t.cpu().pin_memory(), t.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
@@ -299,10 +370,12 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    h2d_bytes, d2h_bytes = host.h2d_bytes, host.d2h_bytes
+    host.close()
+    del h_c, h_u
 
     # ---- the same step under sustained load (informational): after ~70 ms of back-to-back launches the board reaches its
-    # power limit (NVML: sw_power_cap) and lowers the SM clock, which this kernel - 54 % of the issue slots at full clock -
-    # feels; a pure read of the same bytes does not (tools/probes/read_probe.cu sustain)
+    # power limit (NVML: sw_power_cap) and lowers the SM clock; a pure read of the same bytes does not
     sustained = None
     if world == 1:
         sus_steps = 1500
@@ -321,22 +394,41 @@ def run_ours(args):
         sustained = {"steps": sus_steps, "ms_per_step": sus_ms, "value": B * N / (sus_ms * 1e-3), "unit": UNIT,
                      "GBps": B * N * BYTES_PER_TOKEN / (sus_ms * 1e-3) / 1e9, "clocks": sampler2.summary()}
 
-    # ---- beyond the bench line (rank 0, informational; the metric above is untouched): the rows SURVEY §8 marks "next"
-    extras = {}
-    if rank == 0:
+    # ---- beyond the bench line (informational; the metric above is untouched): the other BASELINE configs and the rows
+    # SURVEY §8 marks "next"
+    extras, configs = {}, {}
+    if not args.global_videos:
+        try:
+            time.sleep(1.0)
+            del logits_c, logits_u
+            torch.cuda.empty_cache()
+            configs["config4_strong"] = measure_config4_strong(dev, model, table, world, rank, barrier)
+            if world == 1:
+                configs["config5"] = measure_config5(dev, model, table)
+        except Exception as exc:  # reported in the JSON line, never swallowed
+            configs["error"] = repr(exc)
+    if rank == 0 and world == 1:
         try:
             time.sleep(2.0)  # let the power controller settle after the sustained block
             global _NEXT_ROWS_LOGITS
-            _NEXT_ROWS_LOGITS = (logits_c, logits_u)
+            gen = torch.Generator(device=dev).manual_seed(1000)
+            _NEXT_ROWS_LOGITS = (torch.randn(B, N, K, device=dev, generator=gen), torch.randn(B, N, K, device=dev, generator=gen))
             extras = measure_next_rows(dev, model, table, x_t, t, x_prev)
-        except Exception as exc:  # reported in the JSON line, never swallowed
-            extras = {"error": repr(exc)}
+            _NEXT_ROWS_LOGITS = None
+            torch.cuda.empty_cache()
+            extras["config3"] = measure_config3(dev)
+        except Exception as exc:
+            extras["error"] = repr(exc)
 
     times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)  # max over ranks, measured on the device
-        gathered = d3pm_b200.gather_tokens(x_prev, B_global)  # the path's only collective (not timed: once per chain)
-        assert gathered.shape == (B_global, N)
+    per_rank_e2e = [e2e_ms]
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, (e2e_ms, affinity))
+        per_rank_e2e = [e[0] for e in every]
+        affinity = [e[1] for e in every]
     elapsed_ms, e2e_ms = float(times[0]), float(times[1])
 
     if rank == 0:
@@ -350,11 +442,13 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = B * N * BYTES_PER_TOKEN / (ms_per_step * 1e-3) / 1e9  # per GPU: one launch per step per rank
         traffic, traffic_src = None, None  # dram bytes per launch of the same kernel/workload, from the committed ncu capture
-        summ = os.path.join(ROOT, "profiles", "r01_summary.json")
-        if os.path.isfile(summ):
-            sj = json.load(open(summ))
-            traffic, traffic_src = sj.get("traffic_bytes_per_launch"), sj.get("source")
-        cpu_base, _ = cpu_reference(steps=2, warmup=1, sample_videos=2) if world == 1 else (None, None)
+        for name in ("r02_summary.json", "r01_summary.json"):
+            summ = os.path.join(ROOT, "profiles", name)
+            if os.path.isfile(summ):
+                sj = json.load(open(summ))
+                traffic, traffic_src = sj.get("traffic_bytes_per_launch"), sj.get("source")
+                break
+        cpu_base, _ = cpu_reference(steps=2, warmup=1, sample_videos=4) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -362,24 +456,121 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": config_dict(world, B),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "d3pm fused step (one launch per step)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "step_stream_kernel<4, 8, true, false> (one launch per step)",
                          "algorithmic_bytes_per_launch": B * N * BYTES_PER_TOKEN,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": tokens_global / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "d3pm_b200.ops.HostStep (pinned host logits -> d3pm_fused_step -> host tokens)"},
-            "gpu_launches": args.steps,
+                    "h2d_GBps_per_rank": [h2d_bytes / (m / e2e_steps * 1e-3) / 1e9 for m in per_rank_e2e],
+                    "cpu_affinity_per_rank": affinity,
+                    "api": "C ABI d3pm_host_step_run via d3pm_b200.ops.HostStep (pinned host logits -> chunked H2D overlapped with "
+                           "d3pm_fused_step -> host tokens); the step is 2.15 GB of fp32 logits per rank on PCIe, see e2e of the "
+                           "hidden-state entry in next_rows"},
+            "gpu_launches": timed_launches,
             "clocks": sampler.summary(),
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if sustained is not None:
             line["sustained"] = sustained
+        if gather is not None:
+            line["config4_gather_check"] = gather
+        line["configs"] = configs
         line["next_rows"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed_steps(fn, n, dev, warm=3):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(n):
+        fn(warm + i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / n
+
+
+def measure_config4_strong(dev, model, table, world, rank, barrier, total_videos=128, steps=40):
+    """BASELINE config 4: the SAME 128 videos split over the ranks (128 / 64 / 32 / 16 per GPU at 1 / 2 / 4 / 8 GPUs), one
+    fused step, device-resident, max over ranks.  (Inputs are regenerated from the global per-video seeds.)"""
+    import torch
+    import torch.distributed as dist
+    from d3pm_b200 import _lib, ops
+    import d3pm_b200
+
+    if total_videos % world:
+        return {"skipped": f"{total_videos} videos do not split over {world} ranks"}
+    N, K = N_TOKENS, K_CODES
+    B = total_videos // world
+    b0, _ = d3pm_b200.shard_range(total_videos, world, rank)
+    p_mask = float(model.log_cumprod_ct[T_NOW].exp())
+    lc = torch.empty(B, N, K, device=dev)
+    lu = torch.empty(B, N, K, device=dev)
+    x = torch.empty(B, N, dtype=torch.int64, device=dev)
+    for i in range(B):
+        lc[i], lu[i], x[i] = _video_inputs(b0 + i, N, K, p_mask, dev)
+    t = torch.full((B,), T_NOW, dtype=torch.int64, device=dev)
+    out = torch.empty_like(x)
+    barrier()
+    ms = _timed_steps(lambda i: ops.fused_step(lc, lu, x, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX, seed=7,
+                                               offset=i, row_offset=b0 * N, x_prev_out=out), steps, dev)
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm[0])
+    del lc, lu
+    torch.cuda.empty_cache()
+    return {"what": f"config 4 (strong scaling): {total_videos} videos in total, {B} per GPU on {world} GPU(s), one fused step, "
+                    f"device-resident, max over ranks", "videos_per_gpu": B, "ms_per_step": ms, "steps": steps,
+            "value": total_videos * N / (ms * 1e-3), "unit": UNIT, "GBps_per_gpu": B * N * BYTES_PER_TOKEN / (ms * 1e-3) / 1e9}
+
+
+def measure_config5(dev, model, table, videos=64, steps=30):
+    """BASELINE config 5: MSRVTT text-conditioned shape, 64 videos x 4096 tokens, guidance on / off, one fused step."""
+    import torch
+    from d3pm_b200 import _lib, ops
+    N, K = N_TOKENS, K_CODES
+    gen = torch.Generator(device=dev).manual_seed(5)
+    lc = torch.randn(videos, N, K, device=dev, generator=gen)
+    lu = torch.randn(videos, N, K, device=dev, generator=gen)
+    p_mask = float(model.log_cumprod_ct[T_NOW].exp())
+    x = torch.where(torch.rand(videos, N, device=dev, generator=gen) < p_mask, torch.full((videos, N), K, device=dev),
+                    torch.randint(0, K, (videos, N), device=dev, generator=gen))
+    t = torch.full((videos,), T_NOW, dtype=torch.int64, device=dev)
+    out = torch.empty_like(x)
+    peak = 6554.2
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+    res = {"what": f"config 5: {videos} videos x {N} tokens x {K}+1 classes, one fused step, guidance on (scale {GUIDANCE:g}) and off "
+                   f"(predict_start only), device-resident, one B200"}
+    for name, u, bytes_per_token in (("guidance_on", lu, 2 * K * 4 + 16), ("guidance_off", None, K * 4 + 16)):
+        time.sleep(1.0)
+        ms = _timed_steps(lambda i: ops.fused_step(lc, u, x, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX, seed=9,
+                                                   offset=i, x_prev_out=out), steps, dev)
+        gbps = videos * N * bytes_per_token / (ms * 1e-3) / 1e9
+        res[name] = {"ms_per_step": ms, "value": videos * N / (ms * 1e-3), "unit": UNIT, "GBps_algorithmic": gbps,
+                     "frac_of_measured_peak": gbps / peak, "bytes_per_token": bytes_per_token}
+    del lc, lu
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_config3(dev, window=2):
+    """BASELINE config 3 with the reference's REAL denoiser (tools/config3.py): the reference's own sample loop on this GPU
+    against the drop-in class with the same weights, over a window of reverse steps, scaled to the 100-step chain."""
+    from baseline import reference_loader as RL
+    if not RL.reference_available():
+        return {"skipped": "reference not staged on this box (baseline/_ref absent)"}
+    from tools import config3
+    return config3.run(B=VIDEOS_PER_GPU, grid=GRID, K=K_CODES, T=T_STEPS, window=window, dev=dev, guidance=GUIDANCE, quiet=True)
 
 
 _NEXT_ROWS_LOGITS = None
@@ -442,11 +633,29 @@ def measure_next_rows(dev, model, table, x_t, t, x_prev, reps=20):
     pd = timed(purity, reps)
     n_reveal = torch.full((B,), 40, dtype=torch.int32, device=dev)
     ps = timed(lambda i: ops.purity_select(x_t, pur["o"]["x_prev"], pur["o"]["score"], n_reveal, K, seed=1, offset=i), reps)
+    # the host entry of the fused head: pinned host HIDDEN STATES in, host tokens out (d3pm_host_head_step_run) - the boundary
+    # a deployment whose denoiser runs elsewhere would use: 64x fewer bytes on the bus than the logits
+    hh = ops.HostStep(B, N, K, table, guidance=True, T=T_STEPS, hidden_dim=D)
+    h_hc, h_hu = hc.cpu().pin_memory(), hu.cpu().pin_memory()
+    h_x, h_t = x_t.cpu().pin_memory(), t.cpu().pin_memory()
+    e2e_head = timed(lambda i: hh.head(hw, h_hc, h_hu, h_x, h_t, guidance_scale=GUIDANCE, seed=5, offset=i), 10)
+    head_h2d, head_d2h = hh.h2d_bytes, hh.d2h_bytes
+    hh.close()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 0.0)) if os.path.isfile(peaks_path) else 0.0
+    mma_flops = 2.0 * B * N * K * D * 3 * 2  # 3xTF32 split, two passes over the classes
     return {
+        "e2e_host_hidden_states": {"ms_per_step": e2e_head, "value": B * N / (e2e_head * 1e-3), "unit": UNIT,
+                                   "h2d_bytes_per_step": head_h2d, "d2h_bytes_per_step": head_d2h,
+                                   "what": "C ABI d3pm_host_head_step_run: pinned host hidden states [B, N, 64] x2 -> fused head + "
+                                           "update -> host tokens, copies inside the timed region"},
         "purity_prior_step": {"ms_candidate_draw_and_purity": pd, "ms_reveal": ps,
                               "what": "p_sample with prior_rule 2: d3pm_fused_step (D3PM_FROM_RECON + score, stream kernel) + d3pm_purity_select"},
         "q_sample_tokens": {"ms_per_step": qs, "what": "d3pm_q_sample_tokens, 16 x 1024 tokens: forward noising of the training step, one kernel"},
         "head_fused_step": {"ms_per_step": fused, "token_updates_per_s": B * N / (fused * 1e-3), "valid_weight_bound": bool(hw.valid),
+                            "tf32_TFLOPs_issued": mma_flops / (fused * 1e-3) / 1e12, "useful_fp32_TFLOPs": 2.0 * B * N * K * D * 2 / (fused * 1e-3) / 1e12,
+                            "measured_bf16_peak_TFLOPs": bf16_peak,
+                            "tf32_frac_of_half_bf16_peak": (mma_flops / (fused * 1e-3) / 1e12) / (0.5 * bf16_peak) if bf16_peak else None,
                             "what": "d3pm_head_step: LayerNorm + Linear(64 -> 4096) of both denoiser passes + the whole update, "
                                     "tcgen05 3xTF32, logits never in memory"},
         "head_in_torch_then_fused_step": {"ms_per_step": unf, "what": "torch LayerNorm + Linear (fp32) x2, then d3pm_fused_step"},

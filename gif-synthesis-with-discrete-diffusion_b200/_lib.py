@@ -18,6 +18,8 @@ EXPORTED_SYMBOLS = (
     "d3pm_to_token_major", "d3pm_q_pred", "d3pm_q_sample_tokens", "d3pm_train_rows", "d3pm_purity_select",
     "d3pm_head_image_floats", "d3pm_head_prepare", "d3pm_head_step", "d3pm_scale_rows",
     "d3pm_decode_lut", "d3pm_tokens_to_features",
+    "d3pm_host_step_create", "d3pm_host_step_destroy", "d3pm_host_step_h2d_bytes", "d3pm_host_step_d2h_bytes",
+    "d3pm_host_step_run", "d3pm_host_head_step_run",
 )
 
 COEF_STRIDE = 32
@@ -143,6 +145,21 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_scale_rows.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.d3pm_train_rows.restype = c_int
     lib.d3pm_train_rows.argtypes = [POINTER(TrainDesc)]
+    lib.d3pm_host_step_create.restype = c_int
+    lib.d3pm_host_step_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.d3pm_host_step_destroy.restype = c_int
+    lib.d3pm_host_step_destroy.argtypes = [c_void_p]
+    lib.d3pm_host_step_h2d_bytes.restype = c_int64
+    lib.d3pm_host_step_h2d_bytes.argtypes = [c_void_p]
+    lib.d3pm_host_step_d2h_bytes.restype = c_int64
+    lib.d3pm_host_step_d2h_bytes.argtypes = [c_void_p]
+    lib.d3pm_host_step_run.restype = c_int
+    lib.d3pm_host_step_run.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_uint64,
+                                       c_int64, c_void_p, POINTER(c_uint32)]
+    lib.d3pm_host_head_step_run.restype = c_int
+    lib.d3pm_host_head_step_run.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                            c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_uint64, c_int64, c_void_p,
+                                            POINTER(c_uint32)]
     lib.d3pm_to_token_major.restype = c_int
     lib.d3pm_to_token_major.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     _lib = lib

@@ -1,6 +1,7 @@
 // C ABI of libd3pm_b200.so (see include/d3pm_b200.h).  Host side only validates, picks a kernel
 // instantiation and launches on the caller's stream; nothing here allocates, synchronises or keeps
-// state beyond a thread-local error string.
+// state beyond a thread-local error string -- except the explicit d3pm_host_step handle at the end of
+// the file, which owns device staging buffers and two streams for callers whose inputs are HOST buffers.
 #include <cstdarg>
 #include <cstdio>
 
@@ -472,3 +473,182 @@ int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- host-buffer entry points
+// The reference's tensors live wherever its caller put them; a caller whose logits (or hidden states) are HOST
+// buffers goes through a handle that owns the device staging memory, a copy stream and a compute stream.  The inputs
+// travel in chunks of whole videos on the copy stream and the fused step of a chunk runs while the next chunk is on
+// the bus (the noise is keyed by the global row, so the chunks reproduce the one-launch result bit for bit).
+struct d3pm_host_step {
+  int device = 0;
+  int B = 0, N = 0, K = 0, T = 0, D = 0, chunks = 1;
+  bool guidance = false;
+  float *logits_c = nullptr, *logits_u = nullptr, *hidden_c = nullptr, *hidden_u = nullptr;
+  int64_t *x_t = nullptr, *t = nullptr, *x_prev = nullptr;
+  int32_t* redo_rows = nullptr;
+  uint32_t *redo_count = nullptr, *status = nullptr;
+  cudaStream_t copy = nullptr, compute = nullptr;
+  cudaEvent_t landed[16] = {};
+  cudaEvent_t idle = nullptr;
+};
+
+namespace {
+class SetDevice {  // make `dev` current for the scope
+ public:
+  explicit SetDevice(int dev) {
+    if (cudaGetDevice(&prev_) == cudaSuccess && prev_ != dev) switched_ = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~SetDevice() {
+    if (switched_) cudaSetDevice(prev_);
+  }
+ private:
+  int prev_ = 0;
+  bool switched_ = false;
+};
+#define D3PM_CUDA_OK(call, what)                                                                   \
+  do {                                                                                             \
+    const cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) return fail(D3PM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e_));     \
+  } while (0)
+}  // namespace
+
+extern "C" int d3pm_host_step_destroy(d3pm_host_step* h) {
+  if (h == nullptr) return D3PM_OK;
+  const SetDevice on(h->device);
+  if (h->compute != nullptr) cudaStreamSynchronize(h->compute);
+  if (h->copy != nullptr) cudaStreamSynchronize(h->copy);
+  for (void* ptr : {static_cast<void*>(h->logits_c), static_cast<void*>(h->logits_u), static_cast<void*>(h->hidden_c),
+                    static_cast<void*>(h->hidden_u), static_cast<void*>(h->x_t), static_cast<void*>(h->t),
+                    static_cast<void*>(h->x_prev), static_cast<void*>(h->redo_rows), static_cast<void*>(h->redo_count),
+                    static_cast<void*>(h->status)})
+    if (ptr != nullptr) cudaFree(ptr);
+  for (cudaEvent_t ev : h->landed)
+    if (ev != nullptr) cudaEventDestroy(ev);
+  if (h->idle != nullptr) cudaEventDestroy(h->idle);
+  if (h->copy != nullptr) cudaStreamDestroy(h->copy);
+  if (h->compute != nullptr) cudaStreamDestroy(h->compute);
+  delete h;
+  cudaGetLastError();
+  return D3PM_OK;
+}
+
+extern "C" int d3pm_host_step_create(d3pm_host_step** out, int device, int B, int N, int K, int T, int D, int guidance, int chunks) {
+  if (out == nullptr) return fail(D3PM_ERR_INVALID, "host_step_create: null handle pointer");
+  *out = nullptr;
+  if (B <= 0 || N <= 0 || T <= 0 || (K != 1024 && K != 2048 && K != 4096) || (D != 0 && D != 64))
+    return fail(D3PM_ERR_UNSUPPORTED, "host_step_create: B=%d N=%d T=%d must be positive, K=%d in {1024,2048,4096}, D=%d in {0,64}", B, N, T, K, D);
+  if (chunks <= 0) chunks = (B % 4 == 0 && static_cast<int64_t>(B) * N / 4 >= 1024) ? 4 : 1;
+  if (chunks > 16 || B % chunks != 0) return fail(D3PM_ERR_INVALID, "host_step_create: chunks=%d must divide B=%d and be <= 16", chunks, B);
+  const SetDevice on(device);
+  d3pm_host_step* h = new d3pm_host_step;
+  h->device = device, h->B = B, h->N = N, h->K = K, h->T = T, h->D = D, h->chunks = chunks, h->guidance = guidance != 0;
+  const size_t rows = static_cast<size_t>(B) * N;
+  auto alloc = [&](auto** ptr, size_t bytes) { return cudaMalloc(reinterpret_cast<void**>(ptr), bytes) == cudaSuccess; };
+  bool ok = true;
+  if (D == 0) {
+    ok = ok && alloc(&h->logits_c, rows * K * sizeof(float));
+    if (h->guidance) ok = ok && alloc(&h->logits_u, rows * K * sizeof(float));
+  } else {
+    ok = ok && alloc(&h->hidden_c, rows * D * sizeof(float));
+    if (h->guidance) ok = ok && alloc(&h->hidden_u, rows * D * sizeof(float));
+    ok = ok && alloc(&h->redo_rows, rows * sizeof(int32_t)) && alloc(&h->redo_count, sizeof(uint32_t));
+  }
+  ok = ok && alloc(&h->x_t, rows * 8) && alloc(&h->t, static_cast<size_t>(B) * 8) && alloc(&h->x_prev, rows * 8) && alloc(&h->status, 4);
+  ok = ok && cudaMemset(h->status, 0, 4) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking) == cudaSuccess;
+  for (int c = 0; c < chunks && ok; ++c) ok = cudaEventCreateWithFlags(&h->landed[c], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->idle, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    const cudaError_t e = cudaGetLastError();
+    d3pm_host_step_destroy(h);
+    return fail(D3PM_ERR_CUDA, "host_step_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return D3PM_OK;
+}
+
+extern "C" int64_t d3pm_host_step_h2d_bytes(const d3pm_host_step* h) {
+  if (h == nullptr) return 0;
+  const int64_t rows = static_cast<int64_t>(h->B) * h->N;
+  const int64_t width = h->D == 0 ? h->K : h->D;
+  return rows * width * 4 * (h->guidance ? 2 : 1) + rows * 8 + static_cast<int64_t>(h->B) * 8;
+}
+extern "C" int64_t d3pm_host_step_d2h_bytes(const d3pm_host_step* h) { return h == nullptr ? 0 : static_cast<int64_t>(h->B) * h->N * 8; }
+
+// shared driver of the two run calls: `launch(b0, nb)` enqueues the step of videos [b0, b0 + nb) on h->compute
+template <typename Launch>
+static int host_step_run(d3pm_host_step* h, const float* in_c, const float* in_u, float* dev_c, float* dev_u, int64_t width,
+                         const int64_t* x_t, const int64_t* t, int64_t* x_prev, uint32_t* status_out, Launch launch) {
+  const SetDevice on(h->device);
+  const size_t rows = static_cast<size_t>(h->B) * h->N;
+  D3PM_CUDA_OK(cudaMemcpyAsync(h->x_t, x_t, rows * 8, cudaMemcpyHostToDevice, h->compute), "host_step: x_t copy");
+  D3PM_CUDA_OK(cudaMemcpyAsync(h->t, t, static_cast<size_t>(h->B) * 8, cudaMemcpyHostToDevice, h->compute), "host_step: t copy");
+  const int per = h->B / h->chunks;
+  const size_t chunk_floats = static_cast<size_t>(per) * h->N * width;
+  for (int c = 0; c < h->chunks; ++c) {
+    D3PM_CUDA_OK(cudaMemcpyAsync(dev_c + c * chunk_floats, in_c + c * chunk_floats, chunk_floats * 4, cudaMemcpyHostToDevice, h->copy),
+                 "host_step: input copy");
+    if (h->guidance)
+      D3PM_CUDA_OK(cudaMemcpyAsync(dev_u + c * chunk_floats, in_u + c * chunk_floats, chunk_floats * 4, cudaMemcpyHostToDevice, h->copy),
+                   "host_step: input copy");
+    D3PM_CUDA_OK(cudaEventRecord(h->landed[c], h->copy), "host_step: event");
+    D3PM_CUDA_OK(cudaStreamWaitEvent(h->compute, h->landed[c], 0), "host_step: wait");
+    const int rc = launch(c * per, per);
+    if (rc != D3PM_OK) return rc;
+  }
+  D3PM_CUDA_OK(cudaMemcpyAsync(x_prev, h->x_prev, rows * 8, cudaMemcpyDeviceToHost, h->compute), "host_step: token copy");
+  uint32_t st = 0;
+  D3PM_CUDA_OK(cudaMemcpyAsync(&st, h->status, 4, cudaMemcpyDeviceToHost, h->compute), "host_step: status copy");
+  D3PM_CUDA_OK(cudaMemsetAsync(h->status, 0, 4, h->compute), "host_step: status reset");
+  // the next call's copies must not overwrite staging buffers a kernel of this call still reads
+  D3PM_CUDA_OK(cudaEventRecord(h->idle, h->compute), "host_step: event");
+  D3PM_CUDA_OK(cudaStreamWaitEvent(h->copy, h->idle, 0), "host_step: wait");
+  D3PM_CUDA_OK(cudaStreamSynchronize(h->compute), "host_step: synchronize");
+  if (status_out != nullptr) *status_out = st;
+  return D3PM_OK;
+}
+
+extern "C" int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, const float* logits_u, const int64_t* x_t, const int64_t* t,
+                       const float* coef_table, float guidance_scale, uint64_t seed, uint64_t offset, int64_t row_offset,
+                       int64_t* x_prev, uint32_t* status_out) {
+  if (h == nullptr || logits_c == nullptr || x_t == nullptr || t == nullptr || coef_table == nullptr || x_prev == nullptr)
+    return fail(D3PM_ERR_INVALID, "host_step_run: handle, logits_c, x_t, t, coef_table and x_prev are required");
+  if (h->D != 0) return fail(D3PM_ERR_INVALID, "host_step_run: the handle was created for hidden states (D = %d)", h->D);
+  if (h->guidance != (logits_u != nullptr)) return fail(D3PM_ERR_INVALID, "host_step_run: logits_u must be given exactly when the handle has guidance");
+  auto launch = [&](int b0, int nb) {
+    d3pm_step_desc d = {};
+    const size_t at = static_cast<size_t>(b0) * h->N;
+    d.logits_c = h->logits_c + at * h->K, d.logits_u = h->guidance ? h->logits_u + at * h->K : nullptr;
+    d.x_t = h->x_t + at, d.t = h->t + b0, d.coef_table = coef_table, d.x_prev = h->x_prev + at, d.status = h->status;
+    d.B = nb, d.N = h->N, d.K = h->K, d.T = h->T, d.pitch_logits = h->K;
+    d.guidance_scale = guidance_scale, d.sample_mode = D3PM_SAMPLE_PHILOX;
+    d.seed = seed, d.offset = offset, d.row_offset = row_offset + static_cast<int64_t>(at);
+    d.kernel = D3PM_KERNEL_AUTO, d.stream = h->compute;
+    return d3pm_fused_step(&d);
+  };
+  return host_step_run(h, logits_c, logits_u, h->logits_c, h->logits_u, h->K, x_t, t, x_prev, status_out, launch);
+}
+
+extern "C" int d3pm_host_head_step_run(d3pm_host_step* h, const float* hidden_c, const float* hidden_u, const int64_t* x_t, const int64_t* t,
+                            const float* ln_weight, const float* ln_bias, float ln_eps, const float* w_image, const float* bias2,
+                            const float* coef_table, float guidance_scale, uint64_t seed, uint64_t offset, int64_t row_offset,
+                            int64_t* x_prev, uint32_t* status_out) {
+  if (h == nullptr || hidden_c == nullptr || x_t == nullptr || t == nullptr || coef_table == nullptr || x_prev == nullptr)
+    return fail(D3PM_ERR_INVALID, "host_head_step_run: handle, hidden_c, x_t, t, coef_table and x_prev are required");
+  if (h->D == 0) return fail(D3PM_ERR_INVALID, "host_head_step_run: the handle was created for logits (D = 0)");
+  if (h->guidance != (hidden_u != nullptr)) return fail(D3PM_ERR_INVALID, "host_head_step_run: hidden_u must be given exactly when the handle has guidance");
+  auto launch = [&](int b0, int nb) {
+    d3pm_head_desc d = {};
+    const size_t at = static_cast<size_t>(b0) * h->N;
+    d.hidden_c = h->hidden_c + at * h->D, d.hidden_u = h->guidance ? h->hidden_u + at * h->D : nullptr;
+    d.ln_weight = ln_weight, d.ln_bias = ln_bias, d.w_image = w_image, d.bias2 = bias2;
+    d.x_t = h->x_t + at, d.t = h->t + b0, d.coef_table = coef_table, d.x_prev = h->x_prev + at, d.status = h->status;
+    d.redo_rows = h->redo_rows + at, d.redo_count = h->redo_count;
+    d.B = nb, d.N = h->N, d.K = h->K, d.T = h->T, d.D = h->D, d.mode = D3PM_HEAD_STEP;
+    d.ln_eps = ln_eps, d.guidance_scale = guidance_scale;
+    d.seed = seed, d.offset = offset, d.row_offset = row_offset + static_cast<int64_t>(at), d.stream = h->compute;
+    return d3pm_head_step(&d);
+  };
+  return host_step_run(h, hidden_c, hidden_u, h->hidden_c, h->hidden_u, h->D, x_t, t, x_prev, status_out, launch);
+}

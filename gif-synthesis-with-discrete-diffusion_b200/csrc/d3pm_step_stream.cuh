@@ -1,21 +1,30 @@
 // Fused reverse step, production kernel: persistent CTAs, TMA-staged rows, register-resident math.
 //
-// One CTA per SM, four independent groups of 128 threads.  A group owns every G-th token row (G = number
-// of groups in the grid).  Per row:
-//   * one elected thread issues two bulk-TMA copies (cp.async.bulk, 16 KiB each for K = 4096) of the
-//     conditional / unconditional logit rows into the group's shared-memory stage, completion signalled
-//     on an mbarrier; the copy of row r+1 flies while row r is being computed from registers;
-//   * the 128 threads pull the row into registers (32 class pairs per thread, packed for the f32x2 pipe)
-//     and run the softmax statistics, the guidance combine and the posterior entirely in registers with
-//     thread-local maxima, so that only two 128-thread named barriers per row are needed;
+// One CTA of 512 threads per SM, split into independent GROUPS; a group owns every G-th token row (G = number of
+// groups in the grid).  A thread always holds 32 classes of the row (64 without guidance, where the softmax numerators
+// overwrite the logits in place), so the group is K/32 (K/64) threads wide:
+//
+//     K = 4096, guidance on : 4 groups of 128 threads      K = 4096, guidance off : 8 groups of 64 threads
+//     K = 2048, guidance on : 8 groups of  64 threads      K = 2048, guidance off : 16 groups of one warp
+//     K = 1024              : 16 groups of one warp
+//
+// The per-row work that does not depend on the class (reductions, row coefficients, thinning thresholds, loop
+// bookkeeping: ~250 of the ~690 instructions a warp spends on a row at K = 4096) is executed by every warp of a group, so
+// its cost per class is the same for every codebook size instead of doubling each time K halves (round 1: 79 % / 51 % of
+// the copy peak at K = 2048 / 1024, 72 % without guidance).  One-warp groups need no barrier at all.  Per row:
+//   * one elected thread issues the bulk-TMA copies (cp.async.bulk) of the conditional / unconditional logit rows into
+//     the group's shared-memory stage, completion signalled on an mbarrier; the copy of row r+1 flies while row r is
+//     being computed from registers;
+//   * the threads pull the row into registers (class pairs packed for the f32x2 pipe) and run the softmax statistics,
+//     the guidance combine and the posterior entirely in registers with thread-local maxima, so that only two group
+//     barriers per row are needed;
 //   * sampling is the thinned exponential race (see ThinRule): 16 Philox bits per class decide whether the
 //     class can still win; the ~6 survivors per row are appended to a per-row list in shared memory;
 //   * every kScoreBatch rows the group scores the survivors of the whole batch exactly (Gumbel score in
 //     accurate fp32, argmax with first-index ties), two rows per warp pass, and writes the tokens;
 //   * rows whose best survivor does not clear the acceptance bound (probability ~e^-c, ~200 of 65 536 rows)
 //     are queued and redone by the same group after its main loop: the same race thinned at c = 16 with the
-//     survivors scored on the spot (4 us per row; exhaustive scoring, 10 us per row, made the unluckiest
-//     group - three such rows - lengthen the launch by 5 %), and exhaustively only if that fails too (e^-16).
+//     survivors scored on the spot, and exhaustively only if that fails too (e^-16).
 // HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
 #pragma once
 
@@ -23,13 +32,12 @@
 
 namespace d3pm {
 
+// the training kernel (d3pm_train_stream.cuh) keeps the fixed four-groups-of-128 shape
 constexpr int kGroupThreads = 128;
 constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kGroupsPerCta = 4;
 constexpr int kStreamThreads = kGroupThreads * kGroupsPerCta;
-constexpr int kScoreBatch = 64;   // rows whose survivors are scored together
 constexpr int kCandPerRow = 14;   // survivors kept per row (a row with more is redone); +2 lanes: [MASK] and x_t
-constexpr int kRedoCap = 2048;    // rows a group can queue for exhaustive rescoring (= max rows per group)
 constexpr float kStreamThin = 6.0f;
 constexpr float kRedoThin = 16.0f;  // bound of the second attempt at a row whose best survivor did not clear the first
 constexpr int kCoefSmemRows = 256;  // timesteps whose coefficients are staged in shared memory (16 KiB)
@@ -40,20 +48,36 @@ struct RowInfo {  // what the scoring pass needs to finish a row
   int32_t pad;
 };
 
-template <int NP>
+// Shape of one instantiation.  NP = K / 1024; CPT = float4 chunks a thread holds per tensor (8, or 16 without guidance).
+template <int NP, int CPT, bool HAS_U>
+struct StreamShape {
+  static_assert(CPT == 8 || (CPT == 16 && !HAS_U), "64 classes per thread only fit in registers without the second tensor");
+  static constexpr int K = 1024 * NP;
+  static constexpr int GT = 256 * NP / CPT;        // threads per group
+  static constexpr int NW = GT / 32;               // warps per group
+  static constexpr int NG = kStreamThreads / GT;   // groups per CTA
+  static constexpr int SB = 256 / NG;              // rows whose survivors are scored together
+  static constexpr int RC = 8192 / NG;             // rows a group can queue for rescoring (= max rows per group)
+  static constexpr int PS = 128 / GT;              // a coarse Philox call serves chunks q and q + 128: slots i and i + PS
+  static constexpr int NCALL = CPT / 2;            // coarse calls per thread and row
+  static_assert(GT >= 32 && GT <= 128 && NG <= 16, "unsupported group shape");
+};
+
+template <int NP, int CPT, bool HAS_U>
 struct __align__(128) GroupSmem {
-  float c[1024 * NP];  // conditional logits of the row in flight
-  float u[1024 * NP];  // unconditional logits
-  alignas(16) float red[3][6 * kGroupWarps];  // reduction scratch, read back with 128-bit loads
-  unsigned long long full;                    // mbarrier: TMA bytes landed
-  unsigned long long keys[kGroupWarps];
+  using Sh = StreamShape<NP, CPT, HAS_U>;
+  float c[1024 * NP];                   // conditional logits of the row in flight
+  float u[HAS_U ? 1024 * NP : 4];       // unconditional logits
+  alignas(16) float red[3][6 * 4];      // reduction scratch, read back with 128-bit loads
+  unsigned long long full;              // mbarrier: TMA bytes landed
+  unsigned long long keys[4];
   uint32_t redo_cnt;
   uint32_t pad;
-  RowInfo info[kScoreBatch];
-  uint32_t cand_cnt[kScoreBatch];
-  uint32_t cand_k[kScoreBatch][kCandPerRow];
-  float cand_p[kScoreBatch][kCandPerRow];
-  int32_t redo[kRedoCap];
+  RowInfo info[Sh::SB];
+  uint32_t cand_cnt[Sh::SB];
+  uint32_t cand_k[Sh::SB][kCandPerRow];
+  float cand_p[Sh::SB][kCandPerRow];
+  int32_t redo[Sh::RC];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -94,33 +118,59 @@ struct GroupSync {
   int id;
   __device__ __forceinline__ void operator()() const { group_bar(id); }
 };
+// barrier of a group of NW warps (named barrier `id`); a one-warp group only needs the warp to reconverge
+template <int NW>
+struct StreamSync {
+  int id;
+  __device__ __forceinline__ void operator()() const {
+    if (NW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * NW) : "memory");
+  }
+};
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// the NW per-warp values of a reduction, read back in one shared-memory load (unused lanes of the float4 = neutral)
+template <int NW>
+__device__ __forceinline__ float4 lds_warps(const float* p, float neutral) {
+  if (NW == 4) return lds4(p);
+  const float2 a = *reinterpret_cast<const float2*>(p);
+  return make_float4(a.x, a.y, neutral, neutral);
+}
 // Group-wide (max, sum) of per-thread softmax partials, one barrier.  m: thread-local max (natural units),
 // s: sum of 2^(x*log2e - fl(m*log2e)).  Returns the group max and the sum relative to it.
-template <int NV, typename Sync>
+template <int NW, int NV, typename Sync>
 __device__ __forceinline__ void stream_max_sum(float (&m)[NV], float (&s)[NV], float* scratch, Sync sync) {
-  constexpr int NW = kGroupWarps;
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float mw = warp_max(m[v]);
     const float mw2 = to_log2_units(mw);
     const float sw = warp_sum(s[v] * ex2(to_log2_units(m[v]) - mw2));
-    if (lane == 0) {
-      scratch[(3 * v) * NW + warp] = mw;
-      scratch[(3 * v + 1) * NW + warp] = mw2;
-      scratch[(3 * v + 2) * NW + warp] = sw;
+    if (NW == 1) {
+      m[v] = mw, s[v] = sw;
+    } else if (lane == 0) {
+      scratch[(3 * v) * 4 + warp] = mw;
+      scratch[(3 * v + 1) * 4 + warp] = mw2;
+      scratch[(3 * v + 2) * 4 + warp] = sw;
     }
   }
   sync();
+  if constexpr (NW > 1) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float4 mw = lds4(scratch + (3 * v) * NW), mw2 = lds4(scratch + (3 * v + 1) * NW);
-    const float4 sw = lds4(scratch + (3 * v + 2) * NW);
-    const float M = fmaxf(fmaxf(mw.x, mw.y), fmaxf(mw.z, mw.w));
-    const float M2 = to_log2_units(M);
-    m[v] = M;
-    s[v] = fmaf(sw.x, ex2(mw2.x - M2), fmaf(sw.y, ex2(mw2.y - M2), fmaf(sw.z, ex2(mw2.z - M2), sw.w * ex2(mw2.w - M2))));
+    const float4 mw = lds_warps<NW>(scratch + (3 * v) * 4, -CUDART_INF_F), mw2 = lds_warps<NW>(scratch + (3 * v + 1) * 4, 0.f);
+    const float4 sw = lds_warps<NW>(scratch + (3 * v + 2) * 4, 0.f);
+    if (NW == 4) {
+      const float M = fmaxf(fmaxf(mw.x, mw.y), fmaxf(mw.z, mw.w));
+      const float M2 = to_log2_units(M);
+      m[v] = M;
+      s[v] = fmaf(sw.x, ex2(mw2.x - M2), fmaf(sw.y, ex2(mw2.y - M2), fmaf(sw.z, ex2(mw2.z - M2), sw.w * ex2(mw2.w - M2))));
+    } else {
+      const float M = fmaxf(mw.x, mw.y);
+      const float M2 = to_log2_units(M);
+      m[v] = M;
+      s[v] = fmaf(sw.x, ex2(mw2.x - M2), sw.y * ex2(mw2.y - M2));
+    }
+  }
   }
 }
 
@@ -131,51 +181,73 @@ __device__ __forceinline__ float warp_min(float x) {
 }
 
 // Group-wide max of NV values (one CREDUX per value, one barrier).
-template <int NV, typename Sync>
+template <int NW, int NV, typename Sync>
 __device__ __forceinline__ void stream_max(float* mx, float* scratch, Sync sync) {
-  constexpr int NW = kGroupWarps;
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float a = warp_max(mx[v]);
-    if (lane == 0) scratch[v * NW + warp] = a;
+    if (NW == 1) mx[v] = a;
+    else if (lane == 0) scratch[v * 4 + warp] = a;
   }
   sync();
+  if constexpr (NW > 1) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float4 a = lds4(scratch + v * NW);
+    const float4 a = lds_warps<NW>(scratch + v * 4, -CUDART_INF_F);
     mx[v] = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+  }
   }
 }
 
 // Group-wide sums (all relative to the same, already global, maximum).
-template <int NV, typename Sync>
+template <int NW, int NV, typename Sync>
 __device__ __forceinline__ void stream_sum(float (&s)[NV], float* scratch, Sync sync) {
-  constexpr int NW = kGroupWarps;
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float sw = warp_sum(s[v]);
-    if (lane == 0) scratch[v * NW + warp] = sw;
+    if (NW == 1) s[v] = sw;
+    else if (lane == 0) scratch[v * 4 + warp] = sw;
   }
   sync();
+  if constexpr (NW > 1) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float4 a = lds4(scratch + v * NW);
+    const float4 a = lds_warps<NW>(scratch + v * 4, 0.f);
     s[v] = (a.x + a.y) + (a.z + a.w);
   }
+  }
+}
+
+// group arg-max of 64-bit keys (rare paths only)
+template <int NW, typename Sync>
+__device__ __forceinline__ unsigned long long stream_max_u64(unsigned long long key, unsigned long long* scratch, Sync sync) {
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (NW - 1);
+  key = warp_max_u64(key);
+  if (NW == 1) {
+    sync();
+    return key;
+  }
+  if (lane == 0) scratch[warp] = key;
+  sync();
+  unsigned long long best = scratch[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) best = scratch[w] > best ? scratch[w] : best;
+  return best;
 }
 
 // Exact finish of a batch of rows from their survivor lists: 16 lanes per row (14 survivors, the [MASK] class,
 // the row's own class), every lane scores one class exactly as the log-domain kernel does, a 16-lane
 // segmented argmax picks the winner, which is accepted if it clears the row's bound and queued otherwise.
-template <int NP>
-__device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const NoiseStream& rng, const StepParams& p, int G,
+template <int NP, int CPT, bool HAS_U>
+__device__ __noinline__ void score_batch(GroupSmem<NP, CPT, HAS_U>& S, int nslots, const NoiseStream& rng, const StepParams& p, int G,
                                          int first_row) {
+  using Sh = StreamShape<NP, CPT, HAS_U>;
   constexpr uint32_t K = 1024u * NP;
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (kGroupWarps - 1);
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & (Sh::NW - 1);
   const int sub = lane & 15;
-  for (int slot = 2 * warp + (lane >> 4); slot - (lane >> 4) < nslots; slot += 2 * kGroupWarps) {
+  for (int slot = 2 * warp + (lane >> 4); slot - (lane >> 4) < nslots; slot += 2 * Sh::NW) {
     unsigned long long key = 0ull;
     float lp = 0.f;  // log-posterior of this lane's class (kept for the optional winner_post output)
     const bool live = slot < nslots;
@@ -228,28 +300,30 @@ __device__ __noinline__ void score_batch(GroupSmem<NP>& S, int nslots, const Noi
 
 // RECON: the purity-prior variant (draw from p(x0 | x_t), write the purity score); its own instantiation so that the
 // plain step's code is not perturbed
-template <int NP, bool HAS_U, bool RECON>
+template <int NP, int CPT, bool HAS_U, bool RECON>
 __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int K = 1024 * NP;
-  constexpr int NC = 2 * NP;  // float4 chunks per thread per tensor
+  using Sh = StreamShape<NP, CPT, HAS_U>;
+  using Smem = GroupSmem<NP, CPT, HAS_U>;
+  constexpr int K = Sh::K, GT = Sh::GT, NW = Sh::NW, NG = Sh::NG, PS = Sh::PS, NCALL = Sh::NCALL;
+  constexpr int NC = CPT;  // float4 chunks per thread per tensor
   constexpr uint32_t kRowBytes = K * sizeof(float);
   uint32_t tid;  // read once: a volatile read cannot be rematerialised as an S2R in every row
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const int g = tid / kGroupThreads;
-  const int tg = tid % kGroupThreads;
-  GroupSmem<NP>& S = reinterpret_cast<GroupSmem<NP>*>(smem_raw)[g];
+  const int g = tid / GT;
+  const int tg = tid % GT;
+  Smem& S = reinterpret_cast<Smem*>(smem_raw)[g];
   // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits: per-row lookups become LDS
-  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(GroupSmem<NP>) * kGroupsPerCta);
+  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(Smem) * NG);
   const bool coef_in_smem = p.T <= kCoefSmemRows;
   if (coef_in_smem) {
     for (int i = tid; i < p.T * 16; i += kStreamThreads)
       coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
     __syncthreads();
   }
-  const GroupSync sync{g + 1};
+  const StreamSync<NW> sync{g + 1};
   // row indices are 32-bit throughout (the launcher refuses more than 2^31 - 1 rows)
-  const int G = static_cast<int>(gridDim.x) * kGroupsPerCta;
+  const int G = static_cast<int>(gridDim.x) * NG;
   const int first_row = g * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);  // neighbouring rows -> different SMs
   const int rows = static_cast<int>(p.rows);
   const uint32_t pitch = static_cast<uint32_t>(p.pitch_logits);
@@ -260,7 +334,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     mbar_init(&S.full, 1);
     S.redo_cnt = 0;
   }
-  if (tg < kScoreBatch) S.cand_cnt[tg] = 0;
+  for (int i = tg; i < Sh::SB; i += GT) S.cand_cnt[i] = 0;
   sync();
 
   auto issue_row = [&](int row) {  // elected thread: arm the barrier and launch both row copies
@@ -270,6 +344,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     tma_load_row(S.c, p.logits_c + at, kRowBytes, &S.full);
     if (HAS_U) tma_load_row(S.u, p.logits_u + at, kRowBytes, &S.full);
   };
+  // slot (register chunk index) of the low chunk of coarse call c: chunks q and q + 128 share a call, i.e. slots
+  // i and i + PS of the same thread
+  auto slot_lo = [](int c) { return (c / PS) * 2 * PS + (c % PS); };
 
   uint32_t phase = 0;
   uint32_t status_bits = 0;
@@ -290,12 +367,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     mbar_wait(&S.full, phase);
     phase ^= 1u;
 
-    // ---- shared -> registers: chunk i of this thread is float4 number 128*i + tg (conflict-free 128-bit
-    //      reads); x[i][0] = classes (0,1) of the chunk, x[i][1] = classes (2,3), packed for the f32x2 pipe ----
-    float2 x[NC][2], z[NC][2];
+    // ---- shared -> registers: chunk i of this thread is float4 number GT*i + tg (conflict-free 128-bit
+    //      reads); x[i][0] = classes (0,1) of the chunk, x[i][1] = classes (2,3), packed for the f32x2 pipe.
+    //      Without guidance the softmax numerators later overwrite x in place (e_of below) ----
+    float2 x[NC][2], z[HAS_U ? NC : 1][2];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      const int q = 128 * i + tg;
+      const int q = GT * i + tg;
       const float4 a = lds4(S.c + 4 * q);
       x[i][0] = make_float2(a.x, a.y), x[i][1] = make_float2(a.z, a.w);
       if (HAS_U) {
@@ -303,6 +381,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         z[i][0] = make_float2(b.x, b.y), z[i][1] = make_float2(b.z, b.w);
       }
     }
+    auto e_of = [&](int i, int h) -> float2& {  // the softmax numerators of the row (relative to the thread-local max)
+      if constexpr (HAS_U) return z[i][h];
+      else return x[i][h];
+    };
     const float xj = masked ? 0.f : S.c[j];
     const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
 
@@ -319,19 +401,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       if (HAS_U)
         am[1] = fmaxf(fmaxf(am[1], fabsf(z[i][0].x)), fmaxf(fabsf(z[i][0].y), fmaxf(fabsf(z[i][1].x), fabsf(z[i][1].y))));
     }
-    if (HAS_U) stream_max<2>(am, S.red[0], sync);  // barrier 1: every thread is done with the stage
-    else sync();                                   // (without guidance nothing depends on the range of the logits)
+    if (HAS_U) stream_max<NW, 2>(am, S.red[0], sync);  // barrier 1: every thread is done with the stage
+    else sync();                                        // (without guidance nothing depends on the range of the logits)
     // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
     if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
 
-    // the row's coarse noise: one Philox call = 8 x 16 bits, word w of call i serves classes (2w, 2w+1) of the
-    // chunk pair (2i, 2i+1)
     const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
-    uint4 cws[NP];
-    auto draw_coarse = [&]() {
-#pragma unroll
-      for (int i = 0; i < NP; ++i) cws[i] = rng.coarse((i << 7) | tg, grow);
-    };
 
     float My2, rSy, r, yj;
     const float2 l2e = make_float2(kLog2e, kLog2e);
@@ -369,7 +444,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
           mx[0] = fmaxf(fmaxf(mx[0], x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
           mx[1] = fmaxf(fmaxf(mx[1], z[i][0].x), fmaxf(z[i][0].y, fmaxf(z[i][1].x, z[i][1].y)));
         }
-        stream_max<2>(mx, S.red[2], sync);  // extra barriers, general path only
+        stream_max<NW, 2>(mx, S.red[2], sync);  // extra barriers, general path only
         mx[0] = fmaxf(mx[0], -3.0e38f), mx[1] = fmaxf(mx[1], -3.0e38f);  // an all--inf row stays finite
         {
           const float mc2 = to_log2_units(mx[0]), mu2 = to_log2_units(mx[1]);
@@ -386,7 +461,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
           s[0] = (sc[0].x + sc[0].y) + (sc[1].x + sc[1].y);
           s[1] = (su[0].x + su[0].y) + (su[1].x + su[1].y);
         }
-        stream_sum<2>(s, S.red[2] + 2 * kGroupWarps, sync);
+        stream_sum<NW, 2>(s, S.red[2] + 2 * 4, sync);
         const float lnSc = ln_rel_sum(mx[0], s[0]), lnSu = ln_rel_sum(mx[1], s[1]);
         const float ta = kClampLo + lnSc, tb = kClampLo + lnSu;
         const float C = fmaf(-gs, lnSc, -og * lnSu);
@@ -415,11 +490,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
           for (int h = 0; h < 2; ++h) {
             const float2 ay = __ffma2_rn(x[i][h], l2e, nmy);
             const float2 ey = make_float2(ex2(ay.x), ex2(ay.y));
-            z[i][h] = ey;
+            e_of(i, h) = ey;
             sy[h] = __fadd2_rn(sy[h], ey);
           }
         float mm[1] = {my}, ss[1] = {(sy[0].x + sy[0].y) + (sy[1].x + sy[1].y)};
-        stream_max_sum<1>(mm, ss, S.red[1], sync);  // barrier 2
+        stream_max_sum<NW, 1>(mm, ss, S.red[1], sync);  // barrier 2
         My2 = to_log2_units(mm[0]);
         rSy = __fdividef(1.0f, ss[0]);
       }
@@ -440,11 +515,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         for (int h = 0; h < 2; ++h) {
           const float2 ac = __ffma2_rn(x[i][h], l2e, nmc);
           const float2 ec = make_float2(ex2(ac.x), ex2(ac.y));
-          z[i][h] = ec;
+          e_of(i, h) = ec;  // in place: the logits themselves are not needed any more
           sc[h] = __fadd2_rn(sc[h], ec);
         }
       float ss[1] = {(sc[0].x + sc[0].y) + (sc[1].x + sc[1].y)};
-      stream_max_sum<1>(mx, ss, S.red[1], sync);  // barrier 2
+      stream_max_sum<NW, 1>(mx, ss, S.red[1], sync);  // barrier 2
       My2 = to_log2_units(mx[0]);
       rSy = __fdividef(1.0f, ss[0]);
       r = ex2(mc2 - My2) * rSy;
@@ -469,8 +544,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     }
 
     if (!exact) {
-      // ---- thinned race: 16 noise bits per class, survivors go to this row's slot ----
-      draw_coarse();  // all calls of the row up front: four independent Philox chains to interleave
+      // ---- thinned race: 16 noise bits per class, survivors go to this row's slot.  One Philox call = 8 x 16 bits:
+      //      word w of call c serves classes (2w, 2w+1) of chunk slot_lo(c) (w < 2) / slot_lo(c) + PS (w >= 2);
+      //      four calls are drawn together (four independent Philox chains to interleave) ----
       const ThinRule thin(rm, thin_c);
       const float thrA = r * thin.scaleA;
       const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
@@ -481,33 +557,41 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         S.info[slot] = ri;
       }
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        // the halves are spliced under the exponent of -1.0f so that -(1 + h 2^-23) comes out of one PRMT
-        const uint32_t w4[4] = {cws[i].x, cws[i].y, cws[i].z, cws[i].w};
-        float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
+      for (int c0 = 0; c0 < NCALL; c0 += 4) {
+        uint4 cws[4];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
-                                        __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
-          const float2 d = __ffma2_rn(z[2 * i + (w >> 1)][w & 1], tA2, __fadd2_rn(tB2, nf));
-          slack = fmaxf(slack, fmaxf(d.x, d.y));
-        }
-        if (slack >= 0.0f) {
+        for (int c = 0; c < 4; ++c) cws[c] = rng.coarse(NoiseStream::coarse_call_of_chunk(GT * slot_lo(c0 + c) + tg), grow);
 #pragma unroll
-          for (int w = 0; w < 4; ++w)
+        for (int c = 0; c < 4; ++c) {
+          const int lo = slot_lo(c0 + c);
+          // the halves are spliced under the exponent of -1.0f so that -(1 + h 2^-23) comes out of one PRMT
+          const uint32_t w4[4] = {cws[c].x, cws[c].y, cws[c].z, cws[c].w};
+          float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
 #pragma unroll
-            for (int hl = 0; hl < 2; ++hl) {
-              const float e = hl ? z[2 * i + (w >> 1)][w & 1].y : z[2 * i + (w >> 1)][w & 1].x;
-              const uint32_t h16 = hl ? (w4[w] >> 16) : (w4[w] & 0xffffu);
-              const float nf = __uint_as_float(0xbf800000u | h16);
-              if (fmaf(e, thrA, thin.thrB + nf) >= 0.0f) {
-                const uint32_t pos = atomicAdd(&S.cand_cnt[slot], 1u);
-                if (pos < static_cast<uint32_t>(kCandPerRow)) {
-                  S.cand_k[slot][pos] = 4u * (128u * (2 * i + (w >> 1)) + tg) + 2u * (w & 1) + hl;
-                  S.cand_p[slot][pos] = e * r;
+          for (int w = 0; w < 4; ++w) {
+            const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
+                                          __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
+            const float2 d = __ffma2_rn(e_of(lo + (w >> 1) * PS, w & 1), tA2, __fadd2_rn(tB2, nf));
+            slack = fmaxf(slack, fmaxf(d.x, d.y));
+          }
+          if (slack >= 0.0f) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+              for (int hl = 0; hl < 2; ++hl) {
+                const float2 ee = e_of(lo + (w >> 1) * PS, w & 1);
+                const float e = hl ? ee.y : ee.x;
+                const uint32_t h16 = hl ? (w4[w] >> 16) : (w4[w] & 0xffffu);
+                const float nf = __uint_as_float(0xbf800000u | h16);
+                if (fmaf(e, thrA, thin.thrB + nf) >= 0.0f) {
+                  const uint32_t pos = atomicAdd(&S.cand_cnt[slot], 1u);
+                  if (pos < static_cast<uint32_t>(kCandPerRow)) {
+                    S.cand_k[slot][pos] = 4u * (GT * (lo + (w >> 1) * PS) + tg) + 2u * (w & 1) + hl;
+                    S.cand_p[slot][pos] = e * r;
+                  }
                 }
               }
-            }
+          }
         }
       }
       return;
@@ -520,40 +604,39 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     if (!exact_mode) {
       // a row whose best survivor missed the acceptance bound: the same thinned race at a bound that fails with
       // probability e^-16, survivors scored on the spot (exactly as score_batch scores them)
-      draw_coarse();
       // (a test knob: thin_factor < 0.01 is used for this attempt too, which then fails and reaches the code below)
       const ThinRule thin2(rm, (p.thin_factor > 0.f && p.thin_factor < 0.01f) ? p.thin_factor : kRedoThin);
       const float thrA = r * thin2.scaleA;
       const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin2.thrB, thin2.thrB);
-      uint32_t hits = 0;  // bit 8 i + 2 w + h: class h of word w of Philox call i passed the coarse test
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const uint32_t w4[4] = {cws[i].x, cws[i].y, cws[i].z, cws[i].w};
+      for (int c = 0; c < NCALL; ++c) {
+        const int lo = slot_lo(c);
+        const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(GT * lo + tg), grow);
+        const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+        uint32_t hits = 0;  // bit 2 w + h: class h of word w passed the coarse test
+        float ev[8];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
+          const float2 ee = e_of(lo + (w >> 1) * PS, w & 1);
+          ev[2 * w] = ee.x, ev[2 * w + 1] = ee.y;
           const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
                                         __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
-          const float2 d = __ffma2_rn(z[2 * i + (w >> 1)][w & 1], tA2, __fadd2_rn(tB2, nf));
-          hits |= (d.x >= 0.0f ? 1u : 0u) << (8 * i + 2 * w);
-          hits |= (d.y >= 0.0f ? 1u : 0u) << (8 * i + 2 * w + 1);
+          const float2 d = __ffma2_rn(ee, tA2, __fadd2_rn(tB2, nf));
+          hits |= (d.x >= 0.0f ? 1u : 0u) << (2 * w);
+          hits |= (d.y >= 0.0f ? 1u : 0u) << (2 * w + 1);
         }
-      }
-      while (hits != 0) {  // ~16 classes per row in all
-        const int b = __ffs(hits) - 1;
-        hits &= hits - 1;
-        float e = 0.f;  // z viewed as float[8 NP] is indexed by b; picked with selects, never through memory
+        while (hits != 0) {  // ~16 classes per row in all
+          const int b = __ffs(hits) - 1;
+          hits &= hits - 1;
+          float e = 0.f;
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            e = (b == 4 * c + 2 * h) ? z[c][h].x : e;
-            e = (b == 4 * c + 2 * h + 1) ? z[c][h].y : e;
+          for (int q = 0; q < 8; ++q) e = (b == q) ? ev[q] : e;  // picked with selects, never through memory
+          const uint32_t k = 4u * (GT * (lo + (b >> 2) * PS) + tg) + static_cast<uint32_t>(b & 3);
+          if (k != j) {
+            const float lpk = rm.post_of(k, e, r);
+            const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow))), k);
+            if (key > best) best = key, best_lp = lpk;
           }
-        const uint32_t k = 4u * (128u * static_cast<uint32_t>(b >> 2) + tg) + static_cast<uint32_t>(b & 3);
-        if (k != j) {
-          const float lpk = rm.post_of(k, e, r);
-          const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow))), k);
-          if (key > best) best = key, best_lp = lpk;
         }
       }
       if (tg == 0) {
@@ -561,13 +644,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(K, grow))), K);
         if (key > best) best = key, best_lp = lpk;
       }
-      if (tg == 32 && !masked) {  // the row's own class has its own coefficients
+      if (tg == GT - 1 && !masked) {  // the row's own class has its own coefficients
         const float lpk = rm.post_self();
         const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(j, grow))), j);
         if (key > best) best = key, best_lp = lpk;
       }
       const unsigned long long mine = best;
-      best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3
+      best = stream_max_u64<NW>(best, S.keys, sync);  // barrier 3
       settled = key_score(best) >= thin2.accept;
       if (settled) {
         if (p.winner_post != nullptr && mine == best) p.winner_post[row] = best_lp;
@@ -578,14 +661,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     }
     if (!settled) {
       // ---- exhaustive scoring (PHILOX_EXACT mode, or the second attempt failed too): kept small rather than
-      //      fast.  The softmax numerators are parked in the idle unconditional stage and scored in a rolled loop.
+      //      fast.  The softmax numerators are parked in the idle conditional stage (the prefetch of the next row is
+      //      deferred to the end of an exhaustive row) and scored in a rolled loop.
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
-        *reinterpret_cast<float4*>(S.u + 4 * (128 * i + tg)) = make_float4(z[i][0].x, z[i][0].y, z[i][1].x, z[i][1].y);
+      for (int i = 0; i < NC; ++i) {
+        const float2 a = e_of(i, 0), b = e_of(i, 1);
+        *reinterpret_cast<float4*>(S.c + 4 * (GT * i + tg)) = make_float4(a.x, a.y, b.x, b.y);
+      }
 #pragma unroll 1
       for (int i = 0; i < NC; ++i) {
-        const uint32_t q = 128u * i + tg;
-        const float4 e4 = lds4(S.u + 4 * q);
+        const uint32_t q = static_cast<uint32_t>(GT) * i + tg;
+        const float4 e4 = lds4(S.c + 4 * q);
         const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
         const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
         const uint4 fw = rng.fine(q >> 2, grow);
@@ -605,7 +691,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         if (key > best) best = key, best_lp = lpk;
       }
       const unsigned long long mine = best;
-      best = group_max_u64<kGroupWarps>(best, S.keys, sync);  // barrier 3
+      best = stream_max_u64<NW>(best, S.keys, sync);  // barrier 3 (also: every thread has read its parked numerators)
       if (p.winner_post != nullptr && mine == best) p.winner_post[row] = best_lp;
     }
     if (tg == 0) {
@@ -632,10 +718,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
   }
   int it = 0, in_batch = 0;
   for (;;) {
-    if (row < 0 || in_batch == kScoreBatch) {  // finish the rows accumulated so far
+    if (row < 0 || in_batch == Sh::SB) {  // finish the rows accumulated so far
       if (in_batch > 0) {
         sync();  // every thread has finished appending survivors
-        score_batch<NP>(S, in_batch, rng, p, G, first_row);
+        score_batch<NP, CPT, HAS_U>(S, in_batch, rng, p, G, first_row);
         sync();  // slots may be reused, redo_cnt is final for this batch
         in_batch = 0;
       }
@@ -656,11 +742,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     }
     // Consume this row's scalars (loaded one row ahead) BEFORE issuing the next prefetch: the consumer waits on
     // the scoreboard slot the loads share, so the other order would stall on the loads just issued.
-    if (tt < 0 || tt >= p.T) {
+    if (static_cast<unsigned long long>(tt) >= static_cast<unsigned long long>(p.T)) {
       status_bits |= D3PM_STATUS_BAD_T;
       tt = tt < 0 ? 0 : p.T - 1;
     }
-    if (jj < 0 || jj > K) {
+    if (static_cast<unsigned long long>(jj) > static_cast<unsigned long long>(K)) {
       status_bits |= D3PM_STATUS_BAD_TOKEN;
       jj = K;
     }
@@ -697,7 +783,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 #ifdef D3PM_STREAM_TIMING
   if (tg == 0 && p.status != nullptr) {
     const unsigned long long tm_end = now_ns();
-    uint32_t* o = p.status + 8 * (blockIdx.x * kGroupsPerCta + g);
+    uint32_t* o = p.status + 8 * (blockIdx.x * NG + g);
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     if (tm_main == 0) tm_main = tm_end;
@@ -722,38 +808,40 @@ inline bool stream_kernel_supports(const StepParams& p) {
   return true;
 }
 
-// every group must be able to queue all of its rows for rescoring
+// every group must be able to queue all of its rows for rescoring (RC * NG = 8192 rows per CTA in every shape)
 inline long long stream_kernel_max_rows() {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  return static_cast<long long>(kRedoCap) * kGroupsPerCta * sms;
+  return 8192LL * sms;
 }
 
-template <int NP, bool HAS_U, bool RECON>
+template <int NP, int CPT, bool HAS_U, bool RECON>
 int launch_step_stream_r(const StepParams& p, cudaStream_t s) {
+  using Sh = StreamShape<NP, CPT, HAS_U>;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
-  const size_t smem = sizeof(GroupSmem<NP>) * kGroupsPerCta + kCoefSmemRows * 16 * sizeof(float);
-  auto kern = step_stream_kernel<NP, HAS_U, RECON>;
+  const size_t smem = sizeof(GroupSmem<NP, CPT, HAS_U>) * Sh::NG + kCoefSmemRows * 16 * sizeof(float);
+  auto kern = step_stream_kernel<NP, CPT, HAS_U, RECON>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
   kern<<<static_cast<unsigned>(sms), kStreamThreads, smem, s>>>(p);
   return D3PM_OK;
 }
 
-template <int NP, bool HAS_U>
+template <int NP, int CPT, bool HAS_U>
 int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
-  return p.sample_from == D3PM_FROM_RECON ? launch_step_stream_r<NP, HAS_U, true>(p, s) : launch_step_stream_r<NP, HAS_U, false>(p, s);
+  return p.sample_from == D3PM_FROM_RECON ? launch_step_stream_r<NP, CPT, HAS_U, true>(p, s)
+                                          : launch_step_stream_r<NP, CPT, HAS_U, false>(p, s);
 }
 
 inline int launch_step_stream(const StepParams& p, cudaStream_t s) {
   const bool has_u = p.logits_u != nullptr;
   switch (p.K) {
-    case 1024: return has_u ? launch_step_stream_t<1, true>(p, s) : launch_step_stream_t<1, false>(p, s);
-    case 2048: return has_u ? launch_step_stream_t<2, true>(p, s) : launch_step_stream_t<2, false>(p, s);
-    case 4096: return has_u ? launch_step_stream_t<4, true>(p, s) : launch_step_stream_t<4, false>(p, s);
+    case 1024: return has_u ? launch_step_stream_t<1, 8, true>(p, s) : launch_step_stream_t<1, 8, false>(p, s);
+    case 2048: return has_u ? launch_step_stream_t<2, 8, true>(p, s) : launch_step_stream_t<2, 16, false>(p, s);
+    case 4096: return has_u ? launch_step_stream_t<4, 8, true>(p, s) : launch_step_stream_t<4, 16, false>(p, s);
     default: return D3PM_ERR_UNSUPPORTED;
   }
 }

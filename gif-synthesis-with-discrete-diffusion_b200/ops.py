@@ -280,52 +280,83 @@ def argmax_classes(x: torch.Tensor) -> torch.Tensor:
 class HostStep:
     """The fused step for callers whose logits live in HOST memory (the reference's CPU tensors).
 
-    Owns the device staging buffers for one batch shape; `__call__` copies the pinned host inputs to
-    the device, runs `d3pm_fused_step` (production Philox sampling) and copies the int64 tokens back,
-    all on the current stream, then waits for the result.  Per call it moves
+    A thin wrapper of the C handle `d3pm_host_step` (include/d3pm_b200.h): the library owns the device staging buffers
+    for one batch shape, a copy stream and a compute stream; `__call__` hands it the HOST pointers, the inputs travel
+    in chunks of whole videos and each chunk's fused step (production Philox sampling) overlaps the next transfer, the
+    int64 tokens come back into a pinned host tensor and the call returns when they are there.  Per call it moves
     `h2d_bytes` up and `d2h_bytes` down; this is the path `bench.py` reports as `e2e`.
+
+    `hidden_dim=64` makes it the host entry of the fused head instead (`d3pm_host_head_step_run`): the inputs are the
+    hidden states `[B, N, 64]` that enter `to_logits`, 64x fewer bytes on the bus than the logits.
     """
 
-    def __init__(self, B: int, N: int, K: int, coef_table: torch.Tensor, guidance: bool = True):
+    def __init__(self, B: int, N: int, K: int, coef_table: torch.Tensor, guidance: bool = True, *, T: Optional[int] = None,
+                 hidden_dim: int = 0, chunks: int = 0):
         dev = coef_table.device
-        self.coef_table, self.guidance = coef_table, guidance
-        self.logits_c = torch.empty(B, N, K, dtype=torch.float32, device=dev)
-        self.logits_u = torch.empty(B, N, K, dtype=torch.float32, device=dev) if guidance else None
-        self.x_t = torch.empty(B, N, dtype=torch.int64, device=dev)
-        self.t = torch.empty(B, dtype=torch.int64, device=dev)
-        self.x_prev = torch.empty(B, N, dtype=torch.int64, device=dev)
+        if dev.type != "cuda":
+            raise D3PMError("HostStep needs the coefficient table on a CUDA device")
+        self.coef_table, self.guidance, self.shape, self.hidden_dim = coef_table, guidance, (B, N, K), hidden_dim
+        self.device = dev
+        self._lib = _lib.load_library()
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.d3pm_host_step_create(ctypes.byref(handle), dev.index if dev.index is not None else torch.cuda.current_device(),
+                                                   B, N, K, int(T if T is not None else coef_table.shape[0]), hidden_dim,
+                                                   1 if guidance else 0, chunks), "d3pm_host_step_create")
+        self._handle = handle
         self.x_prev_host = torch.empty(B, N, dtype=torch.int64).pin_memory()
-        self._copy_stream = torch.cuda.Stream(device=dev)
-        self._events = [torch.cuda.Event() for _ in range(4)]
-        self.h2d_bytes = (self.logits_c.numel() * 4 * (2 if guidance else 1) + self.x_t.numel() * 8 + self.t.numel() * 8)
-        self.d2h_bytes = self.x_prev.numel() * 8
+        self.h2d_bytes = int(self._lib.d3pm_host_step_h2d_bytes(handle))
+        self.d2h_bytes = int(self._lib.d3pm_host_step_d2h_bytes(handle))
+        self.last_status = 0
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.d3pm_host_step_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check_host(self, width, a, b, x_t, t):
+        B, N, _ = self.shape
+        for name, ten, shape, dt in (("conditional input", a, (B, N, width), torch.float32), ("unconditional input", b, (B, N, width), torch.float32),
+                                     ("x_t", x_t, (B, N), torch.int64), ("t", t, (B,), torch.int64)):
+            if ten is None:
+                continue
+            if ten.is_cuda:
+                raise D3PMError("HostStep takes host tensors; use fused_step for device-resident inputs")
+            if tuple(ten.shape) != shape or ten.dtype != dt or not ten.is_contiguous():
+                raise D3PMError(f"{name} must be a contiguous {dt} tensor of shape {shape}")
+        if self.guidance != (b is not None):
+            raise D3PMError("the unconditional input must be given exactly when the handle was created with guidance")
 
     def __call__(self, logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: torch.Tensor, t: torch.Tensor,
                  *, guidance_scale: float, seed: int, offset: int, row_offset: int = 0) -> torch.Tensor:
-        for src in (logits_c, logits_u, x_t, t):
-            if src is not None and src.is_cuda:
-                raise D3PMError("HostStep takes host tensors; use fused_step for device-resident inputs")
-        dev = self.x_prev.device
-        main = torch.cuda.current_stream(dev)
-        self.x_t.copy_(x_t, non_blocking=True)
-        self.t.copy_(t, non_blocking=True)
-        # the logits travel in chunks of whole videos on a copy stream; the step of a chunk runs while the next one is on
-        # the bus (the noise is keyed by the global row, so the chunks reproduce the one-launch result)
-        B, N = self.x_t.shape
-        nchunk = 4 if B % 4 == 0 and B * N // 4 >= 1024 else 1
-        per = B // nchunk
-        self._copy_stream.wait_stream(main)
-        for c in range(nchunk):
-            b0, b1 = c * per, (c + 1) * per
-            with torch.cuda.stream(self._copy_stream):
-                self.logits_c[b0:b1].copy_(logits_c[b0:b1], non_blocking=True)
-                if self.guidance:
-                    self.logits_u[b0:b1].copy_(logits_u[b0:b1], non_blocking=True)
-                self._events[c].record(self._copy_stream)
-            main.wait_event(self._events[c])
-            fused_step(self.logits_c[b0:b1], self.logits_u[b0:b1] if self.guidance else None, self.x_t[b0:b1], self.t[b0:b1],
-                       self.coef_table, guidance_scale=guidance_scale, sample_mode=_lib.SAMPLE_PHILOX, seed=seed, offset=offset,
-                       row_offset=row_offset + b0 * N, x_prev_out=self.x_prev[b0:b1])
-        self.x_prev_host.copy_(self.x_prev, non_blocking=True)
-        main.synchronize()
+        if self.hidden_dim:
+            raise D3PMError("this handle stages hidden states; call .head(...)")
+        self._check_host(self.shape[2], logits_c, logits_u, x_t, t)
+        st = ctypes.c_uint32(0)
+        _lib.check(self._lib.d3pm_host_step_run(self._handle, logits_c.data_ptr(), _ptr(logits_u), x_t.data_ptr(), t.data_ptr(),
+                                                self.coef_table.data_ptr(), float(guidance_scale), seed & (2**64 - 1),
+                                                offset & (2**64 - 1), int(row_offset), self.x_prev_host.data_ptr(),
+                                                ctypes.byref(st)), "d3pm_host_step_run")
+        self.last_status = int(st.value)
+        return self.x_prev_host
+
+    def head(self, hw, hidden_c: torch.Tensor, hidden_u: Optional[torch.Tensor], x_t: torch.Tensor, t: torch.Tensor,
+             *, guidance_scale: float, seed: int, offset: int, row_offset: int = 0) -> torch.Tensor:
+        """Host hidden states -> tokens through the fused head (`hw`: `head.HeadWeights` on this device)."""
+        if not self.hidden_dim:
+            raise D3PMError("this handle stages logits; call it directly")
+        self._check_host(self.hidden_dim, hidden_c, hidden_u, x_t, t)
+        st = ctypes.c_uint32(0)
+        _lib.check(self._lib.d3pm_host_head_step_run(self._handle, hidden_c.data_ptr(), _ptr(hidden_u), x_t.data_ptr(), t.data_ptr(),
+                                                     hw.ln_weight.data_ptr(), hw.ln_bias.data_ptr(), float(hw.ln_eps),
+                                                     hw.w_image.data_ptr(), hw.bias2.data_ptr(), self.coef_table.data_ptr(),
+                                                     float(guidance_scale), seed & (2**64 - 1), offset & (2**64 - 1),
+                                                     int(row_offset), self.x_prev_host.data_ptr(), ctypes.byref(st)),
+                   "d3pm_host_head_step_run")
+        self.last_status = int(st.value)
         return self.x_prev_host

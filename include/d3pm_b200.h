@@ -6,7 +6,8 @@
  *     src/models/motionencoder/diffusion_transformer.py  class DiffusionTransformer
  * Each entry point below names the reference method(s) (file:line) it replaces.  All pointers are
  * DEVICE pointers owned by the caller (PyTorch); the library allocates nothing persistent, keeps no
- * pointer past return, launches asynchronously on the given CUDA stream and never synchronises.
+ * pointer past return, launches asynchronously on the given CUDA stream and never synchronises
+ * (the one exception is the explicit d3pm_host_step handle near the end, for HOST input buffers).
  * Return value: 0 (D3PM_OK) or a negative error code; d3pm_last_error() gives the text.
  *
  * Memory layout ("token-major rows"): a logical [B, C, N] tensor of the reference (class dim = 1)
@@ -260,6 +261,30 @@ int d3pm_decode_lut(const float* codebook, const float* conv_weight, const float
                     d3pm_stream_t stream);
 int d3pm_tokens_to_features(const int64_t* tokens, const float* lut, float* out, int B, int N, int K, int C,
                             uint32_t* status, d3pm_stream_t stream);
+
+/* ---------------------------------------------------------------- host-buffer entry points
+ * For a caller whose denoiser output lives in HOST memory (the reference's CPU tensors; bench.py's `e2e`): a handle owns
+ * the device staging buffers for one batch shape, a copy stream and a compute stream.  `run` copies the inputs up in
+ * chunks of whole videos, runs d3pm_fused_step (production Philox sampling) on each chunk while the next one is on the
+ * bus, copies the int64 tokens down into x_prev and RETURNS WHEN THEY ARE THERE (the one synchronous entry point of the
+ * library).  Host buffers should be page-locked (cudaHostRegister / torch pin_memory) for the copies to overlap.
+ * coef_table (and the head weights of the second form) stay DEVICE pointers on `device`: they are per-model constants.
+ * status_out (nullable) receives the OR of D3PM_STATUS_* of this call.
+ *   D = 0: the handle stages logits [B*N][K] (+ the unconditional tensor when guidance != 0)   -> d3pm_host_step_run
+ *   D = 64: it stages the hidden states [B*N][D] that enter to_logits                           -> d3pm_host_head_step_run
+ * chunks <= 0 picks the default (4 when B % 4 == 0 and a chunk holds >= 1024 rows, else 1).                          */
+typedef struct d3pm_host_step d3pm_host_step;
+int d3pm_host_step_create(d3pm_host_step** out, int device, int B, int N, int K, int T, int D, int guidance, int chunks);
+int d3pm_host_step_destroy(d3pm_host_step* h);
+int64_t d3pm_host_step_h2d_bytes(const d3pm_host_step* h); /* bytes one run moves host -> device */
+int64_t d3pm_host_step_d2h_bytes(const d3pm_host_step* h); /* and device -> host */
+int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, const float* logits_u, const int64_t* x_t, const int64_t* t,
+                       const float* coef_table, float guidance_scale, uint64_t seed, uint64_t offset, int64_t row_offset,
+                       int64_t* x_prev, uint32_t* status_out);
+int d3pm_host_head_step_run(d3pm_host_step* h, const float* hidden_c, const float* hidden_u, const int64_t* x_t,
+                            const int64_t* t, const float* ln_weight, const float* ln_bias, float ln_eps,
+                            const float* w_image, const float* bias2, const float* coef_table, float guidance_scale,
+                            uint64_t seed, uint64_t offset, int64_t row_offset, int64_t* x_prev, uint32_t* status_out);
 
 /* [B, C, N] contiguous (reference layout) -> token-major rows [B*N][pitch]. */
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N,

@@ -60,3 +60,49 @@ def test_mask_token_is_flagged():
     assert int(status.item()) & 2 and float(out.abs().max()) == 0.0
     with pytest.raises(D3PMError):
         decode.DecodeTable(torch.zeros(64, 16, device=DEV), torch.zeros(32, 16, 3, 3, 3, device=DEV), None)
+
+
+# ---- pinned to the reference itself: fixtures written by tests/golden/make_golden_decode.py from the imported VQVAE
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["decode_small", "decode_k512"])
+def test_first_stage_against_reference_fixture(name):
+    """`d3pm_decode_lut` + `d3pm_tokens_to_features` against `h`, the tensor the reference's own modules hand to its
+    `Decoder` inside `VQVAE.decode` (videogpt_vq_vae.py:53-56)."""
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    table = decode.DecodeTable(torch.from_numpy(fx["codebook"]).to(DEV), torch.from_numpy(fx["conv_weight"]).to(DEV),
+                               torch.from_numpy(fx["conv_bias"]).to(DEV))
+    status = ops.new_status(DEV)
+    got = decode.tokens_to_features(table, torch.from_numpy(fx["tokens"]).to(DEV), status).cpu()
+    want = torch.from_numpy(fx["h"])
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
+    assert int(status.item()) == 0
+
+
+@pytest.mark.parametrize("name", ["decode_small", "decode_k512"])
+def test_decode_with_the_reference_decoder_against_fixture(name):
+    """`decode.decode(vq, tokens)` = fused first stage + the reference's own `Decoder` (PyTorch, on the GPU) with the
+    fixture's weights, against the video `VQVAE.decode` returned on the CPU when the fixture was made."""
+    from baseline import reference_loader as RL
+    if not RL.reference_available():
+        pytest.skip("reference not staged (baseline/_ref absent)")
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    E, K, H, R, d0, d1, d2, L, res, B = (int(v) for v in fx["hparams"])
+    vq = RL.load_vqvae_module().VQVAE(checkpoint_path=None, embedding_dim=E, n_codes=K, n_hiddens=H, n_res_layers=R,
+                                      downsample=[d0, d1, d2], sequence_length=L, resolution=res)
+    vq.load_state_dict({k[3:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("sd/")}, strict=True)
+    vq = vq.to(DEV).eval()
+    tokens = torch.from_numpy(fx["tokens"]).to(DEV)
+    with torch.no_grad():
+        got = decode.decode(vq, tokens).cpu()
+        ref_gpu = vq.decode(tokens).cpu()  # the reference's own decode on the same device
+    want = torch.from_numpy(fx["video"])
+    scale = float(want.abs().max())
+    assert (got - ref_gpu).abs().max() <= 1e-5 * scale   # same decoder, same device: only the first stage differs
+    assert (got - want).abs().max() <= 2e-4 * scale      # CPU fixture vs GPU convolutions

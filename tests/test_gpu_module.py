@@ -143,3 +143,34 @@ def test_host_step_equals_the_device_resident_step(B, guidance):
     assert torch.equal(got, want.cpu())
     again = host(lc, lu, x_t, t, guidance_scale=2.0, seed=5, offset=9, row_offset=77)
     assert torch.equal(again, got)
+
+
+def test_host_head_step_equals_the_device_resident_head_step():
+    """The host entry of the fused head (`d3pm_host_head_step_run`: pinned host HIDDEN STATES in, host tokens out; 64x fewer
+    bytes on the bus than the logits) against `head.head_step` on device-resident inputs, and a bad timestep is reported
+    through the status word of the call."""
+    from d3pm_b200 import _lib, head, ops
+    from oracle import d3pm_oracle as O
+    T, K, N, B, D = 100, 4096, 1024, 8, 64
+    dev = "cuda:0"
+    table = ops.build_coef_table(O.pack_schedule(O.make_schedule(T, K)).to(dev), T, K)
+    g = torch.Generator().manual_seed(21)
+    tl = torch.nn.Sequential(torch.nn.LayerNorm(D), torch.nn.Linear(D, K)).to(dev)
+    hw = head.HeadWeights.from_module(tl)
+    assert hw.valid
+    hc, hu = torch.randn(B, N, D, generator=g).pin_memory(), torch.randn(B, N, D, generator=g).pin_memory()
+    x_t = torch.randint(0, K + 1, (B, N), generator=g).pin_memory()
+    t = torch.randint(0, T, (B,), generator=g).pin_memory()
+    host = ops.HostStep(B, N, K, table, guidance=True, hidden_dim=D)
+    got = host.head(hw, hc, hu, x_t, t, guidance_scale=2.0, seed=3, offset=4, row_offset=11).clone()
+    want = head.head_step(hw, hc.to(dev), hu.to(dev), x_t.to(dev), t.to(dev), table, guidance_scale=2.0, seed=3, offset=4, row_offset=11)
+    assert torch.equal(got, want.cpu())
+    assert host.last_status & (_lib.STATUS_BAD_T | _lib.STATUS_BAD_TOKEN) == 0
+    assert host.h2d_bytes == 2 * B * N * D * 4 + B * N * 8 + B * 8 and host.d2h_bytes == B * N * 8
+    t_bad = t.clone()
+    t_bad[2] = T + 5
+    host.head(hw, hc, hu, x_t, t_bad.pin_memory(), guidance_scale=2.0, seed=3, offset=4)
+    assert host.last_status & _lib.STATUS_BAD_T
+    host.close()
+    with pytest.raises(ops.D3PMError):
+        ops.HostStep(B, N, K, table, guidance=True)(hc, hu, x_t, t, guidance_scale=2.0, seed=1, offset=1)  # wrong width

@@ -18,11 +18,12 @@ ap.add_argument("--videos", type=int, default=16)
 ap.add_argument("--t", type=int, default=50)
 ap.add_argument("--mode", default="philox")
 ap.add_argument("--no-guidance", action="store_true")
+ap.add_argument("--codes", type=int, default=4096)
 ap.add_argument("--sleep-ms", type=float, default=0.0, help="idle gap before every launch (isolated launches)")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
-T, K, N, B = 100, 4096, 4096, a.videos
+T, K, N, B = 100, a.codes, 4096, a.videos
 
 
 class _Stub(torch.nn.Module):
@@ -60,4 +61,4 @@ for i in range(a.launches):
     ev[i + 1].record()
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.launches)]
-print("ms per launch:", ["%.3f" % x for x in ms], "GB/s:", "%.0f" % (B * N * (32784 if lu is not None else 16400) / min(ms) / 1e6))
+print("ms per launch:", ["%.3f" % x for x in ms], "GB/s:", "%.0f" % (B * N * ((8 * K + 16) if lu is not None else (4 * K + 16)) / min(ms) / 1e6))
