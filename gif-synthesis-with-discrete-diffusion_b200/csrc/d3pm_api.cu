@@ -154,6 +154,7 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   p.rows = rows;
   p.sample_from = d->sample_from, p.score = d->score, p.sharpen = d->sharpen;
   p.winner_post = d->winner_post;
+  d3pm::expand_round_keys(p.seed, p.keys);
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
 
   if (d->kernel < D3PM_KERNEL_AUTO || d->kernel > D3PM_KERNEL_STREAM)

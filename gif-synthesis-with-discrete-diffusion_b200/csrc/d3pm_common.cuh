@@ -134,12 +134,12 @@ constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 constexpr int kPhiloxRounds = 7;  // Philox4x32-7: the fewest rounds that pass BigCrush (Salmon et al., Table 2)
 
-struct NoiseStream {
-  uint32_t rk0[kPhiloxRounds], rk1[kPhiloxRounds];  // round keys (uniform across the grid)
-  uint32_t off_lo, off_hi;
-
-  __device__ __forceinline__ NoiseStream(uint64_t seed, uint64_t offset)
-      : off_lo(static_cast<uint32_t>(offset)), off_hi(static_cast<uint32_t>(offset >> 32) & 0x7fffffffu) {
+// Keys = where the 2 x 7 round keys live: NoiseKeysLocal derives them from the seed in registers; the stream kernel
+// passes NoiseKeysParam, whose keys were expanded on the host into the kernel's parameter block, so that every round's
+// key is a constant-bank operand of its LOP3 (no per-row key arithmetic, no registers).
+struct NoiseKeysLocal {
+  uint32_t rk0[kPhiloxRounds], rk1[kPhiloxRounds];
+  __device__ __forceinline__ explicit NoiseKeysLocal(uint64_t seed) {
     uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
 #pragma unroll
     for (int r = 0; r < kPhiloxRounds; ++r) {
@@ -147,13 +147,40 @@ struct NoiseStream {
       k0 += kPhiloxW0, k1 += kPhiloxW1;
     }
   }
+  __device__ __forceinline__ uint32_t key0(int r) const { return rk0[r]; }
+  __device__ __forceinline__ uint32_t key1(int r) const { return rk1[r]; }
+};
+struct PhiloxRoundKeys {  // host-expanded keys (d3pm_api.cu fills them from the seed)
+  uint32_t rk0[kPhiloxRounds + 1], rk1[kPhiloxRounds + 1];
+};
+inline void expand_round_keys(uint64_t seed, PhiloxRoundKeys& out) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r <= kPhiloxRounds; ++r) {
+    out.rk0[r] = k0, out.rk1[r] = k1;
+    k0 += kPhiloxW0, k1 += kPhiloxW1;
+  }
+}
+struct NoiseKeysParam {
+  const PhiloxRoundKeys& k;
+  __device__ __forceinline__ explicit NoiseKeysParam(const PhiloxRoundKeys& keys) : k(keys) {}
+  __device__ __forceinline__ uint32_t key0(int r) const { return k.rk0[r]; }
+  __device__ __forceinline__ uint32_t key1(int r) const { return k.rk1[r]; }
+};
+
+template <typename Keys>
+struct NoiseStreamT {
+  Keys keys;  // round keys (uniform across the grid)
+  uint32_t off_lo, off_hi;
+
+  __device__ __forceinline__ NoiseStreamT(const Keys& k, uint64_t offset)
+      : keys(k), off_lo(static_cast<uint32_t>(offset)), off_hi(static_cast<uint32_t>(offset >> 32) & 0x7fffffffu) {}
   __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
 #pragma unroll
     for (int r = 0; r < kPhiloxRounds; ++r) {
       const unsigned long long p0 = static_cast<unsigned long long>(kPhiloxM0) * c0;  // one IMAD.WIDE each
       const unsigned long long p1 = static_cast<unsigned long long>(kPhiloxM1) * c2;
-      c0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk0[r];
-      c2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk1[r];
+      c0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ keys.key0(r);
+      c2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ keys.key1(r);
       c1 = static_cast<uint32_t>(p1);
       c3 = static_cast<uint32_t>(p0);
     }
@@ -186,6 +213,10 @@ struct NoiseStream {
     return (word_of(w, byte >> 2) >> (8u * (byte & 3u))) & 0x7fu;
   }
 };
+struct NoiseStream : NoiseStreamT<NoiseKeysLocal> {
+  __device__ __forceinline__ NoiseStream(uint64_t seed, uint64_t offset) : NoiseStreamT<NoiseKeysLocal>(NoiseKeysLocal(seed), offset) {}
+};
+using ParamNoiseStream = NoiseStreamT<NoiseKeysParam>;
 
 __device__ __forceinline__ float uniform_from_draw(uint32_t m) {
   return __uint2float_rn(0x1000000u - (2u * m + 1u)) * kTwoPowM24;

@@ -92,11 +92,11 @@ __global__ void __launch_bounds__(kOpThreads) q_posterior_rows_kernel(
   const float* __restrict__ in = lxs + row * pitch_in;
   float* __restrict__ out = post + row * pitch_out;
 
-  float sum = 0.f;
-  for (int k = threadIdx.x; k < K; k += kOpThreads) sum += ex2(in[k] * kLog2e);
+  float sum = 0.f;  // over the classes other than x_t (summing everything and subtracting p_j would cancel when p_j ~ 1)
+  for (int k = threadIdx.x; k < K; k += kOpThreads) sum += (static_cast<uint32_t>(k) == j) ? 0.f : ex2(in[k] * kLog2e);
   sum = block_sum<kOpThreads / 32>(sum, scratch);
   const float pj = masked ? 0.f : ex2(in[j] * kLog2e);
-  const float eL = masked ? fmaf(cf.W, sum, kTiny) : fmaf(cf.W, sum - pj, fmaf(cf.WS, pj, kTiny));
+  const float eL = masked ? fmaf(cf.W, sum, kTiny) : fmaf(cf.W, sum, fmaf(cf.WS, pj, kTiny));
   const float Bc = cf.BO * eL;
   const float Pj = fmaf(pj, cf.AS, cf.BOS * eL);
   for (int k = threadIdx.x; k < K; k += kOpThreads) {

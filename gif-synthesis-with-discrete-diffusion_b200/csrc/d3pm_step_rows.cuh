@@ -35,6 +35,7 @@ struct StepParams {
   float* score;          // [rows] out: max_k p(x0 = k | x_t)
   const float* sharpen;  // [rows] in: draw from softmax(f * recon)
   float* winner_post;    // [rows] out (stream kernel): log-posterior of the sampled class as the kernel computed it
+  PhiloxRoundKeys keys;  // the round keys of `seed`, expanded on the host (stream kernel: constant-bank operands)
 };
 
 // exact residual of the fp32 product m*log2e (natural-log units -> log2 units)
@@ -55,16 +56,22 @@ struct RowMath {
   float Ptot;       // sum of all K+1 P's (for the thinning threshold)
   uint32_t j;       // x_t (== K when masked)
 
-  // p_j = exp(recon_j) as a probability in [exp(-70), 1]; ignored for masked rows
+  // p_j = exp(recon_j) as a probability in [exp(-70), 1]; ignored for masked rows.  qj = sum_{k != j} p_k: the kernels that
+  // write posterior ROWS (p_pred) accumulate it class by class, because 1 - p_j loses everything when the denoiser is sure
+  // of x_t (p_j within 1e-7 of 1) while W = 1 / b_t is ~1e8 at small t; the token-only kernels pass 1 - p_j, whose error
+  // there is ~1e-7 of absolute probability mass
   __device__ __forceinline__ void init(const RowCoef& cf, bool masked, float pj, uint32_t jj, int K) {
+    init(cf, masked, pj, 1.0f - pj, jj, K);
+  }
+  __device__ __forceinline__ void init(const RowCoef& cf, bool masked, float pj, float qj, uint32_t jj, int K) {
     j = jj;
-    const float eL = masked ? cf.W + kTiny : fmaf(cf.W, 1.0f - pj, fmaf(cf.WS, pj, kTiny));
+    const float eL = masked ? cf.W + kTiny : fmaf(cf.W, qj, fmaf(cf.WS, pj, kTiny));
     A = cf.A;
     Bc = cf.BO * eL;
     Pj = masked ? 0.0f : fmaf(pj, cf.AS, cf.BOS * eL);
     PK = fmaf(cf.PK1, eL, cf.PK0);
     Ptot = masked ? fmaf(static_cast<float>(K), Bc, A) + PK
-                  : fmaf(static_cast<float>(K - 1), Bc, A * (1.0f - pj)) + Pj + PK;
+                  : fmaf(static_cast<float>(K - 1), Bc, A * qj) + Pj + PK;
   }
   // the distribution the purity-prior branch samples (:327-329): log_x_recon itself, i.e. P_k = p_k for the codes
   // and exp(-70) for [MASK]; every sampling path below then works unchanged
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
         }
       }
   }
-  const float m_local_c2 = to_log2_units(m[0]);
+  const float m_local = m[0], m_local_c2 = to_log2_units(m[0]);
   if (HAS_U) {
     group_max_sum_n<2, NW>(m, s, sred[0], sync);
   } else {
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
   }
 
   // ---- guidance combine + renormalisation (:245-247), or pass-through when guidance is off ------
-  float My, Sy, lnSy, r, yj;
+  float My, Sy, Sother, lnSy, r, yj;
   if (HAS_U) {
     const float lnSc = ln_rel_sum(m[0], s[0]), lnSu = ln_rel_sum(m[1], s[1]);
     const float gs = p.guidance_scale;
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
       yj = fmaf(gs, lc - lu, lu);
     }
     const float my2 = to_log2_units(my);
-    float sy = 0.f;
+    float sy = 0.f, so = 0.f;  // so: the classes other than x_t, summed on their own (see RowMath::init)
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
@@ -254,14 +261,24 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
           const float ey = ex2(fmaf(x[i][e], kLog2e, -my2));
           z[i][e] = ey;
           sy += ey;
+          so += (static_cast<uint32_t>(4 * (tid + i * kRowThreads) + e) == j) ? 0.f : ey;
         }
       }
-    float mm[1] = {my}, ss[1] = {sy};
-    group_max_sum_n<1, NW>(mm, ss, sred[1], sync);
-    My = mm[0], Sy = ss[0];
+    float mm[2] = {my, my}, ss[2] = {sy, so};
+    group_max_sum_n<2, NW>(mm, ss, sred[1], sync);
+    My = mm[0], Sy = ss[0], Sother = ss[1];
     r = (nvalid > 0) ? ex2(my2 - to_log2_units(My)) / Sy : 0.f;
   } else {
-    My = m[0], Sy = s[0];
+    // guidance off: z holds the numerators relative to the thread-local maximum of the first pass
+    float so = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i < nvalid) so += (static_cast<uint32_t>(4 * (tid + i * kRowThreads) + e) == j) ? 0.f : z[i][e];
+    float mm[1] = {m_local}, ss[1] = {so};
+    group_max_sum_n<1, NW>(mm, ss, sred[1], sync);
+    My = m[0], Sy = s[0], Sother = ss[0];
     yj = xj;
     r = (nvalid > 0) ? ex2(m_local_c2 - to_log2_units(My)) / Sy : 0.f;
   }
@@ -272,7 +289,7 @@ __global__ void __launch_bounds__(kRowThreads) step_rows_kernel(const StepParams
   RowMath rm;
   const bool from_recon = (p.sample_from == D3PM_FROM_RECON);
   if (from_recon) rm.init_recon(masked ? 0.f : pj, masked ? static_cast<uint32_t>(K) + 1u : j);
-  else rm.init(cf, masked, pj, j, K);
+  else rm.init(cf, masked, pj, masked ? 1.0f : fminf(Sother / Sy, 1.0f), j, K);
   // purity (:318): max_k exp(log_x_recon_k).clamp(0, 1); the largest recon entry is clamp(-lnSy, -70, 0)
   if (p.score != nullptr && tid == 0) p.score[row] = expf(fminf(fmaxf(-lnSy, kClampLo), 0.0f));
 

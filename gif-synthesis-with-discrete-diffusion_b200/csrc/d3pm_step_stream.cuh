@@ -28,6 +28,8 @@
 // HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
 #pragma once
 
+#include <type_traits>
+
 #include "d3pm_step_rows.cuh"
 
 namespace d3pm {
@@ -241,7 +243,7 @@ __device__ __forceinline__ unsigned long long stream_max_u64(unsigned long long 
 // the row's own class), every lane scores one class exactly as the log-domain kernel does, a 16-lane
 // segmented argmax picks the winner, which is accepted if it clears the row's bound and queued otherwise.
 template <int NP, int CPT, bool HAS_U>
-__device__ __noinline__ void score_batch(GroupSmem<NP, CPT, HAS_U>& S, int nslots, const NoiseStream& rng, const StepParams& p, int G,
+__device__ __noinline__ void score_batch(GroupSmem<NP, CPT, HAS_U>& S, int nslots, const ParamNoiseStream& rng, const StepParams& p, int G,
                                          int first_row) {
   using Sh = StreamShape<NP, CPT, HAS_U>;
   constexpr uint32_t K = 1024u * NP;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
   const int first_row = g * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);  // neighbouring rows -> different SMs
   const int rows = static_cast<int>(p.rows);
   const uint32_t pitch = static_cast<uint32_t>(p.pitch_logits);
-  const NoiseStream rng(p.seed, p.offset);
+  const ParamNoiseStream rng(NoiseKeysParam(p.keys), p.offset);  // round keys straight from the parameter block
   const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kStreamThin;
 
   if (tg == 0) {
@@ -359,10 +361,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 #endif
 
   // ------------------------------------------------------------------------------------------------
-  // one row.  `exact`: exhaustive log-space scoring (PHILOX_EXACT mode and redone rows); otherwise the
+  // one row.  `exact` (compile time): rows outside the batched path (PHILOX_EXACT mode and redone rows); otherwise the
   // row's survivors are left in slot `slot` for the next score_batch.
   // ------------------------------------------------------------------------------------------------
-  auto process_row = [&](int row, int next_row, uint32_t j, int tt, bool exact, int slot, int rel) {
+  auto process_row = [&](auto exact_c, int row, int next_row, uint32_t j, int tt, int slot, int rel) {
+    constexpr bool exact = decltype(exact_c)::value;
     const bool masked = (j == static_cast<uint32_t>(K));
     mbar_wait(&S.full, phase);
     phase ^= 1u;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     if (HAS_U) stream_max<NW, 2>(am, S.red[0], sync);  // barrier 1: every thread is done with the stage
     else sync();                                        // (without guidance nothing depends on the range of the logits)
     // the stage is free: prefetch the next row now (exhaustive rows park their numerators in it first)
-    if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);
+    if (!exact && tg == 0 && next_row >= 0) issue_row(next_row);  // (`exact` is a constant here)
 
     const uint64_t grow = static_cast<uint64_t>(p.row_offset + row);
 
@@ -543,13 +546,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       rm.init(cf, masked, pj, j, K);
     }
 
-    if (!exact) {
+    if constexpr (!exact) {
       // ---- thinned race: 16 noise bits per class, survivors go to this row's slot.  One Philox call = 8 x 16 bits:
       //      word w of call c serves classes (2w, 2w+1) of chunk slot_lo(c) (w < 2) / slot_lo(c) + PS (w >= 2);
       //      four calls are drawn together (four independent Philox chains to interleave) ----
       const ThinRule thin(rm, thin_c);
-      const float thrA = r * thin.scaleA;
-      const float2 tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
+      const float thrA = r * thin.scaleA, nthrB = -thin.thrB;
+      const float2 tA2 = make_float2(thrA, thrA);
       if (tg == 0) {
         RowInfo ri;
         ri.A = rm.A, ri.Bc = rm.Bc, ri.Pj = rm.Pj, ri.PK = rm.PK, ri.accept = thin.accept;
@@ -560,21 +563,22 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       for (int c0 = 0; c0 < NCALL; c0 += 4) {
         uint4 cws[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cws[c] = rng.coarse(NoiseStream::coarse_call_of_chunk(GT * slot_lo(c0 + c) + tg), grow);
+        for (int c = 0; c < 4; ++c) cws[c] = rng.coarse(ParamNoiseStream::coarse_call_of_chunk(GT * slot_lo(c0 + c) + tg), grow);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int lo = slot_lo(c0 + c);
-          // the halves are spliced under the exponent of -1.0f so that -(1 + h 2^-23) comes out of one PRMT
+          // the halves are spliced under the exponent of -1.0f so that nf = -(1 + h 2^-23) comes out of one PRMT; a class
+          // survives when e thrA + nf >= -thrB (one packed FMA per two classes, the comparison once per call)
           const uint32_t w4[4] = {cws[c].x, cws[c].y, cws[c].z, cws[c].w};
-          float slack = -1.0f;  // max over the 8 classes of (threshold - draw); >= 0 <=> somebody survives
+          float slack = -4.0f;  // max over the 8 classes of e thrA + nf
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
                                           __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
-            const float2 d = __ffma2_rn(e_of(lo + (w >> 1) * PS, w & 1), tA2, __fadd2_rn(tB2, nf));
+            const float2 d = __ffma2_rn(e_of(lo + (w >> 1) * PS, w & 1), tA2, nf);
             slack = fmaxf(slack, fmaxf(d.x, d.y));
           }
-          if (slack >= 0.0f) {
+          if (slack >= nthrB) {
 #pragma unroll
             for (int w = 0; w < 4; ++w)
 #pragma unroll
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
                 const float e = hl ? ee.y : ee.x;
                 const uint32_t h16 = hl ? (w4[w] >> 16) : (w4[w] & 0xffffu);
                 const float nf = __uint_as_float(0xbf800000u | h16);
-                if (fmaf(e, thrA, thin.thrB + nf) >= 0.0f) {
+                if (fmaf(e, thrA, nf) >= nthrB) {
                   const uint32_t pos = atomicAdd(&S.cand_cnt[slot], 1u);
                   if (pos < static_cast<uint32_t>(kCandPerRow)) {
                     S.cand_k[slot][pos] = 4u * (GT * (lo + (w >> 1) * PS) + tg) + 2u * (w & 1) + hl;
@@ -595,8 +599,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         }
       }
       return;
-    }
-
+    } else {
     // ---- rows outside the batched path ----
     unsigned long long best = 0ull;
     float best_lp = 0.f;  // log-posterior of this thread's best class (winner_post output)
@@ -611,7 +614,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 #pragma unroll
       for (int c = 0; c < NCALL; ++c) {
         const int lo = slot_lo(c);
-        const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(GT * lo + tg), grow);
+        const uint4 cw = rng.coarse(ParamNoiseStream::coarse_call_of_chunk(GT * lo + tg), grow);
         const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
         uint32_t hits = 0;  // bit 2 w + h: class h of word w passed the coarse test
         float ev[8];
@@ -673,13 +676,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
         const uint32_t q = static_cast<uint32_t>(GT) * i + tg;
         const float4 e4 = lds4(S.c + 4 * q);
         const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
-        const uint4 cw = rng.coarse(NoiseStream::coarse_call_of_chunk(q), grow);
+        const uint4 cw = rng.coarse(ParamNoiseStream::coarse_call_of_chunk(q), grow);
         const uint4 fw = rng.fine(q >> 2, grow);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t k = 4u * q + e;
           const uint32_t mdraw =
-              (NoiseStream::half_of(cw, (((q >> 7) & 1u) << 2) | e) << 7) | NoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
+              (ParamNoiseStream::half_of(cw, (((q >> 7) & 1u) << 2) | e) << 7) | ParamNoiseStream::low7_of(fw, ((q & 3u) << 2) | e);
           const float lpk = rm.post_of(k, ev[e], r);
           const unsigned long long key = pack_key(lpk + gumbel_from_uniform(uniform_from_draw(mdraw)), k);
           if (key > best) best = key, best_lp = lpk;
@@ -698,50 +701,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       p.x_prev[row] = key_class(best);
       if (next_row >= 0) issue_row(next_row);
     }
+    }
   };
 
-  // ---- one loop over this group's rows, then over the rows it queued for exhaustive rescoring ----------
-  // video index b = row / N is tracked incrementally (row advances by G per iteration)
+  // ---- the group's rows (main pass, batched scoring), then the rows it queued - or, in PHILOX_EXACT mode, all of them ----
   const int N = p.N;
-  const int stepB = G / N, stepR = G % N;
   auto token_of = [&](int r_) { return static_cast<long long>(p.x_t[r_]); };
   auto time_of = [&](int b_) { return static_cast<long long>(p.t[b_]); };
-  bool redo_phase = false;
-  uint32_t redo_i = 0, n_redo = 0;
-  int row = first_row < rows ? first_row : -1;
-  int vb = first_row / N, vr = first_row % N;  // video index and position of `row`
-  long long jj = 0, tt = 0;
-  if (row >= 0) {
-    if (tg == 0) issue_row(row);
-    jj = token_of(row);
-    tt = time_of(vb);
-  }
-  int it = 0, in_batch = 0;
-  for (;;) {
-    if (row < 0 || in_batch == Sh::SB) {  // finish the rows accumulated so far
-      if (in_batch > 0) {
-        sync();  // every thread has finished appending survivors
-        score_batch<NP, CPT, HAS_U>(S, in_batch, rng, p, G, first_row);
-        sync();  // slots may be reused, redo_cnt is final for this batch
-        in_batch = 0;
-      }
-      if (row < 0) {
-        if (redo_phase) break;
-        redo_phase = true;
-#ifdef D3PM_STREAM_TIMING
-        tm_main = now_ns();
-#endif
-        n_redo = S.redo_cnt;
-        if (n_redo == 0) break;
-        status_bits |= D3PM_STATUS_FALLBACK;
-        row = first_row + S.redo[0] * G;
-        if (tg == 0) issue_row(row);
-        jj = token_of(row);
-        tt = time_of(row / N);
-      }
-    }
-    // Consume this row's scalars (loaded one row ahead) BEFORE issuing the next prefetch: the consumer waits on
-    // the scoreboard slot the loads share, so the other order would stall on the loads just issued.
+  // range checks of a row's scalars (the reference asserts them on the host, :45-46, :253)
+  auto checked = [&](long long tt, long long jj, int& t_cur, uint32_t& j_cur) {
     if (static_cast<unsigned long long>(tt) >= static_cast<unsigned long long>(p.T)) {
       status_bits |= D3PM_STATUS_BAD_T;
       tt = tt < 0 ? 0 : p.T - 1;
@@ -750,35 +718,74 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
       status_bits |= D3PM_STATUS_BAD_TOKEN;
       jj = K;
     }
-    int t_cur = static_cast<int>(tt);
-    uint32_t j_cur = static_cast<uint32_t>(jj);
+    t_cur = static_cast<int>(tt), j_cur = static_cast<uint32_t>(jj);
+    // consume the scalars (loaded one row ahead) BEFORE the next prefetch is issued: the consumer waits on the scoreboard
+    // slot the loads share, so the other order would stall on the loads just issued
     asm volatile("" : "+r"(t_cur), "+r"(j_cur) : : "memory");
-    int next;
-    long long jj_next = 0, tt_next = 0;
-    if (!redo_phase) {
-      next = row + G < rows ? row + G : -1;
+  };
+  if (!exact_mode) {
+    const int stepB = G / N, stepR = G % N;  // video index b = row / N is tracked incrementally (row advances by G)
+    int vb = first_row / N, vr = first_row % N;
+    int row = first_row < rows ? first_row : -1;
+    long long jj = 0, tt = 0;
+    if (row >= 0) {
+      if (tg == 0) issue_row(row);
+      jj = token_of(row);
+      tt = time_of(vb);
+    }
+    int it = 0, in_batch = 0;
+    while (row >= 0) {
+      int t_cur;
+      uint32_t j_cur;
+      checked(tt, jj, t_cur, j_cur);
+      const int next = row + G < rows ? row + G : -1;
       vb += stepB, vr += stepR;
       if (vr >= N) vr -= N, ++vb;
       if (next >= 0) {  // software prefetch of the next row's scalars
-        jj_next = token_of(next);
-        tt_next = time_of(vb);
+        jj = token_of(next);
+        tt = time_of(vb);
       }
-    } else {
-      next = (redo_i + 1 < n_redo) ? first_row + S.redo[redo_i + 1] * G : -1;
-      if (next >= 0) {
-        jj_next = token_of(next);
-        tt_next = time_of(next / N);
+      process_row(std::false_type{}, row, next, j_cur, t_cur, in_batch, it);
+#ifdef D3PM_STREAM_TIMING
+      ++tm_rows;
+#endif
+      row = next;
+      ++it;
+      if (++in_batch == Sh::SB || row < 0) {  // finish the rows accumulated so far
+        sync();  // every thread has finished appending survivors
+        score_batch<NP, CPT, HAS_U>(S, in_batch, rng, p, G, first_row);
+        sync();  // slots may be reused, redo_cnt is final for this batch
+        in_batch = 0;
       }
     }
-    const bool exact = exact_mode || redo_phase;
-    process_row(row, next, j_cur, t_cur, exact, in_batch, it);
+  }
 #ifdef D3PM_STREAM_TIMING
-    if (redo_phase) ++tm_redo; else ++tm_rows;
+  tm_main = now_ns();
 #endif
-    if (!exact) ++in_batch;
-    row = next, jj = jj_next, tt = tt_next;
-    ++it;
-    if (redo_phase) ++redo_i;
+  {
+    const uint32_t n2 = exact_mode ? (first_row < rows ? static_cast<uint32_t>((rows - first_row + G - 1) / G) : 0u) : S.redo_cnt;
+    auto row_at = [&](uint32_t i) { return first_row + (exact_mode ? static_cast<int>(i) : S.redo[i]) * G; };
+    if (n2 > 0) {
+      if (!exact_mode) status_bits |= D3PM_STATUS_FALLBACK;
+      int row = row_at(0);
+      if (tg == 0) issue_row(row);
+      long long jj = token_of(row), tt = time_of(row / N);
+      for (uint32_t i = 0; i < n2; ++i) {
+        int t_cur;
+        uint32_t j_cur;
+        checked(tt, jj, t_cur, j_cur);
+        const int next = (i + 1 < n2) ? row_at(i + 1) : -1;
+        if (next >= 0) {
+          jj = token_of(next);
+          tt = time_of(next / N);
+        }
+        process_row(std::true_type{}, row, next, j_cur, t_cur, 0, 0);
+#ifdef D3PM_STREAM_TIMING
+        ++tm_redo;
+#endif
+        row = next;
+      }
+    }
   }
 #ifdef D3PM_STREAM_TIMING
   if (tg == 0 && p.status != nullptr) {
@@ -786,7 +793,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     uint32_t* o = p.status + 8 * (blockIdx.x * NG + g);
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (tm_main == 0) tm_main = tm_end;
     o[0] = static_cast<uint32_t>(tm_start), o[1] = static_cast<uint32_t>(tm_start >> 32);
     o[2] = static_cast<uint32_t>(tm_main - tm_start), o[3] = static_cast<uint32_t>(tm_end - tm_start);
     o[4] = tm_rows, o[5] = tm_redo, o[6] = smid, o[7] = 0;
