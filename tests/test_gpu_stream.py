@@ -34,6 +34,15 @@ CASES = [
     (1, 37, 4096, 50, 2.0, 1.0),             # fewer rows than groups
     (2, 900, 4096, 30, 2.0, 12.0),           # logit range > 70 - ln K: every row takes the general (clamping) path
     (2, 900, 4096, 0, 2.0, -1.0),            # scale < 0: a few rows spiked by +150 / +90 (mixed fast / general rows)
+    # every group shape of the kernel (threads per row = K / 32, or K / 64 without guidance): <4,16,off> 8 groups of 64,
+    # <2,8,on> 8 groups of 64, <2,16,off> / <1,8,on> / <1,8,off> 16 one-warp groups
+    (2, 1100, 4096, 40, None, 1.0),
+    (2, 700, 4096, [0, 99], None, 12.0),
+    (2, 1300, 2048, 60, 2.0, 1.0),
+    (2, 900, 2048, [5, 77], 2.0, 12.0),
+    (2, 900, 2048, 0, 2.0, -1.0),
+    (1, 2100, 1024, 33, None, 1.0),
+    (3, 500, 1024, [0, 50, 99], 2.0, -1.0),
 ]
 
 
