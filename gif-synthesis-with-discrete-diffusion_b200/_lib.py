@@ -71,7 +71,7 @@ class HeadDesc(ctypes.Structure):
         ("x_prev", c_void_p), ("logits_out", c_void_p), ("status", c_void_p), ("redo_rows", c_void_p),
         ("redo_count", c_void_p),
         ("B", c_int32), ("N", c_int32), ("K", c_int32), ("T", c_int32), ("D", c_int32), ("mode", c_int32),
-        ("ln_eps", c_float), ("guidance_scale", c_float), ("thin_factor", c_float),
+        ("ln_eps", c_float), ("guidance_scale", c_float), ("thin_factor", c_float), ("stat_slack", c_float),
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64), ("stream", c_void_p),
     ]
 
@@ -158,8 +158,8 @@ def load_library() -> ctypes.CDLL:
                                        c_int64, c_void_p, POINTER(c_uint32)]
     lib.d3pm_host_head_step_run.restype = c_int
     lib.d3pm_host_head_step_run.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                                            c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_uint64, c_int64, c_void_p,
-                                            POINTER(c_uint32)]
+                                            c_void_p, c_void_p, c_void_p, c_float, c_float, c_uint64, c_uint64, c_int64,
+                                            c_void_p, POINTER(c_uint32)]
     lib.d3pm_to_token_major.restype = c_int
     lib.d3pm_to_token_major.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     _lib = lib

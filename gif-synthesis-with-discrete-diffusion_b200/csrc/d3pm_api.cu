@@ -407,6 +407,7 @@ int d3pm_head_step(const d3pm_head_desc* d) {
   p.redo_rows = d->redo_rows, p.redo_count = d->redo_count;
   p.N = d->N, p.K = d->K, p.T = d->T, p.rows = rows;
   p.ln_eps = d->ln_eps, p.guidance_scale = d->guidance_scale, p.thin_factor = d->thin_factor;
+  p.stat_slack = d->stat_slack > 0.f ? d->stat_slack : 0.f;
   p.seed = d->seed, p.offset = d->offset, p.row_offset = d->row_offset;
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
   const bool has_u = d->hidden_u != nullptr;
@@ -633,8 +634,8 @@ extern "C" int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, cons
 
 extern "C" int d3pm_host_head_step_run(d3pm_host_step* h, const float* hidden_c, const float* hidden_u, const int64_t* x_t, const int64_t* t,
                             const float* ln_weight, const float* ln_bias, float ln_eps, const float* w_image, const float* bias2,
-                            const float* coef_table, float guidance_scale, uint64_t seed, uint64_t offset, int64_t row_offset,
-                            int64_t* x_prev, uint32_t* status_out) {
+                            const float* coef_table, float guidance_scale, float stat_slack, uint64_t seed, uint64_t offset,
+                            int64_t row_offset, int64_t* x_prev, uint32_t* status_out) {
   if (h == nullptr || hidden_c == nullptr || x_t == nullptr || t == nullptr || coef_table == nullptr || x_prev == nullptr)
     return fail(D3PM_ERR_INVALID, "host_head_step_run: handle, hidden_c, x_t, t, coef_table and x_prev are required");
   if (h->D == 0) return fail(D3PM_ERR_INVALID, "host_head_step_run: the handle was created for logits (D = 0)");
@@ -647,7 +648,7 @@ extern "C" int d3pm_host_head_step_run(d3pm_host_step* h, const float* hidden_c,
     d.x_t = h->x_t + at, d.t = h->t + b0, d.coef_table = coef_table, d.x_prev = h->x_prev + at, d.status = h->status;
     d.redo_rows = h->redo_rows + at, d.redo_count = h->redo_count;
     d.B = nb, d.N = h->N, d.K = h->K, d.T = h->T, d.D = h->D, d.mode = D3PM_HEAD_STEP;
-    d.ln_eps = ln_eps, d.guidance_scale = guidance_scale;
+    d.ln_eps = ln_eps, d.guidance_scale = guidance_scale, d.stat_slack = stat_slack;
     d.seed = seed, d.offset = offset, d.row_offset = row_offset + static_cast<int64_t>(at), d.stream = h->compute;
     return d3pm_head_step(&d);
   };

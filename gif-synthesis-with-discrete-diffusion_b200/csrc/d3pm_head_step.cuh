@@ -43,10 +43,10 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 32 * (kEpiWarps + 2);
 constexpr int kRowThreads4 = kEpiThreads / kTileM;  // threads that build one row of the A operand (4)
 static_assert(kCols == 32 && kRowThreads4 == 4, "the epilogue below is written for 16 epilogue warps");
-// Survivor lists of 30 classes per row and a thinning constant of 8 (the unfused kernels: 14 and 6): a row the race
+// Survivor lists of 28 classes per row and a thinning constant of 8 (the unfused kernels: 14 and 6): a row the race
 // cannot decide costs a whole CTA of head_redo_kernel (2 MiB of weight image through L2, ~25 us), so they are made
 // rare - e^-8 of the rows, ~20 per 65 536 - at the price of 8 instead of 6 survivors per row to score.
-constexpr int kCand = 30;
+constexpr int kCand = 28;
 constexpr float kThin = 8.0f;
 constexpr int kBlockBytes = kTileM * 128;  // one 128-byte k-block of a 128-row operand
 // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
@@ -70,6 +70,7 @@ struct HeadParams {
   int32_t N, K, T;
   int64_t rows;
   float ln_eps, guidance_scale, thin_factor;
+  float stat_slack;       // > 0: the statistics pass runs in 1xTF32 and its logits are within this many log2 units of the exact ones
   uint64_t seed, offset;
   int64_t row_offset;
 };
@@ -85,14 +86,22 @@ struct Geo {
   static constexpr int kChunkFloats = kBStageBytes / 4;  // floats of the weight image per 128 classes
 };
 
+struct HeadRowInfo {  // what score_tile needs to finish a row exactly
+  uint32_t j;      // x_t, == K when masked
+  int32_t tt;      // timestep of the row's video
+  float yj_rel;    // log2-unit logit of class x_t minus the row's stabiliser
+  float pad;
+};
+
 struct Ctl {
   unsigned long long b_full[kBStages], b_empty[kBStages], acc_full[kAccStages], acc_empty[kAccStages], a_ready, a_free;
   uint32_t tmem_base, pad;
   float stat_m[kColSplit][kTileM], stat_s[kColSplit][kTileM];
   float yj2[kTileM];
-  RowInfo info[kTileM];
+  float sum2[kColSplit][kTileM];   // pass 2: the exact sum of the row's numerators, per column quarter
+  HeadRowInfo info[kTileM];
   uint32_t cand_cnt[kTileM];
-  float cand_p[kTileM][kCand];
+  float cand_p[kTileM][kCand];     // softmax NUMERATORS of the survivors (relative to the row's stabiliser)
   uint16_t cand_k[kTileM][kCand];  // K <= 8192
 };
 
@@ -144,6 +153,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -233,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NCH = p.K / kChunk;                // chunks per pass
   const int NIT = DUMP ? NCH : 2 * NCH;        // accumulator iterations per tile
+  const bool stat1x = !DUMP && p.stat_slack > 0.f;
   const long long ntiles = (p.rows + kTileM - 1) / kTileM;
 
   if (tid == 0) {
@@ -259,11 +278,12 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
         for (int it = 0; it < NIT; ++it, ++g) {
           const int st = static_cast<int>(g & 1);
           mbar_wait_sleep(&C.b_empty[st], static_cast<uint32_t>(((g >> 1) & 1) ^ 1));
-          mbar_expect_tx(&C.b_full[st], G::kBStageBytes);
+          const bool hi_only = stat1x && it < NCH;  // the statistics pass multiplies the hi parts only
+          mbar_expect_tx(&C.b_full[st], hi_only ? G::kTermBytes : G::kBStageBytes);
           const float* src = p.w_image + static_cast<size_t>(chunk_of(it % NCH)) * G::kChunkFloats;
           unsigned char* dst = sB + st * G::kBStageBytes;
-#pragma unroll
-          for (int q = 0; q < G::kBStageBytes / kBlockBytes; ++q)
+          const int nblk = (hi_only ? G::kTermBytes : G::kBStageBytes) / kBlockBytes;
+          for (int q = 0; q < nblk; ++q)
             tma_load_row(dst + q * kBlockBytes, src + q * (kBlockBytes / 4), kBlockBytes, &C.b_full[st]);
         }
     }
@@ -283,9 +303,11 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
           const uint32_t b_addr = smem_u32(sB + st * G::kBStageBytes);
           const uint32_t d_tmem = tmem + acc * kChunk;
           uint32_t accum = 0;
-          // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi
+          // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi (the statistics pass in 1xTF32: a_hi w_hi only)
+          const int term0 = (stat1x && it < NCH) ? 2 : 0;
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
+            if (term < term0) continue;
             const uint32_t a_off = (term == 0) ? G::kTermBytes : 0;  // 0 = hi, 1 = lo
             const uint32_t b_off = (term == 1) ? G::kTermBytes : 0;
 #pragma unroll
@@ -316,18 +338,26 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
     uint32_t tcount = 0;
     long long prev_tile = -1;
 
-    // exact finish of the previous tile's rows from their survivor lists (16 lanes per row, as score_batch)
+    // exact finish of the previous tile's rows from their survivor lists (16 lanes per row, as score_batch).  Everything
+    // that enters a score is formed HERE from exact quantities - the row's sum of numerators accumulated in pass 2 (3xTF32
+    // logits), the fp32 logit of class x_t - so the approximate statistics of a 1xTF32 first pass never reach a result.
     auto score_tile = [&](long long tile) {
       const int sub = lane & 15;
       for (int slot = 2 * (warp - 1) + (lane >> 4); slot < kTileM; slot += 2 * kEpiWarps) {
         const long long lrow = tile * kTileM + slot;
         const bool live = lrow < p.rows;
         unsigned long long key = 0ull;
-        RowInfo ri;
-        ri.accept = 0.f;
+        float accept = 0.f;
         uint32_t cnt = 0;
         if (live) {
-          ri = C.info[slot];
+          const HeadRowInfo hi = C.info[slot];
+          const float S = (C.sum2[0][slot] + C.sum2[1][slot]) + (C.sum2[2][slot] + C.sum2[3][slot]);
+          const float rS = __frcp_rn(S);
+          const bool masked = (hi.j == static_cast<uint32_t>(p.K));
+          const float pj = masked ? 0.f : fminf(fmaxf(ex2(hi.yj_rel) * rS, kPFloor), 1.0f);
+          RowMath rm;
+          rm.init(load_row_coef(p.coef_table, hi.tt, masked), masked, pj, hi.j, p.K);
+          accept = ThinRule(rm, thin_c).accept;
           cnt = C.cand_cnt[slot];
           const uint32_t n = cnt < static_cast<uint32_t>(kCand) ? cnt : static_cast<uint32_t>(kCand);
           // items 0 .. n-1: the survivors, item n: [MASK], item n+1: the row's own class; one or two rounds of 16 lanes
@@ -337,13 +367,13 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
             bool have = false;
             if (item < n) {
               k = C.cand_k[slot][item];
-              const float pe = fminf(fmaxf(C.cand_p[slot][item], kPFloor), 1.0f);
-              P = fmaf(pe, ri.A, ri.Bc);
-              have = (k != ri.j);
+              const float pe = fminf(fmaxf(C.cand_p[slot][item] * rS, kPFloor), 1.0f);
+              P = fmaf(pe, rm.A, rm.Bc);
+              have = (k != hi.j);
             } else if (item == n) {
-              k = static_cast<uint32_t>(p.K), P = ri.PK, have = true;
-            } else if (ri.j != static_cast<uint32_t>(p.K)) {
-              k = ri.j, P = ri.Pj, have = true;
+              k = static_cast<uint32_t>(p.K), P = rm.PK, have = true;
+            } else if (!masked) {
+              k = hi.j, P = rm.Pj, have = true;
             }
             if (have) {
               const float sc = log_prob_clamped(P) +
@@ -359,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
           key = other > key ? other : key;
         }
         if (live && sub == 0) {
-          if (cnt <= static_cast<uint32_t>(kCand) && key_score(key) >= ri.accept) {
+          if (cnt <= static_cast<uint32_t>(kCand) && key_score(key) >= accept) {
             p.x_prev[lrow] = key_class(key);
           } else {
             p.redo_rows[atomicAdd(p.redo_count, 1u)] = static_cast<int32_t>(lrow);
@@ -538,19 +568,34 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       const bool masked = (jj == p.K);
       const uint32_t j = static_cast<uint32_t>(jj);
       const RowCoef cf = load_row_coef(p.coef_table, static_cast<int>(tt), masked);
-      const float pj = masked ? 0.f : fminf(fmaxf(ex2(C.yj2[erow] - M2) * rS, kPFloor), 1.0f);
+      const float yj_rel = masked ? 0.f : C.yj2[erow] - M2;
+      // Thinning thresholds.  With exact statistics (3xTF32 first pass) they are those of the unfused kernels.  With a
+      // 1xTF32 first pass the stabiliser M2 is merely close to the row maximum (harmless: any stabiliser works) and S is
+      // within a factor 2^slack of the exact sum, so the thresholds are made CONSERVATIVE: 1/S and p_j are taken at the
+      // ends of their intervals and the larger threshold of the two ends is used (A c / Ptot and Bc c / Ptot are ratios
+      // of functions linear in p_j, hence monotone) - the survivor lists can only grow, by ~2^(2 slack).  The acceptance
+      // bound and every score are formed from exact quantities in score_tile.
+      const float grow_f = stat1x ? ex2(p.stat_slack) : 1.0f;
+      const float pj_mid = masked ? 0.f : ex2(yj_rel) * rS;
       RowMath rm;
-      rm.init(cf, masked, pj, j, p.K);
-      const ThinRule thin(rm, thin_c);
-      const float thrA = rS * thin.scaleA;
+      rm.init(cf, masked, masked ? 0.f : fminf(fmaxf(pj_mid * grow_f, kPFloor), 1.0f), j, p.K);
+      ThinRule thin(rm, thin_c);
+      if (stat1x && !masked) {
+        RowMath rm_lo;
+        rm_lo.init(cf, masked, fminf(fmaxf(pj_mid / grow_f, kPFloor), 1.0f), j, p.K);
+        const ThinRule thin_lo(rm_lo, thin_c);
+        thin.scaleA = fmaxf(thin.scaleA, thin_lo.scaleA), thin.thrB = fmaxf(thin.thrB, thin_lo.thrB);
+      }
+      const float thrA = rS * grow_f * thin.scaleA;
       if (cs == 0) {
-        RowInfo ri;
-        ri.A = rm.A, ri.Bc = rm.Bc, ri.Pj = rm.Pj, ri.PK = rm.PK, ri.accept = thin.accept;
-        ri.j = j, ri.rel = 0, ri.pad = 0;
-        C.info[erow] = ri;
+        HeadRowInfo hi;
+        hi.j = j, hi.tt = static_cast<int32_t>(tt), hi.yj_rel = yj_rel, hi.pad = 0.f;
+        C.info[erow] = hi;
       }
       const uint64_t grow = static_cast<uint64_t>(p.row_offset + lrow);
-      const float2 nM2 = make_float2(-M2, -M2), tA2 = make_float2(thrA, thrA), tB2 = make_float2(thin.thrB, thin.thrB);
+      const float2 nM2 = make_float2(-M2, -M2), tA2 = make_float2(thrA, thrA);
+      const float nthrB = -thin.thrB;
+      float2 esum = make_float2(0.f, 0.f);  // exact sum of this thread's numerators
 
       // ---------------- pass 2: regenerate the logits, thinned race, survivors to the row's list ----------------
       // The noise (integer pipe) is generated one group of eight classes AHEAD of the exponentials (MUFU pipe) that
@@ -569,52 +614,61 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
         mbar_wait_sleep(&C.acc_full[accA], static_cast<uint32_t>((itA >> 2) & 1));
         mbar_wait_sleep(&C.acc_full[accB], static_cast<uint32_t>((itB >> 2) & 1));
         tc_fence_after();
-        uint32_t va[32], vb[32];
-        tmem_ld32(t_lane + accA * kChunk, va);
-        tmem_ld32(t_lane + accB * kChunk, vb);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&C.acc_empty[accA]), mbar_arrive(&C.acc_empty[accB]);
+        // the accumulators are read 16 columns at a time (two halves of the thread's 32 columns): 32 live registers for
+        // the logits instead of 64, which is what keeps this loop free of spills at 96 registers per thread
+        uint32_t va[16], vb[16];
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
+          if ((c8 & 3) == 0) {
+            tmem_ld16(t_lane + accA * kChunk + 4 * c8, va);
+            tmem_ld16(t_lane + accB * kChunk + 4 * c8, vb);
+            tmem_ld_wait();
+            if (c8 == 4) {  // both halves are in registers: the tensor pipe may overwrite the two accumulators
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&C.acc_empty[accA]), mbar_arrive(&C.acc_empty[accB]);
+            }
+          }
+          const int c4 = c8 & 3;
           const uint4 cw = cw_next;
           if (c8 < 7) cw_next = coarse_of(pr, c8 + 1);
           else if (pr + 1 < NCH / 2) cw_next = coarse_of(pr + 1, 0);
           const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + c8);
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 512) + c8);
           float2 e[4], d[4];
-          e[0] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(va[4 * c8]), __uint_as_float(va[4 * c8 + 1])), make_float2(ba.x, ba.y)), nM2);
-          e[1] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(va[4 * c8 + 2]), __uint_as_float(va[4 * c8 + 3])), make_float2(ba.z, ba.w)), nM2);
-          e[2] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vb[4 * c8]), __uint_as_float(vb[4 * c8 + 1])), make_float2(bb.x, bb.y)), nM2);
-          e[3] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vb[4 * c8 + 2]), __uint_as_float(vb[4 * c8 + 3])), make_float2(bb.z, bb.w)), nM2);
+          e[0] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(va[4 * c4]), __uint_as_float(va[4 * c4 + 1])), make_float2(ba.x, ba.y)), nM2);
+          e[1] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(va[4 * c4 + 2]), __uint_as_float(va[4 * c4 + 3])), make_float2(ba.z, ba.w)), nM2);
+          e[2] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vb[4 * c4]), __uint_as_float(vb[4 * c4 + 1])), make_float2(bb.x, bb.y)), nM2);
+          e[3] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vb[4 * c4 + 2]), __uint_as_float(vb[4 * c4 + 3])), make_float2(bb.z, bb.w)), nM2);
           const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
-          float slack = -1.0f;
+          float slack = -4.0f;  // max over the 8 classes of e thrA + nf, nf = -(1 + h 2^-23); a class survives when >= -thrB
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             e[w] = make_float2(ex2(e[w].x), ex2(e[w].y));
+            esum = __fadd2_rn(esum, e[w]);
             // the 16-bit halves spliced under the exponent of -1.0f: -(1 + h 2^-23)
             const float2 nf = make_float2(__uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5410)),
                                           __uint_as_float(__byte_perm(w4[w], 0xbf80u, 0x5432)));
-            d[w] = __ffma2_rn(e[w], tA2, __fadd2_rn(tB2, nf));
+            d[w] = __ffma2_rn(e[w], tA2, nf);
             slack = fmaxf(slack, fmaxf(d[w].x, d[w].y));
           }
-          if (slack >= 0.0f && live) {  // ~1 % of the lanes: some class of the eight survives
+          if (slack >= nthrB && live) {  // ~1 % of the lanes: some class of the eight survives
 #pragma unroll
             for (int w = 0; w < 4; ++w)
 #pragma unroll
               for (int hl = 0; hl < 2; ++hl)
-                if ((hl ? d[w].y : d[w].x) >= 0.0f) {
+                if ((hl ? d[w].y : d[w].x) >= nthrB) {
                   const uint32_t pos = atomicAdd(&C.cand_cnt[erow], 1u);
                   if (pos < static_cast<uint32_t>(kCand)) {
                     C.cand_k[erow][pos] = static_cast<uint16_t>(k0 + 4 * c8 + (w >> 1) * 512 + 2 * (w & 1) + hl);
-                    C.cand_p[erow][pos] = (hl ? e[w].y : e[w].x) * rS;
+                    C.cand_p[erow][pos] = hl ? e[w].y : e[w].x;
                   }
                 }
           }
         }
       }
-      epi_bar();  // every survivor of the tile is listed
+      C.sum2[cs][erow] = esum.x + esum.y;
+      epi_bar();  // every survivor of the tile is listed, every row's exact sum is in
       prev_tile = tile;
     }
     if (!DUMP && prev_tile >= 0) score_tile(prev_tile);

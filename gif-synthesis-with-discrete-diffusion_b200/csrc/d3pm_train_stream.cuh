@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     const float am = am_n, aa = aa_n;
     asm volatile("" : "+l"(tt), "+l"(jj), "+l"(x0l) : : "memory");  // consume before the next loads are issued
     if (row + G < rows) load_scalars(row + G);
-    if (tt < 0 || tt >= p.T) status_bits |= D3PM_STATUS_BAD_T, tt = tt < 0 ? 0 : p.T - 1;
-    if (jj < 0 || jj > K) status_bits |= D3PM_STATUS_BAD_TOKEN, jj = K;
-    if (x0l < 0 || x0l >= K) status_bits |= D3PM_STATUS_BAD_TOKEN, x0l = 0;
+    if (static_cast<unsigned long long>(tt) >= static_cast<unsigned long long>(p.T)) status_bits |= D3PM_STATUS_BAD_T, tt = tt < 0 ? 0 : p.T - 1;
+    if (static_cast<unsigned long long>(jj) > static_cast<unsigned long long>(K)) status_bits |= D3PM_STATUS_BAD_TOKEN, jj = K;
+    if (static_cast<unsigned long long>(x0l) >= static_cast<unsigned long long>(K)) status_bits |= D3PM_STATUS_BAD_TOKEN, x0l = 0;
     const bool masked = (jj == K), t0 = (tt == 0);
     const uint32_t j = static_cast<uint32_t>(jj), x0 = static_cast<uint32_t>(x0l);
     RowCoef cf;
@@ -202,12 +202,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     const float P_K = fmaf(cf.PK1, eL, cf.PK0);
     const float ptj = j_is_x0 ? 1.0f : kTiny;
     const float eLt = masked ? fmaf(cf.W, 1.0f, kTiny) : fmaf(cf.W, 1.0f - ptj, fmaf(cf.WS, ptj, kTiny));
-    const float Tg_log = log_prob_clamped(fmaf(kTiny, cf.A, cf.BO * eLt));
-    const float Tj_log = log_prob_clamped(masked ? 1.0f : fmaf(ptj, cf.AS, cf.BOS * eLt));
-    const float Tx0_log = j_is_x0 ? Tj_log : log_prob_clamped(fmaf(1.0f, cf.A, cf.BO * eLt));
-    const float TK_log = log_prob_clamped(fmaf(cf.PK1, eLt, cf.PK0));
-    const float Tg = ex2(Tg_log * kLog2e), Tj = ex2(Tj_log * kLog2e), Tx0 = ex2(Tx0_log * kLog2e), TK = ex2(TK_log * kLog2e);
-    const float M_x0 = log_prob_clamped(P_x0), M_j = log_prob_clamped(P_j), M_K = log_prob_clamped(P_K);
+    // the "true" posterior of the one-hot x_0 takes four values per row; clamp(log T, -70, 0) is a clamp of T itself to
+    // [exp(-70), 1], so the linear values every thread needs for the gradient cost no logarithm (the logs are taken by
+    // the one thread that forms the loss)
+    const float Tg = fminf(fmaxf(fmaf(kTiny, cf.A, cf.BO * eLt), kPFloor), 1.0f);
+    const float Tj = masked ? 1.0f : fminf(fmaxf(fmaf(ptj, cf.AS, cf.BOS * eLt), kPFloor), 1.0f);
+    const float Tx0 = j_is_x0 ? Tj : fminf(fmaxf(fmaf(1.0f, cf.A, cf.BO * eLt), kPFloor), 1.0f);
+    const float TK = fminf(fmaxf(fmaf(cf.PK1, eLt, cf.PK0), kPFloor), 1.0f);
     const float wtok = masked ? p.mask_weight_masked : p.mask_weight_unmasked;
 
     // ---- forward sweep over the classes, all by the generic formula ----
@@ -314,14 +315,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     }
     // ---- exchange 2 ----
     {
-      const float a0 = warp_sum(sumM), a1 = WRITE_GRAD ? warp_sum(sInv) : 0.f;
-      const float a2 = WRITE_GRAD ? warp_sum(sPP) : 0.f, a3 = WRITE_GRAD ? warp_sum(sP) : 0.f;
-      if (want_arg) kpost = warp_argmax_key(post_best, post_idx);
-      if (lane == 0) {
-        S.red[1][warp] = a0, S.red[1][kGroupWarps + warp] = a1;
-        S.red[1][2 * kGroupWarps + warp] = a2, S.red[1][3 * kGroupWarps + warp] = a3;
-        if (want_arg) S.keys[1][warp] = kpost;
+      if (WRITE_GRAD) {
+        // four warp sums in one butterfly: after the xor-16 step a lane carries two of the four values, after the xor-8
+        // step one; lanes 0 / 8 / 16 / 24 end with the totals of sumM / sInv / sPP / sP (18 instructions instead of 40)
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        float k0 = (up16 ? sPP : sumM) + __shfl_xor_sync(0xffffffffu, up16 ? sumM : sPP, 16);
+        float k1 = (up16 ? sP : sInv) + __shfl_xor_sync(0xffffffffu, up16 ? sInv : sP, 16);
+        float tot = (up8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        if ((lane & 7) == 0) S.red[1][(lane >> 3) * kGroupWarps + warp] = tot;
+      } else {
+        const float a0 = warp_sum(sumM);
+        if (lane == 0) S.red[1][warp] = a0;
       }
+      if (want_arg) kpost = warp_argmax_key(post_best, post_idx);
+      if (lane == 0 && want_arg) S.keys[1][warp] = kpost;
     }
     sync();
     {
@@ -331,22 +341,22 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       sPP = (a2.x + a2.y) + (a2.z + a2.w), sP = (a3.x + a3.y) + (a3.z + a3.w);
     }
     // remove what the generic formula contributed for the special classes (they are re-added with their own terms)
-    auto generic_terms = [&](float sm_k, float pk, float& Mk, float& iv, float& pp, float& po) {
-      const float Pk = fmaf(pk, cf.A, Bc);
-      const float lp = lg2(Pk) * kLn2;
-      Mk = fminf(fmaxf(lp, kClampLo), 0.0f);
-      const bool inside = (lp >= kClampLo) && (lp <= 0.0f), open = sm_k >= kPFloor;
+    auto generic_terms = [&](float sm_k, float pk, float& Pk, float& iv, float& pp, float& po) {
+      Pk = fmaf(pk, cf.A, Bc);
+      const bool inside = (Pk >= kPFloor) && (Pk <= 1.0f), open = sm_k >= kPFloor;  // the clamp of :283 did not fire
       iv = inside ? rcp_fast(Pk) : 0.f;
       pp = open ? pk * iv : 0.f;
       po = open ? pk : 0.f;
     };
-    float gM_x0, gi_x0, gpp_x0, gpo_x0, gM_j = 0.f, gi_j = 0.f, gpp_j = 0.f, gpo_j = 0.f;
-    generic_terms(sm_x0, p_x0, gM_x0, gi_x0, gpp_x0, gpo_x0);
-    if (j_other) generic_terms(sm_j, p_j, gM_j, gi_j, gpp_j, gpo_j);
-    const float sumM_gen = sumM - gM_x0 - gM_j;
+    float gP_gen_x0, gi_x0, gpp_x0, gpo_x0, gP_gen_j = 1.0f, gi_j = 0.f, gpp_j = 0.f, gpo_j = 0.f;
+    generic_terms(sm_x0, p_x0, gP_gen_x0, gi_x0, gpp_x0, gpo_x0);
+    if (j_other) generic_terms(sm_j, p_j, gP_gen_j, gi_j, gpp_j, gpo_j);
     const int n_generic = K - 1 - (j_other ? 1 : 0);
 
     if (tg == 0) {
+      const float M_x0 = log_prob_clamped(P_x0), M_j = log_prob_clamped(P_j), M_K = log_prob_clamped(P_K);
+      const float sumM_gen = sumM - log_prob_clamped(gP_gen_x0) - (j_other ? log_prob_clamped(gP_gen_j) : 0.f);
+      const float Tg_log = lg2(Tg) * kLn2, Tj_log = lg2(Tj) * kLn2, Tx0_log = lg2(Tx0) * kLn2, TK_log = lg2(TK) * kLn2;
       float kl = Tg * fmaf(static_cast<float>(n_generic), Tg_log, -sumM_gen);
       kl += Tx0 * (Tx0_log - M_x0) + TK * (TK_log - M_K);
       if (j_other) kl += Tj * (Tj_log - M_j);
@@ -366,10 +376,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     if (!WRITE_GRAD) continue;
 
     // ---- gradient (same formulas as train_rows_kernel) ----
-    auto inside_of = [](float Pv) {
-      const float lp = lg2(Pv) * kLn2;
-      return lp >= kClampLo && lp <= 0.0f;
-    };
+    auto inside_of = [](float Pv) { return Pv >= kPFloor && Pv <= 1.0f; };
     const float g_gen = t0 ? 0.f : -am * wtok * Tg;
     const float gP_x0 = inside_of(P_x0) ? (t0 ? -(am + aa) : -am * wtok * Tx0) * rcp_fast(P_x0) : 0.f;
     const float gP_j = (j_other && !t0 && inside_of(P_j)) ? (-am * wtok * Tj) * rcp_fast(P_j) : 0.f;

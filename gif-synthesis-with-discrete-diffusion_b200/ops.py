@@ -355,7 +355,8 @@ class HostStep:
         _lib.check(self._lib.d3pm_host_head_step_run(self._handle, hidden_c.data_ptr(), _ptr(hidden_u), x_t.data_ptr(), t.data_ptr(),
                                                      hw.ln_weight.data_ptr(), hw.ln_bias.data_ptr(), float(hw.ln_eps),
                                                      hw.w_image.data_ptr(), hw.bias2.data_ptr(), self.coef_table.data_ptr(),
-                                                     float(guidance_scale), seed & (2**64 - 1), offset & (2**64 - 1),
+                                                     float(guidance_scale), float(hw.stat_slack(guidance_scale if hidden_u is not None else None)),
+                                                     seed & (2**64 - 1), offset & (2**64 - 1),
                                                      int(row_offset), self.x_prev_host.data_ptr(), ctypes.byref(st)),
                    "d3pm_host_head_step_run")
         self.last_status = int(st.value)

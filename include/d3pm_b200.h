@@ -244,6 +244,11 @@ typedef struct d3pm_head_desc {
   int32_t B, N, K, T, D;
   int32_t mode;            /* D3PM_HEAD_* */
   float ln_eps, guidance_scale, thin_factor;
+  float stat_slack;        /* > 0: the statistics pass (row maximum and sum of exponentials) runs in 1xTF32; the value bounds
+                              |logit_1xTF32 - logit| in log2 units: 2^-9 * max_k ||W_k|| * ||a|| * log2(e) with ||a|| the largest
+                              norm the combined LayerNorm output can have (d3pm_b200.head computes it).  Results do not change:
+                              the thinning thresholds are widened by 2^slack and every score comes from exact 3xTF32 logits.
+                              0 = statistics in 3xTF32 as well */
   uint64_t seed, offset;
   int64_t row_offset;
   d3pm_stream_t stream;
@@ -284,7 +289,8 @@ int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, const float* lo
 int d3pm_host_head_step_run(d3pm_host_step* h, const float* hidden_c, const float* hidden_u, const int64_t* x_t,
                             const int64_t* t, const float* ln_weight, const float* ln_bias, float ln_eps,
                             const float* w_image, const float* bias2, const float* coef_table, float guidance_scale,
-                            uint64_t seed, uint64_t offset, int64_t row_offset, int64_t* x_prev, uint32_t* status_out);
+                            float stat_slack, uint64_t seed, uint64_t offset, int64_t row_offset, int64_t* x_prev,
+                            uint32_t* status_out);
 
 /* [B, C, N] contiguous (reference layout) -> token-major rows [B*N][pitch]. */
 int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int C, int N,

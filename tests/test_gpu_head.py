@@ -104,6 +104,10 @@ def test_fused_equals_unfused_at_scale():
     near = (unf["gap"] < H.NEAR_TIE_GAP).cpu().numpy()
     H.assert_tokens_match(fused.cpu().numpy(), unf["x_prev"].cpu().numpy(), near, "fused vs unfused")
     H.assert_tokens_match(ref.cpu().numpy(), unf["x_prev"].cpu().numpy(), near, "reference vs unfused")
+    # the statistics pass in 3xTF32 instead of 1xTF32 (wider vs exact thinning thresholds): the very same tokens
+    fused3 = head.head_step(hw, hc, hu, x_t, t, table, guidance_scale=s, seed=2, offset=9, stats_1xtf32=False)
+    assert torch.equal(fused3, fused)
+    assert 0.0 < hw.stat_slack(s) < 0.5
     # a forced thinning failure (tiny c): every row goes through the redo kernel and the result is unchanged
     redo = head.head_step(hw, hc[:1], hu[:1], x_t[:1], t[:1], table, guidance_scale=s, seed=2, offset=9, thin_factor=1e-3)
     H.assert_tokens_match(redo.cpu().numpy(), unf["x_prev"][:1].cpu().numpy(), near[:1], "all rows redone")

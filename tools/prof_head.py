@@ -17,6 +17,7 @@ ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--videos", type=int, default=16)
 ap.add_argument("--t", type=int, default=50)
 ap.add_argument("--no-guidance", action="store_true")
+ap.add_argument("--stats3x", action="store_true", help="statistics pass in 3xTF32 (the round-1 kernel) instead of 1xTF32")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 T, K, N, B, D = 100, 4096, 4096, a.videos, 64
@@ -46,7 +47,7 @@ sc = head.head_scratch(B, N, dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
 ev[0].record()
 for i in range(a.launches):
-    head.head_step(hw, hc, hu, x_t, t, table, guidance_scale=2.0, seed=1, offset=i, x_prev_out=xp, scratch=sc)
+    head.head_step(hw, hc, hu, x_t, t, table, guidance_scale=2.0, seed=1, offset=i, x_prev_out=xp, scratch=sc, stats_1xtf32=not a.stats3x)
     ev[i + 1].record()
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.launches)]
