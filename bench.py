@@ -643,7 +643,7 @@ def measure_next_rows(dev, model, table, x_t, t, x_prev, reps=20):
     hh.close()
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     bf16_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 0.0)) if os.path.isfile(peaks_path) else 0.0
-    mma_flops = 2.0 * B * N * K * D * 3 * 2  # 3xTF32 split, two passes over the classes
+    mma_flops = 2.0 * B * N * K * D * (1 + 3)  # statistics pass in 1xTF32, sampling pass in 3xTF32
     return {
         "e2e_host_hidden_states": {"ms_per_step": e2e_head, "value": B * N / (e2e_head * 1e-3), "unit": UNIT,
                                    "h2d_bytes_per_step": head_h2d, "d2h_bytes_per_step": head_d2h,
@@ -657,7 +657,7 @@ def measure_next_rows(dev, model, table, x_t, t, x_prev, reps=20):
                             "measured_bf16_peak_TFLOPs": bf16_peak,
                             "tf32_frac_of_half_bf16_peak": (mma_flops / (fused * 1e-3) / 1e12) / (0.5 * bf16_peak) if bf16_peak else None,
                             "what": "d3pm_head_step: LayerNorm + Linear(64 -> 4096) of both denoiser passes + the whole update, "
-                                    "tcgen05 3xTF32, logits never in memory"},
+                                    "tcgen05 (statistics pass 1xTF32, sampling pass 3xTF32), logits never in memory"},
         "head_in_torch_then_fused_step": {"ms_per_step": unf, "what": "torch LayerNorm + Linear (fp32) x2, then d3pm_fused_step"},
         "train_loss_and_gradient": {"ms_per_step": tr, "GBps_algorithmic": 2 * Bt * Nt * K * 4 / tr / 1e6,
                                     "what": "d3pm_train_rows backward=2, 16 x 1024 tokens x 4096 codes, losses + logits gradient in one pass"},
