@@ -39,8 +39,9 @@ constexpr int kGroupThreads = 128;
 constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kGroupsPerCta = 4;
 constexpr int kStreamThreads = kGroupThreads * kGroupsPerCta;
-constexpr int kCandPerRow = 14;   // survivors kept per row (a row with more is redone); +2 lanes: [MASK] and x_t
-constexpr float kStreamThin = 6.0f;
+constexpr int kCandPerRow = 30;   // survivors kept per row (a row with more is redone); the scoring pass takes one or two
+                                  // rounds of 16 lanes per row: up to 14 survivors + [MASK] + x_t in the first
+constexpr float kStreamThin = 8.0f;  // ~8 survivors per row; a row's best survivor misses the bound with probability e^-8
 constexpr float kRedoThin = 16.0f;  // bound of the second attempt at a row whose best survivor did not clear the first
 constexpr int kCoefSmemRows = 256;  // timesteps whose coefficients are staged in shared memory (16 KiB)
 struct RowInfo {  // what the scoring pass needs to finish a row
@@ -58,7 +59,7 @@ struct StreamShape {
   static constexpr int GT = 256 * NP / CPT;        // threads per group
   static constexpr int NW = GT / 32;               // warps per group
   static constexpr int NG = kStreamThreads / GT;   // groups per CTA
-  static constexpr int SB = 256 / NG;              // rows whose survivors are scored together
+  static constexpr int SB = 128 / NG;              // rows whose survivors are scored together
   static constexpr int RC = 8192 / NG;             // rows a group can queue for rescoring (= max rows per group)
   static constexpr int PS = 128 / GT;              // a coarse Philox call serves chunks q and q + 128: slots i and i + PS
   static constexpr int NCALL = CPT / 2;            // coarse calls per thread and row
@@ -260,24 +261,29 @@ __device__ __noinline__ void score_batch(GroupSmem<NP, CPT, HAS_U>& S, int nslot
       ri = S.info[slot];
       cnt = S.cand_cnt[slot];
       const uint32_t n = cnt < static_cast<uint32_t>(kCandPerRow) ? cnt : static_cast<uint32_t>(kCandPerRow);
-      uint32_t k = 0;
-      float P = 0.f;
-      bool have = false;
-      if (static_cast<uint32_t>(sub) < n) {
-        k = S.cand_k[slot][sub];
-        const float pe = fminf(fmaxf(S.cand_p[slot][sub], kPFloor), 1.0f);
-        P = fmaf(pe, ri.A, ri.Bc);
-        have = (k != ri.j);  // the row's own class has its own coefficients and its own lane
-      } else if (sub == 14) {
-        k = K, P = ri.PK, have = true;
-      } else if (sub == 15 && ri.j != K) {
-        k = ri.j, P = ri.Pj, have = true;
-      }
-      if (have) {
-        const uint64_t grow = static_cast<uint64_t>(p.row_offset + (first_row + ri.rel * G));
-        lp = log_prob_clamped(P);
-        const float sc = lp + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
-        key = pack_key(sc, k);
+      // items 0 .. n-1: the survivors, item n: [MASK], item n+1: the row's own class; one round of 16 lanes, a second one
+      // for the rare row with more than 14 survivors
+      const uint64_t grow = static_cast<uint64_t>(p.row_offset + (first_row + ri.rel * G));
+      for (uint32_t item = static_cast<uint32_t>(sub); item < n + 2u; item += 16u) {
+        uint32_t k = 0;
+        float P = 0.f;
+        bool have = false;
+        if (item < n) {
+          k = S.cand_k[slot][item];
+          const float pe = fminf(fmaxf(S.cand_p[slot][item], kPFloor), 1.0f);
+          P = fmaf(pe, ri.A, ri.Bc);
+          have = (k != ri.j);  // the row's own class has its own coefficients and its own item
+        } else if (item == n) {
+          k = K, P = ri.PK, have = true;
+        } else if (ri.j != K) {
+          k = ri.j, P = ri.Pj, have = true;
+        }
+        if (have) {
+          const float lpk = log_prob_clamped(P);
+          const float sc = lpk + gumbel_from_uniform(uniform_from_draw(rng.draw(k, grow)));
+          const unsigned long long kk = pack_key(sc, k);
+          if (kk > key) key = kk, lp = lpk;
+        }
       }
     }
     const unsigned long long mine = key;
