@@ -321,29 +321,36 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
   const int g = tid / GT;
   const int tg = tid % GT;
   Smem& S = reinterpret_cast<Smem*>(smem_raw)[g];
-  // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits: per-row lookups become LDS
-  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(Smem) * NG);
-  const bool coef_in_smem = p.T <= kCoefSmemRows;
-  if (coef_in_smem) {
-    for (int i = tid; i < p.T * 16; i += kStreamThreads)
-      coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
-    __syncthreads();
-  }
   const StreamSync<NW> sync{g + 1};
   // row indices are 32-bit throughout (the launcher refuses more than 2^31 - 1 rows)
   const int G = static_cast<int>(gridDim.x) * NG;
   const int first_row = g * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);  // neighbouring rows -> different SMs
   const int rows = static_cast<int>(p.rows);
   const uint32_t pitch = static_cast<uint32_t>(p.pitch_logits);
-  const ParamNoiseStream rng(NoiseKeysParam(p.keys), p.offset);  // round keys straight from the parameter block
-  const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kStreamThin;
-
+  const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
+  // The very first thing a group does is to get its first row moving: the elected thread arms the group's mbarrier and
+  // issues the copies, and the set-up below (coefficient table into shared memory, list counters) runs under that latency.
   if (tg == 0) {
     mbar_init(&S.full, 1);
     S.redo_cnt = 0;
+    if (!exact_mode && first_row < rows) {
+      const unsigned long long at = static_cast<unsigned long long>(static_cast<uint32_t>(first_row)) * pitch;
+      mbar_expect_tx(&S.full, HAS_U ? 2 * kRowBytes : kRowBytes);
+      tma_load_row(S.c, p.logits_c + at, kRowBytes, &S.full);
+      if (HAS_U) tma_load_row(S.u, p.logits_u + at, kRowBytes, &S.full);
+    }
   }
+  // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits: per-row lookups become LDS
+  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(Smem) * NG);
+  const bool coef_in_smem = p.T <= kCoefSmemRows;
+  if (coef_in_smem) {
+    for (int i = tid; i < p.T * 16; i += kStreamThreads)
+      coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
+  }
+  const ParamNoiseStream rng(NoiseKeysParam(p.keys), p.offset);  // round keys straight from the parameter block
+  const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kStreamThin;
   for (int i = tg; i < Sh::SB; i += GT) S.cand_cnt[i] = 0;
-  sync();
+  __syncthreads();  // the table, the counters and every group's barrier are set up
 
   auto issue_row = [&](int row) {  // elected thread: arm the barrier and launch both row copies
     const unsigned long long at = static_cast<unsigned long long>(static_cast<uint32_t>(row)) * pitch;
@@ -358,7 +365,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 
   uint32_t phase = 0;
   uint32_t status_bits = 0;
-  const bool exact_mode = (p.sample_mode == D3PM_SAMPLE_PHILOX_EXACT);
 #ifdef D3PM_STREAM_TIMING  // debug build: p.status is a [groups][8] uint32 trace buffer (word 0 of the grid = origin)
   auto now_ns = [] { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; };
   const unsigned long long tm_start = now_ns();
@@ -734,8 +740,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     int vb = first_row / N, vr = first_row % N;
     int row = first_row < rows ? first_row : -1;
     long long jj = 0, tt = 0;
-    if (row >= 0) {
-      if (tg == 0) issue_row(row);
+    if (row >= 0) {  // (its copies were issued at the top of the kernel)
       jj = token_of(row);
       tt = time_of(vb);
     }

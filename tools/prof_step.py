@@ -19,6 +19,7 @@ ap.add_argument("--t", type=int, default=50)
 ap.add_argument("--mode", default="philox")
 ap.add_argument("--no-guidance", action="store_true")
 ap.add_argument("--codes", type=int, default=4096)
+ap.add_argument("--thin", type=float, default=0.0, help="thinning constant c (0 = the kernel's default)")
 ap.add_argument("--sleep-ms", type=float, default=0.0, help="idle gap before every launch (isolated launches)")
 a = ap.parse_args()
 
@@ -43,7 +44,7 @@ x_t = torch.where(torch.rand(B, N, device=dev, generator=g) < pm, torch.full((B,
                   torch.randint(0, K, (B, N), device=dev, generator=g))
 t = torch.full((B,), a.t, dtype=torch.int64, device=dev)
 xp = torch.empty_like(x_t)
-kw = dict(guidance_scale=2.0, seed=1, x_prev_out=xp)
+kw = dict(guidance_scale=2.0, seed=1, x_prev_out=xp, thin_factor=a.thin)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
 ev[0].record()
 for i in range(a.launches):
