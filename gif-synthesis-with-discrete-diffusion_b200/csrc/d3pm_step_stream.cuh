@@ -19,10 +19,10 @@
 //     the guidance combine and the posterior entirely in registers with thread-local maxima, so that only two group
 //     barriers per row are needed;
 //   * sampling is the thinned exponential race (see ThinRule): 16 Philox bits per class decide whether the
-//     class can still win; the ~6 survivors per row are appended to a per-row list in shared memory;
+//     class can still win; the ~8 survivors per row are appended to a per-row list in shared memory;
 //   * every kScoreBatch rows the group scores the survivors of the whole batch exactly (Gumbel score in
 //     accurate fp32, argmax with first-index ties), two rows per warp pass, and writes the tokens;
-//   * rows whose best survivor does not clear the acceptance bound (probability ~e^-c, ~200 of 65 536 rows)
+//   * rows whose best survivor does not clear the acceptance bound (probability e^-8, ~25 of 65 536 rows)
 //     are queued and redone by the same group after its main loop: the same race thinned at c = 16 with the
 //     survivors scored on the spot, and exhaustively only if that fails too (e^-16).
 // HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
