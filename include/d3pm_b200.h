@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define D3PM_VERSION 100 /* major*10000 + minor*100 + patch */
+#define D3PM_VERSION 200 /* major*10000 + minor*100 + patch; 0.2.0: host-buffer handle, d3pm_head_desc.stat_slack */
 
 #define D3PM_OK 0
 #define D3PM_ERR_INVALID (-1)     /* null pointer, non-positive size, t/K/T inconsistent */
