@@ -1,18 +1,18 @@
 // Training-side loss, production kernel: persistent CTAs, TMA-staged logit rows, loss AND gradient in
 // one pass.  Same mathematics as train_rows_kernel (d3pm_train_rows.cuh, `_train_loss` diffusion_transformer.py:391-457);
 // what changes is the schedule:
-//   * one CTA per SM, four independent groups of 128 threads, a group owns every G-th token row;
+//   * one CTA of 512 threads per SM, split into independent groups of K / 32 threads (see TrainShape); a group owns every
+//     G-th token row;
 //   * a two-stage shared-memory ring per group, filled with 1-D bulk TMA (16 KiB per row for K = 4096): two rows per
-//     group are in flight while a third is processed from registers;
-//   * the row lives in registers (32 classes per thread); every class is treated by the GENERIC formula and the (at
-//     most two) special classes x_0 and x_t are corrected on scalars afterwards, so the inner loops carry no per-class
-//     compares;
+//     group are in flight while a third is processed from registers (128 KiB per SM);
+//   * the row lives in registers: first the logits, from the first sweep on their softmax numerators IN PLACE; every class
+//     is treated by the GENERIC formula and the (at most two) special classes x_0 and x_t are corrected on scalars
+//     afterwards, so the inner loops carry no per-class compares;
 //   * the sum over classes of the gradient's softmax term is obtained in closed form from sums accumulated in the
-//     forward sweep, so a row needs two group exchanges (two 128-thread named barriers), not four;
+//     forward sweep, so a row needs two group exchanges (none across warps for the one-warp groups), not four;
 //   * the gradient row is written with streaming 128-bit stores straight from registers;
 //   * a row's scalars (x_0, x_t, t of its video, the per-video gradient weights) are loaded one row ahead and the
-//     coefficient table is staged in shared memory: with ~28 rows per group at the shipped training shape the two
-//     dependent global loads at the top of every row (t, then the table row) were what the kernel waited for.
+//     coefficient table is staged in shared memory.
 // HBM traffic is the algorithmic minimum of a fused forward + backward: 16 KiB read and 16 KiB written per token.
 #pragma once
 
@@ -27,50 +27,65 @@ __device__ __forceinline__ float rcp_fast(float x) {  // MUFU.RCP, 1 ulp: plenty
   return y;
 }
 
+// Shape of one instantiation.  NP = K / 1024.  A thread holds 32 classes of the row (numerators + reciprocals: 64 registers),
+// so a group is K / 32 threads wide - 4 groups of 128 threads at K = 4096 (as in round 1), 8 groups of 64 at K = 2048, 16
+// one-warp groups at K = 1024 - and the per-row scalar work, 59 % of a warp's instructions at K = 4096, costs the same per
+// class for every codebook (round 1 ran 128-thread groups for every K: 0.231 ms instead of 0.100 ms at K = 1024, 64 videos).
+// Measured and NOT kept for K = 4096: 64 classes per thread in groups of 64 threads - with 512 threads per CTA the 128
+// registers spill, with 256 threads (255 registers) the 8 warps left per SM cannot hide the latency of the scalar sections
+// (0.139 instead of 0.104 ms either way).
+template <int NP>
+struct TrainShape {
+  static constexpr int K = 1024 * NP;
+  static constexpr int CPT = 8;                   // float4 chunks per thread
+  static constexpr int THREADS = kStreamThreads;
+  static constexpr int GT = 256 * NP / CPT;       // threads per group: 128 / 64 / 32
+  static constexpr int NW = GT / 32;
+  static constexpr int NG = THREADS / GT;         // groups per CTA: 4 / 8 / 16
+};
+
 template <int NP>
 struct __align__(128) TrainGroupSmem {
-  float stage[2][1024 * NP];
-  alignas(16) float red[2][8 * kGroupWarps];
-  unsigned long long keys[2][kGroupWarps];
+  float stage[2][1024 * NP];           // two rows per group in flight while a third is processed from registers
+  alignas(16) float red[2][4 * 4];     // reduction scratch: [value][warp], padded to four warps
+  unsigned long long keys[2][4];
   unsigned long long full[2];
 };
 
-// MODE 0: forward only (per-token losses, arg-maxes); MODE 1: forward + gradient rows
+// WRITE_GRAD false: forward only (per-token losses, arg-maxes); true: forward + gradient rows in the same pass
 template <int NP, bool WRITE_GRAD>
-__global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const TrainParams p) {
+__global__ void __launch_bounds__(TrainShape<NP>::THREADS, 1) train_stream_kernel(const TrainParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int K = 1024 * NP;
-  constexpr int NC = 2 * NP;  // float4 chunks per thread
+  using Sh = TrainShape<NP>;
+  constexpr int K = Sh::K, NC = Sh::CPT, GT = Sh::GT, NW = Sh::NW, NG = Sh::NG;
   constexpr uint32_t kRowBytes = K * sizeof(float);
   uint32_t tid;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const int g = tid / kGroupThreads, tg = tid % kGroupThreads;
-  const int lane = tid & 31, warp = (tid >> 5) & (kGroupWarps - 1);
+  const int g = tid / GT, tg = tid % GT;
+  const int lane = tid & 31, warp = (tid >> 5) & (NW - 1);
   TrainGroupSmem<NP>& S = reinterpret_cast<TrainGroupSmem<NP>*>(smem_raw)[g];
-  // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits
-  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(TrainGroupSmem<NP>) * kGroupsPerCta);
-  const bool coef_in_smem = p.T <= kCoefSmemRows;
-  if (coef_in_smem) {
-    for (int i = tid; i < p.T * 16; i += kStreamThreads)
-      coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
-    __syncthreads();
-  }
-  const GroupSync sync{g + 1};
+  const StreamSync<NW> sync{g + 1};
   // row indices are 32-bit (the launcher refuses more than 2^31 - 1 rows)
-  const int G = static_cast<int>(gridDim.x) * kGroupsPerCta;
+  const int G = static_cast<int>(gridDim.x) * NG;
   const int first_row = g * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
   const int rows = static_cast<int>(p.rows);
-
-  if (tg == 0) {
-    mbar_init(&S.full[0], 1);
-    mbar_init(&S.full[1], 1);
-  }
-  sync();
   auto issue_row = [&](int row, int st) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&S.full[st], kRowBytes);
     tma_load_row(S.stage[st], p.logits + static_cast<long long>(row) * p.pitch, kRowBytes, &S.full[st]);
   };
+  if (tg == 0) {
+    mbar_init(&S.full[0], 1);
+    mbar_init(&S.full[1], 1);
+  }
+  // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits
+  float* coef_s = reinterpret_cast<float*>(smem_raw + sizeof(TrainGroupSmem<NP>) * NG);
+  const bool coef_in_smem = p.T <= kCoefSmemRows;
+  if (coef_in_smem) {
+    for (int i = tid; i < p.T * 16; i += Sh::THREADS)
+      coef_s[i] = __ldg(p.coef_table + static_cast<size_t>(i >> 4) * D3PM_COEF_STRIDE + (i & 15));
+  }
+  __syncthreads();
   if (tg == 0) {
     if (first_row < rows) issue_row(first_row, 0);
     if (first_row + G < rows) issue_row(first_row + G, 1);
@@ -111,21 +126,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     mbar_wait(&S.full[st], phase[st]);
     phase[st] ^= 1u;
     const float* __restrict__ rowbuf = S.stage[st];
-    float2 x[NC][2];  // class pairs (0,1) and (2,3) of chunk i, packed for the f32x2 pipe
+    // class pairs (0,1) and (2,3) of chunk i (float4 number GT i + tg), packed for the f32x2 pipe; first the logits, from
+    // the first sweep on their softmax numerators (in place)
+    float2 e[NC][2];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      const float4 a = lds4(rowbuf + 4 * (128 * i + tg));
-      x[i][0] = make_float2(a.x, a.y), x[i][1] = make_float2(a.z, a.w);
+      const float4 a = lds4(rowbuf + 4 * (GT * i + tg));
+      e[i][0] = make_float2(a.x, a.y), e[i][1] = make_float2(a.z, a.w);
     }
     const float c_x0 = rowbuf[x0], c_j = masked ? 0.f : rowbuf[j];
 
     // ---- exchange 1: (max, sum of exponentials relative to the thread-local max) and the arg-max of the logits ----
-    float m = fmaxf(fmaxf(x[0][0].x, x[0][0].y), fmaxf(x[0][1].x, x[0][1].y));
-    float lo = fminf(fminf(x[0][0].x, x[0][0].y), fminf(x[0][1].x, x[0][1].y));
+    float m = fmaxf(fmaxf(e[0][0].x, e[0][0].y), fmaxf(e[0][1].x, e[0][1].y));
+    float lo = fminf(fminf(e[0][0].x, e[0][0].y), fminf(e[0][1].x, e[0][1].y));
 #pragma unroll
     for (int i = 1; i < NC; ++i) {  // 3-input min / max: two instructions per four classes each
-      m = fmaxf(fmaxf(m, x[i][0].x), fmaxf(x[i][0].y, fmaxf(x[i][1].x, x[i][1].y)));
-      lo = fminf(fminf(lo, x[i][0].x), fminf(x[i][0].y, fminf(x[i][1].x, x[i][1].y)));
+      m = fmaxf(fmaxf(m, e[i][0].x), fmaxf(e[i][0].y, fmaxf(e[i][1].x, e[i][1].y)));
+      lo = fminf(fminf(lo, e[i][0].x), fminf(e[i][0].y, fminf(e[i][1].x, e[i][1].y)));
     }
     unsigned long long kbest = 0ull;
     uint32_t idx = 0;
@@ -134,14 +151,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       for (int i = NC - 1; i >= 0; --i)
 #pragma unroll
         for (int c = 3; c >= 0; --c) {
-          const float xv = (c & 1) ? x[i][c >> 1].y : x[i][c >> 1].x;
-          idx = (xv == m) ? 4u * (128u * i + tg) + c : idx;
+          const float xv = (c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x;
+          idx = (xv == m) ? 4u * (static_cast<uint32_t>(GT) * i + tg) + c : idx;
         }
     }
     const float e_top = ex2(fmaf(m, kLog2e, -to_log2_units(fmaxf(m, -3.0e38f))));  // numerator of the thread's best class
     m = fmaxf(m, -3.0e38f);
     const float m2 = to_log2_units(m);
-    float2 e[NC][2];
     float sloc;
     {
       const float2 l2e = make_float2(kLog2e, kLog2e), nm2 = make_float2(-m2, -m2);
@@ -150,38 +166,43 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float2 a = __ffma2_rn(x[i][h], l2e, nm2);
+          const float2 a = __ffma2_rn(e[i][h], l2e, nm2);
           e[i][h] = make_float2(ex2(a.x), ex2(a.y));
           s2[h] = __fadd2_rn(s2[h], e[i][h]);
         }
       sloc = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y);
     }
+    float M, Ssum, xmin;
     {
       const float mw = warp_max(m);
       const float mw2 = to_log2_units(mw);
       const float sw = warp_sum(sloc * ex2(m2 - mw2));
       const float lw = warp_min(lo);
       if (want_arg) kbest = warp_argmax_key(m, idx);
-      if (lane == 0) {
-        S.red[0][warp] = mw, S.red[0][kGroupWarps + warp] = sw, S.red[0][2 * kGroupWarps + warp] = lw;
+      if (NW > 1 && lane == 0) {
+        S.red[0][warp] = mw, S.red[0][4 + warp] = sw, S.red[0][8 + warp] = lw;
         if (want_arg) S.keys[0][warp] = kbest;
       }
-    }
-    sync();  // everyone has drained the stage and published its partials
-    if (tg == 0 && row + 2 * G < rows) issue_row(row + 2 * G, st);
-    float M, Ssum, xmin;
-    {
-      const float4 mw = lds4(S.red[0]), sw = lds4(S.red[0] + kGroupWarps), lw = lds4(S.red[0] + 2 * kGroupWarps);
-      xmin = fminf(fminf(lw.x, lw.y), fminf(lw.z, lw.w));
-      M = fmaxf(fmaxf(mw.x, mw.y), fmaxf(mw.z, mw.w));
-      const float M2g = to_log2_units(M);
-      Ssum = fmaf(sw.x, ex2(to_log2_units(mw.x) - M2g),
-                  fmaf(sw.y, ex2(to_log2_units(mw.y) - M2g), fmaf(sw.z, ex2(to_log2_units(mw.z) - M2g), sw.w * ex2(to_log2_units(mw.w) - M2g))));
-      if (want_arg && tg == 0) {
-        unsigned long long kb = S.keys[0][0];
+      sync();  // everyone has drained the stage (and published its partials)
+      if (tg == 0 && row + 2 * G < rows) issue_row(row + 2 * G, st);
+      if (NW > 1) {
+        const float4 mw_ = lds_warps<NW>(S.red[0], -CUDART_INF_F), sw_ = lds_warps<NW>(S.red[0] + 4, 0.f);
+        const float4 lw_ = lds_warps<NW>(S.red[0] + 8, CUDART_INF_F);
+        xmin = fminf(fminf(lw_.x, lw_.y), fminf(lw_.z, lw_.w));
+        M = fmaxf(fmaxf(mw_.x, mw_.y), fmaxf(mw_.z, mw_.w));
+        const float M2g = to_log2_units(M);
+        Ssum = fmaf(sw_.x, ex2(to_log2_units(mw_.x) - M2g), sw_.y * ex2(to_log2_units(mw_.y) - M2g));
+        if (NW == 4) Ssum += fmaf(sw_.z, ex2(to_log2_units(mw_.z) - M2g), sw_.w * ex2(to_log2_units(mw_.w) - M2g));
+      } else {
+        xmin = lw, M = mw, Ssum = sw;
+      }
+      if (want_arg && tg == 0) {  // the thread that writes the arg-max combines the warps' keys
+        if (NW > 1) {
+          kbest = S.keys[0][0];
 #pragma unroll
-        for (int w = 1; w < kGroupWarps; ++w) kb = S.keys[0][w] > kb ? S.keys[0][w] : kb;
-        p.x0_recon[row] = key_class(kb);
+          for (int w = 1; w < NW; ++w) kbest = S.keys[0][w] > kbest ? S.keys[0][w] : kbest;
+        }
+        p.x0_recon[row] = key_class(kbest);
       }
     }
     const float M2 = to_log2_units(M);
@@ -215,12 +236,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     // sumM = sum M_k; with "inside" = the posterior clamp did not fire and "open" = the recon clamp did not fire:
     // sInv = sum_{inside} 1/P_k,  sPP = sum_{inside & open} p_k / P_k,  sP = sum_{open} p_k
     float sumM = 0.f, sInv = 0.f, sPP = 0.f, sP = 0.f;
+    float2 inv[WRITE_GRAD ? NC : 1][2];  // 1 / P_k (0 where the posterior clamp fired), kept for the gradient
     unsigned long long kpost = 0ull;
     float post_best = -CUDART_INF_F;
     uint32_t post_idx = 0;
-    // "open" <=> log-softmax_k >= -70 <=> softmax_k >= exp(-70): decided on the softmax value, so the logits themselves
-    // are dead after the first sweep (registers: numerators e and reciprocals inv only)
-    float2 inv[NC][2];
     // Clamp-free fast path (row-uniform): when no log-softmax entry can reach -70 (smallest logit of the row) and every
     // generic P_k = p_k A + Bc lies in [exp(-70), 1] (Bc and A + Bc say so), none of the clamps of :236 / :283 can fire for
     // a generic class: the sweep needs no predicates, and the posterior arg-max is the logits' arg-max.
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
           const float Mk = fminf(fmaxf(lp, kClampLo), 0.0f);
           sumM += Mk;
           if (WRITE_GRAD) {
-            const bool inside = (lp >= kClampLo) && (lp <= 0.0f), open = sm >= kPFloor;
+            const bool inside = (Pk >= kPFloor) && (Pk <= 1.0f), open = sm >= kPFloor;
             const float iv = inside ? rcp_fast(Pk) : 0.f;
             if (c & 1) inv[i][c >> 1].y = iv;
             else inv[i][c >> 1].x = iv;
@@ -274,15 +293,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
           if (want_arg) {  // strict ">" keeps the lowest class of a tie inside the thread (classes ascend with i, c)
             const bool better = Mk > post_best;
             post_best = better ? Mk : post_best;
-            post_idx = better ? 4u * (128u * i + tg) + c : post_idx;
+            post_idx = better ? 4u * (static_cast<uint32_t>(GT) * i + tg) + c : post_idx;
           }
         }
     }
     // The sweep scored x_t with the generic coefficients; its true term M_j joins at the end (first thread, with
     // [MASK]), so the thread that owns class x_t must offer its best class OTHER than x_t.  Nothing to do unless
     // x_t is that thread's best; then (fast rows) the runner-up among its softmax numerators, or (rows with clamps)
-    // a rescoring of its 32 classes.
-    if (want_arg && !masked && tg == static_cast<int>((j >> 2) & 127u) && post_idx == j) {
+    // a rescoring of its classes.
+    if (want_arg && !masked && tg == static_cast<int>((j >> 2) & static_cast<uint32_t>(GT - 1)) && post_idx == j) {
       if (fast) {
         float e2nd = -1.0f;
         uint32_t i2nd = 0;
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
         for (int i = 0; i < NC; ++i)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t k = 4u * (128u * i + tg) + c;
+            const uint32_t k = 4u * (static_cast<uint32_t>(GT) * i + tg) + c;
             const float ev = (c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x;
             const bool better = (ev > e2nd) && (k != j);
             e2nd = better ? ev : e2nd;
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
         for (int i = 0; i < NC; ++i)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t k = 4u * (128u * i + tg) + c;
+            const uint32_t k = 4u * (static_cast<uint32_t>(GT) * i + tg) + c;
             const float pk = fminf(fmaxf(((c & 1) ? e[i][c >> 1].y : e[i][c >> 1].x) * r, kPFloor), 1.0f);
             const float Mk = log_prob_clamped(fmaf(pk, cf.A, Bc));
             const bool better = (Mk > post_best) && (k != j);
@@ -315,30 +334,41 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     }
     // ---- exchange 2 ----
     {
+      float tot = 0.f;
       if (WRITE_GRAD) {
         // four warp sums in one butterfly: after the xor-16 step a lane carries two of the four values, after the xor-8
         // step one; lanes 0 / 8 / 16 / 24 end with the totals of sumM / sInv / sPP / sP (18 instructions instead of 40)
         const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
-        float k0 = (up16 ? sPP : sumM) + __shfl_xor_sync(0xffffffffu, up16 ? sumM : sPP, 16);
-        float k1 = (up16 ? sP : sInv) + __shfl_xor_sync(0xffffffffu, up16 ? sInv : sP, 16);
-        float tot = (up8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+        const float k0 = (up16 ? sPP : sumM) + __shfl_xor_sync(0xffffffffu, up16 ? sumM : sPP, 16);
+        const float k1 = (up16 ? sP : sInv) + __shfl_xor_sync(0xffffffffu, up16 ? sInv : sP, 16);
+        tot = (up8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
         tot += __shfl_xor_sync(0xffffffffu, tot, 4);
         tot += __shfl_xor_sync(0xffffffffu, tot, 2);
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-        if ((lane & 7) == 0) S.red[1][(lane >> 3) * kGroupWarps + warp] = tot;
       } else {
-        const float a0 = warp_sum(sumM);
-        if (lane == 0) S.red[1][warp] = a0;
+        tot = warp_sum(sumM);
       }
       if (want_arg) kpost = warp_argmax_key(post_best, post_idx);
-      if (lane == 0 && want_arg) S.keys[1][warp] = kpost;
-    }
-    sync();
-    {
-      const float4 a0 = lds4(S.red[1]), a1 = lds4(S.red[1] + kGroupWarps);
-      const float4 a2 = lds4(S.red[1] + 2 * kGroupWarps), a3 = lds4(S.red[1] + 3 * kGroupWarps);
-      sumM = (a0.x + a0.y) + (a0.z + a0.w), sInv = (a1.x + a1.y) + (a1.z + a1.w);
-      sPP = (a2.x + a2.y) + (a2.z + a2.w), sP = (a3.x + a3.y) + (a3.z + a3.w);
+      if (NW > 1) {
+        if (WRITE_GRAD) {
+          if ((lane & 7) == 0) S.red[1][(lane >> 3) * 4 + warp] = tot;
+        } else if (lane == 0) {
+          S.red[1][warp] = tot;
+        }
+        if (lane == 0 && want_arg) S.keys[1][warp] = kpost;
+        sync();
+        const float4 a0 = lds_warps<NW>(S.red[1], 0.f), a1 = lds_warps<NW>(S.red[1] + 4, 0.f);
+        const float4 a2 = lds_warps<NW>(S.red[1] + 8, 0.f), a3 = lds_warps<NW>(S.red[1] + 12, 0.f);
+        sumM = (a0.x + a0.y) + (a0.z + a0.w), sInv = (a1.x + a1.y) + (a1.z + a1.w);
+        sPP = (a2.x + a2.y) + (a2.z + a2.w), sP = (a3.x + a3.y) + (a3.z + a3.w);
+      } else {
+        if (WRITE_GRAD) {  // the four totals sit in lanes 0 / 8 / 16 / 24
+          sumM = __shfl_sync(0xffffffffu, tot, 0), sInv = __shfl_sync(0xffffffffu, tot, 8);
+          sPP = __shfl_sync(0xffffffffu, tot, 16), sP = __shfl_sync(0xffffffffu, tot, 24);
+        } else {
+          sumM = tot;
+        }
+      }
     }
     // remove what the generic formula contributed for the special classes (they are re-added with their own terms)
     auto generic_terms = [&](float sm_k, float pk, float& Pk, float& iv, float& pp, float& po) {
@@ -364,9 +394,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       if (p.tok_main != nullptr) p.tok_main[row] = t0 ? nll : wtok * kl;
       if (p.tok_aux != nullptr) p.tok_aux[row] = t0 ? nll : wtok * aux;
       if (want_arg && p.xtm1_recon != nullptr) {
-        unsigned long long kb = S.keys[1][0];
+        unsigned long long kb = kpost;
+        if (NW > 1) {
+          kb = S.keys[1][0];
 #pragma unroll
-        for (int w = 1; w < kGroupWarps; ++w) kb = S.keys[1][w] > kb ? S.keys[1][w] : kb;
+          for (int w = 1; w < NW; ++w) kb = S.keys[1][w] > kb ? S.keys[1][w] : kb;
+        }
         const unsigned long long kK = pack_key(M_K, K), kJ = masked ? 0ull : pack_key(M_j, j);
         kb = kK > kb ? kK : kb;
         kb = kJ > kb ? kJ : kb;
@@ -397,7 +430,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
     const uint32_t q_x0 = x0 >> 2, q_j = j_other ? (j >> 2) : 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      const uint32_t q = 128u * i + tg;
+      const uint32_t q = static_cast<uint32_t>(GT) * i + tg;
       float o[4];
       if (fast) {
         const float2 r2 = make_float2(r, r), gA2 = make_float2(gA, gA), wh2 = make_float2(WG - hsum, WG - hsum);
@@ -418,8 +451,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) train_stream_kernel(const T
       st_stream4(rg + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
     }
     // the two special classes: their owners overwrite the generic value (same thread, same address: program order)
-    if (tg == static_cast<int>(q_x0 & 127u)) rg[x0] = fmaf(-sm_x0, hsum, h_x0);
-    if (j_other && tg == static_cast<int>(q_j & 127u)) rg[j] = fmaf(-sm_j, hsum, h_j);
+    if (tg == static_cast<int>(q_x0 & static_cast<uint32_t>(GT - 1))) rg[x0] = fmaf(-sm_x0, hsum, h_x0);
+    if (j_other && tg == static_cast<int>(q_j & static_cast<uint32_t>(GT - 1))) rg[j] = fmaf(-sm_j, hsum, h_j);
   }
   if (status_bits != 0 && tg == 0 && p.status != nullptr) atomicOr(p.status, status_bits);
 }
@@ -448,11 +481,11 @@ int launch_train_stream_t(const TrainParams& p, cudaStream_t s) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
-  const size_t smem = sizeof(TrainGroupSmem<NP>) * kGroupsPerCta + kCoefSmemRows * 16 * sizeof(float);
+  const size_t smem = sizeof(TrainGroupSmem<NP>) * TrainShape<NP>::NG + kCoefSmemRows * 16 * sizeof(float);
   auto kern = train_stream_kernel<NP, WRITE_GRAD>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
-  kern<<<static_cast<unsigned>(sms), kStreamThreads, smem, s>>>(p);
+  kern<<<static_cast<unsigned>(sms), TrainShape<NP>::THREADS, smem, s>>>(p);
   return D3PM_OK;
 }
 
