@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
 
   if (tid == 0) {
     for (int i = 0; i < kBStages; ++i) mbar_init(&C.b_full[i], 1), mbar_init(&C.b_empty[i], 1);
-    for (int i = 0; i < kAccStages; ++i) mbar_init(&C.acc_full[i], 1), mbar_init(&C.acc_empty[i], DUMP ? kEpiWarps : kEpiWarps / 2);
+    for (int i = 0; i < kAccStages; ++i) mbar_init(&C.acc_full[i], 1), mbar_init(&C.acc_empty[i], kEpiWarps);
     mbar_init(&C.a_ready, kEpiThreads);
     mbar_init(&C.a_free, 1);
   }
@@ -329,15 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
     // =========================== A producer + epilogue (warps 1..16) ===========================
     const int et = tid - 32;            // 0..511
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int cs = (warp - 1) >> 2;     // 0..3: which of the four threads of a row this is
+    const int cs = (warp - 1) >> 2;     // which 32 of the 128 columns of a chunk
     const int erow = 32 * q + lane;     // row (TMEM lane) of this thread in the epilogue
-    const uint32_t t_row = tmem + (static_cast<uint32_t>(32 * q) << 16);
-    const uint32_t t_lane = t_row + kCols * cs;  // DUMP mode: the thread's quarter of every accumulator
-    // Sampling mode: the 16 epilogue warps form TWO SETS of eight that work on alternate accumulators (pass 1) / accumulator
-    // pairs (pass 2); a thread then owns HALF of the columns (64 = two blocks of 32) of the accumulators of its set.  With
-    // all 16 warps on the same accumulator every warp waited for its tensor-memory load (and for the tensor pipe) at the same
-    // time - 22 % of the stall samples - and nobody issued; now one set computes while the other waits.
-    const int eset = cs >> 1, ehalf = cs & 1;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(32 * q) << 16) + kCols * cs;
     const NoiseStream rng(p.seed, p.offset);
     const float thin_c = p.thin_factor > 0.f ? p.thin_factor : kThin;
     uint32_t status_bits = 0;
@@ -519,47 +513,41 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
 
       // ---------------- pass 1: softmax statistics of the row (log2 units) ----------------
       float m = -CUDART_INF_F, s = 0.f;
-      for (int it = eset; it < NCH; it += 2) {
+      for (int it = 0; it < NCH; ++it) {
         const int acc = it & 3;
         mbar_wait_sleep(&C.acc_full[acc], static_cast<uint32_t>((it >> 2) & 1));
         tc_fence_after();
-#pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-          const int cb = 2 * kCols * ehalf + kCols * blk;  // first of the 32 columns of this block
-          const int k0 = chunk_of(it) * kChunk + cb;
-          uint32_t v[32];
-          tmem_ld32(t_row + acc * kChunk + cb, v);
-          // the bias of these 32 classes while the TMEM load is in flight
-          float4 b[8];
+        const int k0 = chunk_of(it) * kChunk + kCols * cs;
+        uint32_t v[32];
+        tmem_ld32(t_lane + acc * kChunk, v);
+        // the bias of these 32 classes while the TMEM load is in flight
+        float4 b[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + i);
-          tmem_ld_wait();
-          if (blk == 1) {  // the thread's half of the accumulator is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
-          }
-          float2 y[16];
+        for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + i);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
+        float2 y[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            y[2 * i] = __fadd2_rn(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), make_float2(b[i].x, b[i].y));
-            y[2 * i + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), make_float2(b[i].z, b[i].w));
-          }
-          float cm = fmaxf(y[0].x, y[0].y);
-#pragma unroll
-          for (int i = 1; i < 16; ++i) cm = fmaxf(cm, fmaxf(y[i].x, y[i].y));
-          const float mn = fmaxf(m, cm);
-          s *= ex2(m - mn);
-          m = mn;
-          const float2 nm = make_float2(-m, -m);
-          float2 part[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 d = __fadd2_rn(y[i], nm);
-            part[i & 1] = __fadd2_rn(part[i & 1], make_float2(ex2(d.x), ex2(d.y)));
-          }
-          s += (part[0].x + part[0].y) + (part[1].x + part[1].y);
+        for (int i = 0; i < 8; ++i) {
+          y[2 * i] = __fadd2_rn(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), make_float2(b[i].x, b[i].y));
+          y[2 * i + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), make_float2(b[i].z, b[i].w));
         }
+        float cm = fmaxf(y[0].x, y[0].y);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) cm = fmaxf(cm, fmaxf(y[i].x, y[i].y));
+        const float mn = fmaxf(m, cm);
+        s *= ex2(m - mn);
+        m = mn;
+        const float2 nm = make_float2(-m, -m);
+        float2 part[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 d = __fadd2_rn(y[i], nm);
+          part[i & 1] = __fadd2_rn(part[i & 1], make_float2(ex2(d.x), ex2(d.y)));
+        }
+        s += (part[0].x + part[0].y) + (part[1].x + part[1].y);
       }
       C.stat_m[cs][erow] = m;
       C.stat_s[cs][erow] = s;
@@ -613,16 +601,16 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
       // The noise (integer pipe) is generated one group of eight classes AHEAD of the exponentials (MUFU pipe) that
       // consume it, in the same basic block, so that the two pipes overlap inside every warp.
       auto coarse_of = [&](int pr_, int c8_) {
-        const int kk = chunk_of(2 * pr_) * kChunk + 2 * kCols * ehalf;
+        const int kk = chunk_of(2 * pr_) * kChunk + kCols * cs;
         return rng.coarse(NoiseStream::coarse_call_of_chunk(static_cast<uint32_t>(kk >> 2) + c8_), grow);
       };
-      uint4 cw_next = coarse_of(eset, 0);
-      for (int pr = eset; pr < NCH / 2; pr += 2) {  // this set's accumulator pairs
+      uint4 cw_next = coarse_of(0, 0);
+      for (int pr = 0; pr < NCH / 2; ++pr) {
         const int itA = NCH + 2 * pr, itB = itA + 1;
         const int accA = itA & 3, accB = itB & 3;
         // classes k0 .. k0+31 from the first chunk of the pair and the same + 512 from the second (chunk_of(2 pr + 1) =
         // chunk_of(2 pr) + 4): one Philox call serves four classes of each
-        const int k0 = chunk_of(2 * pr) * kChunk + 2 * kCols * ehalf;  // the thread's 64 columns of both accumulators
+        const int k0 = chunk_of(2 * pr) * kChunk + kCols * cs;
         mbar_wait_sleep(&C.acc_full[accA], static_cast<uint32_t>((itA >> 2) & 1));
         mbar_wait_sleep(&C.acc_full[accB], static_cast<uint32_t>((itB >> 2) & 1));
         tc_fence_after();
@@ -630,12 +618,12 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
         // the logits instead of 64, which is what keeps this loop free of spills at 96 registers per thread
         uint32_t va[16], vb[16];
 #pragma unroll
-        for (int c8 = 0; c8 < 16; ++c8) {  // sixteen groups of four columns (of each accumulator)
+        for (int c8 = 0; c8 < 8; ++c8) {
           if ((c8 & 3) == 0) {
-            tmem_ld16(t_row + accA * kChunk + 2 * kCols * ehalf + 4 * c8, va);
-            tmem_ld16(t_row + accB * kChunk + 2 * kCols * ehalf + 4 * c8, vb);
+            tmem_ld16(t_lane + accA * kChunk + 4 * c8, va);
+            tmem_ld16(t_lane + accB * kChunk + 4 * c8, vb);
             tmem_ld_wait();
-            if (c8 == 12) {  // the last quarter is in registers: the tensor pipe may overwrite the two accumulators
+            if (c8 == 4) {  // both halves are in registers: the tensor pipe may overwrite the two accumulators
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&C.acc_empty[accA]), mbar_arrive(&C.acc_empty[accB]);
@@ -643,8 +631,8 @@ __global__ void __launch_bounds__(kThreads, 1) head_step_kernel(const HeadParams
           }
           const int c4 = c8 & 3;
           const uint4 cw = cw_next;
-          if (c8 < 15) cw_next = coarse_of(pr, c8 + 1);
-          else if (pr + 2 < NCH / 2) cw_next = coarse_of(pr + 2, 0);
+          if (c8 < 7) cw_next = coarse_of(pr, c8 + 1);
+          else if (pr + 1 < NCH / 2) cw_next = coarse_of(pr + 1, 0);
           const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0) + c8);
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + k0 + 512) + c8);
           float2 e[4], d[4];
