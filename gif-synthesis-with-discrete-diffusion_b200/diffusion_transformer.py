@@ -129,6 +129,9 @@ class FusedDiffusionTransformer(nn.Module):
         self.inject_exponential: Optional[Callable[[tuple, torch.device], torch.Tensor]] = None
         self._coef_cache = None
         self._status = None
+        # one denoiser pass serves both guidance branches when the two conditionings are bitwise equal (see _same_conditioning)
+        self.share_identical_conditioning = True
+        self._same_cond_cache = None
         # fold the denoiser's `to_logits` head into the update kernel (see enable_fused_head)
         self.fuse_head = False
         self._head_cache = None
@@ -297,6 +300,25 @@ class FusedDiffusionTransformer(nn.Module):
         u = self.inject_uniform((B, self.num_classes, N), self.device)
         return ops.to_rows(u.to(self.device, torch.float32))
 
+    def _same_conditioning(self, cond_emb, cf_cond_emb) -> bool:
+        """True when the conditional and the unconditional pass of this step are the SAME computation: the two embeddings
+        are bitwise equal and the denoiser is deterministic (eval mode).  The reference's shipped pipeline is exactly that
+        case - its caller zeroes both text embeddings (networks/discrete_diffusion.py:25, :49) - and it runs the denoiser
+        twice per step on identical inputs (diffusion_transformer.py:240-245).  The drop-in then runs it ONCE and hands the
+        same logits to the kernel as both tensors: bit-identical to two passes (y = lu + s (lc - lu) with lc == lu), half the
+        denoiser time, and the second read of every row comes from L2.  The comparison costs one host sync, so its result
+        is cached per pair of tensor versions: `sample()` passes the same two tensors at every step."""
+        if not self.share_identical_conditioning or cond_emb is None or cf_cond_emb is None or self.transformer.training:
+            return False
+        if cond_emb is cf_cond_emb:
+            return True
+        if cond_emb.shape != cf_cond_emb.shape or cond_emb.dtype != cf_cond_emb.dtype or cond_emb.device != cf_cond_emb.device:
+            return False
+        key = (cond_emb.data_ptr(), cond_emb._version, cf_cond_emb.data_ptr(), cf_cond_emb._version, tuple(cond_emb.shape))
+        if self._same_cond_cache is None or self._same_cond_cache[0] != key:
+            self._same_cond_cache = (key, bool(torch.equal(cond_emb, cf_cond_emb)))
+        return self._same_cond_cache[1]
+
     def _guidance_off(self) -> bool:
         # the reference's own |s-1|<1e-3 branch raises AttributeError (:242-243); "off" here means the
         # result of predict_start alone, which is what that branch was written to return
@@ -311,7 +333,9 @@ class FusedDiffusionTransformer(nn.Module):
                                  sample_from=sample_from, want_score=want_score, sharpen=sharpen)
         logits_c = self._denoise_rows(x_t, cond_emb, t)
         logits_u = None
-        if guidance and not self._guidance_off():
+        if guidance and not self._guidance_off() and self._same_conditioning(cond_emb, cf_cond_emb):
+            logits_u = logits_c  # the unconditional pass would recompute these very logits
+        elif guidance and not self._guidance_off():
             logits_u = self._denoise_rows(x_t, cf_cond_emb.type_as(cond_emb) if cond_emb is not None else cf_cond_emb, t)
             if logits_u.stride() != logits_c.stride():
                 logits_u = logits_u.contiguous()
@@ -445,7 +469,9 @@ class FusedDiffusionTransformer(nn.Module):
             hw = self._head_weights()
             hidden_c = self._hidden_rows(x_t, cond_emb, t)
             hidden_u = None
-            if not self._guidance_off():
+            if not self._guidance_off() and self._same_conditioning(cond_emb, cf_cond_emb):
+                hidden_u = hidden_c
+            elif not self._guidance_off():
                 hidden_u = self._hidden_rows(x_t, cf_cond_emb.type_as(cond_emb) if cond_emb is not None else cf_cond_emb, t)
             B, N = x_t.shape
             if self._head_scratch is None or self._head_scratch[0].numel() != B * N or self._head_scratch[0].device != x_t.device:

@@ -100,3 +100,49 @@ def test_free_running_sample_both_classes():
     c = ours.manual_seed(4).sample(["x"] * B, None, cond, cf, filter_ratio=0)["content_token"]
     for tok in (a, b, c):
         assert tok.shape == (B, N) and tok.dtype == torch.int64 and int(tok.max()) < K and int(tok.min()) >= 0
+
+
+def test_identical_conditioning_runs_the_denoiser_once_and_changes_nothing():
+    """The reference's pipeline zeroes both text embeddings (networks/discrete_diffusion.py:25, :49): its two denoiser passes
+    per step then compute the same logits.  The drop-in runs ONE pass in that case; tokens and posterior are those of the
+    reference's two-pass `p_sample` / `p_pred` on the same noise, and with the sharing switched off."""
+    B, N, K, T = 2, 256, 1024, 100
+    ref, ours = _models(B, N, K, T, 16)
+    calls = {"n": 0}
+    ours.transformer.register_forward_hook(lambda *a: calls.__setitem__("n", calls["n"] + 1))
+    cond, cf = torch.zeros(B, 1, 512, device=DEV), torch.zeros(B, 1, 512, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.where(torch.rand(B, N, device=DEV, generator=g) < 0.5, torch.full((B, N), K, device=DEV),
+                    torch.randint(0, K, (B, N), device=DEV, generator=g))
+    log_x = ref_index_to_log_onehot(x, K + 1)
+    t = torch.tensor([60, 7], device=DEV)
+    u = torch.rand(B, K + 1, N, device=DEV, generator=g)
+    with torch.no_grad():
+        post_ref, _ = ref.p_pred(log_x, cond, cf, t)
+        with RL.injected_uniform(lambda z: u):
+            nxt_ref, _ = ref.p_sample(log_x, cond, cf, t, [0] * B, ref.n_sample[60])
+    calls["n"] = 0
+    post, _ = ours.p_pred(log_x, cond, cf, t)
+    assert calls["n"] == 1                               # one denoiser pass for both guidance branches
+    ours.inject_uniform = lambda shape, dev: u
+    nxt, _ = ours.p_sample(log_x, cond, cf, t, [0] * B, ours.n_sample[60])
+    ours.inject_uniform = None
+    assert float((post - post_ref).abs().max()) <= H.POST_TOL
+    near = O.near_ties(post_ref.cpu(), u.cpu()).numpy()
+    diff = (nxt.argmax(1) != nxt_ref.argmax(1)).cpu().numpy()
+    assert not (diff & ~near).any()
+    # the same drop-in with the sharing off: two passes, the very same tokens (Philox noise, same key)
+    a = ours.manual_seed(3).p_sample_tokens(x, cond, cf, t)
+    ours.share_identical_conditioning = False
+    calls["n"] = 0
+    b = ours.manual_seed(3).p_sample_tokens(x, cond, cf, t)
+    assert calls["n"] == 2 and torch.equal(a, b)
+    # different embeddings, or a denoiser in training mode (dropout): never shared
+    ours.share_identical_conditioning = True
+    calls["n"] = 0
+    ours.p_sample_tokens(x, cond, cf + 1.0, t)
+    assert calls["n"] == 2
+
+
+def ref_index_to_log_onehot(x, C):
+    return RL.load_diffusion_module().index_to_log_onehot(x, C)
