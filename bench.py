@@ -405,6 +405,7 @@ def run_ours(args):
             configs["config4_strong"] = measure_config4_strong(dev, model, table, world, rank, barrier)
             if world == 1:
                 configs["config5"] = measure_config5(dev, model, table)
+                configs["k2048"] = measure_k2048(dev)
         except Exception as exc:  # reported in the JSON line, never swallowed
             configs["error"] = repr(exc)
     if rank == 0 and world == 1:
@@ -561,6 +562,45 @@ def measure_config5(dev, model, table, videos=64, steps=30):
     del lc, lu
     torch.cuda.empty_cache()
     return res
+
+
+def measure_k2048(dev, videos=32, steps=30):
+    """The codebook the reference's UCF job configures for the denoiser (dalle num_embed 2048, SURVEY §8 a): 32 videos x 4096
+    tokens x 2048 codes (the same 2.15 GB as config 2), guidance on, one fused step."""
+    import torch
+    import d3pm_b200
+    from d3pm_b200 import _lib, ops
+    N, K = N_TOKENS, 2048
+
+    class _Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.content_emb = type("E", (), {"num_embed": K + 1})()
+
+    model = d3pm_b200.FusedDiffusionTransformer(transformer=_Stub(), diffusion_step=T_STEPS, alpha_init_type="alpha1",
+                                                guidance_scale=GUIDANCE, content_seq_len=N).to(dev)
+    table = model.coef_table()
+    gen = torch.Generator(device=dev).manual_seed(6)
+    lc = torch.randn(videos, N, K, device=dev, generator=gen)
+    lu = torch.randn(videos, N, K, device=dev, generator=gen)
+    p_mask = float(model.log_cumprod_ct[T_NOW].exp())
+    x = torch.where(torch.rand(videos, N, device=dev, generator=gen) < p_mask, torch.full((videos, N), K, device=dev),
+                    torch.randint(0, K, (videos, N), device=dev, generator=gen))
+    t = torch.full((videos,), T_NOW, dtype=torch.int64, device=dev)
+    out = torch.empty_like(x)
+    time.sleep(1.0)
+    ms = _timed_steps(lambda i: ops.fused_step(lc, lu, x, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX, seed=9,
+                                               offset=i, x_prev_out=out), steps, dev)
+    peak = 6554.2
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+    gbps = videos * N * (2 * K * 4 + 16) / (ms * 1e-3) / 1e9
+    del lc, lu
+    torch.cuda.empty_cache()
+    return {"what": f"{videos} videos x {N} tokens x {K}+1 classes (the UCF job's denoiser codebook), guidance {GUIDANCE:g}, one fused step, "
+                    f"device-resident, one B200", "ms_per_step": ms, "value": videos * N / (ms * 1e-3), "unit": UNIT,
+            "GBps_algorithmic": gbps, "frac_of_measured_peak": gbps / peak}
 
 
 def measure_config3(dev, window=2):
