@@ -27,6 +27,7 @@ SAMPLE_NONE, SAMPLE_GUMBEL, SAMPLE_PHILOX, SAMPLE_PHILOX_EXACT = 0, 1, 2, 3
 STATUS_BAD_T, STATUS_BAD_TOKEN, STATUS_FALLBACK = 1, 2, 4
 KERNEL_AUTO, KERNEL_ROWS, KERNEL_STREAM = 0, 1, 2
 FROM_POSTERIOR, FROM_RECON = 0, 1
+LOGITS_F32, LOGITS_F16, LOGITS_BF16 = 0, 1, 2
 HEAD_STEP, HEAD_LOGITS, HEAD_REFERENCE = 0, 1, 2
 
 
@@ -45,7 +46,7 @@ class StepDesc(ctypes.Structure):
         ("guidance_scale", c_float), ("sample_mode", c_int32), ("gumbel_is_uniform", c_int32),
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64),
         ("thin_factor", c_float), ("kernel", c_int32), ("stream", c_void_p),
-        ("sample_from", c_int32), ("reserved", c_int32), ("score", c_void_p), ("sharpen", c_void_p),
+        ("sample_from", c_int32), ("logits_dtype", c_int32), ("score", c_void_p), ("sharpen", c_void_p),
         ("winner_post", c_void_p),
     ]
 

@@ -113,8 +113,11 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
     return fail(D3PM_ERR_UNSUPPORTED, "fused_step: K=%d must be a multiple of 4 and <= 8192", d->K);
   const int64_t rows = static_cast<int64_t>(d->B) * d->N;
   if (rows > kMaxGrid) return fail(D3PM_ERR_UNSUPPORTED, "fused_step: B*N=%lld exceeds the grid limit", (long long)rows);
-  if (d->pitch_logits < d->K || d->pitch_logits % 4 != 0)
-    return fail(D3PM_ERR_ALIGN, "fused_step: pitch_logits=%lld must be >= K and a multiple of 4", (long long)d->pitch_logits);
+  if (d->logits_dtype < D3PM_LOGITS_F32 || d->logits_dtype > D3PM_LOGITS_BF16)
+    return fail(D3PM_ERR_INVALID, "fused_step: unknown logits_dtype %d", d->logits_dtype);
+  const int pitch_mult = d->logits_dtype == D3PM_LOGITS_F32 ? 4 : 8;  // rows start on 16-byte boundaries
+  if (d->pitch_logits < d->K || d->pitch_logits % pitch_mult != 0)
+    return fail(D3PM_ERR_ALIGN, "fused_step: pitch_logits=%lld must be >= K and a multiple of %d", (long long)d->pitch_logits, pitch_mult);
   if (!aligned16(d->logits_c) || !aligned16(d->logits_u) || !aligned16(d->coef_table))
     return fail(D3PM_ERR_ALIGN, "fused_step: logits and coef_table must be 16-byte aligned");
   const int mode = d->sample_mode;
@@ -154,6 +157,7 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   p.rows = rows;
   p.sample_from = d->sample_from, p.score = d->score, p.sharpen = d->sharpen;
   p.winner_post = d->winner_post;
+  p.logits_dtype = d->logits_dtype;
   d3pm::expand_round_keys(p.seed, p.keys);
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
 
@@ -163,9 +167,13 @@ int d3pm_fused_step(const d3pm_step_desc* d) {
   if (d->winner_post != nullptr && !(can_stream && d->kernel != D3PM_KERNEL_ROWS))
     return fail(D3PM_ERR_UNSUPPORTED, "fused_step: winner_post is an output of the stream kernel (PHILOX sampling, K in {1024,2048,4096}); "
                                       "the rows kernel offers the whole posterior row (post) instead");
+  if (d->logits_dtype != D3PM_LOGITS_F32 && !(can_stream && d->kernel != D3PM_KERNEL_ROWS))
+    return fail(D3PM_ERR_UNSUPPORTED, "fused_step: 16-bit logits are read by the stream kernel only (PHILOX sampling of the posterior, no row "
+                                      "outputs, K in {1024,2048,4096}); cast to float for the other modes");
   if (d->kernel == D3PM_KERNEL_STREAM && !can_stream)
     return fail(D3PM_ERR_UNSUPPORTED, "fused_step: the stream kernel needs PHILOX sampling, no outputs and K in {1024,2048,4096}");
-  if (d->kernel == D3PM_KERNEL_STREAM || (d->kernel == D3PM_KERNEL_AUTO && can_stream && (rows >= d3pm::kStreamMinRows || d->winner_post != nullptr))) {
+  if (d->kernel == D3PM_KERNEL_STREAM || (d->kernel == D3PM_KERNEL_AUTO && can_stream &&
+                                            (rows >= d3pm::kStreamMinRows || d->winner_post != nullptr || d->logits_dtype != D3PM_LOGITS_F32))) {
     const int rc = d3pm::launch_step_stream(p, s);
     if (rc != D3PM_OK) return fail(rc, "fused_step: stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("fused_step(stream)");

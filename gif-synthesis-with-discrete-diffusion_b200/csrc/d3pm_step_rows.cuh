@@ -35,6 +35,7 @@ struct StepParams {
   float* score;          // [rows] out: max_k p(x0 = k | x_t)
   const float* sharpen;  // [rows] in: draw from softmax(f * recon)
   float* winner_post;    // [rows] out (stream kernel): log-posterior of the sampled class as the kernel computed it
+  int32_t logits_dtype;  // D3PM_LOGITS_*: storage type behind logits_c / logits_u (16-bit: stream kernel only)
   PhiloxRoundKeys keys;  // the round keys of `seed`, expanded on the host (stream kernel: constant-bank operands)
 };
 

@@ -28,6 +28,8 @@
 // HBM traffic is the algorithmic minimum: each logit is read once, 8 bytes of token go out per row.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "d3pm_step_rows.cuh"
@@ -131,6 +133,43 @@ struct StreamSync {
   }
 };
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Logit storage type of a stream-kernel instantiation.  LD = D3PM_LOGITS_F32: the stage holds fp32 rows.  F16 / BF16 (a
+// denoiser run under autocast): the row is copied as it lies in HBM (half the bytes), a chunk of four classes is 8 bytes of
+// the stage and is widened to fp32 in registers - exactly the values `logits.float()` would hold, without the 2 x 1 GB cast
+// pass a caller would otherwise pay at config 2.  Everything downstream of the load is the fp32 code.
+template <int LD>
+struct LogitType {
+  static constexpr uint32_t kBytes = LD == D3PM_LOGITS_F32 ? 4u : 2u;
+  static __device__ __forceinline__ float2 widen(uint32_t pair) {
+    if constexpr (LD == D3PM_LOGITS_BF16) {
+      return make_float2(__uint_as_float(pair << 16), __uint_as_float(pair & 0xffff0000u));
+    } else {
+      return __half22float2(*reinterpret_cast<const __half2*>(&pair));
+    }
+  }
+  // chunk q (classes 4q .. 4q+3) of a staged row: lo = classes (0, 1), hi = classes (2, 3)
+  static __device__ __forceinline__ void chunk(const float* stage, int q, float2& lo, float2& hi) {
+    if constexpr (LD == D3PM_LOGITS_F32) {
+      const float4 a = lds4(stage + 4 * q);
+      lo = make_float2(a.x, a.y), hi = make_float2(a.z, a.w);
+    } else {
+      const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(stage) + 8 * q);
+      lo = widen(raw.x), hi = widen(raw.y);
+    }
+  }
+  static __device__ __forceinline__ float one(const float* stage, uint32_t k) {
+    if constexpr (LD == D3PM_LOGITS_F32) {
+      return stage[k];
+    } else {
+      const uint32_t h = reinterpret_cast<const unsigned short*>(stage)[k];
+      if constexpr (LD == D3PM_LOGITS_BF16) return __uint_as_float(h << 16);
+      else return __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+    }
+  }
+  static __device__ __forceinline__ const void* row(const float* base, unsigned long long elements) {
+    return reinterpret_cast<const unsigned char*>(base) + elements * kBytes;
+  }
+};
 // the NW per-warp values of a reduction, read back in one shared-memory load (unused lanes of the float4 = neutral)
 template <int NW>
 __device__ __forceinline__ float4 lds_warps(const float* p, float neutral) {
@@ -308,14 +347,15 @@ __device__ __noinline__ void score_batch(GroupSmem<NP, CPT, HAS_U>& S, int nslot
 
 // RECON: the purity-prior variant (draw from p(x0 | x_t), write the purity score); its own instantiation so that the
 // plain step's code is not perturbed
-template <int NP, int CPT, bool HAS_U, bool RECON>
+template <int NP, int CPT, bool HAS_U, bool RECON, int LD = D3PM_LOGITS_F32>
 __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using Sh = StreamShape<NP, CPT, HAS_U>;
   using Smem = GroupSmem<NP, CPT, HAS_U>;
   constexpr int K = Sh::K, GT = Sh::GT, NW = Sh::NW, NG = Sh::NG, PS = Sh::PS, NCALL = Sh::NCALL;
   constexpr int NC = CPT;  // float4 chunks per thread per tensor
-  constexpr uint32_t kRowBytes = K * sizeof(float);
+  using LT = LogitType<LD>;
+  constexpr uint32_t kRowBytes = K * LT::kBytes;
   uint32_t tid;  // read once: a volatile read cannot be rematerialised as an S2R in every row
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   const int g = tid / GT;
@@ -336,8 +376,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     if (!exact_mode && first_row < rows) {
       const unsigned long long at = static_cast<unsigned long long>(static_cast<uint32_t>(first_row)) * pitch;
       mbar_expect_tx(&S.full, HAS_U ? 2 * kRowBytes : kRowBytes);
-      tma_load_row(S.c, p.logits_c + at, kRowBytes, &S.full);
-      if (HAS_U) tma_load_row(S.u, p.logits_u + at, kRowBytes, &S.full);
+      tma_load_row(S.c, LT::row(p.logits_c, at), kRowBytes, &S.full);
+      if (HAS_U) tma_load_row(S.u, LT::row(p.logits_u, at), kRowBytes, &S.full);
     }
   }
   // CTA-wide copy of the coefficient table (16 floats per timestep) when it fits: per-row lookups become LDS
@@ -356,8 +396,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
     const unsigned long long at = static_cast<unsigned long long>(static_cast<uint32_t>(row)) * pitch;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&S.full, HAS_U ? 2 * kRowBytes : kRowBytes);
-    tma_load_row(S.c, p.logits_c + at, kRowBytes, &S.full);
-    if (HAS_U) tma_load_row(S.u, p.logits_u + at, kRowBytes, &S.full);
+    tma_load_row(S.c, LT::row(p.logits_c, at), kRowBytes, &S.full);
+    if (HAS_U) tma_load_row(S.u, LT::row(p.logits_u, at), kRowBytes, &S.full);
   };
   // slot (register chunk index) of the low chunk of coarse call c: chunks q and q + 128 share a call, i.e. slots
   // i and i + PS of the same thread
@@ -389,19 +429,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) step_stream_kernel(const __
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int q = GT * i + tg;
-      const float4 a = lds4(S.c + 4 * q);
-      x[i][0] = make_float2(a.x, a.y), x[i][1] = make_float2(a.z, a.w);
-      if (HAS_U) {
-        const float4 b = lds4(S.u + 4 * q);
-        z[i][0] = make_float2(b.x, b.y), z[i][1] = make_float2(b.z, b.w);
-      }
+      LT::chunk(S.c, q, x[i][0], x[i][1]);
+      if (HAS_U) LT::chunk(S.u, q, z[i][0], z[i][1]);
     }
     auto e_of = [&](int i, int h) -> float2& {  // the softmax numerators of the row (relative to the thread-local max)
       if constexpr (HAS_U) return z[i][h];
       else return x[i][h];
     };
-    const float xj = masked ? 0.f : S.c[j];
-    const float zj = (HAS_U && !masked) ? S.u[j] : 0.f;
+    const float xj = masked ? 0.f : LT::one(S.c, j);
+    const float zj = (HAS_U && !masked) ? LT::one(S.u, j) : 0.f;
 
     // ---- largest |logit| of each tensor: thread-local, then one cheap group reduction ----
     float am[2] = {0.f, 0.f};
@@ -822,6 +858,7 @@ inline bool stream_kernel_supports(const StepParams& p) {
   if (p.sharpen != nullptr || (p.score != nullptr && p.sample_from != D3PM_FROM_RECON)) return false;
   if (p.K != 1024 && p.K != 2048 && p.K != 4096) return false;
   if (p.pitch_logits >= (1LL << 32)) return false;  // row offsets are formed as 32 x 32 -> 64 bit products
+  if (p.logits_dtype != D3PM_LOGITS_F32 && (p.sample_from == D3PM_FROM_RECON || p.pitch_logits % 8 != 0)) return false;
   return true;
 }
 
@@ -833,14 +870,14 @@ inline long long stream_kernel_max_rows() {
   return 8192LL * sms;
 }
 
-template <int NP, int CPT, bool HAS_U, bool RECON>
+template <int NP, int CPT, bool HAS_U, bool RECON, int LD>
 int launch_step_stream_r(const StepParams& p, cudaStream_t s) {
   using Sh = StreamShape<NP, CPT, HAS_U>;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return D3PM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return D3PM_ERR_CUDA;
   const size_t smem = sizeof(GroupSmem<NP, CPT, HAS_U>) * Sh::NG + kCoefSmemRows * 16 * sizeof(float);
-  auto kern = step_stream_kernel<NP, CPT, HAS_U, RECON>;
+  auto kern = step_stream_kernel<NP, CPT, HAS_U, RECON, LD>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return D3PM_ERR_CUDA;
   kern<<<static_cast<unsigned>(sms), kStreamThreads, smem, s>>>(p);
@@ -849,8 +886,13 @@ int launch_step_stream_r(const StepParams& p, cudaStream_t s) {
 
 template <int NP, int CPT, bool HAS_U>
 int launch_step_stream_t(const StepParams& p, cudaStream_t s) {
-  return p.sample_from == D3PM_FROM_RECON ? launch_step_stream_r<NP, CPT, HAS_U, true>(p, s)
-                                          : launch_step_stream_r<NP, CPT, HAS_U, false>(p, s);
+  // 16-bit logits: the plain step only (the purity-prior draw of an autocast caller goes through a cast)
+  if (p.logits_dtype == D3PM_LOGITS_F16)
+    return p.sample_from == D3PM_FROM_RECON ? D3PM_ERR_UNSUPPORTED : launch_step_stream_r<NP, CPT, HAS_U, false, D3PM_LOGITS_F16>(p, s);
+  if (p.logits_dtype == D3PM_LOGITS_BF16)
+    return p.sample_from == D3PM_FROM_RECON ? D3PM_ERR_UNSUPPORTED : launch_step_stream_r<NP, CPT, HAS_U, false, D3PM_LOGITS_BF16>(p, s);
+  return p.sample_from == D3PM_FROM_RECON ? launch_step_stream_r<NP, CPT, HAS_U, true, D3PM_LOGITS_F32>(p, s)
+                                          : launch_step_stream_r<NP, CPT, HAS_U, false, D3PM_LOGITS_F32>(p, s);
 }
 
 inline int launch_step_stream(const StepParams& p, cudaStream_t s) {

@@ -269,10 +269,12 @@ class FusedDiffusionTransformer(nn.Module):
         return out.float().contiguous()
 
     # ------------------------------------------------------------------ helpers
-    def _denoise_rows(self, x_t: torch.Tensor, cond_emb, t: torch.Tensor) -> torch.Tensor:
+    def _denoise_rows(self, x_t: torch.Tensor, cond_emb, t: torch.Tensor, keep_16bit: bool = False) -> torch.Tensor:
         """Run the denoiser (:222-230) and hand its logits over as token-major rows `[B, N, K]`.
         The reference transformer returns a `[B, K, N]` permuted view of `[B, N, K]`
-        (transformer_utils.py:442-443), so this is normally zero-copy."""
+        (transformer_utils.py:442-443), so this is normally zero-copy.  Under autocast the denoiser returns float16 /
+        bfloat16 logits; `keep_16bit` hands them on as they are (the production step reads them in place and widens in
+        registers: the same numbers as the `.float()` the reference's `out.double()` implies, :231, without the cast pass)."""
         if self.amp:
             with torch.autocast("cuda"):
                 out = self.transformer(x_t, cond_emb, t)
@@ -281,9 +283,10 @@ class FusedDiffusionTransformer(nn.Module):
         assert out.size(0) == x_t.size(0)
         assert out.size(1) == self.num_classes - 1
         assert out.size()[2:] == x_t.size()[1:]
-        out = out.float()
+        if not (keep_16bit and out.dtype in (torch.float16, torch.bfloat16)):
+            out = out.float()
         got = ops.rows_of(out)
-        if got is not None and got[1] % 4 == 0 and out.data_ptr() % 16 == 0:
+        if got is not None and got[1] % (16 // out.element_size()) == 0 and out.data_ptr() % 16 == 0:
             return got[0]
         return out.permute(0, 2, 1).contiguous()
 
@@ -331,12 +334,18 @@ class FusedDiffusionTransformer(nn.Module):
             return self._step_on(logits[0], logits[1], x_t, t, sample_mode=sample_mode, want_post=want_post,
                                  want_recon=want_recon, want_gap=want_gap, x_prev_out=x_prev_out, thin_factor=thin_factor,
                                  sample_from=sample_from, want_score=want_score, sharpen=sharpen)
-        logits_c = self._denoise_rows(x_t, cond_emb, t)
+        # 16-bit logits (autocast) stay 16-bit when the step is the plain production one: the stream kernel reads them in place
+        keep16 = (sample_mode in (_lib.SAMPLE_PHILOX, _lib.SAMPLE_PHILOX_EXACT) and self.inject_uniform is None
+                  and not (want_post or want_recon or want_gap or want_score) and sharpen is None
+                  and sample_from == _lib.FROM_POSTERIOR and (self.num_classes - 1) in ops.STREAM_CODEBOOKS)
+        logits_c = self._denoise_rows(x_t, cond_emb, t, keep16)
         logits_u = None
         if guidance and not self._guidance_off() and self._same_conditioning(cond_emb, cf_cond_emb):
             logits_u = logits_c  # the unconditional pass would recompute these very logits
         elif guidance and not self._guidance_off():
-            logits_u = self._denoise_rows(x_t, cf_cond_emb.type_as(cond_emb) if cond_emb is not None else cf_cond_emb, t)
+            logits_u = self._denoise_rows(x_t, cf_cond_emb.type_as(cond_emb) if cond_emb is not None else cf_cond_emb, t, keep16)
+            if logits_u.dtype != logits_c.dtype:
+                logits_c, logits_u = logits_c.float(), logits_u.float()
             if logits_u.stride() != logits_c.stride():
                 logits_u = logits_u.contiguous()
                 logits_c = logits_c.contiguous()

@@ -14,6 +14,8 @@ import torch
 from d3pm_b200 import _lib
 from d3pm_b200._lib import D3PMError
 
+LOGITS_DTYPES = {torch.float32: _lib.LOGITS_F32, torch.float16: _lib.LOGITS_F16, torch.bfloat16: _lib.LOGITS_BF16}
+STREAM_CODEBOOKS = (1024, 2048, 4096)  # codebook sizes the persistent stream kernel is instantiated for
 LOG_TINY = -69.07755278982137  # log(1e-30), the reference's one-hot "zero" (diffusion_transformer.py:50)
 
 
@@ -59,7 +61,7 @@ def as_logical(rows: torch.Tensor, num_classes: int) -> torch.Tensor:
 
 def rows_of(x: torch.Tensor) -> Optional[Tuple[torch.Tensor, int]]:
     """If logical `[B, C, N]` tensor `x` is a view of token-major rows, return `(rows [B,N,C], pitch)`."""
-    if x.dim() != 3 or x.dtype != torch.float32:
+    if x.dim() != 3 or x.dtype not in LOGITS_DTYPES:
         return None
     B, C, N = x.shape
     sb, sc, sn = x.stride()
@@ -120,14 +122,15 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
     factor f of softmax(f * log p(x0 | x_t)).
     """
     dev = _need_cuda(logits_c, logits_u, x_t, t, coef_table, gumbel, status)
-    if logits_c.dim() != 3 or logits_c.dtype != torch.float32 or logits_c.stride(2) != 1:
-        raise D3PMError("logits_c must be float32 [B, N, K] rows with the class index contiguous")
+    if logits_c.dim() != 3 or logits_c.dtype not in LOGITS_DTYPES or logits_c.stride(2) != 1:
+        raise D3PMError("logits_c must be float32 (or, for the production Philox step, float16 / bfloat16) [B, N, K] rows with the "
+                        "class index contiguous")
     B, N, K = logits_c.shape
     pitch = logits_c.stride(1) if N > 1 else K
     if B > 1 and logits_c.stride(0) != N * pitch:
         raise D3PMError("logits_c rows must be uniformly pitched across the batch")
     if logits_u is not None and (logits_u.shape != logits_c.shape or logits_u.stride() != logits_c.stride()
-                                 or logits_u.dtype != torch.float32):
+                                 or logits_u.dtype != logits_c.dtype):
         raise D3PMError("logits_u must match logits_c in shape, strides and dtype")
     if x_t.shape != (B, N) or x_t.dtype != torch.int64 or not x_t.is_contiguous():
         raise D3PMError("x_t must be a contiguous int64 [B, N] tensor")
@@ -174,6 +177,7 @@ def fused_step(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], x_t: to
             raise D3PMError("sharpen must be a contiguous float32 [B, N] tensor on the logits' device")
         d.sharpen = _ptr(sharpen)
     d.sample_from = int(sample_from)
+    d.logits_dtype = LOGITS_DTYPES[logits_c.dtype]
     d.status = _ptr(status)
     d.B, d.N, d.K, d.T = B, N, K, T
     d.pitch_logits, d.pitch_out = pitch, pitch_out

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define D3PM_VERSION 200 /* major*10000 + minor*100 + patch; 0.2.0: host-buffer handle, d3pm_head_desc.stat_slack */
+#define D3PM_VERSION 300 /* major*10000 + minor*100 + patch; 0.3.0: 16-bit logits (d3pm_step_desc.logits_dtype), video decoder */
 
 #define D3PM_OK 0
 #define D3PM_ERR_INVALID (-1)     /* null pointer, non-positive size, t/K/T inconsistent */
@@ -73,9 +73,13 @@ int d3pm_build_coef_table(const float* sched, int T, int K, float* table, d3pm_s
 #define D3PM_KERNEL_ROWS 1   /* one CTA per token row, every shape and mode */
 #define D3PM_KERNEL_STREAM 2 /* persistent TMA-pipelined kernel: PHILOX / PHILOX_EXACT, no outputs, K in {1024,2048,4096} */
 
+#define D3PM_LOGITS_F32 0  /* logits_c / logits_u point at float rows */
+#define D3PM_LOGITS_F16 1  /* ... at IEEE half rows (a denoiser run under torch.autocast, transformer_utils.py via :228-230) */
+#define D3PM_LOGITS_BF16 2 /* ... at bfloat16 rows */
+
 typedef struct d3pm_step_desc {
   /* inputs */
-  const float* logits_c;   /* [B*N][pitch_logits] conditional denoiser logits (first K valid) */
+  const float* logits_c;   /* [B*N][pitch_logits] conditional denoiser logits (first K valid); element type = logits_dtype */
   const float* logits_u;   /* same shape, unconditional; NULL = guidance off (predict_start only) */
   const int64_t* x_t;      /* [B*N] current tokens in [0, K]; K = [MASK] */
   const int64_t* t;        /* [B] timestep per video, in [0, T) */
@@ -89,7 +93,7 @@ typedef struct d3pm_step_desc {
   uint32_t* status;    /* one word, OR of D3PM_STATUS_* */
   /* sizes */
   int32_t B, N, K, T;
-  int64_t pitch_logits, pitch_gumbel, pitch_out; /* in floats */
+  int64_t pitch_logits, pitch_gumbel, pitch_out; /* in elements (pitch_logits: of logits_dtype) */
   /* parameters */
   float guidance_scale;
   int32_t sample_mode;   /* D3PM_SAMPLE_* */
@@ -103,7 +107,11 @@ typedef struct d3pm_step_desc {
   /* purity-prior sampling (p_sample with prior_rule 1 / 2, :309-346); all optional.  D3PM_FROM_RECON + score with PHILOX
    * sampling runs on the stream kernel (its RECON instantiation); `sharpen` and the other modes on the rows kernel */
   int32_t sample_from;   /* D3PM_FROM_POSTERIOR (default) or D3PM_FROM_RECON: draw x from p(x0 | x_t) (:327-329) */
-  int32_t reserved;
+  int32_t logits_dtype;  /* D3PM_LOGITS_*.  16-bit rows are read as they lie in HBM and widened in registers - bit-identical to
+                            running the fp32 path on logits.float() (the reference up-casts too: log_softmax(out.double()), :231) at
+                            half the traffic.  Stream kernel only (PHILOX / PHILOX_EXACT sampling, no row outputs, D3PM_FROM_POSTERIOR,
+                            K in {1024,2048,4096}, pitch_logits % 8 == 0); other requests return D3PM_ERR_UNSUPPORTED and the caller
+                            casts */
   float* score;          /* [B*N] out: max_k p(x0 = k | x_t), the purity of :318 before its per-video normalisation */
   const float* sharpen;  /* [B*N] in: f = 1 + score * prior_weight; the draw is from softmax(f * log p(x0 | x_t)) (:323-325);
                             D3PM_FROM_RECON with GUMBEL / PHILOX_EXACT sampling only */

@@ -174,3 +174,35 @@ def test_host_head_step_equals_the_device_resident_head_step():
     host.close()
     with pytest.raises(ops.D3PMError):
         ops.HostStep(B, N, K, table, guidance=True)(hc, hu, x_t, t, guidance_scale=2.0, seed=1, offset=1)  # wrong width
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_16bit_denoiser_logits_are_stepped_in_place(dtype):
+    """A denoiser that returns half-precision logits (autocast): `p_sample_tokens` hands them to the stream kernel as they
+    are (no `.float()` pass) and draws the tokens of the fp32 path on the up-cast logits; the methods that produce rows
+    (`p_pred`) still work through the cast."""
+    K, B, N, Tn = 4096, 2, 1024, 100
+    g = torch.Generator(device=DEV).manual_seed(3)
+    lc, lu = torch.randn(B, N, K, device=DEV, generator=g).to(dtype), torch.randn(B, N, K, device=DEV, generator=g).to(dtype)
+    cond, cf = torch.ones(B, 1, 512, device=DEV), torch.zeros(B, 1, 512, device=DEV)
+
+    def model(a, b):
+        return d3pm_b200.FusedDiffusionTransformer(transformer=StubDenoiser(K, a, b), diffusion_step=Tn, alpha_init_type="alpha1",
+                                                   guidance_scale=2.0, content_seq_len=N).to(DEV)
+
+    m16, m32 = model(lc, lu), model(lc.float(), lu.float())
+    x_t = torch.randint(0, K + 1, (B, N), device=DEV, generator=g)
+    t = torch.full((B,), 40, dtype=torch.long, device=DEV)
+    seen = []
+    real = ops.fused_step
+    try:
+        ops.fused_step = lambda *a, **k: (seen.append(a[0].dtype), real(*a, **k))[1]
+        a = m16.manual_seed(9).p_sample_tokens(x_t, cond, cf, t)
+    finally:
+        ops.fused_step = real
+    b = m32.manual_seed(9).p_sample_tokens(x_t, cond, cf, t)
+    assert seen == [dtype] and torch.equal(a, b)
+    log_x = ops.as_logical(ops.tokens_to_log_onehot_rows(x_t, K + 1), K + 1)
+    pa, pb = m16.p_pred(log_x, cond, cf, t), m32.p_pred(log_x, cond, cf, t)
+    assert torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
+    m16.check_status()

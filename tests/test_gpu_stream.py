@@ -319,3 +319,53 @@ def test_steps_can_be_captured_in_a_cuda_graph():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, eager)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,N,K,tval,s,scale", [
+    (2, 1024, 4096, 50, 2.0, 1.0),
+    (3, 700, 4096, [0, 42, 99], 3.0, 4.0),
+    (2, 900, 4096, 30, 2.0, 12.0),            # general (clamping) path
+    (2, 1100, 4096, 40, None, 1.0),           # guidance off: 64 classes per thread
+    (2, 1300, 2048, 60, 2.0, 1.0),
+    (2, 1500, 2048, 25, None, 1.0),
+    (1, 2100, 1024, 33, 2.0, 1.0),
+    (1, 37, 4096, 50, 2.0, 1.0),
+])
+def test_stream_kernel_16bit_logits(dtype, B, N, K, tval, s, scale):
+    """A denoiser under autocast hands over float16 / bfloat16 logits.  The stream kernel reads them in place (half the
+    HBM traffic) and widens in registers, so its tokens AND its posterior must be bit-identical to the fp32 kernel run on
+    `logits.float()` - which is what the reference computes (`log_softmax(out.double())`, diffusion_transformer.py:231)."""
+    sched = O.make_schedule(T, K)
+    g = torch.Generator(device=DEV).manual_seed(B * 77 + N)
+    lc16 = (torch.randn(B, N, K, device=DEV, generator=g) * scale).to(dtype)
+    lu16 = None if s is None else (torch.randn(B, N, K, device=DEV, generator=g) * scale).to(dtype)
+    lc32, lu32 = lc16.float(), None if lu16 is None else lu16.float()
+    t = (torch.tensor(tval) if isinstance(tval, list) else torch.full((B,), tval)).long().to(DEV)
+    p_mask = sched["log_cumprod_ct"][t.cpu()].exp().view(B, 1).to(DEV)
+    x_t = torch.where(torch.rand(B, N, device=DEV, generator=g) < p_mask, torch.full((B, N), K, device=DEV),
+                      torch.randint(0, K, (B, N), device=DEV, generator=g))
+    kw = dict(guidance_scale=0.0 if s is None else s, seed=7, offset=11, row_offset=555)
+    for mode, tf in ((_lib.SAMPLE_PHILOX, 0.0), (_lib.SAMPLE_PHILOX, 1.0), (_lib.SAMPLE_PHILOX, 1e-3), (_lib.SAMPLE_PHILOX_EXACT, 0.0)):
+        a = ops.fused_step(lc16, lu16, x_t, t, _table(K), sample_mode=mode, thin_factor=tf, want_winner_post=True, **kw)
+        b = ops.fused_step(lc32, lu32, x_t, t, _table(K), sample_mode=mode, thin_factor=tf, want_winner_post=True,
+                           kernel=_lib.KERNEL_STREAM, **kw)
+        assert torch.equal(a["x_prev"], b["x_prev"]), (mode, tf)
+        assert torch.equal(a["winner_post"], b["winner_post"]), (mode, tf)
+    # without the verification output (the production call), AUTO picks the stream kernel for 16-bit rows of any count
+    plain = ops.fused_step(lc16, lu16, x_t, t, _table(K), sample_mode=_lib.SAMPLE_PHILOX, **kw)["x_prev"]
+    assert torch.equal(plain, b["x_prev"])
+    # the oracle on the up-cast logits, a sample of rows
+    rows = torch.arange(0, N, max(1, N // 16))
+    u = ops.philox_uniform(B, N, K, seed=7, offset=11, row_offset=555, device=DEV)[:, rows, :K + 1].cpu().permute(0, 2, 1)
+    out_o, post_o, _ = O.p_sample_step(sched, lc32[:, rows].cpu().permute(0, 2, 1),
+                                       None if lu32 is None else lu32[:, rows].cpu().permute(0, 2, 1),
+                                       O.index_to_log_onehot(x_t[:, rows].cpu(), K + 1), t.cpu(), kw["guidance_scale"], u)
+    H.assert_tokens_match(plain[:, rows].cpu().numpy(), out_o.argmax(1).numpy(), O.near_ties(post_o, u).numpy(), f"{dtype} stream vs oracle")
+    want = post_o.gather(1, plain[:, rows].cpu().unsqueeze(1)).squeeze(1)
+    assert (a["winner_post"][:, rows].cpu() - want).abs().max().item() <= H.POST_TOL
+    # what the 16-bit path does not cover is refused, never silently converted
+    with pytest.raises(Exception):
+        ops.fused_step(lc16, lu16, x_t, t, _table(K), sample_mode=_lib.SAMPLE_NONE, want_post=True, **kw)
+    with pytest.raises(Exception):
+        ops.fused_step(lc16, lu16, x_t, t, _table(K), sample_mode=_lib.SAMPLE_PHILOX, kernel=_lib.KERNEL_ROWS, **kw)

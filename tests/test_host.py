@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     nm = subprocess.run(["nm", "-D", "--defined-only", d3pm_b200.library_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (d3pm_[a-z0-9_]+)", nm))
     assert exported == set(declared)
-    assert lib.d3pm_version() == 200
+    assert lib.d3pm_version() == 300
 
 
 def test_argument_validation_happens_before_any_launch():
