@@ -406,6 +406,7 @@ def run_ours(args):
             if world == 1:
                 configs["config5"] = measure_config5(dev, model, table)
                 configs["k2048"] = measure_k2048(dev)
+                configs["logits_16bit"] = measure_16bit(dev, model, table)
         except Exception as exc:  # reported in the JSON line, never swallowed
             configs["error"] = repr(exc)
     if rank == 0 and world == 1:
@@ -601,6 +602,41 @@ def measure_k2048(dev, videos=32, steps=30):
     return {"what": f"{videos} videos x {N} tokens x {K}+1 classes (the UCF job's denoiser codebook), guidance {GUIDANCE:g}, one fused step, "
                     f"device-resident, one B200", "ms_per_step": ms, "value": videos * N / (ms * 1e-3), "unit": UNIT,
             "GBps_algorithmic": gbps, "frac_of_measured_peak": gbps / peak}
+
+
+def measure_16bit(dev, model, table, videos=VIDEOS_PER_GPU, steps=30):
+    """Config 2 with the logits a denoiser under torch.autocast produces (float16 / bfloat16): the stream kernel reads them in
+    place (half the bytes), next to what such a caller paid before - `.float()` of both tensors, then the fp32 step."""
+    import torch
+    from d3pm_b200 import _lib, ops
+    N, K = N_TOKENS, K_CODES
+    gen = torch.Generator(device=dev).manual_seed(8)
+    p_mask = float(model.log_cumprod_ct[T_NOW].exp())
+    x = torch.where(torch.rand(videos, N, device=dev, generator=gen) < p_mask, torch.full((videos, N), K, device=dev),
+                    torch.randint(0, K, (videos, N), device=dev, generator=gen))
+    t = torch.full((videos,), T_NOW, dtype=torch.int64, device=dev)
+    out = torch.empty_like(x)
+    peak = 6554.2
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+    res = {"what": f"config 2 shape ({videos} videos x {N} tokens x {K}+1 classes, guidance {GUIDANCE:g}) with 16-bit logits: read in "
+                   f"place by step_stream_kernel<4, 8, true, false, F16|BF16> (2*K*2 + 16 = {2 * K * 2 + 16} B per token update), vs. "
+                   f"casting both tensors to fp32 first; tokens identical (tests/test_gpu_stream.py)"}
+    for name, dt in (("float16", torch.float16), ("bfloat16", torch.bfloat16)):
+        lc = torch.randn(videos, N, K, device=dev, generator=gen).to(dt)
+        lu = torch.randn(videos, N, K, device=dev, generator=gen).to(dt)
+        time.sleep(1.0)
+        ms = _timed_steps(lambda i: ops.fused_step(lc, lu, x, t, table, guidance_scale=GUIDANCE, sample_mode=_lib.SAMPLE_PHILOX, seed=9,
+                                                   offset=i, x_prev_out=out), steps, dev)
+        ms_cast = _timed_steps(lambda i: ops.fused_step(lc.float(), lu.float(), x, t, table, guidance_scale=GUIDANCE,
+                                                        sample_mode=_lib.SAMPLE_PHILOX, seed=9, offset=i, x_prev_out=out), 10, dev)
+        gbps = videos * N * (2 * K * 2 + 16) / (ms * 1e-3) / 1e9
+        res[name] = {"ms_per_step": ms, "value": videos * N / (ms * 1e-3), "unit": UNIT, "GBps_algorithmic": gbps,
+                     "frac_of_measured_peak": gbps / peak, "ms_per_step_cast_then_fp32_step": ms_cast}
+        del lc, lu
+    torch.cuda.empty_cache()
+    return res
 
 
 def measure_config3(dev, window=2):
