@@ -126,7 +126,7 @@ def load_vqvae_module():
         raise FileNotFoundError("reference not found")
     sys.dont_write_bytecode = True
     if root not in sys.path:
-        sys.path.insert(0, root)
+        sys.path.append(root)  # at the END: the reference tree has its own `tests/` and `tools/` packages, which must not shadow ours
     return _load(FILES[3], "_d3pm_reference_videogpt_vq_vae")
 
 

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int8, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libd3pm_b200.so"
@@ -18,6 +18,8 @@ EXPORTED_SYMBOLS = (
     "d3pm_to_token_major", "d3pm_q_pred", "d3pm_q_sample_tokens", "d3pm_train_rows", "d3pm_purity_select",
     "d3pm_head_image_floats", "d3pm_head_prepare", "d3pm_head_step", "d3pm_scale_rows",
     "d3pm_decode_lut", "d3pm_tokens_to_features",
+    "d3pm_dec_image_floats", "d3pm_dec_weight_image", "d3pm_dec_conv", "d3pm_dec_embed_rows", "d3pm_dec_axial_attention",
+    "d3pm_dec_col2im",
     "d3pm_host_step_create", "d3pm_host_step_destroy", "d3pm_host_step_h2d_bytes", "d3pm_host_step_d2h_bytes",
     "d3pm_host_step_run", "d3pm_host_head_step_run",
 )
@@ -74,6 +76,23 @@ class HeadDesc(ctypes.Structure):
         ("B", c_int32), ("N", c_int32), ("K", c_int32), ("T", c_int32), ("D", c_int32), ("mode", c_int32),
         ("ln_eps", c_float), ("guidance_scale", c_float), ("thin_factor", c_float), ("stat_slack", c_float),
         ("seed", c_uint64), ("offset", c_uint64), ("row_offset", c_int64), ("stream", c_void_p),
+    ]
+
+
+DEC_MAX_TAPS, DEC_MAX_CLASSES = 32, 8
+
+
+class DecConvDesc(ctypes.Structure):
+    """Mirror of `d3pm_dec_conv_desc`."""
+    _fields_ = [
+        ("x", c_void_p), ("in_scale", c_void_p), ("in_shift", c_void_p), ("w_image", c_void_p), ("bias", c_void_p),
+        ("residual", c_void_p), ("out", c_void_p),
+        ("B", c_int32), ("T", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32),
+        ("ntaps", c_int32), ("nclass", c_int32), ("Nout", c_int32), ("ldo", c_int32),
+        ("stride_t", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
+        ("relu_out", c_int32), ("terms", c_int32), ("n_tile", c_int32),
+        ("tap", c_int8 * 4 * DEC_MAX_TAPS * DEC_MAX_CLASSES), ("cls", c_int8 * 4 * DEC_MAX_CLASSES),
+        ("stream", c_void_p),
     ]
 
 
@@ -161,6 +180,19 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_host_head_step_run.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                             c_void_p, c_void_p, c_void_p, c_float, c_float, c_uint64, c_uint64, c_int64,
                                             c_void_p, POINTER(c_uint32)]
+    lib.d3pm_dec_image_floats.restype = c_int64
+    lib.d3pm_dec_image_floats.argtypes = [c_int, c_int, c_int, c_int]
+    lib.d3pm_dec_weight_image.restype = c_int
+    lib.d3pm_dec_weight_image.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.d3pm_dec_conv.restype = c_int
+    lib.d3pm_dec_conv.argtypes = [POINTER(DecConvDesc)]
+    lib.d3pm_dec_embed_rows.restype = c_int
+    lib.d3pm_dec_embed_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
+    lib.d3pm_dec_axial_attention.restype = c_int
+    lib.d3pm_dec_axial_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.d3pm_dec_col2im.restype = c_int
+    lib.d3pm_dec_col2im.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]
     lib.d3pm_to_token_major.restype = c_int
     lib.d3pm_to_token_major.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     _lib = lib

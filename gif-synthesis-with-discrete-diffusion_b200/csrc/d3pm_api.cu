@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include "d3pm_host.h"
 #include "d3pm_ops.cuh"
 #include "d3pm_step_rows.cuh"
 #include "d3pm_step_stream.cuh"
@@ -13,8 +14,11 @@
 #include "d3pm_head_step.cuh"
 
 namespace {
-
 thread_local char g_err[512] = "";
+}  // namespace
+
+namespace d3pm {
+namespace host {
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -30,38 +34,18 @@ int check_launch(const char* what) {
   return D3PM_OK;
 }
 
+}  // namespace host
+}  // namespace d3pm
+
+namespace {
+
+using d3pm::host::check_launch;
+using d3pm::host::DeviceGuard;
+using d3pm::host::fail;
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int64_t kMaxGrid = 2147483647LL;
-
-// The kernels launch on the CUDA *current* device; the caller's tensors (and stream) may live on another one
-// (model on cuda:1 while cuda:0 is current).  Every entry point therefore makes the device that owns its first
-// device pointer current for the duration of the call and restores the previous one on return.
-class DeviceGuard {
- public:
-  explicit DeviceGuard(const void* device_ptr) {
-    if (cudaGetDevice(&prev_) != cudaSuccess) {
-      cudaGetLastError();
-      return;
-    }
-    cudaPointerAttributes attr;
-    if (device_ptr == nullptr || cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess) {
-      cudaGetLastError();  // not a CUDA allocation: the launch itself will report it
-      return;
-    }
-    if ((attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.device != prev_)
-      switched_ = cudaSetDevice(attr.device) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    if (switched_) cudaSetDevice(prev_);
-  }
-  DeviceGuard(const DeviceGuard&) = delete;
-  DeviceGuard& operator=(const DeviceGuard&) = delete;
-
- private:
-  int prev_ = 0;
-  bool switched_ = false;
-};
 
 template <int V, bool HAS_U>
 void launch_rows(const d3pm::StepParams& p, cudaStream_t s) {

@@ -1,0 +1,136 @@
+// C ABI of the VQ-VAE decoder kernels (include/d3pm_b200.h, "token -> video, second stage").
+#include "d3pm_decoder.cuh"
+#include "d3pm_host.h"
+
+namespace {
+using d3pm::host::fail;
+using d3pm::host::check_launch;
+using d3pm::host::DeviceGuard;
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+}  // namespace
+
+extern "C" {
+
+int64_t d3pm_dec_image_floats(int nclass, int N, int Ktot, int n_tile) {
+  if (nclass <= 0 || N <= 0 || Ktot <= 0 || Ktot % 32 != 0 || (n_tile != 128 && n_tile != 256)) return 0;
+  const int Npad = (N + n_tile - 1) / n_tile * n_tile;
+  return static_cast<int64_t>(nclass) * d3pm::dec::image_floats(Npad, Ktot);
+}
+
+int d3pm_dec_weight_image(const float* w, int nclass, int N, int Ktot, int n_tile, float* image, d3pm_stream_t stream) {
+  if (w == nullptr || image == nullptr) return fail(D3PM_ERR_INVALID, "dec_weight_image: null pointer");
+  if (nclass <= 0 || nclass > D3PM_DEC_MAX_CLASSES || N <= 0 || Ktot <= 0 || Ktot % 32 != 0 || (n_tile != 128 && n_tile != 256))
+    return fail(D3PM_ERR_INVALID, "dec_weight_image: nclass=%d N=%d Ktot=%d n_tile=%d (Ktot %% 32 == 0, n_tile in {128, 256})", nclass, N, Ktot, n_tile);
+  if (!aligned16(w) || !aligned16(image)) return fail(D3PM_ERR_ALIGN, "dec_weight_image: w and image must be 16-byte aligned");
+  const DeviceGuard on_device(image);
+  const int Npad = (N + n_tile - 1) / n_tile * n_tile;
+  const int64_t pieces = static_cast<int64_t>(Npad) * (Ktot / 32) * 8;
+  const dim3 grid(static_cast<unsigned>((pieces + 255) / 256), static_cast<unsigned>(nclass));
+  d3pm::dec::weight_image_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, N, Npad, Ktot, n_tile, image);
+  return check_launch("dec_weight_image");
+}
+
+int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
+  namespace D = d3pm::dec;
+  if (d == nullptr) return fail(D3PM_ERR_INVALID, "dec_conv: null descriptor");
+  if (d->x == nullptr || d->w_image == nullptr || d->out == nullptr) return fail(D3PM_ERR_INVALID, "dec_conv: x, w_image and out are required");
+  if ((d->in_scale == nullptr) != (d->in_shift == nullptr)) return fail(D3PM_ERR_INVALID, "dec_conv: in_scale and in_shift come together");
+  if (d->B <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cin % 32 != 0 || d->Cin > D::kMaxCin)
+    return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: B=%d T=%d H=%d W=%d must be positive, Cin=%d a multiple of 32 and <= %d", d->B, d->T, d->H, d->W,
+                d->Cin, D::kMaxCin);
+  if (d->ntaps <= 0 || d->ntaps > D3PM_DEC_MAX_TAPS || d->nclass <= 0 || d->nclass > D3PM_DEC_MAX_CLASSES)
+    return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: ntaps=%d (<= %d), nclass=%d (<= %d)", d->ntaps, D3PM_DEC_MAX_TAPS, d->nclass, D3PM_DEC_MAX_CLASSES);
+  if (d->Nout <= 0 || d->Nout % 4 != 0 || d->ldo < d->Nout || d->ldo % 4 != 0)
+    return fail(D3PM_ERR_ALIGN, "dec_conv: Nout=%d and ldo=%d must be multiples of 4, ldo >= Nout", d->Nout, d->ldo);
+  if (d->n_tile != 128 && d->n_tile != 256) return fail(D3PM_ERR_INVALID, "dec_conv: n_tile=%d must be 128 or 256", d->n_tile);
+  if (d->terms != 1 && d->terms != 3) return fail(D3PM_ERR_INVALID, "dec_conv: terms=%d must be 1 (TF32) or 3 (3xTF32)", d->terms);
+  if (d->stride_t < 1 || d->stride_h < 1 || d->stride_w < 1) return fail(D3PM_ERR_INVALID, "dec_conv: strides must be >= 1");
+  for (int c = 0; c < d->nclass; ++c)
+    if (d->cls[c][0] < 0 || d->cls[c][0] >= d->stride_t || d->cls[c][1] < 0 || d->cls[c][1] >= d->stride_h || d->cls[c][2] < 0 ||
+        d->cls[c][2] >= d->stride_w)
+      return fail(D3PM_ERR_INVALID, "dec_conv: class %d offset outside its stride", c);
+  if (!aligned16(d->x) || !aligned16(d->w_image) || !aligned16(d->out) || !aligned16(d->bias) || !aligned16(d->residual) ||
+      !aligned16(d->in_scale) || !aligned16(d->in_shift))
+    return fail(D3PM_ERR_ALIGN, "dec_conv: every pointer must be 16-byte aligned");
+  const DeviceGuard on_device(d->out);
+  D::GemmParams p;
+  p.x = d->x, p.in_scale = d->in_scale, p.in_shift = d->in_shift, p.w_image = d->w_image, p.bias = d->bias;
+  p.residual = d->residual, p.out = d->out;
+  p.B = d->B, p.T = d->T, p.H = d->H, p.W = d->W, p.Cin = d->Cin, p.ntaps = d->ntaps, p.nclass = d->nclass;
+  p.Nout = d->Nout, p.Npad = (d->Nout + d->n_tile - 1) / d->n_tile * d->n_tile, p.ldo = d->ldo;
+  p.st = d->stride_t, p.sh = d->stride_h, p.sw = d->stride_w;
+  p.To = d->T * p.st, p.Ho = d->H * p.sh, p.Wo = d->W * p.sw;
+  p.relu_out = d->relu_out, p.terms = d->terms;
+  for (int c = 0; c < D3PM_DEC_MAX_CLASSES; ++c) {
+    for (int t = 0; t < D3PM_DEC_MAX_TAPS; ++t)
+      for (int e = 0; e < 4; ++e) p.tap[c][t][e] = d->tap[c][t][e];
+    for (int e = 0; e < 4; ++e) p.cls[c][e] = d->cls[c][e];
+  }
+  const long long M = static_cast<long long>(d->B) * d->T * d->H * d->W;
+  const long long tiles = (M + D::kTileM - 1) / D::kTileM * (p.Npad / d->n_tile);
+  if (tiles > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: too many tiles");
+  const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(d->nclass));
+  const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+  auto launch = [&](auto kern, size_t smem) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return fail(D3PM_ERR_CUDA, "dec_conv: %s", cudaGetErrorString(cudaGetLastError()));
+    kern<<<grid, D::kThreads, smem, s>>>(p);
+    return check_launch("dec_conv");
+  };
+  return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128>, D::gemm_smem_bytes<128>())
+                          : launch(D::conv_gemm_kernel<256>, D::gemm_smem_bytes<256>());
+}
+
+int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int64_t rows, int K, int C, uint32_t* status,
+                        d3pm_stream_t stream) {
+  if (tokens == nullptr || lut == nullptr || out == nullptr || rows <= 0 || K <= 0 || C <= 0 || C % 4 != 0)
+    return fail(D3PM_ERR_INVALID, "dec_embed_rows: bad arguments (rows=%lld K=%d C=%d, C %% 4 == 0)", (long long)rows, K, C);
+  if (!aligned16(lut) || !aligned16(out)) return fail(D3PM_ERR_ALIGN, "dec_embed_rows: lut and out must be 16-byte aligned");
+  const DeviceGuard on_device(out);
+  const long long n = rows * (C / 4);
+  if ((n + 255) / 256 > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_embed_rows: too many rows");
+  d3pm::dec::embed_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, lut, out, rows, K,
+                                                                                                                     C, status);
+  return check_launch("dec_embed_rows");
+}
+
+int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, int W, int heads, int head_dim, d3pm_stream_t stream) {
+  namespace D = d3pm::dec;
+  if (qkv == nullptr || att == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0 || heads <= 0)
+    return fail(D3PM_ERR_INVALID, "dec_axial_attention: bad arguments");
+  if (T > 32 || H > 32 || W > 32) return fail(D3PM_ERR_UNSUPPORTED, "dec_axial_attention: grid %dx%dx%d, every axis must be <= 32", T, H, W);
+  if (head_dim != 32 && head_dim != 64 && head_dim != 128)
+    return fail(D3PM_ERR_UNSUPPORTED, "dec_axial_attention: head_dim=%d must be 32, 64 or 128", head_dim);
+  const DeviceGuard on_device(att);
+  const long long M = static_cast<long long>(B) * T * H * W;
+  const int Lmin = T < H ? (T < W ? T : W) : (H < W ? H : W);
+  const long long jobs = M / Lmin * heads;
+  const dim3 grid(static_cast<unsigned>((jobs + D::kAttnWarps - 1) / D::kAttnWarps), 3);
+  const size_t smem = static_cast<size_t>(D::kAttnWarps) * 2 * 32 * head_dim * sizeof(float);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto launch = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return fail(D3PM_ERR_CUDA, "dec_axial_attention: %s", cudaGetErrorString(cudaGetLastError()));
+    kern<<<grid, 32 * D::kAttnWarps, smem, s>>>(qkv, att, B, T, H, W, heads);
+    return check_launch("dec_axial_attention");
+  };
+  if (head_dim == 32) return launch(D::axial_attention_kernel<1>);
+  if (head_dim == 64) return launch(D::axial_attention_kernel<2>);
+  return launch(D::axial_attention_kernel<4>);
+}
+
+int d3pm_dec_col2im(const float* y, int ldy, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh, int sw,
+                    d3pm_stream_t stream) {
+  if (y == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return fail(D3PM_ERR_INVALID, "dec_col2im: bad arguments");
+  if (Cout <= 0 || Cout > 4 || ldy < 64 * Cout) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: Cout=%d must be <= 4 and ldy=%d >= 64 * Cout", Cout, ldy);
+  if ((st != 1 && st != 2) || (sh != 1 && sh != 2) || (sw != 1 && sw != 2)) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: strides must be 1 or 2");
+  const DeviceGuard on_device(out);
+  const long long total = static_cast<long long>(B) * T * st * H * sh * W * sw;
+  if ((total + 255) / 256 > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: output too large");
+  d3pm::dec::col2im_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, ldy, bias, out, B, T, H,
+                                                                                                                      W, Cout, st, sh, sw);
+  return check_launch("dec_col2im");
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// Token -> video, second stage: the reference's VQ-VAE `Decoder` (videogpt_vq_vae.py:258-287) in eval
+// mode - attention residual blocks (:120-136: BatchNorm3d, ReLU, SamePadConv3d 3x3x3, 1x1x1, AxialBlock :100-118 with the
+// MultiHeadAttention of utils/model_utils.py:214-297) followed by SamePadConvTranspose3d layers (:312-334).
+//
+// Every convolution and every Linear of the decoder is ONE kernel here, an implicit GEMM on the 5th-gen tensor cores:
+//   * activations are channels-last rows [B*T*H*W][C] (one 128-byte line per 32 channels of a position);
+//   * a tile is 128 positions x NT output channels, accumulated in tensor memory (tcgen05.mma kind::tf32, M = 128,
+//     N = NT, K = 8 per instruction) as a 3xTF32 split (a_lo w_hi + a_hi w_lo + a_hi w_hi: fp32-grade results; `terms = 1`
+//     multiplies the hi parts only, which is what cuDNN's default TF32 convolutions of the reference on a GPU do);
+//   * the A operand is produced in the kernel, k-block by k-block (one filter tap x 32 input channels): eight warps
+//     gather the shifted input rows (zero outside the grid: the SamePad padding), apply the BatchNorm + ReLU that
+//     precedes the convolution in the reference as a per-channel affine, split hi / lo and store into the 128-byte
+//     swizzled K-major layout the tensor core reads; the B operand (weights, BatchNorms that FOLLOW a convolution folded
+//     in) is a pre-swizzled image streamed with 1-D bulk TMA through the same ring of shared-memory stages;
+//   * the epilogue reads the accumulator row per thread (tcgen05.ld 32x32b), adds bias / residual, applies ReLU and stores
+//     channels-last rows (128 contiguous bytes per thread and 32 channels).
+// A transposed convolution with stride 2 is decomposed by output parity: every parity class is an ordinary convolution over
+// the INPUT grid with 2 taps per strided dimension (4 per unit-stride dimension), its results scattered to the class's
+// output positions, so no zero-stuffed input is ever formed.  The last layer (3 output channels) runs the other way round:
+// a plain GEMM [positions x C] x [C x 64 taps * 3] followed by col2im_kernel, which sums the 16 contributions of each
+// output voxel and writes the channels-first video the reference returns.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "d3pm_b200.h"
+
+namespace d3pm {
+namespace dec {
+
+constexpr int kTileM = 128;
+constexpr int kProdWarps = 8;                     // A producers, then the epilogue
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kThreads = 32 * (kProdWarps + 2);   // + MMA issue warp + weight TMA warp
+constexpr int kBlockBytes = kTileM * 128;         // one k-block (32 floats) of a 128-row operand
+constexpr int kMaxTaps = D3PM_DEC_MAX_TAPS;
+constexpr int kMaxClasses = D3PM_DEC_MAX_CLASSES;
+constexpr int kMaxCin = 1024;
+
+struct GemmParams {
+  const float* x;         // [B*T*H*W][Cin]
+  const float* in_scale;  // [Cin] or null
+  const float* in_shift;
+  const float* w_image;   // [class][N tile][k-block][term][NT rows x 128 B swizzled]
+  const float* bias;      // [Npad] or null
+  const float* residual;  // rows laid out like `out`, or null
+  float* out;
+  int B, T, H, W, Cin;
+  int ntaps, nclass;
+  int Npad, Nout, ldo;
+  int To, Ho, Wo, st, sh, sw;
+  int relu_out, terms;
+  signed char tap[kMaxClasses][kMaxTaps][4];  // (dt, dh, dw) of every tap of every class
+  signed char cls[kMaxClasses][4];            // (pt, ph, pw): output position = input position * stride + this
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand, 128-byte swizzle: rows at 128 B, 8-row groups at SBO = 1024 B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return static_cast<uint64_t>((addr >> 4) & 0x3fffu) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- weight image ---------------------------------------------------------------------------------------------
+// floats of the image of one parity class: [Npad / NT][Ktot / 32][2 terms][NT][32]
+__host__ __device__ inline int64_t image_floats(int Npad, int Ktot) { return static_cast<int64_t>(Npad) * Ktot * 2; }
+
+// w: [nclass][N][Ktot] row-major fp32 (k contiguous: the K-major operand), rows n >= N are zero in the image.
+// hi = w with the 13 low mantissa bits cleared (exactly a tf32 number), lo = w - hi (exact in fp32).
+__global__ void weight_image_kernel(const float* __restrict__ w, int N, int Npad, int Ktot, int NT, float* __restrict__ image) {
+  const int KB = Ktot / 32;
+  const int64_t pieces = static_cast<int64_t>(Npad) * KB * 8;  // 16-byte pieces of one class
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= pieces) return;
+  const int cls = blockIdx.y;
+  const int piece = static_cast<int>(idx & 7);
+  const int kb = static_cast<int>((idx >> 3) % KB);
+  const int n = static_cast<int>((idx >> 3) / KB);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) v = *reinterpret_cast<const float4*>(w + (static_cast<size_t>(cls) * N + n) * Ktot + kb * 32 + piece * 4);
+  const float s[4] = {v.x, v.y, v.z, v.w};
+  float hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    hi[e] = __uint_as_float(__float_as_uint(s[e]) & 0xffffe000u);
+    lo[e] = s[e] - hi[e];
+  }
+  const int ntile = n / NT, r = n % NT;
+  float* blk = image + static_cast<size_t>(cls) * image_floats(Npad, Ktot) +
+               (static_cast<size_t>(ntile) * KB + kb) * (2 * NT * 32);
+  const int at = r * 32 + ((piece ^ (r & 7)) << 2);
+  *reinterpret_cast<float4*>(blk + at) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(blk + NT * 32 + at) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---- the implicit-GEMM convolution ------------------------------------------------------------------------------
+template <int NT>
+struct GemmGeo {
+  static constexpr int kStages = NT == 128 ? 3 : 2;
+  static constexpr int kBBytes = NT * 128;                        // one term of the weight k-block
+  static constexpr int kStageBytes = 2 * kBlockBytes + 2 * kBBytes;
+  // instruction descriptor: D = f32, A = B = tf32, both K-major, N = NT, M = 128
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NT >> 3) << 17) | ((kTileM >> 4) << 24);
+};
+
+struct GemmCtl {
+  unsigned long long full_a[3], full_b[3], empty[3], acc_full;
+  uint32_t tmem_base, pad;
+  signed char taps[kMaxTaps][4];  // this CTA's parity class
+  alignas(16) float scale[kMaxCin];
+  alignas(16) float shift[kMaxCin];
+};
+
+template <int NT>
+constexpr size_t gemm_smem_bytes() {
+  return 1024 + GemmGeo<NT>::kStages * GemmGeo<NT>::kStageBytes + sizeof(GemmCtl);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using G = GemmGeo<NT>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  GemmCtl& C = *reinterpret_cast<GemmCtl*>(smem + G::kStages * G::kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles_n = p.Npad / NT;
+  const int ntile = static_cast<int>(blockIdx.x % ntiles_n);
+  const long long mtile = blockIdx.x / ntiles_n;
+  const int cls = blockIdx.y;
+  const int CB = p.Cin >> 5;            // k-blocks per tap
+  const int KB = p.ntaps * CB;          // k-blocks in all
+  const long long M = static_cast<long long>(p.B) * p.T * p.H * p.W;
+
+  if (tid == 0) {
+    for (int i = 0; i < G::kStages; ++i) mbar_init(&C.full_a[i], kProdThreads), mbar_init(&C.full_b[i], 1), mbar_init(&C.empty[i], 1);
+    mbar_init(&C.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.in_scale != nullptr)
+    for (int i = tid; i < p.Cin; i += kThreads) C.scale[i] = p.in_scale[i], C.shift[i] = p.in_shift[i];
+  if (tid < p.ntaps)
+    for (int e = 0; e < 4; ++e) C.taps[tid][e] = p.tap[cls][tid][e];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(NT) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = C.tmem_base;
+
+  if (warp == 1) {
+    // =========================== weight stream (bulk TMA) ===========================
+    if (lane == 0) {
+      const uint32_t bytes = p.terms == 1 ? G::kBBytes : 2 * G::kBBytes;
+      const float* src = p.w_image + static_cast<size_t>(cls) * image_floats(p.Npad, KB * 32) +
+                         static_cast<size_t>(ntile) * KB * (2 * NT * 32);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int st = kb % G::kStages;
+        mbar_wait(&C.empty[st], static_cast<uint32_t>(((kb / G::kStages) & 1) ^ 1));
+        mbar_expect_tx(&C.full_b[st], bytes);
+        unsigned char* dst = smem + st * G::kStageBytes + 2 * kBlockBytes;
+        const float* s = src + static_cast<size_t>(kb) * (2 * NT * 32);
+        for (uint32_t q = 0; q < bytes; q += kBlockBytes) tma_load(dst + q, s + q / 4, kBlockBytes, &C.full_b[st]);
+      }
+    }
+  } else if (warp == 0) {
+    // =========================== MMA issue ===========================
+    if (lane == 0) {
+      uint32_t accum = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int st = kb % G::kStages;
+        const uint32_t par = static_cast<uint32_t>((kb / G::kStages) & 1);
+        mbar_wait(&C.full_a[st], par);
+        mbar_wait(&C.full_b[st], par);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + st * G::kStageBytes);
+        const uint32_t b_addr = a_addr + 2 * kBlockBytes;
+        // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi (terms == 1: a_hi w_hi only)
+        for (int term = (p.terms == 1 ? 2 : 0); term < 3; ++term) {
+          const uint32_t a_off = (term == 0) ? kBlockBytes : 0;
+          const uint32_t b_off = (term == 1) ? G::kBBytes : 0;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 4 MMAs of K = 8 per 128-byte k-block
+            tc_mma_tf32(tmem, smem_desc(a_addr + a_off + ks * 32), smem_desc(b_addr + b_off + ks * 32), G::kIdesc, accum);
+            accum = 1;
+          }
+        }
+        tc_commit(&C.empty[st]);
+      }
+      tc_commit(&C.acc_full);
+    }
+  } else {
+    // =========================== A producer (warps 2..9) ===========================
+    const int pt = tid - 64;        // 0..255
+    const int piece = pt & 7;       // 16-byte piece of the 128-byte k-block row
+    const int r0 = pt >> 3;         // rows r0 + 32 i
+    const int HW = p.H * p.W;
+    int ct[4], ch[4], cw[4];
+    long long base[4];
+    bool rowok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = mtile * kTileM + r0 + 32 * i;
+      rowok[i] = m < M;
+      const long long mm = rowok[i] ? m : 0;
+      const int inb = static_cast<int>(mm % (static_cast<long long>(p.T) * HW));
+      ct[i] = inb / HW;
+      ch[i] = (inb % HW) / p.W;
+      cw[i] = inb % p.W;
+      base[i] = mm * p.Cin + piece * 4;
+    }
+    auto fetch = [&](int kb, float4 (&v)[4], uint32_t& okmask) {
+      const int tap = kb / CB, cb = kb - tap * CB;
+      const int dt = C.taps[tap][0], dh = C.taps[tap][1], dw = C.taps[tap][2];
+      const long long shift = (static_cast<long long>(dt) * HW + dh * p.W + dw) * p.Cin + cb * 32;
+      okmask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = rowok[i] && static_cast<unsigned>(ct[i] + dt) < static_cast<unsigned>(p.T) &&
+                        static_cast<unsigned>(ch[i] + dh) < static_cast<unsigned>(p.H) &&
+                        static_cast<unsigned>(cw[i] + dw) < static_cast<unsigned>(p.W);
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.x + base[i] + shift)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        okmask |= (ok ? 1u : 0u) << i;
+      }
+    };
+    const bool affine = p.in_scale != nullptr;
+    float4 nxt[4];
+    uint32_t nxt_ok = 0;
+    fetch(0, nxt, nxt_ok);
+    for (int kb = 0; kb < KB; ++kb) {
+      float4 cur[4];
+      const uint32_t cur_ok = nxt_ok;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      if (kb + 1 < KB) fetch(kb + 1, nxt, nxt_ok);
+      const int st = kb % G::kStages;
+      mbar_wait(&C.empty[st], static_cast<uint32_t>(((kb / G::kStages) & 1) ^ 1));
+      unsigned char* a_hi = smem + st * G::kStageBytes;
+      const int cb = kb % CB;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (affine) {
+        sc = *reinterpret_cast<const float4*>(C.scale + cb * 32 + piece * 4);
+        sh = *reinterpret_cast<const float4*>(C.shift + cb * 32 + piece * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+        if (affine) {  // the BatchNorm + ReLU in front of the convolution; the zero padding comes AFTER it (F.pad of the activated tensor)
+          const bool ok = (cur_ok >> i) & 1u;
+          a[0] = ok ? fmaxf(fmaf(a[0], sc.x, sh.x), 0.f) : 0.f;
+          a[1] = ok ? fmaxf(fmaf(a[1], sc.y, sh.y), 0.f) : 0.f;
+          a[2] = ok ? fmaxf(fmaf(a[2], sc.z, sh.z), 0.f) : 0.f;
+          a[3] = ok ? fmaxf(fmaf(a[3], sc.w, sh.w), 0.f) : 0.f;
+        }
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[e] = __uint_as_float(__float_as_uint(a[e]) & 0xffffe000u);
+          lo[e] = a[e] - hi[e];
+        }
+        const int r = r0 + 32 * i;
+        const int at = r * 128 + ((piece ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(a_hi + at) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a_hi + kBlockBytes + at) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&C.full_a[st]);
+    }
+
+    // =========================== epilogue ===========================
+    mbar_wait(&C.acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the NT columns
+    const int r = 32 * q + lane;
+    const long long m = mtile * kTileM + r;
+    const bool live = m < M;
+    long long orow = 0;
+    if (live) {
+      const long long THW = static_cast<long long>(p.T) * HW;
+      const long long b = m / THW;
+      const int inb = static_cast<int>(m - b * THW);
+      const int t = inb / HW, h = (inb % HW) / p.W, w = inb % p.W;
+      orow = ((b * p.To + (t * p.st + p.cls[cls][0])) * p.Ho + (h * p.sh + p.cls[cls][1])) * p.Wo + (w * p.sw + p.cls[cls][2]);
+    }
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(32 * q) << 16);
+#pragma unroll 1
+    for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + c0, v);
+      tmem_ld_wait();
+      const int n0 = ntile * NT + c0;
+      if (live) {
+        float* dst = p.out + orow * p.ldo + n0;
+        const float* res = p.residual != nullptr ? p.residual + orow * p.ldo + n0 : nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (n0 + 4 * i < p.Nout) {
+            float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+            if (p.bias != nullptr) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+              o.x += b4.x, o.y += b4.y, o.z += b4.z, o.w += b4.w;
+            }
+            if (res != nullptr) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res) + i);
+              o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
+            }
+            if (p.relu_out) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            *reinterpret_cast<float4*>(dst + 4 * i) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NT) : "memory");
+  }
+}
+
+// ---- codebook rows ----------------------------------------------------------------------------------------------
+// h[row][0..C) = lut[tokens[row]][0..C): the channels-last form of post_vq_conv(embedding(tokens)) (videogpt_vq_vae.py:54-55)
+__global__ void embed_rows_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ lut, float* __restrict__ out,
+                                  long long rows, int K, int C, uint32_t* status) {
+  const int per_row = C >> 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * per_row) return;
+  const long long row = idx / per_row;
+  const int c4 = static_cast<int>(idx - row * per_row);
+  const long long tok = tokens[row];
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tok >= 0 && tok < K) v = __ldg(reinterpret_cast<const float4*>(lut + tok * C) + c4);
+  else if (c4 == 0 && status != nullptr) atomicOr(status, D3PM_STATUS_BAD_TOKEN);
+  reinterpret_cast<float4*>(out + row * C)[c4] = v;
+}
+
+// ---- axial attention (AxialBlock, videogpt_vq_vae.py:100-118; scaled_dot_product_attention, model_utils.py:586-600) ----
+// qkv: [M][3 axes][q, k, v][heads][dh]; att: [M][3 axes][heads][dh].  One warp per (sequence along the axis, head): K and V
+// of the sequence (L <= 32 positions) staged in shared memory, a lane holds VPL = dh / 32 channels of every vector.
+constexpr int kAttnWarps = 4;
+
+template <int VPL>
+__global__ void __launch_bounds__(32 * kAttnWarps) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
+                                                                          int T, int H, int W, int heads) {
+  extern __shared__ float attn_smem[];
+  constexpr int DH = 32 * VPL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int axis = blockIdx.y;  // 0: along W (attn_w, axial_dim -2), 1: along H, 2: along T
+  const int L = axis == 0 ? W : (axis == 1 ? H : T);
+  const long long M = static_cast<long long>(B) * T * H * W;
+  const long long nseq = M / L;
+  const long long job = static_cast<long long>(blockIdx.x) * kAttnWarps + warp;
+  if (job >= nseq * heads) return;
+  const long long seq = job / heads;
+  const int head = static_cast<int>(job - seq * heads);
+  long long row0, rstride;
+  if (axis == 0) row0 = seq * W, rstride = 1;
+  else if (axis == 1) row0 = (seq / W) * (static_cast<long long>(H) * W) + seq % W, rstride = W;
+  else row0 = (seq / (static_cast<long long>(H) * W)) * (static_cast<long long>(T) * H * W) + seq % (static_cast<long long>(H) * W), rstride = static_cast<long long>(H) * W;
+  const int C = heads * DH;
+  const int ldq = 9 * C;  // floats per row of qkv
+  float* ks = attn_smem + static_cast<size_t>(warp) * 2 * 32 * DH;
+  float* vs = ks + 32 * DH;
+  const float* qbase = qkv + static_cast<size_t>(axis) * 3 * C + head * DH + lane * VPL;
+  for (int j = 0; j < L; ++j) {
+    const float* rowp = qbase + (row0 + j * rstride) * ldq;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) {
+      ks[j * DH + lane * VPL + e] = rowp[C + e];
+      vs[j * DH + lane * VPL + e] = rowp[2 * C + e];
+    }
+  }
+  __syncwarp();
+  const float scale = rsqrtf(static_cast<float>(DH));
+  for (int i = 0; i < L; ++i) {
+    const float* rowp = qbase + (row0 + i * rstride) * ldq;
+    float qv[VPL];
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) qv[e] = rowp[e];
+    float mine = -3.0e38f;  // lane j keeps the score of key j
+    for (int j = 0; j < L; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < VPL; ++e) s = fmaf(qv[e], ks[j * DH + lane * VPL + e], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == j) mine = s * scale;
+    }
+    float mx = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e_ = lane < L ? expf(mine - mx) : 0.f;
+    float sum = e_;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float pr = e_ / sum;
+    float acc[VPL];
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) acc[e] = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, pr, j);
+#pragma unroll
+      for (int e = 0; e < VPL; ++e) acc[e] = fmaf(pj, vs[j * DH + lane * VPL + e], acc[e]);
+    }
+    float* o = att + (row0 + i * rstride) * (3 * C) + axis * C + head * DH + lane * VPL;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) o[e] = acc[e];
+  }
+}
+
+// ---- col2im of the last transposed convolution ----------------------------------------------------------------------
+// y: [B*T*H*W][ldy], column ((kt*4 + kh)*4 + kw)*Cout + c = contribution of input position (row) through filter tap (kt, kh, kw)
+// to output channel c.  out: [B][Cout][To][Ho][Wo] (the reference's layout), out = bias + sum of the contributions that land
+// on the voxel: along a dimension of stride s, tap k of input i lands on y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2)
+// (F.pad of SamePadConvTranspose3d :324-328, then ConvTranspose3d with padding 3 :330-332).
+__global__ void col2im_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias, float* __restrict__ out, int B, int T,
+                              int H, int W, int Cout, int st, int sh, int sw) {
+  const int To = T * st, Ho = H * sh, Wo = W * sw;
+  const long long total = static_cast<long long>(B) * To * Ho * Wo;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int yw = static_cast<int>(idx % Wo);
+  const int yh = static_cast<int>((idx / Wo) % Ho);
+  const int yt = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % To);
+  const long long b = idx / (static_cast<long long>(Wo) * Ho * To);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int pft = (4 - st + 1) / 2, pfh = (4 - sh + 1) / 2, pfw = (4 - sw + 1) / 2;
+  for (int kt = 0; kt < 4; ++kt) {
+    const int nt = yt + 3 - kt;
+    if (nt % st != 0) continue;
+    const int it = nt / st - pft;
+    if (it < 0 || it >= T) continue;
+    for (int kh = 0; kh < 4; ++kh) {
+      const int nh = yh + 3 - kh;
+      if (nh % sh != 0) continue;
+      const int ih = nh / sh - pfh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 4; ++kw) {
+        const int nw = yw + 3 - kw;
+        if (nw % sw != 0) continue;
+        const int iw = nw / sw - pfw;
+        if (iw < 0 || iw >= W) continue;
+        const float* src = y + (((b * T + it) * H + ih) * W + iw) * ldy + ((kt * 4 + kh) * 4 + kw) * Cout;
+        for (int c = 0; c < Cout && c < 4; ++c) acc[c] += __ldg(src + c);
+      }
+    }
+  }
+  for (int c = 0; c < Cout && c < 4; ++c)
+    out[(((b * Cout + c) * To + yt) * Ho + yh) * Wo + yw] = acc[c] + (bias != nullptr ? bias[c] : 0.f);
+}
+
+}  // namespace dec
+}  // namespace d3pm

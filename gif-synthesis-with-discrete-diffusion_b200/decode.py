@@ -1,12 +1,21 @@
-"""Token -> video, first stage: the consumer of the int64 `[B, N]` tokens this path samples.
+"""Token -> video: the consumer of the int64 `[B, N]` tokens this path samples.
 
 `VQVAE.decode` (videogpt_vq_vae.py:53-56) is `decoder(post_vq_conv(shift_dim(F.embedding(tokens, codebook), -1, 1)))`.
-The embedding gather and the 1x1x1 convolution are both per-token, so they fold into one `[K, C]` table and a single
-gather kernel that writes the channels-first tensor the decoder's convolutions take; the 3-D (transposed-)convolution
-decoder itself stays the reference's PyTorch module.  CUDA only.
+
+* First stage: the embedding gather and the 1x1x1 convolution are both per-token, so they fold into one `[K, C]` table
+  (`DecodeTable`) and a single gather kernel.
+* Second stage: `NativeDecoder` runs the reference's `Decoder` (:258-287; eval mode) layer by layer on channels-last
+  activations - every convolution, transposed convolution and Linear is `d3pm_dec_conv` (tcgen05 implicit GEMM, 3xTF32),
+  the axial attentions `d3pm_dec_axial_attention`, the last 3-channel transposed convolution a GEMM + `d3pm_dec_col2im`.
+  BatchNorm3d (eval) + ReLU pairs are folded: one that FOLLOWS a bias-free convolution into that convolution's weights and
+  bias, one that PRECEDES a convolution into the per-channel affine the kernel applies while it gathers its A operand.
+
+`decode(autoencoder, tokens, decoder=NativeDecoder...)` is the drop-in for `VQVAE.decode`; without `decoder` the reference's
+own PyTorch `Decoder` module runs behind the fused first stage.  CUDA only.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -57,8 +66,252 @@ def tokens_to_features(table: DecodeTable, tokens: torch.Tensor, status: Optiona
     return out.view(B, table.C, *tokens.shape[1:])
 
 
-def decode(autoencoder, tokens: torch.Tensor, table: Optional[DecodeTable] = None) -> torch.Tensor:
-    """Drop-in for `VQVAE.decode(encodings)` (videogpt_vq_vae.py:53-56): fused gather + 1x1x1 conv, then the reference's
-    own `decoder` module."""
+def embed_rows(table: DecodeTable, tokens: torch.Tensor, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int64 tokens `[B, ...]` -> channels-last rows `[B * N, C]` of `post_vq_conv(embedding)` (the native decoder's input)."""
+    dev = ops._need_cuda(tokens, table.lut, status)
+    if tokens.dtype != torch.int64 or tokens.dim() < 2:
+        raise D3PMError("tokens must be an int64 tensor [B, ...]")
+    flat = tokens.reshape(-1).contiguous()
+    out = torch.empty(flat.numel(), table.C, dtype=torch.float32, device=dev)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_dec_embed_rows(flat.data_ptr(), table.lut.data_ptr(), out.data_ptr(), flat.numel(), table.K, table.C,
+                                       ops._ptr(status), ops._stream(dev)), "d3pm_dec_embed_rows")
+    return out
+
+
+def _bn_affine(bn) -> tuple:
+    """Eval-mode BatchNorm3d as y = x * scale + shift (float64 arithmetic, fp32 result)."""
+    var, mean = bn.running_var.detach().double(), bn.running_mean.detach().double()
+    w = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(var)
+    b = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(var)
+    scale = w / torch.sqrt(var + bn.eps)
+    return scale, b - mean * scale
+
+
+def _convt_taps(stride):
+    """Parity classes of SamePadConvTranspose3d (kernel 4, padding as :319-332) with `stride` in {1, 2} per dimension.
+    Along one dimension, output y = m * s + par receives x[m + d] * w[k] for every k with (par + 3 - k) % s == 0,
+    d = (par + 3 - k) / s - ceil((4 - s) / 2).  Returns [(class offsets (pt, ph, pw), [((kt, kh, kw), (dt, dh, dw)), ...])]."""
+    per_dim = []
+    for s in stride:
+        if s not in (1, 2):
+            raise D3PMError(f"transposed-convolution stride {tuple(stride)}: only 1 and 2 are built")
+        pf = (4 - s + 1) // 2
+        per_dim.append([[(k, (par + 3 - k) // s - pf) for k in range(4) if (par + 3 - k) % s == 0] for par in range(s)])
+    classes = []
+    for pt in range(stride[0]):
+        for ph in range(stride[1]):
+            for pw in range(stride[2]):
+                taps = [((kt, kh, kw), (dt, dh, dw)) for kt, dt in per_dim[0][pt] for kh, dh in per_dim[1][ph]
+                        for kw, dw in per_dim[2][pw]]
+                classes.append(((pt, ph, pw), taps))
+    return classes
+
+
+class LayerSpec:
+    """One `d3pm_dec_conv` call, device-independent: the K-major weight matrix `[nclass, Nout, ntaps * cin]`, the tap
+    offsets of every parity class, and what surrounds the product (input affine + ReLU, bias, output ReLU)."""
+
+    def __init__(self, wmat, *, cin, taps, classes, stride=(1, 1, 1), bias=None, in_affine=None, relu_out=False):
+        nclass, nout, ktot = wmat.shape
+        assert ktot == len(taps[0]) * cin and nclass == len(classes) == len(taps)
+        assert nclass <= _lib.DEC_MAX_CLASSES and len(taps[0]) <= _lib.DEC_MAX_TAPS
+        self.wmat, self.cin, self.nout, self.taps, self.classes = wmat.float().contiguous(), cin, nout, taps, classes
+        self.stride, self.relu_out = tuple(int(s) for s in stride), bool(relu_out)
+        self.bias = None if bias is None else bias.float().contiguous()
+        self.in_affine = None if in_affine is None else tuple(a.float().contiguous() for a in in_affine)
+
+
+def decoder_plan(decoder: torch.nn.Module) -> dict:
+    """Read the reference's `Decoder` module (eval mode) into the list of `LayerSpec`s `NativeDecoder` executes.  Pure torch,
+    any device: the CPU tests run this plan through an emulation of the C contract against the oracle."""
+    if decoder.training:
+        raise D3PMError("NativeDecoder folds BatchNorm running statistics: put the decoder in eval() mode first "
+                        "(train-mode batch statistics stay with the PyTorch module)")
+    blocks = list(decoder.res_stack)
+    bn_final, res_blocks = blocks[-2], blocks[:-2]
+    C = bn_final.num_features
+    if C % 64 != 0 or (C // 2) not in (32, 64, 128):
+        raise D3PMError(f"n_hiddens={C}: the native decoder is built for n_hiddens in (64, 128, 256) (two heads of 32 / 64 / 128)")
+    one = [(0, 0, 0)]
+    conv3_taps = [(kt - 1, kh - 1, kw - 1) for kt in range(3) for kh in range(3) for kw in range(3)]
+    plan = {"C": C, "heads": 2, "blocks": [], "convts": []}
+    with torch.no_grad():
+        for rb in res_blocks:
+            bn1, _, conv3, bn2, _, conv1, bn3, _, axial = list(rb.block)
+            w3, w1 = conv3.conv.weight.detach().double(), conv1.conv.weight.detach().double()
+            if tuple(w3.shape[2:]) != (3, 3, 3) or tuple(w1.shape[2:]) != (1, 1, 1) or conv3.conv.bias is not None or conv1.conv.bias is not None:
+                raise D3PMError("AttentionResidualBlock: expected a bias-free 3x3x3 and a bias-free 1x1x1 convolution (:124-131)")
+            s2, b2 = _bn_affine(bn2)
+            s3, b3 = _bn_affine(bn3)
+            m3 = (w3 * s2.view(-1, 1, 1, 1, 1)).permute(0, 2, 3, 4, 1).reshape(1, w3.shape[0], -1)   # [n][tap][cin]
+            m1 = (w1 * s3.view(-1, 1, 1, 1, 1)).reshape(1, w1.shape[0], -1)
+            L3 = LayerSpec(m3, cin=C, taps=[conv3_taps], classes=[(0, 0, 0)], bias=b2, in_affine=_bn_affine(bn1), relu_out=True)
+            L1 = LayerSpec(m1, cin=C // 2, taps=[one], classes=[(0, 0, 0)], bias=b3, relu_out=True)
+            if axial.attn_w.n_head != 2 or axial.attn_w.d_k != C // 2:
+                raise D3PMError("AxialBlock: expected two heads of n_hiddens / 2 channels (:103-111)")
+            att = (axial.attn_w, axial.attn_h, axial.attn_t)  # axes W, H, T = the kernel's axis 0, 1, 2
+            wqkv = torch.cat([torch.cat([a.w_qs.weight, a.w_ks.weight, a.w_vs.weight], 0) for a in att], 0).detach()
+            Lq = LayerSpec(wqkv.unsqueeze(0), cin=C, taps=[one], classes=[(0, 0, 0)])
+            wfc = torch.cat([a.fc.weight for a in att], 1).detach()
+            bfc = sum(a.fc.bias.detach().double() for a in att)
+            Lf = LayerSpec(wfc.unsqueeze(0), cin=3 * C, taps=[one], classes=[(0, 0, 0)], bias=bfc)
+            plan["blocks"].append((L3, L1, Lq, Lf))
+        in_aff = _bn_affine(bn_final)
+        n = len(decoder.convts)
+        for i, ct in enumerate(decoder.convts):
+            w = ct.convt.weight.detach()   # [Cin, Cout, 4, 4, 4]
+            stride = tuple(int(v) for v in ct.convt.stride)
+            if tuple(w.shape[2:]) != (4, 4, 4) or tuple(ct.convt.padding) != (3, 3, 3):
+                raise D3PMError("SamePadConvTranspose3d: expected kernel 4 and padding 3 (:330-332)")
+            bias = ct.convt.bias.detach() if ct.convt.bias is not None else torch.zeros(w.shape[1], device=w.device)
+            if i < n - 1:
+                classes = _convt_taps(stride)
+                mats = [torch.stack([w[:, :, kt, kh, kw].t() for (kt, kh, kw), _ in taps], 1).reshape(w.shape[1], -1)
+                        for _, taps in classes]   # [Cout][tap][Cin]
+                spec = LayerSpec(torch.stack(mats, 0), cin=w.shape[0], taps=[[d for _, d in taps] for _, taps in classes],
+                                 classes=[c for c, _ in classes], stride=stride, bias=bias, in_affine=in_aff, relu_out=True)
+                plan["convts"].append(("conv", spec, stride))
+            else:
+                cout = w.shape[1]
+                if cout > 4:
+                    raise D3PMError(f"last transposed convolution has {cout} output channels; col2im is built for <= 4 (RGB)")
+                m = w.permute(2, 3, 4, 1, 0).reshape(1, 64 * cout, w.shape[0])   # [(kt, kh, kw, co)][cin]
+                spec = LayerSpec(m, cin=w.shape[0], taps=[one], classes=[(0, 0, 0)], in_affine=in_aff)
+                plan["convts"].append(("col2im", spec, stride, bias.float().contiguous(), cout))
+            in_aff = None  # later layers read an already activated tensor (the ReLU sits in the previous epilogue)
+    return plan
+
+
+class _Layer:
+    """A `LayerSpec` bound to a device: the weight image and the static part of the launch descriptor."""
+
+    def __init__(self, spec: LayerSpec, dev, n_tile: Optional[int] = None):
+        nclass, nout, ktot = spec.wmat.shape
+        self.cin, self.nout, self.nclass, self.ntaps, self.stride = spec.cin, nout, nclass, len(spec.taps[0]), spec.stride
+        self.n_tile = n_tile if n_tile is not None else (128 if nout <= 128 else 256)
+        npad = (nout + self.n_tile - 1) // self.n_tile * self.n_tile
+        lib = _lib.load_library()
+        self.image = torch.empty(lib.d3pm_dec_image_floats(nclass, nout, ktot, self.n_tile), dtype=torch.float32, device=dev)
+        w = spec.wmat.to(dev)
+        _lib.check(lib.d3pm_dec_weight_image(w.data_ptr(), nclass, nout, ktot, self.n_tile, self.image.data_ptr(), ops._stream(dev)),
+                   "d3pm_dec_weight_image")
+        torch.cuda.current_stream(dev).synchronize()  # `w` may be a temporary
+        self.bias = None
+        if spec.bias is not None:
+            self.bias = torch.zeros(npad, dtype=torch.float32, device=dev)
+            self.bias[:nout] = spec.bias.to(dev)
+        self.in_scale = self.in_shift = None
+        if spec.in_affine is not None:
+            self.in_scale, self.in_shift = (a.to(dev) for a in spec.in_affine)
+        self.relu_out = spec.relu_out
+        self.desc = _lib.DecConvDesc()
+        for c, (offs, tl) in enumerate(zip(spec.classes, spec.taps)):
+            for e in range(3):
+                self.desc.cls[c][e] = offs[e]
+            for i, d in enumerate(tl):
+                for e in range(3):
+                    self.desc.tap[c][i][e] = d[e]
+
+    def __call__(self, x: torch.Tensor, B: int, grid, *, terms: int, residual: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        T, H, W = grid
+        rows_out = B * T * H * W * self.stride[0] * self.stride[1] * self.stride[2]
+        if x.shape != (B * T * H * W, self.cin) or not x.is_contiguous() or x.dtype != torch.float32:
+            raise D3PMError(f"expected contiguous float32 rows [{B * T * H * W}, {self.cin}], got {tuple(x.shape)}")
+        if out is None:
+            out = torch.empty(rows_out, self.nout, dtype=torch.float32, device=x.device)
+        d = self.desc
+        d.x, d.in_scale, d.in_shift = x.data_ptr(), ops._ptr(self.in_scale), ops._ptr(self.in_shift)
+        d.w_image, d.bias, d.residual, d.out = self.image.data_ptr(), ops._ptr(self.bias), ops._ptr(residual), out.data_ptr()
+        d.B, d.T, d.H, d.W, d.Cin = B, T, H, W, self.cin
+        d.ntaps, d.nclass, d.Nout, d.ldo = self.ntaps, self.nclass, self.nout, out.shape[1]
+        d.stride_t, d.stride_h, d.stride_w = self.stride
+        d.relu_out, d.terms, d.n_tile = int(self.relu_out), terms, self.n_tile
+        d.stream = ops._stream(x.device)
+        _lib.check(_lib.load_library().d3pm_dec_conv(ctypes.byref(d)), "d3pm_dec_conv")
+        return out
+
+
+class NativeDecoder:
+    """The reference's `Decoder` (videogpt_vq_vae.py:258-287) in eval mode on the library's kernels.
+
+    `precision="fp32"`: every product as 3xTF32 on the tensor cores (fp32-grade: what the reference computes on the CPU, or
+    on a GPU with TF32 disabled); `"tf32"`: single TF32 products, the accuracy class of the reference's default GPU path
+    (cuDNN convolutions run TF32 unless `torch.backends.cudnn.allow_tf32 = False`), about three times less tensor work.
+    Rebuild the object when the module's weights or BatchNorm statistics change (they are folded at construction).
+    """
+
+    def __init__(self, decoder: torch.nn.Module, precision: str = "fp32", n_tile: Optional[int] = None):
+        if precision not in ("fp32", "tf32"):
+            raise D3PMError("precision must be 'fp32' (3xTF32) or 'tf32'")
+        self.terms = 3 if precision == "fp32" else 1
+        plan = decoder_plan(decoder)
+        dev = next(decoder.parameters()).device
+        if dev.type != "cuda":
+            raise D3PMError("d3pm_b200 operates on CUDA tensors only (there is no CPU path)")
+        self.C, self.heads, self.device = plan["C"], plan["heads"], dev
+        with torch.cuda.device(dev):
+            self.blocks = [tuple(_Layer(sp, dev, n_tile) for sp in blk) for blk in plan["blocks"]]
+            self.convts = []
+            for item in plan["convts"]:
+                if item[0] == "conv":
+                    self.convts.append(("conv", _Layer(item[1], dev, n_tile), item[2]))
+                else:
+                    self.convts.append(("col2im", _Layer(item[1], dev, n_tile), item[2], item[3].to(dev), item[4]))
+
+    @classmethod
+    def from_autoencoder(cls, autoencoder, precision: str = "fp32") -> "NativeDecoder":
+        return cls(autoencoder.decoder, precision)
+
+    def forward_rows(self, x: torch.Tensor, B: int, grid) -> torch.Tensor:
+        """Channels-last rows `[B * T * H * W, C]` -> video `[B, Cout, T', H', W']`."""
+        T, H, W = (int(v) for v in grid)
+        if max(T, H, W) > 32:
+            raise D3PMError(f"latent grid {T}x{H}x{W}: the axial attention kernel covers axes of up to 32 positions")
+        lib = _lib.load_library()
+        dev = x.device
+        M = B * T * H * W
+        for L3, L1, Lq, Lf in self.blocks:
+            y = L1(L3(x, B, (T, H, W), terms=self.terms), B, (T, H, W), terms=self.terms)
+            qkv = Lq(y, B, (T, H, W), terms=self.terms)
+            att = torch.empty(M, 3 * self.C, dtype=torch.float32, device=dev)
+            _lib.check(lib.d3pm_dec_axial_attention(qkv.data_ptr(), att.data_ptr(), B, T, H, W, self.heads, self.C // self.heads,
+                                                    ops._stream(dev)), "d3pm_dec_axial_attention")
+            x = Lf(att, B, (T, H, W), terms=self.terms, residual=x)
+        grid = (T, H, W)
+        for item in self.convts:
+            if item[0] == "conv":
+                _, layer, stride = item
+                x = layer(x, B, grid, terms=self.terms)
+                grid = tuple(g * s for g, s in zip(grid, stride))
+            else:
+                _, layer, stride, bias, cout = item
+                y = layer(x, B, grid, terms=self.terms)
+                out = torch.empty(B, cout, *(g * s for g, s in zip(grid, stride)), dtype=torch.float32, device=dev)
+                _lib.check(lib.d3pm_dec_col2im(y.data_ptr(), y.shape[1], bias.data_ptr(), out.data_ptr(), B, *grid, cout, *stride,
+                                               ops._stream(dev)), "d3pm_dec_col2im")
+                return out
+        raise D3PMError("decoder without transposed convolutions")
+
+    def __call__(self, h: torch.Tensor) -> torch.Tensor:
+        """Drop-in for `Decoder.forward(h)`: `h` is the reference's channels-first `[B, C, T, H, W]` tensor."""
+        ops._need_cuda(h)
+        if h.dim() != 5 or h.shape[1] != self.C:
+            raise D3PMError(f"expected [B, {self.C}, T, H, W], got {tuple(h.shape)}")
+        B, _, T, H, W = h.shape
+        rows = h.detach().float().permute(0, 2, 3, 4, 1).reshape(B * T * H * W, self.C).contiguous()
+        return self.forward_rows(rows, B, (T, H, W))
+
+
+def decode(autoencoder, tokens: torch.Tensor, table: Optional[DecodeTable] = None, decoder: Optional[NativeDecoder] = None,
+           status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for `VQVAE.decode(encodings)` (videogpt_vq_vae.py:53-56).  With `decoder` (a `NativeDecoder` built from
+    `autoencoder.decoder`) the whole chain runs on the library's kernels; without it the fused gather + 1x1x1 conv feeds the
+    reference's own `decoder` module."""
     table = table if table is not None else DecodeTable.from_autoencoder(autoencoder)
-    return autoencoder.decoder(tokens_to_features(table, tokens))
+    if decoder is None:
+        return autoencoder.decoder(tokens_to_features(table, tokens, status))
+    if tokens.dim() != 4:
+        raise D3PMError("tokens must be [B, T', H', W'] (reshape the sampler's [B, N] with the latent grid, discrete_diffusion.py:62)")
+    return decoder.forward_rows(embed_rows(table, tokens, status), tokens.shape[0], tokens.shape[1:])

@@ -275,6 +275,66 @@ int d3pm_decode_lut(const float* codebook, const float* conv_weight, const float
 int d3pm_tokens_to_features(const int64_t* tokens, const float* lut, float* out, int B, int N, int K, int C,
                             uint32_t* status, d3pm_stream_t stream);
 
+/* ---------------------------------------------------------------- token -> video, second stage
+ * The reference's VQ-VAE `Decoder` (videogpt_vq_vae.py:258-287) in eval mode, layer by layer on channels-last activations
+ * [B*T*H*W][C] (C % 32 == 0).  Every convolution / Linear is one call of d3pm_dec_conv, an implicit GEMM on the tensor cores
+ * (tcgen05, 3xTF32 = fp32-grade, or terms = 1 for plain TF32 as cuDNN's default on the reference's GPU path);
+ * d3pm_b200.decode.NativeDecoder holds the layer plan (which BatchNorm folds where, the parity classes of the transposed
+ * convolutions).
+ *
+ * d3pm_dec_weight_image: w [nclass][N][Ktot] (row n = output channel, k = tap * Cin + input channel, contiguous) -> the
+ * tf32 hi / lo parts in the swizzled K-major layout the kernel streams with bulk TMA; n_tile in {128, 256} is the tile
+ * width d3pm_dec_conv will be called with, Ktot % 32 == 0.  d3pm_dec_image_floats gives the size of `image`.            */
+#define D3PM_DEC_MAX_TAPS 32
+#define D3PM_DEC_MAX_CLASSES 8
+int64_t d3pm_dec_image_floats(int nclass, int N, int Ktot, int n_tile);
+int d3pm_dec_weight_image(const float* w, int nclass, int N, int Ktot, int n_tile, float* image, d3pm_stream_t stream);
+
+/* out[o(pos, class)][n] = act( bias[n] + residual[o][n] + sum_{tap, c} a(pos + tap_offset)[c] * w[class][n][tap * Cin + c] )
+ * with a(q) = relu(x[q] * in_scale + in_shift) (or x[q] when in_scale == NULL) inside the input grid and 0 outside (the
+ * reference's F.pad comes after the BatchNorm + ReLU: SamePadConv3d :302-310, SamePadConvTranspose3d :324-334), and
+ * o(pos, class) = (b, t * stride_t + cls[class][0], h * stride_h + cls[class][1], w * stride_w + cls[class][2]) in the output
+ * grid (T * stride_t, H * stride_h, W * stride_w): an ordinary convolution is one class with unit strides; a stride-2
+ * transposed convolution is one class per output parity.  Replaces SamePadConv3d (:289-310), SamePadConvTranspose3d
+ * (:312-334), the BatchNorm3d / ReLU pairs of AttentionResidualBlock (:120-136) and the four Linears of MultiHeadAttention
+ * (model_utils.py:224-236).                                                                                          */
+typedef struct d3pm_dec_conv_desc {
+  const float* x;         /* [B*T*H*W][Cin] */
+  const float* in_scale;  /* [Cin] or NULL */
+  const float* in_shift;  /* [Cin], required with in_scale */
+  const float* w_image;   /* from d3pm_dec_weight_image (same nclass, N = Nout, Ktot = ntaps * Cin, n_tile) */
+  const float* bias;      /* [Nout rounded up to n_tile] or NULL */
+  const float* residual;  /* rows like `out` (same ldo) or NULL */
+  float* out;             /* [B*To*Ho*Wo][ldo], columns [0, Nout) written */
+  int32_t B, T, H, W, Cin;
+  int32_t ntaps, nclass;
+  int32_t Nout, ldo;      /* Nout % 4 == 0, ldo % 4 == 0 */
+  int32_t stride_t, stride_h, stride_w;
+  int32_t relu_out;
+  int32_t terms;          /* 3: 3xTF32 (fp32-grade), 1: TF32 */
+  int32_t n_tile;         /* 128 or 256 */
+  int8_t tap[D3PM_DEC_MAX_CLASSES][D3PM_DEC_MAX_TAPS][4]; /* (dt, dh, dw, 0) per class and tap */
+  int8_t cls[D3PM_DEC_MAX_CLASSES][4];                    /* (pt, ph, pw, 0) per class */
+  d3pm_stream_t stream;
+} d3pm_dec_conv_desc;
+int d3pm_dec_conv(const d3pm_dec_conv_desc* desc);
+
+/* h[row] = lut[tokens[row]] (lut from d3pm_decode_lut): the channels-last input of the decoder. */
+int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int64_t rows, int K, int C, uint32_t* status,
+                        d3pm_stream_t stream);
+
+/* AxialBlock's three attentions (videogpt_vq_vae.py:100-118; AxialAttention / scaled_dot_product_attention,
+ * model_utils.py:318-336, :586-600) on qkv [M][3 axes (W, H, T)][q, k, v][heads][head_dim] -> att [M][3 axes][heads][head_dim];
+ * softmax(q k^T / sqrt(head_dim)) v along one grid axis, fp32.  head_dim in {32, 64, 128}, T, H, W <= 32.             */
+int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, int W, int heads, int head_dim,
+                             d3pm_stream_t stream);
+
+/* Last SamePadConvTranspose3d (kernel 4, stride (st, sh, sw) in {1, 2}, Cout <= 4): y [B*T*H*W][ldy] holds the per-tap
+ * contributions (column ((kt*4 + kh)*4 + kw) * Cout + c, from d3pm_dec_conv with one tap and N = 64 * Cout); out
+ * [B][Cout][T*st][H*sh][W*sw] = bias + the contributions landing on each voxel: the reference's video layout.          */
+int d3pm_dec_col2im(const float* y, int ldy, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh,
+                    int sw, d3pm_stream_t stream);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * For a caller whose denoiser output lives in HOST memory (the reference's CPU tensors; bench.py's `e2e`): a handle owns
  * the device staging buffers for one batch shape, a copy stream and a compute stream.  `run` copies the inputs up in

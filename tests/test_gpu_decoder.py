@@ -1,0 +1,174 @@
+"""Token -> video, second stage: the native VQ-VAE decoder kernels against the contracts of
+include/d3pm_b200.h (emulated in float64 torch ops, tests/test_decoder_plan.py), the fixtures generated from the imported
+reference, the oracle, and the live reference `Decoder` module on the same GPU.  Needs a B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from baseline import reference_loader as RL
+from d3pm_b200 import _lib, decode, ops
+from d3pm_b200._lib import D3PMError
+from oracle import decoder_oracle as DO
+from tests.test_decoder_plan import emulate_attention, emulate_col2im, emulate_conv
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_FP32 = 2e-5   # 3xTF32 products accumulated in fp32 vs float64, relative to the largest output
+TOL_TF32 = 5e-3   # single TF32 products (10-bit mantissas)
+
+
+def _spec(g, *, nclass, nout, cin, taps, classes, stride=(1, 1, 1), bias=False, affine=False, relu=False):
+    w = torch.randn(nclass, nout, len(taps[0]) * cin, generator=g) / (len(taps[0]) * cin) ** 0.5
+    return decode.LayerSpec(w, cin=cin, taps=taps, classes=classes, stride=stride,
+                            bias=torch.randn(nout, generator=g) if bias else None,
+                            in_affine=(torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.3) if affine else None,
+                            relu_out=relu)
+
+
+CONV3 = [(a - 1, b - 1, c - 1) for a in range(3) for b in range(3) for c in range(3)]
+CONV_CASES = {
+    # name: (B, grid, spec kwargs, residual, n_tile)
+    "pointwise_k32": (2, (2, 4, 4), dict(nclass=1, nout=64, cin=32, taps=[[(0, 0, 0)]], classes=[(0, 0, 0)]), False, 128),
+    "pointwise_bias_relu_res": (3, (3, 5, 5), dict(nclass=1, nout=256, cin=128, taps=[[(0, 0, 0)]], classes=[(0, 0, 0)], bias=True,
+                                                   relu=True), True, 256),
+    "qkv_2304": (1, (4, 8, 8), dict(nclass=1, nout=2304, cin=256, taps=[[(0, 0, 0)]], classes=[(0, 0, 0)]), False, 256),
+    "conv3_affine": (2, (4, 6, 5), dict(nclass=1, nout=128, cin=256, taps=[CONV3], classes=[(0, 0, 0)], bias=True, affine=True,
+                                        relu=True), False, 128),
+    "conv3_ragged_two_tiles": (1, (3, 7, 9), dict(nclass=1, nout=32, cin=64, taps=[CONV3], classes=[(0, 0, 0)], affine=True), False, 128),
+    "nout_192_padded": (2, (2, 6, 6), dict(nclass=1, nout=192, cin=64, taps=[[(0, 0, 0)]], classes=[(0, 0, 0)], affine=True), False, 256),
+    "nout_192_tiles_of_128": (2, (2, 6, 6), dict(nclass=1, nout=192, cin=64, taps=[[(0, 0, 0)]], classes=[(0, 0, 0)]), False, 128),
+}
+
+
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("name", sorted(CONV_CASES))
+def test_dec_conv_honours_its_contract(name, terms):
+    B, grid, kw, with_res, n_tile = CONV_CASES[name]
+    g = torch.Generator().manual_seed(len(name))
+    spec = _spec(g, **kw)
+    M = B * grid[0] * grid[1] * grid[2]
+    x = torch.randn(M, spec.cin, generator=g)
+    res = torch.randn(M, spec.nout, generator=g) if with_res else None
+    want = emulate_conv(spec, x, B, grid, residual=res)
+    layer = decode._Layer(spec, torch.device(DEV), n_tile)
+    got = layer(x.to(DEV), B, grid, terms=terms, residual=None if res is None else res.to(DEV)).cpu()
+    assert got.shape == want.shape
+    tol = (TOL_FP32 if terms == 3 else TOL_TF32) * float(want.abs().max())
+    assert (got - want).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("stride", [(1, 2, 2), (2, 2, 2)])
+def test_dec_conv_parity_classes_of_a_transposed_convolution(stride):
+    """A whole SamePadConvTranspose3d (kernel 4) as parity classes, against torch's conv_transpose3d on the CPU."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(7)
+    B, grid, cin, cout = 2, (3, 5, 6), 64, 96
+    w = torch.randn(cin, cout, 4, 4, 4, generator=g) / (cin * 16) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    x = torch.randn(B, cin, *grid, generator=g)
+    want = F.conv_transpose3d(F.pad(x, DO.same_pad((4, 4, 4), stride)), w, bias, stride=stride, padding=(3, 3, 3))
+    classes = decode._convt_taps(stride)
+    mats = [torch.stack([w[:, :, kt, kh, kw].t() for (kt, kh, kw), _ in taps], 1).reshape(cout, -1) for _, taps in classes]
+    spec = decode.LayerSpec(torch.stack(mats, 0), cin=cin, taps=[[d for _, d in taps] for _, taps in classes],
+                            classes=[c for c, _ in classes], stride=stride, bias=bias)
+    rows = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous()
+    got = decode._Layer(spec, torch.device(DEV))(rows.to(DEV), B, grid, terms=3).cpu()
+    got = got.view(B, *(n * s for n, s in zip(grid, stride)), cout).permute(0, 4, 1, 2, 3)
+    assert (got - want).abs().max().item() <= TOL_FP32 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("B,grid,C", [(2, (4, 16, 16), 256), (1, (3, 5, 7), 128), (2, (2, 4, 4), 64), (1, (16, 16, 16), 256), (1, (1, 32, 2), 64)])
+def test_axial_attention(B, grid, C):
+    g = torch.Generator().manual_seed(C + grid[0])
+    M = B * grid[0] * grid[1] * grid[2]
+    qkv = torch.randn(M, 9 * C, generator=g)
+    want = emulate_attention(qkv, B, grid, 2, C)
+    att = torch.empty(M, 3 * C, device=DEV)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_dec_axial_attention(qkv.to(DEV).data_ptr(), att.data_ptr(), B, *grid, 2, C // 2, 0), "d3pm_dec_axial_attention")
+    torch.cuda.synchronize()
+    assert (att.cpu() - want).abs().max().item() <= 2e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("stride", [(1, 2, 2), (2, 2, 2), (1, 1, 2)])
+def test_col2im(stride):
+    g = torch.Generator().manual_seed(3)
+    B, grid, cout = 2, (3, 4, 5), 3
+    y = torch.randn(B * grid[0] * grid[1] * grid[2], 64 * cout, generator=g)
+    bias = torch.randn(cout, generator=g)
+    want = emulate_col2im(y, bias, B, grid, cout, stride)
+    out = torch.empty(*want.shape, device=DEV)
+    lib = _lib.load_library()
+    _lib.check(lib.d3pm_dec_col2im(y.to(DEV).data_ptr(), 64 * cout, bias.to(DEV).data_ptr(), out.data_ptr(), B, *grid, cout, *stride, 0),
+               "d3pm_dec_col2im")
+    torch.cuda.synchronize()
+    assert (out.cpu() - want).abs().max().item() <= 1e-5 * float(want.abs().max())
+
+
+def _vqvae_from_fixture(fx):
+    E, K, Hd, R, d0, d1, d2, L, res, B = (int(v) for v in fx["hparams"])
+    vq = RL.load_vqvae_module().VQVAE(checkpoint_path=None, embedding_dim=E, n_codes=K, n_hiddens=Hd, n_res_layers=R,
+                                      downsample=[d0, d1, d2], sequence_length=L, resolution=res)
+    vq.load_state_dict({k[3:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("sd/")}, strict=False)
+    return vq.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["decode_h64", "decode_h128"])
+def test_native_decoder_against_reference_fixture(name):
+    """tokens -> video entirely on the library's kernels, against the video the imported reference's `VQVAE.decode` returned."""
+    if not RL.reference_available():
+        pytest.skip("reference not staged (baseline/_ref absent): the decoder plan is read off the reference's module")
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    vq = _vqvae_from_fixture(fx)
+    tokens = torch.from_numpy(fx["tokens"]).to(DEV)
+    want = torch.from_numpy(fx["video"])
+    scale = float(want.abs().max())
+    table = decode.DecodeTable.from_autoencoder(vq)
+    status = ops.new_status(DEV)
+    got = decode.decode(vq, tokens, table, decode.NativeDecoder(vq.decoder), status).cpu()
+    assert got.shape == want.shape and int(status.item()) == 0
+    assert (got - want).abs().max().item() <= 5e-5 * scale
+    fast = decode.decode(vq, tokens, table, decode.NativeDecoder(vq.decoder, precision="tf32")).cpu()
+    assert (fast - want).abs().max().item() <= 2e-2 * scale
+    # the reference's own entry: Decoder.forward on the channels-first tensor
+    again = decode.NativeDecoder(vq.decoder)(torch.from_numpy(fx["h"]).to(DEV)).cpu()
+    assert (again - want).abs().max().item() <= 5e-5 * scale
+    with pytest.raises(D3PMError):
+        decode.NativeDecoder(vq.decoder.train())
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_native_decoder_at_the_shipped_shape_against_the_live_reference(B):
+    """n_hiddens 256, 3 residual blocks, downsample [1, 8, 8], 4 x 128 x 128 video (ucf-ddiff-train.job:15): the reference's
+    own `VQVAE.decode` on this GPU in fp32 (TF32 off) vs the native chain with the same weights."""
+    if not RL.reference_available():
+        pytest.skip("reference not staged (baseline/_ref absent)")
+    torch.manual_seed(21)
+    vq = RL.load_vqvae_module().VQVAE(checkpoint_path=None, embedding_dim=128, n_codes=4096, n_hiddens=256, n_res_layers=3,
+                                      downsample=[1, 8, 8], sequence_length=4, resolution=128)
+    with torch.no_grad():
+        for m in vq.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    vq = vq.to(DEV).eval()
+    tokens = torch.randint(0, 4096, (B, 4, 16, 16), device=DEV)
+    tf32_conv, tf32_mm = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = vq.decode(tokens).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_conv, tf32_mm
+    table = decode.DecodeTable.from_autoencoder(vq)
+    got = decode.decode(vq, tokens, table, decode.NativeDecoder(vq.decoder)).cpu()
+    scale = float(want.abs().max())
+    assert got.shape == want.shape == (B, 3, 4, 128, 128)
+    assert (got - want).abs().max().item() <= 1e-4 * scale
+    # and the oracle (CPU, fp32) on the same weights for one video
+    sd = {k: v.detach().cpu() for k, v in vq.state_dict().items()}
+    orc = DO.vqvae_decode(sd, tokens[:1].cpu(), 3, (1, 8, 8))
+    assert (got[:1] - orc).abs().max().item() <= 1e-4 * scale
