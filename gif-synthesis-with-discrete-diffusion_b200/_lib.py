@@ -88,8 +88,8 @@ class DecConvDesc(ctypes.Structure):
         ("x", c_void_p), ("in_scale", c_void_p), ("in_shift", c_void_p), ("w_image", c_void_p), ("bias", c_void_p),
         ("residual", c_void_p), ("out", c_void_p),
         ("B", c_int32), ("T", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32),
-        ("ntaps", c_int32), ("nclass", c_int32), ("Nout", c_int32), ("ldo", c_int32),
-        ("stride_t", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
+        ("ntaps", c_int32), ("nclass", c_int32), ("reserved", c_int32), ("Nout", c_int32), ("out_transposed", c_int32),
+        ("ldo", c_int64), ("stride_t", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
         ("relu_out", c_int32), ("terms", c_int32), ("n_tile", c_int32),
         ("tap", c_int8 * 4 * DEC_MAX_TAPS * DEC_MAX_CLASSES), ("cls", c_int8 * 4 * DEC_MAX_CLASSES),
         ("stream", c_void_p),
@@ -191,7 +191,7 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_dec_axial_attention.restype = c_int
     lib.d3pm_dec_axial_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.d3pm_dec_col2im.restype = c_int
-    lib.d3pm_dec_col2im.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    lib.d3pm_dec_col2im.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]
     lib.d3pm_to_token_major.restype = c_int
     lib.d3pm_to_token_major.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]

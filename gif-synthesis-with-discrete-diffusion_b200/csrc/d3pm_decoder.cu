@@ -1,4 +1,6 @@
 // C ABI of the VQ-VAE decoder kernels (include/d3pm_b200.h, "token -> video, second stage").
+#include <type_traits>
+
 #include "d3pm_decoder.cuh"
 #include "d3pm_host.h"
 
@@ -41,8 +43,12 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
                 d->Cin, D::kMaxCin);
   if (d->ntaps <= 0 || d->ntaps > D3PM_DEC_MAX_TAPS || d->nclass <= 0 || d->nclass > D3PM_DEC_MAX_CLASSES)
     return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: ntaps=%d (<= %d), nclass=%d (<= %d)", d->ntaps, D3PM_DEC_MAX_TAPS, d->nclass, D3PM_DEC_MAX_CLASSES);
-  if (d->Nout <= 0 || d->Nout % 4 != 0 || d->ldo < d->Nout || d->ldo % 4 != 0)
-    return fail(D3PM_ERR_ALIGN, "dec_conv: Nout=%d and ldo=%d must be multiples of 4, ldo >= Nout", d->Nout, d->ldo);
+  const long long rows_out = static_cast<long long>(d->B) * d->T * d->H * d->W * d->stride_t * d->stride_h * d->stride_w;
+  if (d->out_transposed) {
+    if (d->residual != nullptr || d->ldo < rows_out) return fail(D3PM_ERR_INVALID, "dec_conv: transposed output takes no residual and needs ldo >= output rows");
+  } else if (d->Nout <= 0 || d->Nout % 4 != 0 || d->ldo < d->Nout || d->ldo % 4 != 0) {
+    return fail(D3PM_ERR_ALIGN, "dec_conv: Nout=%d and ldo=%lld must be multiples of 4, ldo >= Nout", d->Nout, (long long)d->ldo);
+  }
   if (d->n_tile != 128 && d->n_tile != 256) return fail(D3PM_ERR_INVALID, "dec_conv: n_tile=%d must be 128 or 256", d->n_tile);
   if (d->terms != 1 && d->terms != 3) return fail(D3PM_ERR_INVALID, "dec_conv: terms=%d must be 1 (TF32) or 3 (3xTF32)", d->terms);
   if (d->stride_t < 1 || d->stride_h < 1 || d->stride_w < 1) return fail(D3PM_ERR_INVALID, "dec_conv: strides must be >= 1");
@@ -61,7 +67,7 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
   p.Nout = d->Nout, p.Npad = (d->Nout + d->n_tile - 1) / d->n_tile * d->n_tile, p.ldo = d->ldo;
   p.st = d->stride_t, p.sh = d->stride_h, p.sw = d->stride_w;
   p.To = d->T * p.st, p.Ho = d->H * p.sh, p.Wo = d->W * p.sw;
-  p.relu_out = d->relu_out, p.terms = d->terms;
+  p.relu_out = d->relu_out, p.terms = d->terms, p.out_transposed = d->out_transposed ? 1 : 0;
   for (int c = 0; c < D3PM_DEC_MAX_CLASSES; ++c) {
     for (int t = 0; t < D3PM_DEC_MAX_TAPS; ++t)
       for (int e = 0; e < 4; ++e) p.tap[c][t][e] = d->tap[c][t][e];
@@ -104,31 +110,40 @@ int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, 
     return fail(D3PM_ERR_UNSUPPORTED, "dec_axial_attention: head_dim=%d must be 32, 64 or 128", head_dim);
   const DeviceGuard on_device(att);
   const long long M = static_cast<long long>(B) * T * H * W;
-  const int Lmin = T < H ? (T < W ? T : W) : (H < W ? H : W);
-  const long long jobs = M / Lmin * heads;
-  const dim3 grid(static_cast<unsigned>((jobs + D::kAttnWarps - 1) / D::kAttnWarps), 3);
-  const size_t smem = static_cast<size_t>(D::kAttnWarps) * 2 * 32 * head_dim * sizeof(float);
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto launch = [&](auto kern) -> int {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-      return fail(D3PM_ERR_CUDA, "dec_axial_attention: %s", cudaGetErrorString(cudaGetLastError()));
-    kern<<<grid, 32 * D::kAttnWarps, smem, s>>>(qkv, att, B, T, H, W, heads);
-    return check_launch("dec_axial_attention");
-  };
-  if (head_dim == 32) return launch(D::axial_attention_kernel<1>);
-  if (head_dim == 64) return launch(D::axial_attention_kernel<2>);
-  return launch(D::axial_attention_kernel<4>);
+  for (int axis = 0; axis < 3; ++axis) {
+    const int L = axis == 0 ? W : (axis == 1 ? H : T);
+    const long long jobs = M / L * heads;
+    auto launch = [&](auto vpl, auto lmax) {
+      constexpr int V = decltype(vpl)::value, LM = decltype(lmax)::value;
+      constexpr int NW = D::attn_warps(V, LM);
+      D::axial_attention_kernel<V, LM><<<static_cast<unsigned>((jobs + NW - 1) / NW), 32 * NW, 0, s>>>(qkv, att, B, T, H, W, heads, axis);
+    };
+    auto by_len = [&](auto vpl) {
+      if (L <= 4) launch(vpl, std::integral_constant<int, 4>{});
+      else if (L <= 8) launch(vpl, std::integral_constant<int, 8>{});
+      else if (L <= 16) launch(vpl, std::integral_constant<int, 16>{});
+      else launch(vpl, std::integral_constant<int, 32>{});
+    };
+    if (head_dim == 32) by_len(std::integral_constant<int, 1>{});
+    else if (head_dim == 64) by_len(std::integral_constant<int, 2>{});
+    else by_len(std::integral_constant<int, 4>{});
+    const int rc = check_launch("dec_axial_attention");
+    if (rc != D3PM_OK) return rc;
+  }
+  return D3PM_OK;
 }
 
-int d3pm_dec_col2im(const float* y, int ldy, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh, int sw,
+int d3pm_dec_col2im(const float* y_t, int64_t ldt, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh, int sw,
                     d3pm_stream_t stream) {
-  if (y == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return fail(D3PM_ERR_INVALID, "dec_col2im: bad arguments");
-  if (Cout <= 0 || Cout > 4 || ldy < 64 * Cout) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: Cout=%d must be <= 4 and ldy=%d >= 64 * Cout", Cout, ldy);
+  if (y_t == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return fail(D3PM_ERR_INVALID, "dec_col2im: bad arguments");
+  const long long M = static_cast<long long>(B) * T * H * W;
+  if (Cout <= 0 || Cout > 4 || ldt < M) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: Cout=%d must be <= 4 and ldt=%lld >= B*T*H*W", Cout, (long long)ldt);
   if ((st != 1 && st != 2) || (sh != 1 && sh != 2) || (sw != 1 && sw != 2)) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: strides must be 1 or 2");
   const DeviceGuard on_device(out);
-  const long long total = static_cast<long long>(B) * T * st * H * sh * W * sw;
+  const long long total = static_cast<long long>(B) * T * st * H * sh * W;
   if ((total + 255) / 256 > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: output too large");
-  d3pm::dec::col2im_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, ldy, bias, out, B, T, H,
+  d3pm::dec::col2im_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y_t, ldt, bias, out, B, T, H,
                                                                                                                       W, Cout, st, sh, sw);
   return check_launch("dec_col2im");
 }

@@ -48,9 +48,11 @@ struct GemmParams {
   float* out;
   int B, T, H, W, Cin;
   int ntaps, nclass;
-  int Npad, Nout, ldo;
+  int Npad, Nout;
+  long long ldo;
   int To, Ho, Wo, st, sh, sw;
   int relu_out, terms;
+  int out_transposed;     // 1: out[n * ldo + row] (rows of one output channel contiguous: the col2im input), no residual
   signed char tap[kMaxClasses][kMaxTaps][4];  // (dt, dh, dw) of every tap of every class
   signed char cls[kMaxClasses][4];            // (pt, ph, pw): output position = input position * stride + this
 };
@@ -345,7 +347,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tmem_ld32(t_lane + c0, v);
       tmem_ld_wait();
       const int n0 = ntile * NT + c0;
-      if (live) {
+      if (live && p.out_transposed) {
+        // lanes = consecutive rows: every column is one coalesced 128-byte store of the warp
+        float* dst = p.out + static_cast<long long>(n0) * p.ldo + orow;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (n0 + i < p.Nout) {
+            float o = __uint_as_float(v[i]);
+            if (p.bias != nullptr) o += __ldg(p.bias + n0 + i);
+            if (p.relu_out) o = fmaxf(o, 0.f);
+            dst[static_cast<long long>(i) * p.ldo] = o;
+          }
+        }
+      } else if (live) {
         float* dst = p.out + orow * p.ldo + n0;
         const float* res = p.residual != nullptr ? p.residual + orow * p.ldo + n0 : nullptr;
 #pragma unroll
@@ -394,17 +408,24 @@ __global__ void embed_rows_kernel(const int64_t* __restrict__ tokens, const floa
 }
 
 // ---- axial attention (AxialBlock, videogpt_vq_vae.py:100-118; scaled_dot_product_attention, model_utils.py:586-600) ----
-// qkv: [M][3 axes][q, k, v][heads][dh]; att: [M][3 axes][heads][dh].  One warp per (sequence along the axis, head): K and V
-// of the sequence (L <= 32 positions) staged in shared memory, a lane holds VPL = dh / 32 channels of every vector.
-constexpr int kAttnWarps = 4;
+// qkv: [M][3 axes][q, k, v][heads][dh]; att: [M][3 axes][heads][dh].  One launch per axis, one warp per (sequence along the
+// axis, head): K and V of the sequence (L <= LMAX positions) staged in shared memory, a lane holds VPL = dh / 32 channels of
+// every vector.  Per query the L partial dot products are formed first and reduced together (LMAX independent butterflies
+// in flight), every lane then holds all L scores and evaluates the softmax on its own - no dependent shuffle chains.
+// warps per block: as many as fit the 48 KiB of static shared memory, at most 4
+__host__ __device__ constexpr int attn_warps(int vpl, int lmax) {
+  const int per_warp = 2 * lmax * 32 * vpl * 4;
+  return per_warp * 4 <= 49152 ? 4 : (per_warp * 2 <= 49152 ? 2 : 1);
+}
 
-template <int VPL>
-__global__ void __launch_bounds__(32 * kAttnWarps) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
-                                                                          int T, int H, int W, int heads) {
-  extern __shared__ float attn_smem[];
+template <int VPL, int LMAX>
+__global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
+                                                                          int T, int H, int W, int heads, int axis) {
   constexpr int DH = 32 * VPL;
+  constexpr int kAttnWarps = attn_warps(VPL, LMAX);
+  __shared__ __align__(16) float kv_smem[kAttnWarps][2][LMAX][DH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int axis = blockIdx.y;  // 0: along W (attn_w, axial_dim -2), 1: along H, 2: along T
+  // axis 0: along W (attn_w, axial_dim -2), 1: along H, 2: along T
   const int L = axis == 0 ? W : (axis == 1 ? H : T);
   const long long M = static_cast<long long>(B) * T * H * W;
   const long long nseq = M / L;
@@ -413,77 +434,97 @@ __global__ void __launch_bounds__(32 * kAttnWarps) axial_attention_kernel(const 
   const long long seq = job / heads;
   const int head = static_cast<int>(job - seq * heads);
   long long row0, rstride;
+  const long long HW = static_cast<long long>(H) * W;
   if (axis == 0) row0 = seq * W, rstride = 1;
-  else if (axis == 1) row0 = (seq / W) * (static_cast<long long>(H) * W) + seq % W, rstride = W;
-  else row0 = (seq / (static_cast<long long>(H) * W)) * (static_cast<long long>(T) * H * W) + seq % (static_cast<long long>(H) * W), rstride = static_cast<long long>(H) * W;
+  else if (axis == 1) row0 = (seq / W) * HW + seq % W, rstride = W;
+  else row0 = (seq / HW) * (T * HW) + seq % HW, rstride = HW;
   const int C = heads * DH;
   const int ldq = 9 * C;  // floats per row of qkv
-  float* ks = attn_smem + static_cast<size_t>(warp) * 2 * 32 * DH;
-  float* vs = ks + 32 * DH;
+  float (*ks)[DH] = kv_smem[warp][0];
+  float (*vs)[DH] = kv_smem[warp][1];
   const float* qbase = qkv + static_cast<size_t>(axis) * 3 * C + head * DH + lane * VPL;
-  for (int j = 0; j < L; ++j) {
-    const float* rowp = qbase + (row0 + j * rstride) * ldq;
+#pragma unroll
+  for (int j = 0; j < LMAX; ++j) {
+    const bool in = j < L;
+    const float* rowp = qbase + (row0 + (in ? j : 0) * rstride) * ldq;
 #pragma unroll
     for (int e = 0; e < VPL; ++e) {
-      ks[j * DH + lane * VPL + e] = rowp[C + e];
-      vs[j * DH + lane * VPL + e] = rowp[2 * C + e];
+      ks[j][lane * VPL + e] = in ? __ldg(rowp + C + e) : 0.f;
+      vs[j][lane * VPL + e] = in ? __ldg(rowp + 2 * C + e) : 0.f;
     }
   }
   __syncwarp();
-  const float scale = rsqrtf(static_cast<float>(DH));
+  const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // scores in log2 units
+  float qn[VPL];
+#pragma unroll
+  for (int e = 0; e < VPL; ++e) qn[e] = __ldg(qbase + row0 * ldq + e);
   for (int i = 0; i < L; ++i) {
-    const float* rowp = qbase + (row0 + i * rstride) * ldq;
     float qv[VPL];
 #pragma unroll
-    for (int e = 0; e < VPL; ++e) qv[e] = rowp[e];
-    float mine = -3.0e38f;  // lane j keeps the score of key j
-    for (int j = 0; j < L; ++j) {
-      float s = 0.f;
+    for (int e = 0; e < VPL; ++e) qv[e] = qn[e];
+    if (i + 1 < L) {
+      const float* rowp = qbase + (row0 + (i + 1) * rstride) * ldq;
 #pragma unroll
-      for (int e = 0; e < VPL; ++e) s = fmaf(qv[e], ks[j * DH + lane * VPL + e], s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == j) mine = s * scale;
+      for (int e = 0; e < VPL; ++e) qn[e] = __ldg(rowp + e);
     }
-    float mx = mine;
+    float s[LMAX];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float e_ = lane < L ? expf(mine - mx) : 0.f;
-    float sum = e_;
+    for (int j = 0; j < LMAX; ++j) {
+      float d = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float pr = e_ / sum;
+      for (int e = 0; e < VPL; ++e) d = fmaf(qv[e], ks[j][lane * VPL + e], d);
+      s[j] = d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < LMAX; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < LMAX; ++j) {
+      s[j] = j < L ? s[j] * scale : -3.0e38f;
+      mx = fmaxf(mx, s[j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < LMAX; ++j) {
+      s[j] = j < L ? exp2f(s[j] - mx) : 0.f;
+      sum += s[j];
+    }
+    const float rs = 1.0f / sum;
     float acc[VPL];
 #pragma unroll
     for (int e = 0; e < VPL; ++e) acc[e] = 0.f;
-    for (int j = 0; j < L; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, pr, j);
 #pragma unroll
-      for (int e = 0; e < VPL; ++e) acc[e] = fmaf(pj, vs[j * DH + lane * VPL + e], acc[e]);
-    }
+    for (int j = 0; j < LMAX; ++j)
+#pragma unroll
+      for (int e = 0; e < VPL; ++e) acc[e] = fmaf(s[j], vs[j][lane * VPL + e], acc[e]);
     float* o = att + (row0 + i * rstride) * (3 * C) + axis * C + head * DH + lane * VPL;
 #pragma unroll
-    for (int e = 0; e < VPL; ++e) o[e] = acc[e];
+    for (int e = 0; e < VPL; ++e) o[e] = acc[e] * rs;
   }
 }
 
 // ---- col2im of the last transposed convolution ----------------------------------------------------------------------
-// y: [B*T*H*W][ldy], column ((kt*4 + kh)*4 + kw)*Cout + c = contribution of input position (row) through filter tap (kt, kh, kw)
-// to output channel c.  out: [B][Cout][To][Ho][Wo] (the reference's layout), out = bias + sum of the contributions that land
-// on the voxel: along a dimension of stride s, tap k of input i lands on y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2)
-// (F.pad of SamePadConvTranspose3d :324-328, then ConvTranspose3d with padding 3 :330-332).
-__global__ void col2im_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias, float* __restrict__ out, int B, int T,
-                              int H, int W, int Cout, int st, int sh, int sw) {
-  const int To = T * st, Ho = H * sh, Wo = W * sw;
-  const long long total = static_cast<long long>(B) * To * Ho * Wo;
+// yT: [64 * Cout][Mtot] (TRANSPOSED rows of the last GEMM: row ((kt*4 + kh)*4 + kw)*Cout + c, column = input position) =
+// contribution of an input position through filter tap (kt, kh, kw) to output channel c.  out: [B][Cout][To][Ho][Wo] (the
+// reference's layout) = bias + the contributions that land on each voxel: along a dimension of stride s, tap k of input i
+// lands on y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2) (F.pad of SamePadConvTranspose3d :324-328, then ConvTranspose3d
+// with padding 3 :330-332).  A thread owns the sw output voxels above one input column position, so the lanes of a warp read
+// consecutive input positions of one (tap, channel) row: coalesced.
+__global__ void col2im_kernel(const float* __restrict__ yT, long long ldT, const float* __restrict__ bias, float* __restrict__ out, int B,
+                              int T, int H, int W, int Cout, int st, int sh, int sw) {
+  const int To = T * st, Ho = H * sh;
+  const long long Wo = static_cast<long long>(W) * sw;
+  const long long total = static_cast<long long>(B) * To * Ho * W;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int yw = static_cast<int>(idx % Wo);
-  const int yh = static_cast<int>((idx / Wo) % Ho);
-  const int yt = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % To);
-  const long long b = idx / (static_cast<long long>(Wo) * Ho * To);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int mw = static_cast<int>(idx % W);
+  const int yh = static_cast<int>((idx / W) % Ho);
+  const int yt = static_cast<int>((idx / (static_cast<long long>(W) * Ho)) % To);
+  const long long b = idx / (static_cast<long long>(W) * Ho * To);
   const int pft = (4 - st + 1) / 2, pfh = (4 - sh + 1) / 2, pfw = (4 - sw + 1) / 2;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (int kt = 0; kt < 4; ++kt) {
     const int nt = yt + 3 - kt;
     if (nt % st != 0) continue;
@@ -494,18 +535,29 @@ __global__ void col2im_kernel(const float* __restrict__ y, int ldy, const float*
       if (nh % sh != 0) continue;
       const int ih = nh / sh - pfh;
       if (ih < 0 || ih >= H) continue;
-      for (int kw = 0; kw < 4; ++kw) {
-        const int nw = yw + 3 - kw;
-        if (nw % sw != 0) continue;
-        const int iw = nw / sw - pfw;
-        if (iw < 0 || iw >= W) continue;
-        const float* src = y + (((b * T + it) * H + ih) * W + iw) * ldy + ((kt * 4 + kh) * 4 + kw) * Cout;
-        for (int c = 0; c < Cout && c < 4; ++c) acc[c] += __ldg(src + c);
+      const long long rowpos = ((b * T + it) * H + ih) * W;
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        if (pw >= sw) break;
+        const int yw = mw * sw + pw;
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+          const int nw = yw + 3 - kw;
+          if (nw % sw != 0) continue;
+          const int iw = nw / sw - pfw;
+          if (iw < 0 || iw >= W) continue;
+          const float* src = yT + static_cast<long long>(((kt * 4 + kh) * 4 + kw) * Cout) * ldT + rowpos + iw;
+          for (int c = 0; c < Cout && c < 4; ++c) acc[pw][c] += __ldg(src + c * ldT);
+        }
       }
     }
   }
-  for (int c = 0; c < Cout && c < 4; ++c)
-    out[(((b * Cout + c) * To + yt) * Ho + yh) * Wo + yw] = acc[c] + (bias != nullptr ? bias[c] : 0.f);
+  for (int c = 0; c < Cout && c < 4; ++c) {
+    float* dst = out + (((b * Cout + c) * To + yt) * Ho + yh) * Wo + static_cast<long long>(mw) * sw;
+    const float bc = bias != nullptr ? bias[c] : 0.f;
+    if (sw == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0][c] + bc, acc[1][c] + bc);
+    else dst[0] = acc[0][c] + bc;
+  }
 }
 
 }  // namespace dec

@@ -58,7 +58,8 @@ def emulate_attention(qkv, B, grid, heads, C):
 
 
 def emulate_col2im(y, bias, B, grid, cout, stride):
-    """d3pm_dec_col2im: tap k of input i lands on y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2), per dimension."""
+    """d3pm_dec_col2im (on the untransposed contributions y [positions][64 * cout]): tap k of input i lands on
+    y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2), per dimension."""
     T, H, W = grid
     To, Ho, Wo = (g * s for g, s in zip(grid, stride))
     yy = y.double().view(B, T, H, W, 4, 4, 4, cout)

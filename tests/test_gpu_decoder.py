@@ -16,7 +16,9 @@ from tests.test_decoder_plan import emulate_attention, emulate_col2im, emulate_c
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL_FP32 = 2e-5   # 3xTF32 products accumulated in fp32 vs float64, relative to the largest output
+# 3xTF32 products vs float64, relative to the largest output.  The products themselves are fp32-grade (2^-22); what shows at
+# K = 27 x 256 = 6912 is the tensor core's accumulator, which does not round to nearest: ~3e-5 of the scale there, ~1e-6 at K <= 256
+TOL_FP32 = 1e-4
 TOL_TF32 = 5e-3   # single TF32 products (10-bit mantissas)
 
 
@@ -58,6 +60,9 @@ def test_dec_conv_honours_its_contract(name, terms):
     assert got.shape == want.shape
     tol = (TOL_FP32 if terms == 3 else TOL_TF32) * float(want.abs().max())
     assert (got - want).abs().max().item() <= tol
+    if not with_res:  # the transposed store of the epilogue (the layout col2im reads)
+        got_t = layer(x.to(DEV), B, grid, terms=terms, transposed=True).cpu()
+        assert got_t.shape == (spec.nout, M) and torch.equal(got_t.t(), got)
 
 
 @pytest.mark.parametrize("stride", [(1, 2, 2), (2, 2, 2)])
@@ -102,7 +107,8 @@ def test_col2im(stride):
     want = emulate_col2im(y, bias, B, grid, cout, stride)
     out = torch.empty(*want.shape, device=DEV)
     lib = _lib.load_library()
-    _lib.check(lib.d3pm_dec_col2im(y.to(DEV).data_ptr(), 64 * cout, bias.to(DEV).data_ptr(), out.data_ptr(), B, *grid, cout, *stride, 0),
+    y_t = y.t().contiguous().to(DEV)   # the kernel reads the transposed rows d3pm_dec_conv writes with out_transposed = 1
+    _lib.check(lib.d3pm_dec_col2im(y_t.data_ptr(), y_t.shape[1], bias.to(DEV).data_ptr(), out.data_ptr(), B, *grid, cout, *stride, 0),
                "d3pm_dec_col2im")
     torch.cuda.synchronize()
     assert (out.cpu() - want).abs().max().item() <= 1e-5 * float(want.abs().max())
