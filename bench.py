@@ -418,6 +418,7 @@ def run_ours(args):
             extras = measure_next_rows(dev, model, table, x_t, t, x_prev)
             _NEXT_ROWS_LOGITS = None
             torch.cuda.empty_cache()
+            extras["decode"] = measure_decode(dev)
             extras["config3"] = measure_config3(dev)
         except Exception as exc:
             extras["error"] = repr(exc)
@@ -636,6 +637,25 @@ def measure_16bit(dev, model, table, videos=VIDEOS_PER_GPU, steps=30):
                      "frac_of_measured_peak": gbps / peak, "ms_per_step_cast_then_fp32_step": ms_cast}
         del lc, lu
     torch.cuda.empty_cache()
+    return res
+
+
+def measure_decode(dev):
+    """SURVEY §8 f4, the step after the path: VQVAE.decode of the sampled tokens at the shipped shape (tools/decode_bench.py) -
+    the reference's PyTorch decoder on this GPU next to the native chain (tcgen05 implicit-GEMM convolutions)."""
+    from tools import decode_bench
+    res = decode_bench.run(videos=VIDEOS_PER_GPU, dev=dev, reps=5, quiet=True)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if "native_fp32_ms" in res and os.path.isfile(peaks_path):
+        bf16 = float(json.load(open(peaks_path)).get("bf16_tflops", 0.0))
+        if bf16:
+            res["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": 0.5 * bf16,
+                               "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate)",
+                               "achieved_fp32_mode": 3.0 * res["native_fp32_useful_TFLOPs"], "achieved_tf32_mode": res["native_tf32_useful_TFLOPs"],
+                               "frac_fp32_mode": 3.0 * res["native_fp32_useful_TFLOPs"] / (0.5 * bf16),
+                               "frac_tf32_mode": res["native_tf32_useful_TFLOPs"] / (0.5 * bf16),
+                               "note": "fp32 mode issues three TF32 products per useful multiply-add (3xTF32), whole chain incl. attention, "
+                                       "col2im and launch gaps"}
     return res
 
 

@@ -74,6 +74,7 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
     for (int e = 0; e < 4; ++e) p.cls[c][e] = d->cls[c][e];
   }
   const long long M = static_cast<long long>(d->B) * d->T * d->H * d->W;
+  if (M * d->Cin >= (1LL << 32)) return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: the input has %lld elements; element offsets are 32-bit", M * d->Cin);
   const long long tiles = (M + D::kTileM - 1) / D::kTileM * (p.Npad / d->n_tile);
   if (tiles > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: too many tiles");
   const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(d->nclass));

@@ -116,12 +116,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// nearest tf32 number (10 mantissa bits, ties away from zero): the tensor core ignores the 13 low bits, so rounding here makes
+// the single-product mode unbiased; in the 3xTF32 mode lo = x - hi stays exact either way
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 // ---- weight image ---------------------------------------------------------------------------------------------
 // floats of the image of one parity class: [Npad / NT][Ktot / 32][2 terms][NT][32]
 __host__ __device__ inline int64_t image_floats(int Npad, int Ktot) { return static_cast<int64_t>(Npad) * Ktot * 2; }
 
 // w: [nclass][N][Ktot] row-major fp32 (k contiguous: the K-major operand), rows n >= N are zero in the image.
-// hi = w with the 13 low mantissa bits cleared (exactly a tf32 number), lo = w - hi (exact in fp32).
+// hi = w rounded to the nearest tf32 number, lo = w - hi (exact in fp32).
 __global__ void weight_image_kernel(const float* __restrict__ w, int N, int Npad, int Ktot, int NT, float* __restrict__ image) {
   const int KB = Ktot / 32;
   const int64_t pieces = static_cast<int64_t>(Npad) * KB * 8;  // 16-byte pieces of one class
@@ -137,7 +141,7 @@ __global__ void weight_image_kernel(const float* __restrict__ w, int N, int Npad
   float hi[4], lo[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    hi[e] = __uint_as_float(__float_as_uint(s[e]) & 0xffffe000u);
+    hi[e] = tf32_round(s[e]);
     lo[e] = s[e] - hi[e];
   }
   const int ntile = n / NT, r = n % NT;
@@ -162,6 +166,7 @@ struct GemmCtl {
   unsigned long long full_a[3], full_b[3], empty[3], acc_full;
   uint32_t tmem_base, pad;
   signed char taps[kMaxTaps][4];  // this CTA's parity class
+  int tap_shift[kMaxTaps];        // element offset of a tap's source row relative to the row itself
   alignas(16) float scale[kMaxCin];
   alignas(16) float shift[kMaxCin];
 };
@@ -194,8 +199,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   if (p.in_scale != nullptr)
     for (int i = tid; i < p.Cin; i += kThreads) C.scale[i] = p.in_scale[i], C.shift[i] = p.in_shift[i];
-  if (tid < p.ntaps)
+  if (tid < p.ntaps) {
     for (int e = 0; e < 4; ++e) C.taps[tid][e] = p.tap[cls][tid][e];
+    C.tap_shift[tid] = ((p.tap[cls][tid][0] * p.H + p.tap[cls][tid][1]) * p.W + p.tap[cls][tid][2]) * p.Cin;
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(NT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -248,61 +255,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else {
     // =========================== A producer (warps 2..9) ===========================
+    // Everything that depends on the tile only is formed once: per row a bit mask of the taps that stay inside the grid
+    // and a 32-bit element offset; per tap the element shift of its source row (shared memory).  A k-block then costs four
+    // 128-bit loads, the transform and four (eight) 128-bit shared stores per thread.
     const int pt = tid - 64;        // 0..255
     const int piece = pt & 7;       // 16-byte piece of the 128-byte k-block row
     const int r0 = pt >> 3;         // rows r0 + 32 i
     const int HW = p.H * p.W;
-    int ct[4], ch[4], cw[4];
-    long long base[4];
-    bool rowok[4];
+    uint32_t okmask[4];             // bit `tap`: the tap's source position of row i exists
+    uint32_t base[4];               // element offset of the row's own position (+ this thread's piece)
+    uint32_t soff[4];               // byte offset of (row, piece) inside a swizzled k-block
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long m = mtile * kTileM + r0 + 32 * i;
-      rowok[i] = m < M;
-      const long long mm = rowok[i] ? m : 0;
+      const bool rowok = m < M;
+      const long long mm = rowok ? m : 0;
       const int inb = static_cast<int>(mm % (static_cast<long long>(p.T) * HW));
-      ct[i] = inb / HW;
-      ch[i] = (inb % HW) / p.W;
-      cw[i] = inb % p.W;
-      base[i] = mm * p.Cin + piece * 4;
+      const int ct = inb / HW, ch = (inb % HW) / p.W, cw = inb % p.W;
+      uint32_t mask = 0;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const bool ok = rowok && static_cast<unsigned>(ct + C.taps[tap][0]) < static_cast<unsigned>(p.T) &&
+                        static_cast<unsigned>(ch + C.taps[tap][1]) < static_cast<unsigned>(p.H) &&
+                        static_cast<unsigned>(cw + C.taps[tap][2]) < static_cast<unsigned>(p.W);
+        mask |= (ok ? 1u : 0u) << tap;
+      }
+      okmask[i] = mask;
+      base[i] = static_cast<uint32_t>(mm * p.Cin + piece * 4);
+      const int r = r0 + 32 * i;
+      soff[i] = static_cast<uint32_t>(r * 128 + ((piece ^ (r & 7)) << 4));
     }
-    auto fetch = [&](int kb, float4 (&v)[4], uint32_t& okmask) {
-      const int tap = kb / CB, cb = kb - tap * CB;
-      const int dt = C.taps[tap][0], dh = C.taps[tap][1], dw = C.taps[tap][2];
-      const long long shift = (static_cast<long long>(dt) * HW + dh * p.W + dw) * p.Cin + cb * 32;
-      okmask = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t scale_at = smem_u32(C.scale) + piece * 16, shift_at = smem_u32(C.shift) + piece * 16;
+    // (tap, channel block) of the next k-block to fetch, advanced incrementally
+    int f_tap = 0, f_cb = 0;
+    auto fetch = [&](float4 (&v)[4], uint32_t& ok4) {
+      const int shift = C.tap_shift[f_tap] + f_cb * 32;  // may be negative: 32-bit wrap-around arithmetic on the offsets
+      ok4 = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const bool ok = rowok[i] && static_cast<unsigned>(ct[i] + dt) < static_cast<unsigned>(p.T) &&
-                        static_cast<unsigned>(ch[i] + dh) < static_cast<unsigned>(p.H) &&
-                        static_cast<unsigned>(cw[i] + dw) < static_cast<unsigned>(p.W);
-        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.x + base[i] + shift)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        okmask |= (ok ? 1u : 0u) << i;
+        const bool ok = (okmask[i] >> f_tap) & 1u;
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.x + static_cast<uint32_t>(base[i] + static_cast<uint32_t>(shift))))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        ok4 |= (ok ? 1u : 0u) << i;
       }
+      if (++f_cb == CB) f_cb = 0, ++f_tap;
     };
     const bool affine = p.in_scale != nullptr;
-    float4 nxt[4];
-    uint32_t nxt_ok = 0;
-    fetch(0, nxt, nxt_ok);
-    for (int kb = 0; kb < KB; ++kb) {
-      float4 cur[4];
-      const uint32_t cur_ok = nxt_ok;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-      if (kb + 1 < KB) fetch(kb + 1, nxt, nxt_ok);
-      const int st = kb % G::kStages;
-      mbar_wait(&C.empty[st], static_cast<uint32_t>(((kb / G::kStages) & 1) ^ 1));
-      unsigned char* a_hi = smem + st * G::kStageBytes;
-      const int cb = kb % CB;
+    const bool want_lo = p.terms != 1;
+    int e_st = 0, e_cb = 0;
+    uint32_t e_par = 1;  // parity to wait for on the stage's `empty` barrier (first round: passes at once)
+    // transform (BatchNorm + ReLU in front of the convolution; the zero padding comes AFTER it: F.pad of the activated
+    // tensor), hi / lo split and swizzled store of one k-block
+    auto emit = [&](const float4 (&cur)[4], uint32_t cur_ok) {
+      mbar_wait(&C.empty[e_st], e_par);
+      const uint32_t a_hi = smem_base + e_st * G::kStageBytes;
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (affine) {
-        sc = *reinterpret_cast<const float4*>(C.scale + cb * 32 + piece * 4);
-        sh = *reinterpret_cast<const float4*>(C.shift + cb * 32 + piece * 4);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(scale_at + e_cb * 128));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w) : "r"(shift_at + e_cb * 128));
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float a[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
-        if (affine) {  // the BatchNorm + ReLU in front of the convolution; the zero padding comes AFTER it (F.pad of the activated tensor)
+        if (affine) {
           const bool ok = (cur_ok >> i) & 1u;
           a[0] = ok ? fmaxf(fmaf(a[0], sc.x, sh.x), 0.f) : 0.f;
           a[1] = ok ? fmaxf(fmaf(a[1], sc.y, sh.y), 0.f) : 0.f;
@@ -312,16 +327,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         float hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          hi[e] = __uint_as_float(__float_as_uint(a[e]) & 0xffffe000u);
+          hi[e] = tf32_round(a[e]);
           lo[e] = a[e] - hi[e];
         }
-        const int r = r0 + 32 * i;
-        const int at = r * 128 + ((piece ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(a_hi + at) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(a_hi + kBlockBytes + at) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + soff[i]), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+        if (want_lo)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + kBlockBytes + soff[i]), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3])
+                       : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&C.full_a[st]);
+      mbar_arrive(&C.full_a[e_st]);
+      if (++e_st == G::kStages) e_st = 0, e_par ^= 1u;
+      if (++e_cb == CB) e_cb = 0;
+    };
+    // two k-blocks of loads in flight per thread (32 KiB per SM): the gather is latency-bound at one
+    float4 buf0[4], buf1[4];
+    uint32_t ok0 = 0, ok1 = 0;
+    fetch(buf0, ok0);
+    if (KB > 1) fetch(buf1, ok1);
+    for (int kb = 0; kb < KB; kb += 2) {
+      {
+        float4 cur[4];
+        const uint32_t cur_ok = ok0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = buf0[i];
+        if (kb + 2 < KB) fetch(buf0, ok0);
+        emit(cur, cur_ok);
+      }
+      if (kb + 1 < KB) {
+        float4 cur[4];
+        const uint32_t cur_ok = ok1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = buf1[i];
+        if (kb + 3 < KB) fetch(buf1, ok1);
+        emit(cur, cur_ok);
+      }
     }
 
     // =========================== epilogue ===========================
