@@ -75,14 +75,16 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
   }
   const long long M = static_cast<long long>(d->B) * d->T * d->H * d->W;
   if (M * d->Cin >= (1LL << 32)) return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: the input has %lld elements; element offsets are 32-bit", M * d->Cin);
-  const long long tiles = (M + D::kTileM - 1) / D::kTileM * (p.Npad / d->n_tile);
-  if (tiles > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: too many tiles");
-  const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(d->nclass));
+  const long long tiles = (M + D::kTileM - 1) / D::kTileM * (p.Npad / d->n_tile) * d->nclass;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return fail(D3PM_ERR_CUDA, "dec_conv: cannot query the device");
+  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);  // persistent: one CTA per SM walks the tiles
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
   auto launch = [&](auto kern, size_t smem) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return fail(D3PM_ERR_CUDA, "dec_conv: %s", cudaGetErrorString(cudaGetLastError()));
-    kern<<<grid, D::kThreads, smem, s>>>(p);
+    kern<<<grid, D::kGemmThreads, smem, s>>>(p);
     return check_launch("dec_conv");
   };
   return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128>, D::gemm_smem_bytes<128>())

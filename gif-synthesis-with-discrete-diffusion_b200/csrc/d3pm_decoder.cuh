@@ -32,7 +32,6 @@ namespace dec {
 constexpr int kTileM = 128;
 constexpr int kProdWarps = 8;                     // A producers, then the epilogue
 constexpr int kProdThreads = 32 * kProdWarps;
-constexpr int kThreads = 32 * (kProdWarps + 2);   // + MMA issue warp + weight TMA warp
 constexpr int kBlockBytes = kTileM * 128;         // one k-block (32 floats) of a 128-row operand
 constexpr int kMaxTaps = D3PM_DEC_MAX_TAPS;
 constexpr int kMaxClasses = D3PM_DEC_MAX_CLASSES;
@@ -163,12 +162,13 @@ struct GemmGeo {
 };
 
 struct GemmCtl {
-  unsigned long long full_a[3], full_b[3], empty[3], acc_full;
+  unsigned long long full_a[3], full_b[3], empty[3], acc_full[2], acc_empty[2];
   uint32_t tmem_base, pad;
-  signed char taps[kMaxTaps][4];  // this CTA's parity class
-  int tap_shift[kMaxTaps];        // element offset of a tap's source row relative to the row itself
+  signed char taps[kMaxClasses][kMaxTaps][4];
+  int tap_shift[kMaxClasses][kMaxTaps];  // element offset of a tap's source row relative to the row itself
   alignas(16) float scale[kMaxCin];
   alignas(16) float shift[kMaxCin];
+  alignas(16) float stage[4][32][36];    // epilogue: 32 rows x 32 columns per warp, rows padded to 144 B (conflict-free 128-bit access)
 };
 
 template <int NT>
@@ -176,8 +176,17 @@ constexpr size_t gemm_smem_bytes() {
   return 1024 + GemmGeo<NT>::kStages * GemmGeo<NT>::kStageBytes + sizeof(GemmCtl);
 }
 
+// Persistent: a CTA walks the tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the launch, tile t = (parity class, M tile,
+// N tile) with the N tile fastest (neighbouring CTAs gather the same input rows: L2).  Fourteen warps:
+//   warp 0      one lane issues the MMAs of a tile into accumulator (tile & 1) and the commits that free stages / publish it
+//   warp 1      one lane streams the weight image (bulk TMA)
+//   warps 2-9   produce the A operand, k-block after k-block, running ahead across tile boundaries
+//   warps 10-13 epilogue of tile i while the MMAs of tile i + 1 fill the other accumulator
+constexpr int kEpiWarps = 4;
+constexpr int kGemmThreads = 32 * (2 + kProdWarps + kEpiWarps);
+
 template <int NT>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   using G = GemmGeo<NT>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -185,26 +194,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles_n = p.Npad / NT;
-  const int ntile = static_cast<int>(blockIdx.x % ntiles_n);
-  const long long mtile = blockIdx.x / ntiles_n;
-  const int cls = blockIdx.y;
   const int CB = p.Cin >> 5;            // k-blocks per tap
-  const int KB = p.ntaps * CB;          // k-blocks in all
+  const int KB = p.ntaps * CB;          // k-blocks of a tile
   const long long M = static_cast<long long>(p.B) * p.T * p.H * p.W;
+  const long long mtiles = (M + kTileM - 1) / kTileM;
+  const long long per_class = mtiles * ntiles_n;
+  const long long total = per_class * p.nclass;
+  const int HW = p.H * p.W;
 
   if (tid == 0) {
     for (int i = 0; i < G::kStages; ++i) mbar_init(&C.full_a[i], kProdThreads), mbar_init(&C.full_b[i], 1), mbar_init(&C.empty[i], 1);
-    mbar_init(&C.acc_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&C.acc_full[i], 1), mbar_init(&C.acc_empty[i], kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.in_scale != nullptr)
-    for (int i = tid; i < p.Cin; i += kThreads) C.scale[i] = p.in_scale[i], C.shift[i] = p.in_shift[i];
-  if (tid < p.ntaps) {
-    for (int e = 0; e < 4; ++e) C.taps[tid][e] = p.tap[cls][tid][e];
-    C.tap_shift[tid] = ((p.tap[cls][tid][0] * p.H + p.tap[cls][tid][1]) * p.W + p.tap[cls][tid][2]) * p.Cin;
+    for (int i = tid; i < p.Cin; i += kGemmThreads) C.scale[i] = p.in_scale[i], C.shift[i] = p.in_shift[i];
+  for (int i = tid; i < p.nclass * p.ntaps; i += kGemmThreads) {
+    const int c = i / p.ntaps, t = i - c * p.ntaps;
+    for (int e = 0; e < 4; ++e) C.taps[c][t][e] = p.tap[c][t][e];
+    C.tap_shift[c][t] = ((p.tap[c][t][0] * p.H + p.tap[c][t][1]) * p.W + p.tap[c][t][2]) * p.Cin;
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(NT) : "memory");
+  if (warp == 0) {  // two accumulators of NT columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(2 * NT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -216,80 +227,100 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // =========================== weight stream (bulk TMA) ===========================
     if (lane == 0) {
       const uint32_t bytes = p.terms == 1 ? G::kBBytes : 2 * G::kBBytes;
-      const float* src = p.w_image + static_cast<size_t>(cls) * image_floats(p.Npad, KB * 32) +
-                         static_cast<size_t>(ntile) * KB * (2 * NT * 32);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int st = kb % G::kStages;
-        mbar_wait(&C.empty[st], static_cast<uint32_t>(((kb / G::kStages) & 1) ^ 1));
-        mbar_expect_tx(&C.full_b[st], bytes);
-        unsigned char* dst = smem + st * G::kStageBytes + 2 * kBlockBytes;
-        const float* s = src + static_cast<size_t>(kb) * (2 * NT * 32);
-        for (uint32_t q = 0; q < bytes; q += kBlockBytes) tma_load(dst + q, s + q / 4, kBlockBytes, &C.full_b[st]);
+      int st = 0;
+      uint32_t par = 1;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int cls = static_cast<int>(tile / per_class);
+        const int ntile = static_cast<int>(tile % ntiles_n);
+        const float* src = p.w_image + static_cast<size_t>(cls) * image_floats(p.Npad, KB * 32) + static_cast<size_t>(ntile) * KB * (2 * NT * 32);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&C.empty[st], par);
+          mbar_expect_tx(&C.full_b[st], bytes);
+          unsigned char* dst = smem + st * G::kStageBytes + 2 * kBlockBytes;
+          const float* s = src + static_cast<size_t>(kb) * (2 * NT * 32);
+          for (uint32_t q = 0; q < bytes; q += kBlockBytes) tma_load(dst + q, s + q / 4, kBlockBytes, &C.full_b[st]);
+          if (++st == G::kStages) st = 0, par ^= 1u;
+        }
       }
     }
   } else if (warp == 0) {
     // =========================== MMA issue ===========================
     if (lane == 0) {
-      uint32_t accum = 0;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int st = kb % G::kStages;
-        const uint32_t par = static_cast<uint32_t>((kb / G::kStages) & 1);
-        mbar_wait(&C.full_a[st], par);
-        mbar_wait(&C.full_b[st], par);
+      int st = 0;
+      uint32_t par = 0, tc = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+        const uint32_t acc = tc & 1u;
+        mbar_wait(&C.acc_empty[acc], ((tc >> 1) & 1u) ^ 1u);  // the epilogue of tile tc - 2 has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * G::kStageBytes);
-        const uint32_t b_addr = a_addr + 2 * kBlockBytes;
-        // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi (terms == 1: a_hi w_hi only)
-        for (int term = (p.terms == 1 ? 2 : 0); term < 3; ++term) {
-          const uint32_t a_off = (term == 0) ? kBlockBytes : 0;
-          const uint32_t b_off = (term == 1) ? G::kBBytes : 0;
+        const uint32_t d_tmem = tmem + acc * NT;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&C.full_a[st], par);
+          mbar_wait(&C.full_b[st], par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + st * G::kStageBytes);
+          const uint32_t b_addr = a_addr + 2 * kBlockBytes;
+          // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi (terms == 1: a_hi w_hi only)
+          for (int term = (p.terms == 1 ? 2 : 0); term < 3; ++term) {
+            const uint32_t a_off = (term == 0) ? kBlockBytes : 0;
+            const uint32_t b_off = (term == 1) ? G::kBBytes : 0;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {  // 4 MMAs of K = 8 per 128-byte k-block
-            tc_mma_tf32(tmem, smem_desc(a_addr + a_off + ks * 32), smem_desc(b_addr + b_off + ks * 32), G::kIdesc, accum);
-            accum = 1;
+            for (int ks = 0; ks < 4; ++ks) {  // 4 MMAs of K = 8 per 128-byte k-block
+              tc_mma_tf32(d_tmem, smem_desc(a_addr + a_off + ks * 32), smem_desc(b_addr + b_off + ks * 32), G::kIdesc, accum);
+              accum = 1;
+            }
           }
+          tc_commit(&C.empty[st]);
+          if (++st == G::kStages) st = 0, par ^= 1u;
         }
-        tc_commit(&C.empty[st]);
+        tc_commit(&C.acc_full[acc]);
       }
-      tc_commit(&C.acc_full);
     }
-  } else {
+  } else if (warp < 2 + kProdWarps) {
     // =========================== A producer (warps 2..9) ===========================
-    // Everything that depends on the tile only is formed once: per row a bit mask of the taps that stay inside the grid
-    // and a 32-bit element offset; per tap the element shift of its source row (shared memory).  A k-block then costs four
-    // 128-bit loads, the transform and four (eight) 128-bit shared stores per thread.
+    // Everything that depends on the tile only is formed once per tile: per row a bit mask of the taps that stay inside the
+    // grid and a 32-bit element offset.  A k-block then costs four 128-bit loads, the transform and four (eight) 128-bit
+    // shared stores per thread.  The fetch side runs two k-blocks ahead of the store side, across tile boundaries.
     const int pt = tid - 64;        // 0..255
     const int piece = pt & 7;       // 16-byte piece of the 128-byte k-block row
     const int r0 = pt >> 3;         // rows r0 + 32 i
-    const int HW = p.H * p.W;
     uint32_t okmask[4];             // bit `tap`: the tap's source position of row i exists
     uint32_t base[4];               // element offset of the row's own position (+ this thread's piece)
     uint32_t soff[4];               // byte offset of (row, piece) inside a swizzled k-block
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long m = mtile * kTileM + r0 + 32 * i;
-      const bool rowok = m < M;
-      const long long mm = rowok ? m : 0;
-      const int inb = static_cast<int>(mm % (static_cast<long long>(p.T) * HW));
-      const int ct = inb / HW, ch = (inb % HW) / p.W, cw = inb % p.W;
-      uint32_t mask = 0;
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        const bool ok = rowok && static_cast<unsigned>(ct + C.taps[tap][0]) < static_cast<unsigned>(p.T) &&
-                        static_cast<unsigned>(ch + C.taps[tap][1]) < static_cast<unsigned>(p.H) &&
-                        static_cast<unsigned>(cw + C.taps[tap][2]) < static_cast<unsigned>(p.W);
-        mask |= (ok ? 1u : 0u) << tap;
-      }
-      okmask[i] = mask;
-      base[i] = static_cast<uint32_t>(mm * p.Cin + piece * 4);
       const int r = r0 + 32 * i;
       soff[i] = static_cast<uint32_t>(r * 128 + ((piece ^ (r & 7)) << 4));
     }
+    long long f_tile = blockIdx.x;  // tile the fetch side is in
+    int f_cls = 0, f_tap = 0, f_cb = 0;
+    auto enter_tile = [&]() {
+      if (f_tile >= total) return;
+      f_cls = static_cast<int>(f_tile / per_class);
+      const long long mtile = (f_tile % per_class) / ntiles_n;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long m = mtile * kTileM + r0 + 32 * i;
+        const bool rowok = m < M;
+        const long long mm = rowok ? m : 0;
+        const int inb = static_cast<int>(mm % (static_cast<long long>(p.T) * HW));
+        const int ct = inb / HW, ch = (inb % HW) / p.W, cw = inb % p.W;
+        uint32_t mask = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const bool ok = rowok && static_cast<unsigned>(ct + C.taps[f_cls][tap][0]) < static_cast<unsigned>(p.T) &&
+                          static_cast<unsigned>(ch + C.taps[f_cls][tap][1]) < static_cast<unsigned>(p.H) &&
+                          static_cast<unsigned>(cw + C.taps[f_cls][tap][2]) < static_cast<unsigned>(p.W);
+          mask |= (ok ? 1u : 0u) << tap;
+        }
+        okmask[i] = mask;
+        base[i] = static_cast<uint32_t>(mm * p.Cin + piece * 4);
+      }
+    };
+    enter_tile();
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t scale_at = smem_u32(C.scale) + piece * 16, shift_at = smem_u32(C.shift) + piece * 16;
-    // (tap, channel block) of the next k-block to fetch, advanced incrementally
-    int f_tap = 0, f_cb = 0;
     auto fetch = [&](float4 (&v)[4], uint32_t& ok4) {
-      const int shift = C.tap_shift[f_tap] + f_cb * 32;  // may be negative: 32-bit wrap-around arithmetic on the offsets
+      const int shift = C.tap_shift[f_cls][f_tap] + f_cb * 32;  // may be negative: 32-bit wrap-around arithmetic on the offsets
       ok4 = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -298,7 +329,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                   : make_float4(0.f, 0.f, 0.f, 0.f);
         ok4 |= (ok ? 1u : 0u) << i;
       }
-      if (++f_cb == CB) f_cb = 0, ++f_tap;
+      if (++f_cb == CB) {
+        f_cb = 0;
+        if (++f_tap == p.ntaps) {
+          f_tap = 0;
+          f_tile += gridDim.x;
+          enter_tile();
+        }
+      }
     };
     const bool affine = p.in_scale != nullptr;
     const bool want_lo = p.terms != 1;
@@ -340,86 +378,110 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (++e_st == G::kStages) e_st = 0, e_par ^= 1u;
       if (++e_cb == CB) e_cb = 0;
     };
-    // two k-blocks of loads in flight per thread (32 KiB per SM): the gather is latency-bound at one
+    // k-blocks this CTA produces in all; two of them in flight per thread (32 KiB per SM): the gather is latency-bound at one
+    const long long my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long nkb = my_tiles * KB;
     float4 buf0[4], buf1[4];
     uint32_t ok0 = 0, ok1 = 0;
-    fetch(buf0, ok0);
-    if (KB > 1) fetch(buf1, ok1);
-    for (int kb = 0; kb < KB; kb += 2) {
+    if (nkb > 0) fetch(buf0, ok0);
+    if (nkb > 1) fetch(buf1, ok1);
+    for (long long g = 0; g < nkb; g += 2) {
       {
         float4 cur[4];
         const uint32_t cur_ok = ok0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cur[i] = buf0[i];
-        if (kb + 2 < KB) fetch(buf0, ok0);
+        if (g + 2 < nkb) fetch(buf0, ok0);
         emit(cur, cur_ok);
       }
-      if (kb + 1 < KB) {
+      if (g + 1 < nkb) {
         float4 cur[4];
         const uint32_t cur_ok = ok1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cur[i] = buf1[i];
-        if (kb + 3 < KB) fetch(buf1, ok1);
+        if (g + 3 < nkb) fetch(buf1, ok1);
         emit(cur, cur_ok);
       }
     }
-
-    // =========================== epilogue ===========================
-    mbar_wait(&C.acc_full, 0);
-    tc_fence_after();
+  } else {
+    // =========================== epilogue (warps 10..13) ===========================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which half of the NT columns
     const int r = 32 * q + lane;
-    const long long m = mtile * kTileM + r;
-    const bool live = m < M;
-    long long orow = 0;
-    if (live) {
-      const long long THW = static_cast<long long>(p.T) * HW;
-      const long long b = m / THW;
-      const int inb = static_cast<int>(m - b * THW);
-      const int t = inb / HW, h = (inb % HW) / p.W, w = inb % p.W;
-      orow = ((b * p.To + (t * p.st + p.cls[cls][0])) * p.Ho + (h * p.sh + p.cls[cls][1])) * p.Wo + (w * p.sw + p.cls[cls][2]);
-    }
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(32 * q) << 16);
+    uint32_t tc = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+      const int cls = static_cast<int>(tile / per_class);
+      const long long mtile = (tile % per_class) / ntiles_n;
+      const int ntile = static_cast<int>(tile % ntiles_n);
+      const long long m = mtile * kTileM + r;
+      const bool live = m < M;
+      long long orow = 0;
+      if (live) {
+        const long long THW = static_cast<long long>(p.T) * HW;
+        const long long b = m / THW;
+        const int inb = static_cast<int>(m - b * THW);
+        const int t = inb / HW, h = (inb % HW) / p.W, w = inb % p.W;
+        orow = ((b * p.To + (t * p.st + p.cls[cls][0])) * p.Ho + (h * p.sh + p.cls[cls][1])) * p.Wo + (w * p.sw + p.cls[cls][2]);
+      }
+      const uint32_t acc = tc & 1u;
+      mbar_wait(&C.acc_full[acc], (tc >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_lane = tmem + acc * NT + (static_cast<uint32_t>(32 * q) << 16);
 #pragma unroll 1
-    for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + c0, v);
-      tmem_ld_wait();
-      const int n0 = ntile * NT + c0;
-      if (live && p.out_transposed) {
-        // lanes = consecutive rows: every column is one coalesced 128-byte store of the warp
-        float* dst = p.out + static_cast<long long>(n0) * p.ldo + orow;
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        const int n0 = ntile * NT + c0;
+        if (n0 >= p.Nout) break;  // (uniform) the padded columns of the last N tile
+        uint32_t v[32];
+        tmem_ld32(t_lane + c0, v);
+        tmem_ld_wait();
+        if (live && p.out_transposed) {
+          // lanes = consecutive rows: every column is one coalesced 128-byte store of the warp
+          float* dst = p.out + static_cast<long long>(n0) * p.ldo + orow;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (n0 + i < p.Nout) {
-            float o = __uint_as_float(v[i]);
-            if (p.bias != nullptr) o += __ldg(p.bias + n0 + i);
-            if (p.relu_out) o = fmaxf(o, 0.f);
-            dst[static_cast<long long>(i) * p.ldo] = o;
+          for (int i = 0; i < 32; ++i) {
+            if (n0 + i < p.Nout) {
+              float o = __uint_as_float(v[i]);
+              if (p.bias != nullptr) o += __ldg(p.bias + n0 + i);
+              if (p.relu_out) o = fmaxf(o, 0.f);
+              dst[static_cast<long long>(i) * p.ldo] = o;
+            }
           }
-        }
-      } else if (live) {
-        float* dst = p.out + orow * p.ldo + n0;
-        const float* res = p.residual != nullptr ? p.residual + orow * p.ldo + n0 : nullptr;
+        } else if (!p.out_transposed) {
+          // Through shared memory so that the global accesses are coalesced: a thread owns a ROW of the accumulator, but
+          // eight lanes should write the 128 contiguous bytes of one output row.  Row r of this warp's 32 x 32 block goes to
+          // stage[r][*]; then lane l handles piece (l & 7) of rows 4 j + (l >> 3), j = 0..7.
+          float (*stg)[36] = C.stage[warp - (2 + kProdWarps)];
+          __syncwarp();  // the previous chunk's readers are done with the block
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (n0 + 4 * i < p.Nout) {
-            float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                   __uint_as_float(v[4 * i + 3]));
-            if (p.bias != nullptr) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(&stg[lane][4 * i]) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                        __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          __syncwarp();
+          const int pc = lane & 7, rsub = lane >> 3;
+          const bool col_ok = n0 + 4 * pc < p.Nout;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + pc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + rsub;
+            const long long orr = __shfl_sync(0xffffffffu, orow, rr);
+            const bool ok = __shfl_sync(0xffffffffu, live ? 1 : 0, rr) != 0 && col_ok;
+            float4 o = *reinterpret_cast<const float4*>(&stg[rr][4 * pc]);
+            if (ok) {
               o.x += b4.x, o.y += b4.y, o.z += b4.z, o.w += b4.w;
+              if (p.residual != nullptr) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + orr * p.ldo + n0) + pc);
+                o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
+              }
+              if (p.relu_out) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+              reinterpret_cast<float4*>(p.out + orr * p.ldo + n0)[pc] = o;
             }
-            if (res != nullptr) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res) + i);
-              o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
-            }
-            if (p.relu_out) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            *reinterpret_cast<float4*>(dst + 4 * i) = o;
           }
         }
       }
+      // this warp's tensor-memory reads of the accumulator are complete: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
     }
   }
 
@@ -427,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NT) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
   }
 }
 
