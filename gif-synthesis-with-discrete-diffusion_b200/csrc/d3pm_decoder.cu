@@ -45,7 +45,8 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
     return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: ntaps=%d (<= %d), nclass=%d (<= %d)", d->ntaps, D3PM_DEC_MAX_TAPS, d->nclass, D3PM_DEC_MAX_CLASSES);
   const long long rows_out = static_cast<long long>(d->B) * d->T * d->H * d->W * d->stride_t * d->stride_h * d->stride_w;
   if (d->out_transposed) {
-    if (d->residual != nullptr || d->ldo < rows_out) return fail(D3PM_ERR_INVALID, "dec_conv: transposed output takes no residual and needs ldo >= output rows");
+    if (d->residual != nullptr || d->ldo <= 0 || rows_out % d->ldo != 0)
+      return fail(D3PM_ERR_INVALID, "dec_conv: transposed output takes no residual; ldo (rows per plane) must divide the %lld output rows", rows_out);
   } else if (d->Nout <= 0 || d->Nout % 4 != 0 || d->ldo < d->Nout || d->ldo % 4 != 0) {
     return fail(D3PM_ERR_ALIGN, "dec_conv: Nout=%d and ldo=%lld must be multiples of 4, ldo >= Nout", d->Nout, (long long)d->ldo);
   }
@@ -137,17 +138,16 @@ int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, 
   return D3PM_OK;
 }
 
-int d3pm_dec_col2im(const float* y_t, int64_t ldt, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh, int sw,
+int d3pm_dec_col2im(const float* y_t, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh, int sw,
                     d3pm_stream_t stream) {
   if (y_t == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0) return fail(D3PM_ERR_INVALID, "dec_col2im: bad arguments");
-  const long long M = static_cast<long long>(B) * T * H * W;
-  if (Cout <= 0 || Cout > 4 || ldt < M) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: Cout=%d must be <= 4 and ldt=%lld >= B*T*H*W", Cout, (long long)ldt);
+  if (Cout <= 0 || Cout > 4) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: Cout=%d must be <= 4", Cout);
   if ((st != 1 && st != 2) || (sh != 1 && sh != 2) || (sw != 1 && sw != 2)) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: strides must be 1 or 2");
   const DeviceGuard on_device(out);
   const long long total = static_cast<long long>(B) * T * st * H * sh * W;
   if ((total + 255) / 256 > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: output too large");
-  d3pm::dec::col2im_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y_t, ldt, bias, out, B, T, H,
-                                                                                                                      W, Cout, st, sh, sw);
+  d3pm::dec::col2im_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y_t, bias, out, B, T, H, W,
+                                                                                                                      Cout, st, sh, sw);
   return check_launch("dec_col2im");
 }
 

@@ -51,7 +51,8 @@ struct GemmParams {
   long long ldo;
   int To, Ho, Wo, st, sh, sw;
   int relu_out, terms;
-  int out_transposed;     // 1: out[n * ldo + row] (rows of one output channel contiguous: the col2im input), no residual
+  int out_transposed;     // 1: out[(row / ldo) * Nout * ldo + n * ldo + row % ldo]: planes of ldo rows, channel-major inside a plane
+                          // (the col2im input; a plane = one (video, frame) keeps a tile's 64 * Cout rows within a few pages)
   signed char tap[kMaxClasses][kMaxTaps][4];  // (dt, dh, dw) of every tap of every class
   signed char cls[kMaxClasses][4];            // (pt, ph, pw): output position = input position * stride + this
 };
@@ -435,7 +436,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         tmem_ld_wait();
         if (live && p.out_transposed) {
           // lanes = consecutive rows: every column is one coalesced 128-byte store of the warp
-          float* dst = p.out + static_cast<long long>(n0) * p.ldo + orow;
+          const long long plane = orow / p.ldo;
+          float* dst = p.out + (plane * p.Nout + n0) * p.ldo + (orow - plane * p.ldo);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (n0 + i < p.Nout) {
@@ -512,19 +514,37 @@ __global__ void embed_rows_kernel(const int64_t* __restrict__ tokens, const floa
 // ---- axial attention (AxialBlock, videogpt_vq_vae.py:100-118; scaled_dot_product_attention, model_utils.py:586-600) ----
 // qkv: [M][3 axes][q, k, v][heads][dh]; att: [M][3 axes][heads][dh].  One launch per axis, one warp per (sequence along the
 // axis, head): K and V of the sequence (L <= LMAX positions) staged in shared memory, a lane holds VPL = dh / 32 channels of
-// every vector.  Per query the L partial dot products are formed first and reduced together (LMAX independent butterflies
-// in flight), every lane then holds all L scores and evaluates the softmax on its own - no dependent shuffle chains.
+// every vector.  Per query the LMAX partial dot products of a lane are reduced over the warp by a transposing butterfly
+// (at every level a lane keeps half of its values and hands the other half to its partner: LMAX - 1 shuffles instead of
+// 5 LMAX), after which lane l holds the complete score of key l >> (5 - log2 LMAX); the softmax then runs across lanes.
 // warps per block: as many as fit the 48 KiB of static shared memory, at most 4
 __host__ __device__ constexpr int attn_warps(int vpl, int lmax) {
   const int per_warp = 2 * lmax * 32 * vpl * 4;
   return per_warp * 4 <= 49152 ? 4 : (per_warp * 2 <= 49152 ? 2 : 1);
 }
 
+template <int N>
+__device__ __forceinline__ void transpose_reduce(float (&s)[N], int lane, int o) {
+  // pairs (m, m + N/2): the lane whose bit `o` is clear keeps the lower half, its partner the upper half
+  if constexpr (N >= 2) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+      const float keep = up ? s[m + N / 2] : s[m];
+      const float send = up ? s[m] : s[m + N / 2];
+      s[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+
 template <int VPL, int LMAX>
 __global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
-                                                                          int T, int H, int W, int heads, int axis) {
+                                                                                     int T, int H, int W, int heads, int axis) {
   constexpr int DH = 32 * VPL;
   constexpr int kAttnWarps = attn_warps(VPL, LMAX);
+  constexpr int LOG = LMAX == 32 ? 5 : (LMAX == 16 ? 4 : (LMAX == 8 ? 3 : 2));
+  constexpr int REP = 32 / LMAX;  // lanes that end up holding the same key's score
+  static_assert(LMAX == 4 || LMAX == 8 || LMAX == 16 || LMAX == 32, "LMAX must be 4, 8, 16 or 32");
   __shared__ __align__(16) float kv_smem[kAttnWarps][2][LMAX][DH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // axis 0: along W (attn_w, axial_dim -2), 1: along H, 2: along T
@@ -545,30 +565,40 @@ __global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_ke
   float (*ks)[DH] = kv_smem[warp][0];
   float (*vs)[DH] = kv_smem[warp][1];
   const float* qbase = qkv + static_cast<size_t>(axis) * 3 * C + head * DH + lane * VPL;
+  auto load_vec = [](const float* src, float (&dst)[VPL]) {
+    if constexpr (VPL == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      dst[0] = t.x, dst[1] = t.y, dst[2] = t.z, dst[3] = t.w;
+    } else if constexpr (VPL == 2) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(src));
+      dst[0] = t.x, dst[1] = t.y;
+    } else {
+      dst[0] = __ldg(src);
+    }
+  };
 #pragma unroll
   for (int j = 0; j < LMAX; ++j) {
-    const bool in = j < L;
-    const float* rowp = qbase + (row0 + (in ? j : 0) * rstride) * ldq;
+    float kk[VPL], vv[VPL];
 #pragma unroll
-    for (int e = 0; e < VPL; ++e) {
-      ks[j][lane * VPL + e] = in ? __ldg(rowp + C + e) : 0.f;
-      vs[j][lane * VPL + e] = in ? __ldg(rowp + 2 * C + e) : 0.f;
+    for (int e = 0; e < VPL; ++e) kk[e] = 0.f, vv[e] = 0.f;
+    if (j < L) {
+      const float* rowp = qbase + (row0 + j * rstride) * ldq;
+      load_vec(rowp + C, kk);
+      load_vec(rowp + 2 * C, vv);
     }
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) ks[j][lane * VPL + e] = kk[e], vs[j][lane * VPL + e] = vv[e];
   }
   __syncwarp();
   const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // scores in log2 units
+  const int myj = lane >> (5 - LOG);  // the key whose score this lane holds after the reduction
   float qn[VPL];
-#pragma unroll
-  for (int e = 0; e < VPL; ++e) qn[e] = __ldg(qbase + row0 * ldq + e);
+  load_vec(qbase + row0 * ldq, qn);
   for (int i = 0; i < L; ++i) {
     float qv[VPL];
 #pragma unroll
     for (int e = 0; e < VPL; ++e) qv[e] = qn[e];
-    if (i + 1 < L) {
-      const float* rowp = qbase + (row0 + (i + 1) * rstride) * ldq;
-#pragma unroll
-      for (int e = 0; e < VPL; ++e) qn[e] = __ldg(rowp + e);
-    }
+    if (i + 1 < L) load_vec(qbase + (row0 + (i + 1) * rstride) * ldq, qn);
     float s[LMAX];
 #pragma unroll
     for (int j = 0; j < LMAX; ++j) {
@@ -577,45 +607,51 @@ __global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_ke
       for (int e = 0; e < VPL; ++e) d = fmaf(qv[e], ks[j][lane * VPL + e], d);
       s[j] = d;
     }
+    // transposing butterfly: after the level with offset o a lane holds the values whose index has bit (o's rank) equal to
+    // its own lane bit; log2(LMAX) levels leave one value per lane, the remaining levels are plain butterflies
+    if constexpr (LOG >= 1) transpose_reduce<LMAX>(s, lane, 16);
+    if constexpr (LOG >= 2) transpose_reduce<LMAX / 2>(reinterpret_cast<float (&)[LMAX / 2]>(s), lane, 8);
+    if constexpr (LOG >= 3) transpose_reduce<LMAX / 4>(reinterpret_cast<float (&)[LMAX / 4]>(s), lane, 4);
+    if constexpr (LOG >= 4) transpose_reduce<LMAX / 8>(reinterpret_cast<float (&)[LMAX / 8]>(s), lane, 2);
+    if constexpr (LOG >= 5) transpose_reduce<LMAX / 16>(reinterpret_cast<float (&)[LMAX / 16]>(s), lane, 1);
+    float sc = s[0];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = 16 >> LOG; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    // lane l: score of key myj (bits of the key index follow the lane bits from the top: level 16 decided the highest bit)
+    sc = myj < L ? sc * scale : -3.0e38f;
+    float mx = sc;
 #pragma unroll
-      for (int j = 0; j < LMAX; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-    float mx = -3.0e38f;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e_ = myj < L ? exp2f(sc - mx) : 0.f;
+    float sum = e_;
 #pragma unroll
-    for (int j = 0; j < LMAX; ++j) {
-      s[j] = j < L ? s[j] * scale : -3.0e38f;
-      mx = fmaxf(mx, s[j]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < LMAX; ++j) {
-      s[j] = j < L ? exp2f(s[j] - mx) : 0.f;
-      sum += s[j];
-    }
-    const float rs = 1.0f / sum;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float pr = e_ * (static_cast<float>(REP) / sum);  // every key is counted REP times in `sum`
     float acc[VPL];
 #pragma unroll
     for (int e = 0; e < VPL; ++e) acc[e] = 0.f;
 #pragma unroll
-    for (int j = 0; j < LMAX; ++j)
+    for (int j = 0; j < LMAX; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, pr, j << (5 - LOG));
 #pragma unroll
-      for (int e = 0; e < VPL; ++e) acc[e] = fmaf(s[j], vs[j][lane * VPL + e], acc[e]);
+      for (int e = 0; e < VPL; ++e) acc[e] = fmaf(pj, vs[j][lane * VPL + e], acc[e]);
+    }
     float* o = att + (row0 + i * rstride) * (3 * C) + axis * C + head * DH + lane * VPL;
-#pragma unroll
-    for (int e = 0; e < VPL; ++e) o[e] = acc[e] * rs;
+    if constexpr (VPL == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else if constexpr (VPL == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+    else o[0] = acc[0];
   }
 }
 
 // ---- col2im of the last transposed convolution ----------------------------------------------------------------------
-// yT: [64 * Cout][Mtot] (TRANSPOSED rows of the last GEMM: row ((kt*4 + kh)*4 + kw)*Cout + c, column = input position) =
-// contribution of an input position through filter tap (kt, kh, kw) to output channel c.  out: [B][Cout][To][Ho][Wo] (the
-// reference's layout) = bias + the contributions that land on each voxel: along a dimension of stride s, tap k of input i
-// lands on y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2) (F.pad of SamePadConvTranspose3d :324-328, then ConvTranspose3d
-// with padding 3 :330-332).  A thread owns the sw output voxels above one input column position, so the lanes of a warp read
-// consecutive input positions of one (tap, channel) row: coalesced.
-__global__ void col2im_kernel(const float* __restrict__ yT, long long ldT, const float* __restrict__ bias, float* __restrict__ out, int B,
-                              int T, int H, int W, int Cout, int st, int sh, int sw) {
+// yT: [B * T][64 * Cout][H * W] (the plane-transposed rows of the last GEMM: row ((kt*4 + kh)*4 + kw)*Cout + c of plane (b, it),
+// column = (ih, iw)) = contribution of an input position through filter tap (kt, kh, kw) to output channel c.
+// out: [B][Cout][To][Ho][Wo] (the reference's layout) = bias + the contributions that land on each voxel: along a dimension
+// of stride s, tap k of input i lands on y = (i + pf) * s + k - 3, pf = ceil((4 - s) / 2) (F.pad of SamePadConvTranspose3d
+// :324-328, then ConvTranspose3d with padding 3 :330-332).  A thread owns the sw output voxels above one input column
+// position, so the lanes of a warp read consecutive input positions of one (tap, channel) row: coalesced.
+__global__ void col2im_kernel(const float* __restrict__ yT, const float* __restrict__ bias, float* __restrict__ out, int B, int T, int H,
+                              int W, int Cout, int st, int sh, int sw) {
   const int To = T * st, Ho = H * sh;
   const long long Wo = static_cast<long long>(W) * sw;
   const long long total = static_cast<long long>(B) * To * Ho * W;
@@ -626,18 +662,19 @@ __global__ void col2im_kernel(const float* __restrict__ yT, long long ldT, const
   const int yt = static_cast<int>((idx / (static_cast<long long>(W) * Ho)) % To);
   const long long b = idx / (static_cast<long long>(W) * Ho * To);
   const int pft = (4 - st + 1) / 2, pfh = (4 - sh + 1) / 2, pfw = (4 - sw + 1) / 2;
+  const long long P = static_cast<long long>(H) * W;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (int kt = 0; kt < 4; ++kt) {
     const int nt = yt + 3 - kt;
     if (nt % st != 0) continue;
     const int it = nt / st - pft;
     if (it < 0 || it >= T) continue;
+    const float* plane = yT + (b * T + it) * (64LL * Cout) * P;
     for (int kh = 0; kh < 4; ++kh) {
       const int nh = yh + 3 - kh;
       if (nh % sh != 0) continue;
       const int ih = nh / sh - pfh;
       if (ih < 0 || ih >= H) continue;
-      const long long rowpos = ((b * T + it) * H + ih) * W;
 #pragma unroll
       for (int pw = 0; pw < 2; ++pw) {
         if (pw >= sw) break;
@@ -648,8 +685,8 @@ __global__ void col2im_kernel(const float* __restrict__ yT, long long ldT, const
           if (nw % sw != 0) continue;
           const int iw = nw / sw - pfw;
           if (iw < 0 || iw >= W) continue;
-          const float* src = yT + static_cast<long long>(((kt * 4 + kh) * 4 + kw) * Cout) * ldT + rowpos + iw;
-          for (int c = 0; c < Cout && c < 4; ++c) acc[pw][c] += __ldg(src + c * ldT);
+          const float* src = plane + static_cast<long long>(((kt * 4 + kh) * 4 + kw) * Cout) * P + ih * W + iw;
+          for (int c = 0; c < Cout && c < 4; ++c) acc[pw][c] += __ldg(src + c * P);
         }
       }
     }

@@ -215,17 +215,18 @@ class _Layer:
 
     def __call__(self, x: torch.Tensor, B: int, grid, *, terms: int, residual: Optional[torch.Tensor] = None,
                  transposed: bool = False) -> torch.Tensor:
-        """-> rows `[B * T' * H' * W', Nout]`, or with `transposed` `[Nout, B * T' * H' * W']` (what d3pm_dec_col2im reads)."""
+        """-> rows `[B * T' * H' * W', Nout]`, or with `transposed` planes `[B * T', Nout, H' * W']` (what d3pm_dec_col2im reads)."""
         T, H, W = grid
         rows_out = B * T * H * W * self.stride[0] * self.stride[1] * self.stride[2]
         if x.shape != (B * T * H * W, self.cin) or not x.is_contiguous() or x.dtype != torch.float32:
             raise D3PMError(f"expected contiguous float32 rows [{B * T * H * W}, {self.cin}], got {tuple(x.shape)}")
-        out = torch.empty((self.nout, rows_out) if transposed else (rows_out, self.nout), dtype=torch.float32, device=x.device)
+        plane = H * W * self.stride[1] * self.stride[2]
+        out = torch.empty((rows_out // plane, self.nout, plane) if transposed else (rows_out, self.nout), dtype=torch.float32, device=x.device)
         d = self.desc
         d.x, d.in_scale, d.in_shift = x.data_ptr(), ops._ptr(self.in_scale), ops._ptr(self.in_shift)
         d.w_image, d.bias, d.residual, d.out = self.image.data_ptr(), ops._ptr(self.bias), ops._ptr(residual), out.data_ptr()
         d.B, d.T, d.H, d.W, d.Cin = B, T, H, W, self.cin
-        d.ntaps, d.nclass, d.Nout, d.ldo, d.out_transposed = self.ntaps, self.nclass, self.nout, out.shape[1], int(transposed)
+        d.ntaps, d.nclass, d.Nout, d.ldo, d.out_transposed = self.ntaps, self.nclass, self.nout, out.shape[-1], int(transposed)
         d.stride_t, d.stride_h, d.stride_w = self.stride
         d.relu_out, d.terms, d.n_tile = int(self.relu_out), terms, self.n_tile
         d.stream = ops._stream(x.device)
@@ -287,9 +288,9 @@ class NativeDecoder:
                 grid = tuple(g * s for g, s in zip(grid, stride))
             else:
                 _, layer, stride, bias, cout = item
-                y_t = layer(x, B, grid, terms=self.terms, transposed=True)   # [64 * cout, positions]
+                y_t = layer(x, B, grid, terms=self.terms, transposed=True)   # [B * T, 64 * cout, H * W]
                 out = torch.empty(B, cout, *(g * s for g, s in zip(grid, stride)), dtype=torch.float32, device=dev)
-                _lib.check(lib.d3pm_dec_col2im(y_t.data_ptr(), y_t.shape[1], bias.data_ptr(), out.data_ptr(), B, *grid, cout, *stride,
+                _lib.check(lib.d3pm_dec_col2im(y_t.data_ptr(), bias.data_ptr(), out.data_ptr(), B, *grid, cout, *stride,
                                                ops._stream(dev)), "d3pm_dec_col2im")
                 return out
         raise D3PMError("decoder without transposed convolutions")

@@ -309,8 +309,9 @@ typedef struct d3pm_dec_conv_desc {
   int32_t B, T, H, W, Cin;
   int32_t ntaps, nclass, reserved;
   int32_t Nout;           /* Nout % 4 == 0 */
-  int32_t out_transposed; /* 1: out[n * ldo + row] instead of out[row * ldo + n] (the layout d3pm_dec_col2im reads); no residual */
-  int64_t ldo;            /* row pitch of out in floats, % 4 == 0 (transposed: >= number of output rows) */
+  int32_t out_transposed; /* 1: out[(row / ldo) * Nout * ldo + n * ldo + row % ldo] - planes of ldo consecutive output rows, channel-major
+                             inside a plane (with ldo = H * W: the layout d3pm_dec_col2im reads); no residual */
+  int64_t ldo;            /* row pitch of out in floats, % 4 == 0 (transposed: rows per plane, must divide the number of output rows) */
   int32_t stride_t, stride_h, stride_w;
   int32_t relu_out;
   int32_t terms;          /* 3: 3xTF32 (fp32-grade), 1: TF32 */
@@ -331,12 +332,12 @@ int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int
 int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, int W, int heads, int head_dim,
                              d3pm_stream_t stream);
 
-/* Last SamePadConvTranspose3d (kernel 4, stride (st, sh, sw) in {1, 2}, Cout <= 4): y_t [64 * Cout][ldt] holds the per-tap
- * contributions (row ((kt*4 + kh)*4 + kw) * Cout + c, column = input position; from d3pm_dec_conv with one tap, N = 64 * Cout
- * and out_transposed = 1); out [B][Cout][T*st][H*sh][W*sw] = bias + the contributions landing on each voxel: the
- * reference's video layout.                                                                                          */
-int d3pm_dec_col2im(const float* y_t, int64_t ldt, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st,
-                    int sh, int sw, d3pm_stream_t stream);
+/* Last SamePadConvTranspose3d (kernel 4, stride (st, sh, sw) in {1, 2}, Cout <= 4): y_t [B*T][64 * Cout][H*W] holds the per-tap
+ * contributions (row ((kt*4 + kh)*4 + kw) * Cout + c of plane (b, t), column = (h, w); from d3pm_dec_conv with one tap,
+ * N = 64 * Cout, out_transposed = 1 and ldo = H*W); out [B][Cout][T*st][H*sh][W*sw] = bias + the contributions landing on
+ * each voxel: the reference's video layout.                                                                             */
+int d3pm_dec_col2im(const float* y_t, const float* bias, float* out, int B, int T, int H, int W, int Cout, int st, int sh, int sw,
+                    d3pm_stream_t stream);
 
 /* ---------------------------------------------------------------- host-buffer entry points
  * For a caller whose denoiser output lives in HOST memory (the reference's CPU tensors; bench.py's `e2e`): a handle owns

@@ -61,8 +61,9 @@ def test_dec_conv_honours_its_contract(name, terms):
     tol = (TOL_FP32 if terms == 3 else TOL_TF32) * float(want.abs().max())
     assert (got - want).abs().max().item() <= tol
     if not with_res:  # the transposed store of the epilogue (the layout col2im reads)
-        got_t = layer(x.to(DEV), B, grid, terms=terms, transposed=True).cpu()
-        assert got_t.shape == (spec.nout, M) and torch.equal(got_t.t(), got)
+        got_t = layer(x.to(DEV), B, grid, terms=terms, transposed=True).cpu()   # planes [B * T, Nout, H * W]
+        assert got_t.shape == (B * grid[0], spec.nout, grid[1] * grid[2])
+        assert torch.equal(got_t.transpose(1, 2).reshape(M, spec.nout), got)
 
 
 @pytest.mark.parametrize("stride", [(1, 2, 2), (2, 2, 2)])
@@ -107,9 +108,9 @@ def test_col2im(stride):
     want = emulate_col2im(y, bias, B, grid, cout, stride)
     out = torch.empty(*want.shape, device=DEV)
     lib = _lib.load_library()
-    y_t = y.t().contiguous().to(DEV)   # the kernel reads the transposed rows d3pm_dec_conv writes with out_transposed = 1
-    _lib.check(lib.d3pm_dec_col2im(y_t.data_ptr(), y_t.shape[1], bias.to(DEV).data_ptr(), out.data_ptr(), B, *grid, cout, *stride, 0),
-               "d3pm_dec_col2im")
+    # the kernel reads the plane-transposed rows d3pm_dec_conv writes with out_transposed = 1: [B * T][64 * cout][H * W]
+    y_t = y.view(B * grid[0], grid[1] * grid[2], 64 * cout).transpose(1, 2).contiguous().to(DEV)
+    _lib.check(lib.d3pm_dec_col2im(y_t.data_ptr(), bias.to(DEV).data_ptr(), out.data_ptr(), B, *grid, cout, *stride, 0), "d3pm_dec_col2im")
     torch.cuda.synchronize()
     assert (out.cpu() - want).abs().max().item() <= 1e-5 * float(want.abs().max())
 
