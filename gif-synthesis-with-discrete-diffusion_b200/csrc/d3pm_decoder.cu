@@ -88,8 +88,11 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
     kern<<<grid, D::kGemmThreads, smem, s>>>(p);
     return check_launch("dec_conv");
   };
-  return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128>, D::gemm_smem_bytes<128>())
-                          : launch(D::conv_gemm_kernel<256>, D::gemm_smem_bytes<256>());
+  if (d->terms == 1)
+    return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128, 1>, D::gemm_smem_bytes<128, 1>())
+                            : launch(D::conv_gemm_kernel<256, 1>, D::gemm_smem_bytes<256, 1>());
+  return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128, 3>, D::gemm_smem_bytes<128, 3>())
+                          : launch(D::conv_gemm_kernel<256, 3>, D::gemm_smem_bytes<256, 3>());
 }
 
 int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int64_t rows, int K, int C, uint32_t* status,

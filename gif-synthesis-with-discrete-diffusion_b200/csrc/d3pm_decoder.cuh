@@ -153,17 +153,21 @@ __global__ void weight_image_kernel(const float* __restrict__ w, int N, int Npad
 }
 
 // ---- the implicit-GEMM convolution ------------------------------------------------------------------------------
-template <int NT>
+// TERMS = 3: 3xTF32, a stage holds the hi and lo halves of both operands; TERMS = 1: plain TF32, hi halves only, so twice
+// as many stages fit (the single-product mode is bound by the producers' latency, which deeper staging hides)
+template <int NT, int TERMS>
 struct GemmGeo {
-  static constexpr int kStages = NT == 128 ? 3 : 2;
+  static constexpr int kHalves = TERMS == 1 ? 1 : 2;
+  static constexpr int kStages = (NT == 128 ? 3 : 2) * (TERMS == 1 ? 2 : 1);
   static constexpr int kBBytes = NT * 128;                        // one term of the weight k-block
-  static constexpr int kStageBytes = 2 * kBlockBytes + 2 * kBBytes;
+  static constexpr int kABytes = kHalves * kBlockBytes;           // A part of a stage
+  static constexpr int kStageBytes = kABytes + kHalves * kBBytes;
   // instruction descriptor: D = f32, A = B = tf32, both K-major, N = NT, M = 128
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NT >> 3) << 17) | ((kTileM >> 4) << 24);
 };
 
 struct GemmCtl {
-  unsigned long long full_a[3], full_b[3], empty[3], acc_full[2], acc_empty[2];
+  unsigned long long full_a[6], full_b[6], empty[6], acc_full[2], acc_empty[2];
   uint32_t tmem_base, pad;
   signed char taps[kMaxClasses][kMaxTaps][4];
   int tap_shift[kMaxClasses][kMaxTaps];  // element offset of a tap's source row relative to the row itself
@@ -172,9 +176,9 @@ struct GemmCtl {
   alignas(16) float stage[4][32][36];    // epilogue: 32 rows x 32 columns per warp, rows padded to 144 B (conflict-free 128-bit access)
 };
 
-template <int NT>
+template <int NT, int TERMS>
 constexpr size_t gemm_smem_bytes() {
-  return 1024 + GemmGeo<NT>::kStages * GemmGeo<NT>::kStageBytes + sizeof(GemmCtl);
+  return 1024 + GemmGeo<NT, TERMS>::kStages * GemmGeo<NT, TERMS>::kStageBytes + sizeof(GemmCtl);
 }
 
 // Persistent: a CTA walks the tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the launch, tile t = (parity class, M tile,
@@ -186,9 +190,9 @@ constexpr size_t gemm_smem_bytes() {
 constexpr int kEpiWarps = 4;
 constexpr int kGemmThreads = 32 * (2 + kProdWarps + kEpiWarps);
 
-template <int NT>
+template <int NT, int TERMS>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using G = GemmGeo<NT>;
+  using G = GemmGeo<NT, TERMS>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   GemmCtl& C = *reinterpret_cast<GemmCtl*>(smem + G::kStages * G::kStageBytes);
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 1) {
     // =========================== weight stream (bulk TMA) ===========================
     if (lane == 0) {
-      const uint32_t bytes = p.terms == 1 ? G::kBBytes : 2 * G::kBBytes;
+      constexpr uint32_t bytes = G::kHalves * G::kBBytes;
       int st = 0;
       uint32_t par = 1;
       for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&C.empty[st], par);
           mbar_expect_tx(&C.full_b[st], bytes);
-          unsigned char* dst = smem + st * G::kStageBytes + 2 * kBlockBytes;
+          unsigned char* dst = smem + st * G::kStageBytes + G::kABytes;
           const float* s = src + static_cast<size_t>(kb) * (2 * NT * 32);
           for (uint32_t q = 0; q < bytes; q += kBlockBytes) tma_load(dst + q, s + q / 4, kBlockBytes, &C.full_b[st]);
           if (++st == G::kStages) st = 0, par ^= 1u;
@@ -260,9 +264,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           mbar_wait(&C.full_b[st], par);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + st * G::kStageBytes);
-          const uint32_t b_addr = a_addr + 2 * kBlockBytes;
+          const uint32_t b_addr = a_addr + G::kABytes;
           // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi (terms == 1: a_hi w_hi only)
-          for (int term = (p.terms == 1 ? 2 : 0); term < 3; ++term) {
+          #pragma unroll
+          for (int term = (TERMS == 1 ? 2 : 0); term < 3; ++term) {
             const uint32_t a_off = (term == 0) ? kBlockBytes : 0;
             const uint32_t b_off = (term == 1) ? G::kBBytes : 0;
 #pragma unroll
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       }
     };
     const bool affine = p.in_scale != nullptr;
-    const bool want_lo = p.terms != 1;
+    constexpr bool want_lo = TERMS != 1;
     int e_st = 0, e_cb = 0;
     uint32_t e_par = 1;  // parity to wait for on the stage's `empty` barrier (first round: passes at once)
     // transform (BatchNorm + ReLU in front of the convolution; the zero padding comes AFTER it: F.pad of the activated

@@ -316,3 +316,14 @@ def decode(autoencoder, tokens: torch.Tensor, table: Optional[DecodeTable] = Non
     if tokens.dim() != 4:
         raise D3PMError("tokens must be [B, T', H', W'] (reshape the sampler's [B, N] with the latent grid, discrete_diffusion.py:62)")
     return decoder.forward_rows(embed_rows(table, tokens, status), tokens.shape[0], tokens.shape[1:])
+
+
+def sample_and_decode(diffusion_model, autoencoder, text, text_emb: torch.Tensor, cf_text_emb: torch.Tensor, latent_shape,
+                      table: Optional[DecodeTable] = None, decoder: Optional[NativeDecoder] = None) -> torch.Tensor:
+    """The inference branch of the reference's caller, `DiscreteDiffusion.forward` (networks/discrete_diffusion.py:53-62):
+    `sample(text, None, text_emb, cf_text_emb, content_token=None, filter_ratio=0)['content_token']`, viewed on the latent
+    grid `(T', H', W')` (`.view(quant.shape)`, :62), then `autoencoder.decode`.  `diffusion_model` is the drop-in
+    `FusedDiffusionTransformer` (or the reference's class: same `sample` signature)."""
+    out = diffusion_model.sample(text, None, text_emb, cf_text_emb, content_token=None, filter_ratio=0)
+    tokens = out["content_token"]
+    return decode(autoencoder, tokens.view(tokens.shape[0], *latent_shape), table, decoder)

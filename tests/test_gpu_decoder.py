@@ -179,3 +179,38 @@ def test_native_decoder_at_the_shipped_shape_against_the_live_reference(B):
     sd = {k: v.detach().cpu() for k, v in vq.state_dict().items()}
     orc = DO.vqvae_decode(sd, tokens[:1].cpu(), 3, (1, 8, 8))
     assert (got[:1] - orc).abs().max().item() <= 1e-4 * scale
+
+
+def test_sample_then_decode_like_the_reference_caller():
+    """`DiscreteDiffusion.forward`'s inference branch (networks/discrete_diffusion.py:53-62): sample the tokens with the drop-in
+    diffusion class, view them on the latent grid, decode - natively and through the reference's own `VQVAE.decode`."""
+    if not RL.reference_available():
+        pytest.skip("reference not staged (baseline/_ref absent)")
+    import types
+    import d3pm_b200
+    K, B, grid = 256, 2, (2, 4, 4)
+    N = grid[0] * grid[1] * grid[2]
+
+    class Denoiser(torch.nn.Module):  # any module with the reference transformer's surface: logits [B, K, N] as a view of [B, N, K]
+        def __init__(self):
+            super().__init__()
+            self.content_emb = types.SimpleNamespace(num_embed=K + 1)
+            self.to_logits = torch.nn.Sequential(torch.nn.Identity(), torch.nn.Linear(1, 1))
+            self.table = torch.nn.Parameter(torch.randn(K + 1, K, generator=torch.Generator().manual_seed(1)))
+
+        def forward(self, x_t, cond, t):
+            return self.table[x_t].permute(0, 2, 1)
+
+    model = d3pm_b200.FusedDiffusionTransformer(transformer=Denoiser(), diffusion_step=20, alpha_init_type="alpha1", guidance_scale=2.0,
+                                                content_seq_len=N).to(DEV)
+    torch.manual_seed(5)
+    vq = RL.load_vqvae_module().VQVAE(checkpoint_path=None, embedding_dim=32, n_codes=K, n_hiddens=64, n_res_layers=1,
+                                      downsample=[1, 4, 4], sequence_length=grid[0], resolution=4 * grid[1]).to(DEV).eval()
+    cond = torch.zeros(B, 1, 512, device=DEV)
+    video = decode.sample_and_decode(model.manual_seed(3), vq, ["a"] * B, cond, cond, grid, decoder=decode.NativeDecoder(vq.decoder))
+    tokens = model.manual_seed(3).sample(["a"] * B, None, cond, cond, content_token=None, filter_ratio=0)["content_token"]
+    assert not (tokens == K).any()
+    with torch.no_grad():
+        want = vq.decode(tokens.view(B, *grid))
+    assert video.shape == want.shape == (B, 3, grid[0], 4 * grid[1], 4 * grid[2])
+    assert (video - want).abs().max().item() <= 2e-3 * float(want.abs().max())   # the reference arm runs cuDNN's default TF32 here
