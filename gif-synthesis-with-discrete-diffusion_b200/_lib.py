@@ -88,7 +88,7 @@ class DecConvDesc(ctypes.Structure):
         ("x", c_void_p), ("in_scale", c_void_p), ("in_shift", c_void_p), ("w_image", c_void_p), ("bias", c_void_p),
         ("residual", c_void_p), ("out", c_void_p),
         ("B", c_int32), ("T", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32),
-        ("ntaps", c_int32), ("nclass", c_int32), ("reserved", c_int32), ("Nout", c_int32), ("out_transposed", c_int32),
+        ("ntaps", c_int32), ("nclass", c_int32), ("cta_pair", c_int32), ("Nout", c_int32), ("out_transposed", c_int32),
         ("ldo", c_int64), ("stride_t", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
         ("relu_out", c_int32), ("terms", c_int32), ("n_tile", c_int32),
         ("tap", c_int8 * 4 * DEC_MAX_TAPS * DEC_MAX_CLASSES), ("cls", c_int8 * 4 * DEC_MAX_CLASSES),

@@ -76,23 +76,40 @@ int d3pm_dec_conv(const d3pm_dec_conv_desc* d) {
   }
   const long long M = static_cast<long long>(d->B) * d->T * d->H * d->W;
   if (M * d->Cin >= (1LL << 32)) return fail(D3PM_ERR_UNSUPPORTED, "dec_conv: the input has %lld elements; element offsets are 32-bit", M * d->Cin);
-  const long long tiles = (M + D::kTileM - 1) / D::kTileM * (p.Npad / d->n_tile) * d->nclass;
+  const int ctas = d->cta_pair ? 2 : 1;
+  const long long mtiles = ((M + D::kTileM - 1) / D::kTileM + ctas - 1) / ctas;
+  const long long tiles = mtiles * (p.Npad / d->n_tile) * d->nclass;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return fail(D3PM_ERR_CUDA, "dec_conv: cannot query the device");
-  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);  // persistent: one CTA per SM walks the tiles
+  const long long units = tiles < sms / ctas ? tiles : sms / ctas;  // persistent: one CTA (or pair) per SM (TPC) walks the tiles
   const cudaStream_t s = static_cast<cudaStream_t>(d->stream);
   auto launch = [&](auto kern, size_t smem) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return fail(D3PM_ERR_CUDA, "dec_conv: %s", cudaGetErrorString(cudaGetLastError()));
-    kern<<<grid, D::kGemmThreads, smem, s>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(units * ctas));
+    cfg.blockDim = dim3(D::kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(ctas), attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return fail(D3PM_ERR_CUDA, "dec_conv: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("dec_conv");
   };
-  if (d->terms == 1)
-    return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128, 1>, D::gemm_smem_bytes<128, 1>())
-                            : launch(D::conv_gemm_kernel<256, 1>, D::gemm_smem_bytes<256, 1>());
-  return d->n_tile == 128 ? launch(D::conv_gemm_kernel<128, 3>, D::gemm_smem_bytes<128, 3>())
-                          : launch(D::conv_gemm_kernel<256, 3>, D::gemm_smem_bytes<256, 3>());
+  const int sel = (d->n_tile == 256 ? 4 : 0) | (d->terms == 1 ? 2 : 0) | (ctas == 2 ? 1 : 0);
+  switch (sel) {
+    case 0: return launch(D::conv_gemm_kernel<128, 3, 1>, D::gemm_smem_bytes<128, 3, 1>());
+    case 1: return launch(D::conv_gemm_kernel<128, 3, 2>, D::gemm_smem_bytes<128, 3, 2>());
+    case 2: return launch(D::conv_gemm_kernel<128, 1, 1>, D::gemm_smem_bytes<128, 1, 1>());
+    case 3: return launch(D::conv_gemm_kernel<128, 1, 2>, D::gemm_smem_bytes<128, 1, 2>());
+    case 4: return launch(D::conv_gemm_kernel<256, 3, 1>, D::gemm_smem_bytes<256, 3, 1>());
+    case 5: return launch(D::conv_gemm_kernel<256, 3, 2>, D::gemm_smem_bytes<256, 3, 2>());
+    case 6: return launch(D::conv_gemm_kernel<256, 1, 1>, D::gemm_smem_bytes<256, 1, 1>());
+    default: return launch(D::conv_gemm_kernel<256, 1, 2>, D::gemm_smem_bytes<256, 1, 2>());
+  }
 }
 
 int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int64_t rows, int K, int C, uint32_t* status,

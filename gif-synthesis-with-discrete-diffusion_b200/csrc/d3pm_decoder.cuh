@@ -98,6 +98,57 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- pairs of CTAs (cta_group::2): the leader CTA issues M = 256 MMAs over both CTAs' shared memory and tensor memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(unsigned long long* bar, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(unsigned long long* bar) {  // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<unsigned short>(3))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major operand, 128-byte swizzle: rows at 128 B, 8-row groups at SBO = 1024 B, descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return static_cast<uint64_t>((addr >> 4) & 0x3fffu) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -155,19 +206,23 @@ __global__ void weight_image_kernel(const float* __restrict__ w, int N, int Npad
 // ---- the implicit-GEMM convolution ------------------------------------------------------------------------------
 // TERMS = 3: 3xTF32, a stage holds the hi and lo halves of both operands; TERMS = 1: plain TF32, hi halves only, so twice
 // as many stages fit (the single-product mode is bound by the producers' latency, which deeper staging hides)
-template <int NT, int TERMS>
+// CTAS = 2: a pair of CTAs (cluster of two on one TPC) computes 256 positions x NT channels with M = 256 MMAs
+// (tcgen05 cta_group::2): every CTA gathers the A rows of its own 128 positions and stages HALF of the weight rows, so its L2
+// weight stream and the shared-memory reads of the B operand are halved - the two floors of the single-CTA kernel.
+template <int NT, int TERMS, int CTAS>
 struct GemmGeo {
   static constexpr int kHalves = TERMS == 1 ? 1 : 2;
-  static constexpr int kStages = (NT == 128 ? 3 : 2) * (TERMS == 1 ? 2 : 1);
-  static constexpr int kBBytes = NT * 128;                        // one term of the weight k-block
+  static constexpr int kBRows = NT / CTAS;                        // weight rows this CTA stages
+  static constexpr int kBBytes = kBRows * 128;                    // one term of them
   static constexpr int kABytes = kHalves * kBlockBytes;           // A part of a stage
   static constexpr int kStageBytes = kABytes + kHalves * kBBytes;
-  // instruction descriptor: D = f32, A = B = tf32, both K-major, N = NT, M = 128
-  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NT >> 3) << 17) | ((kTileM >> 4) << 24);
+  static constexpr int kStages = 196608 / kStageBytes < 6 ? 196608 / kStageBytes : 6;
+  // instruction descriptor: D = f32, A = B = tf32, both K-major, N = NT, M = 128 per CTA
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NT >> 3) << 17) | (((kTileM * CTAS) >> 4) << 24);
 };
 
 struct GemmCtl {
-  unsigned long long full_a[6], full_b[6], empty[6], acc_full[2], acc_empty[2];
+  unsigned long long full_a[6], full_b[6], empty[6], peer_full[6], acc_full[2], acc_empty[2];
   uint32_t tmem_base, pad;
   signed char taps[kMaxClasses][kMaxTaps][4];
   int tap_shift[kMaxClasses][kMaxTaps];  // element offset of a tap's source row relative to the row itself
@@ -176,9 +231,9 @@ struct GemmCtl {
   alignas(16) float stage[4][32][36];    // epilogue: 32 rows x 32 columns per warp, rows padded to 144 B (conflict-free 128-bit access)
 };
 
-template <int NT, int TERMS>
+template <int NT, int TERMS, int CTAS>
 constexpr size_t gemm_smem_bytes() {
-  return 1024 + GemmGeo<NT, TERMS>::kStages * GemmGeo<NT, TERMS>::kStageBytes + sizeof(GemmCtl);
+  return 1024 + GemmGeo<NT, TERMS, CTAS>::kStages * GemmGeo<NT, TERMS, CTAS>::kStageBytes + sizeof(GemmCtl);
 }
 
 // Persistent: a CTA walks the tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the launch, tile t = (parity class, M tile,
@@ -190,26 +245,30 @@ constexpr size_t gemm_smem_bytes() {
 constexpr int kEpiWarps = 4;
 constexpr int kGemmThreads = 32 * (2 + kProdWarps + kEpiWarps);
 
-template <int NT, int TERMS>
+template <int NT, int TERMS, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using G = GemmGeo<NT, TERMS>;
+  using G = GemmGeo<NT, TERMS, CTAS>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   GemmCtl& C = *reinterpret_cast<GemmCtl*>(smem + G::kStages * G::kStageBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair is the leader: it issues the MMAs
+  const long long unit0 = blockIdx.x / CTAS;                  // a "unit" = the CTA or the pair that walks tiles together
+  const long long nunits = gridDim.x / CTAS;
   const int ntiles_n = p.Npad / NT;
   const int CB = p.Cin >> 5;            // k-blocks per tap
   const int KB = p.ntaps * CB;          // k-blocks of a tile
   const long long M = static_cast<long long>(p.B) * p.T * p.H * p.W;
-  const long long mtiles = (M + kTileM - 1) / kTileM;
+  const long long mtiles = ((M + kTileM - 1) / kTileM + CTAS - 1) / CTAS;  // tiles of 128 * CTAS positions
   const long long per_class = mtiles * ntiles_n;
   const long long total = per_class * p.nclass;
   const int HW = p.H * p.W;
 
   if (tid == 0) {
-    for (int i = 0; i < G::kStages; ++i) mbar_init(&C.full_a[i], kProdThreads), mbar_init(&C.full_b[i], 1), mbar_init(&C.empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&C.acc_full[i], 1), mbar_init(&C.acc_empty[i], kEpiWarps);
+    for (int i = 0; i < G::kStages; ++i)
+      mbar_init(&C.full_a[i], kProdThreads), mbar_init(&C.full_b[i], 1), mbar_init(&C.empty[i], 1), mbar_init(&C.peer_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&C.acc_full[i], 1), mbar_init(&C.acc_empty[i], kEpiWarps * CTAS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.in_scale != nullptr)
@@ -219,12 +278,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     for (int e = 0; e < 4; ++e) C.taps[c][t][e] = p.tap[c][t][e];
     C.tap_shift[c][t] = ((p.tap[c][t][0] * p.H + p.tap[c][t][1]) * p.W + p.tap[c][t][2]) * p.Cin;
   }
-  if (warp == 0) {  // two accumulators of NT columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(2 * NT) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 0) {  // two accumulators of NT columns (in both CTAs of a pair: the same warp of each allocates)
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(2 * NT) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&C.tmem_base)), "n"(2 * NT) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync();  // the partner's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = C.tmem_base;
 
@@ -232,54 +297,85 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     // =========================== weight stream (bulk TMA) ===========================
     if (lane == 0) {
       constexpr uint32_t bytes = G::kHalves * G::kBBytes;
+      constexpr uint32_t piece = G::kBBytes < kBlockBytes ? G::kBBytes : kBlockBytes;
       int st = 0;
       uint32_t par = 1;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (long long tile = unit0; tile < total; tile += nunits) {
         const int cls = static_cast<int>(tile / per_class);
         const int ntile = static_cast<int>(tile % ntiles_n);
-        const float* src = p.w_image + static_cast<size_t>(cls) * image_floats(p.Npad, KB * 32) + static_cast<size_t>(ntile) * KB * (2 * NT * 32);
+        // this CTA's rows of the N tile: [rank * kBRows, (rank + 1) * kBRows) of the hi block and of the lo block
+        const float* src = p.w_image + static_cast<size_t>(cls) * image_floats(p.Npad, KB * 32) + static_cast<size_t>(ntile) * KB * (2 * NT * 32) +
+                           static_cast<size_t>(rank) * (G::kBBytes / 4);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&C.empty[st], par);
           mbar_expect_tx(&C.full_b[st], bytes);
           unsigned char* dst = smem + st * G::kStageBytes + G::kABytes;
           const float* s = src + static_cast<size_t>(kb) * (2 * NT * 32);
-          for (uint32_t q = 0; q < bytes; q += kBlockBytes) tma_load(dst + q, s + q / 4, kBlockBytes, &C.full_b[st]);
+#pragma unroll
+          for (int half = 0; half < G::kHalves; ++half)
+            for (uint32_t q = 0; q < G::kBBytes; q += piece)
+              tma_load(dst + half * G::kBBytes + q, s + half * (NT * 32) + q / 4, piece, &C.full_b[st]);
           if (++st == G::kStages) st = 0, par ^= 1u;
         }
       }
     }
   } else if (warp == 0) {
-    // =========================== MMA issue ===========================
-    if (lane == 0) {
+    if (rank != 0) {
+      // =========================== partner CTA: tell the leader when this CTA's half of a stage is in place ===========================
+      // one lane per stage, so that the remote arrivals of consecutive k-blocks do not queue behind each other
+      // (polled without suspending: a lane that slept on its stage would hold up the lanes of the stages that complete first)
+      const long long my_tiles = unit0 < total ? (total - unit0 + nunits - 1) / nunits : 0;
+      const long long nkb = my_tiles * KB;
+      long long g = lane;
+      uint32_t par = 0;
+      bool active = lane < G::kStages && g < nkb;
+      const int st = lane < G::kStages ? lane : 0;
+      while (__any_sync(0xffffffffu, active)) {
+        if (active && mbar_test(&C.full_a[st], par) && mbar_test(&C.full_b[st], par)) {
+          mbar_arrive_remote(&C.peer_full[st], 0);
+          g += G::kStages, par ^= 1u;
+          active = g < nkb;
+        }
+      }
+    } else if (lane == 0) {
+      // =========================== MMA issue ===========================
       int st = 0;
       uint32_t par = 0, tc = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+      for (long long tile = unit0; tile < total; tile += nunits, ++tc) {
         const uint32_t acc = tc & 1u;
-        mbar_wait(&C.acc_empty[acc], ((tc >> 1) & 1u) ^ 1u);  // the epilogue of tile tc - 2 has drained this accumulator
+        // the epilogue (of both CTAs) of tile tc - 2 has drained this accumulator
+        if constexpr (CTAS == 2) mbar_wait_cluster(&C.acc_empty[acc], ((tc >> 1) & 1u) ^ 1u);
+        else mbar_wait(&C.acc_empty[acc], ((tc >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem + acc * NT;
         uint32_t accum = 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&C.full_a[st], par);
           mbar_wait(&C.full_b[st], par);
+          if constexpr (CTAS == 2) mbar_wait_cluster(&C.peer_full[st], par);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + st * G::kStageBytes);
           const uint32_t b_addr = a_addr + G::kABytes;
           // small terms first: a_lo w_hi, a_hi w_lo, then a_hi w_hi (terms == 1: a_hi w_hi only)
-          #pragma unroll
+#pragma unroll
           for (int term = (TERMS == 1 ? 2 : 0); term < 3; ++term) {
             const uint32_t a_off = (term == 0) ? kBlockBytes : 0;
             const uint32_t b_off = (term == 1) ? G::kBBytes : 0;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {  // 4 MMAs of K = 8 per 128-byte k-block
-              tc_mma_tf32(d_tmem, smem_desc(a_addr + a_off + ks * 32), smem_desc(b_addr + b_off + ks * 32), G::kIdesc, accum);
+              if constexpr (CTAS == 2)
+                tc_mma_tf32_pair(d_tmem, smem_desc(a_addr + a_off + ks * 32), smem_desc(b_addr + b_off + ks * 32), G::kIdesc, accum);
+              else
+                tc_mma_tf32(d_tmem, smem_desc(a_addr + a_off + ks * 32), smem_desc(b_addr + b_off + ks * 32), G::kIdesc, accum);
               accum = 1;
             }
           }
-          tc_commit(&C.empty[st]);
+          if constexpr (CTAS == 2) tc_commit_pair(&C.empty[st]);
+          else tc_commit(&C.empty[st]);
           if (++st == G::kStages) st = 0, par ^= 1u;
         }
-        tc_commit(&C.acc_full[acc]);
+        if constexpr (CTAS == 2) tc_commit_pair(&C.acc_full[acc]);
+        else tc_commit(&C.acc_full[acc]);
       }
     }
   } else if (warp < 2 + kProdWarps) {
@@ -298,12 +394,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const int r = r0 + 32 * i;
       soff[i] = static_cast<uint32_t>(r * 128 + ((piece ^ (r & 7)) << 4));
     }
-    long long f_tile = blockIdx.x;  // tile the fetch side is in
+    long long f_tile = unit0;  // tile the fetch side is in
     int f_cls = 0, f_tap = 0, f_cb = 0;
     auto enter_tile = [&]() {
       if (f_tile >= total) return;
       f_cls = static_cast<int>(f_tile / per_class);
-      const long long mtile = (f_tile % per_class) / ntiles_n;
+      const long long mtile = (f_tile % per_class) / ntiles_n * CTAS + rank;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const long long m = mtile * kTileM + r0 + 32 * i;
@@ -339,7 +435,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         f_cb = 0;
         if (++f_tap == p.ntaps) {
           f_tap = 0;
-          f_tile += gridDim.x;
+          f_tile += nunits;
           enter_tile();
         }
       }
@@ -385,7 +481,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       if (++e_cb == CB) e_cb = 0;
     };
     // k-blocks this CTA produces in all; two of them in flight per thread (32 KiB per SM): the gather is latency-bound at one
-    const long long my_tiles = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long my_tiles = unit0 < total ? (total - unit0 + nunits - 1) / nunits : 0;
     const long long nkb = my_tiles * KB;
     float4 buf0[4], buf1[4];
     uint32_t ok0 = 0, ok1 = 0;
@@ -414,9 +510,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = 32 * q + lane;
     uint32_t tc = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+    for (long long tile = unit0; tile < total; tile += nunits, ++tc) {
       const int cls = static_cast<int>(tile / per_class);
-      const long long mtile = (tile % per_class) / ntiles_n;
+      const long long mtile = (tile % per_class) / ntiles_n * CTAS + rank;
       const int ntile = static_cast<int>(tile % ntiles_n);
       const long long m = mtile * kTileM + r;
       const bool live = m < M;
@@ -488,15 +584,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       // this warp's tensor-memory reads of the accumulator are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&C.acc_empty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2 && rank != 0) mbar_arrive_remote(&C.acc_empty[acc], 0);  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&C.acc_empty[acc]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync();  // both CTAs are done with the pair's tensor memory and barriers
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
+    if constexpr (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT) : "memory");
   }
 }
 

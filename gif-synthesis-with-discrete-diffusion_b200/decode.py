@@ -186,10 +186,11 @@ def decoder_plan(decoder: torch.nn.Module) -> dict:
 class _Layer:
     """A `LayerSpec` bound to a device: the weight image and the static part of the launch descriptor."""
 
-    def __init__(self, spec: LayerSpec, dev, n_tile: Optional[int] = None):
+    def __init__(self, spec: LayerSpec, dev, n_tile: Optional[int] = None, cta_pair: bool = False):
         nclass, nout, ktot = spec.wmat.shape
         self.cin, self.nout, self.nclass, self.ntaps, self.stride = spec.cin, nout, nclass, len(spec.taps[0]), spec.stride
         self.n_tile = n_tile if n_tile is not None else (128 if nout <= 128 else 256)
+        self.cta_pair = bool(cta_pair)
         npad = (nout + self.n_tile - 1) // self.n_tile * self.n_tile
         lib = _lib.load_library()
         self.image = torch.empty(lib.d3pm_dec_image_floats(nclass, nout, ktot, self.n_tile), dtype=torch.float32, device=dev)
@@ -228,7 +229,7 @@ class _Layer:
         d.B, d.T, d.H, d.W, d.Cin = B, T, H, W, self.cin
         d.ntaps, d.nclass, d.Nout, d.ldo, d.out_transposed = self.ntaps, self.nclass, self.nout, out.shape[-1], int(transposed)
         d.stride_t, d.stride_h, d.stride_w = self.stride
-        d.relu_out, d.terms, d.n_tile = int(self.relu_out), terms, self.n_tile
+        d.relu_out, d.terms, d.n_tile, d.cta_pair = int(self.relu_out), terms, self.n_tile, int(self.cta_pair)
         d.stream = ops._stream(x.device)
         _lib.check(_lib.load_library().d3pm_dec_conv(ctypes.byref(d)), "d3pm_dec_conv")
         return out
@@ -243,7 +244,7 @@ class NativeDecoder:
     Rebuild the object when the module's weights or BatchNorm statistics change (they are folded at construction).
     """
 
-    def __init__(self, decoder: torch.nn.Module, precision: str = "fp32", n_tile: Optional[int] = None):
+    def __init__(self, decoder: torch.nn.Module, precision: str = "fp32", n_tile: Optional[int] = None, cta_pair: bool = False):
         if precision not in ("fp32", "tf32"):
             raise D3PMError("precision must be 'fp32' (3xTF32) or 'tf32'")
         self.terms = 3 if precision == "fp32" else 1
@@ -253,13 +254,13 @@ class NativeDecoder:
             raise D3PMError("d3pm_b200 operates on CUDA tensors only (there is no CPU path)")
         self.C, self.heads, self.device = plan["C"], plan["heads"], dev
         with torch.cuda.device(dev):
-            self.blocks = [tuple(_Layer(sp, dev, n_tile) for sp in blk) for blk in plan["blocks"]]
+            self.blocks = [tuple(_Layer(sp, dev, n_tile, cta_pair) for sp in blk) for blk in plan["blocks"]]
             self.convts = []
             for item in plan["convts"]:
                 if item[0] == "conv":
-                    self.convts.append(("conv", _Layer(item[1], dev, n_tile), item[2]))
+                    self.convts.append(("conv", _Layer(item[1], dev, n_tile, cta_pair), item[2]))
                 else:
-                    self.convts.append(("col2im", _Layer(item[1], dev, n_tile), item[2], item[3].to(dev), item[4]))
+                    self.convts.append(("col2im", _Layer(item[1], dev, n_tile, cta_pair), item[2], item[3].to(dev), item[4]))
 
     @classmethod
     def from_autoencoder(cls, autoencoder, precision: str = "fp32") -> "NativeDecoder":

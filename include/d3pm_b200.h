@@ -307,7 +307,9 @@ typedef struct d3pm_dec_conv_desc {
   const float* residual;  /* rows like `out` (same ldo) or NULL */
   float* out;             /* [B*To*Ho*Wo][ldo], columns [0, Nout) written */
   int32_t B, T, H, W, Cin;
-  int32_t ntaps, nclass, reserved;
+  int32_t ntaps, nclass;
+  int32_t cta_pair;       /* 1: pairs of CTAs (tcgen05 cta_group::2, M = 256 per instruction) share a weight tile, each staging half of its
+                             rows: half the L2 weight stream and half the shared-memory operand reads per CTA; same results */
   int32_t Nout;           /* Nout % 4 == 0 */
   int32_t out_transposed; /* 1: out[(row / ldo) * Nout * ldo + n * ldo + row % ldo] - planes of ldo consecutive output rows, channel-major
                              inside a plane (with ldo = H * W: the layout d3pm_dec_col2im reads); no residual */

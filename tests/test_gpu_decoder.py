@@ -45,9 +45,10 @@ CONV_CASES = {
 }
 
 
+@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("name", sorted(CONV_CASES))
-def test_dec_conv_honours_its_contract(name, terms):
+def test_dec_conv_honours_its_contract(name, terms, pair):
     B, grid, kw, with_res, n_tile = CONV_CASES[name]
     g = torch.Generator().manual_seed(len(name))
     spec = _spec(g, **kw)
@@ -55,7 +56,7 @@ def test_dec_conv_honours_its_contract(name, terms):
     x = torch.randn(M, spec.cin, generator=g)
     res = torch.randn(M, spec.nout, generator=g) if with_res else None
     want = emulate_conv(spec, x, B, grid, residual=res)
-    layer = decode._Layer(spec, torch.device(DEV), n_tile)
+    layer = decode._Layer(spec, torch.device(DEV), n_tile, cta_pair=pair)   # pair: cta_group::2, two CTAs per 256 positions
     got = layer(x.to(DEV), B, grid, terms=terms, residual=None if res is None else res.to(DEV)).cpu()
     assert got.shape == want.shape
     tol = (TOL_FP32 if terms == 3 else TOL_TF32) * float(want.abs().max())
@@ -81,9 +82,10 @@ def test_dec_conv_parity_classes_of_a_transposed_convolution(stride):
     spec = decode.LayerSpec(torch.stack(mats, 0), cin=cin, taps=[[d for _, d in taps] for _, taps in classes],
                             classes=[c for c, _ in classes], stride=stride, bias=bias)
     rows = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous()
-    got = decode._Layer(spec, torch.device(DEV))(rows.to(DEV), B, grid, terms=3).cpu()
-    got = got.view(B, *(n * s for n, s in zip(grid, stride)), cout).permute(0, 4, 1, 2, 3)
-    assert (got - want).abs().max().item() <= TOL_FP32 * float(want.abs().max())
+    for pair in (False, True):
+        got = decode._Layer(spec, torch.device(DEV), cta_pair=pair)(rows.to(DEV), B, grid, terms=3).cpu()
+        got = got.view(B, *(n * s for n, s in zip(grid, stride)), cout).permute(0, 4, 1, 2, 3)
+        assert (got - want).abs().max().item() <= TOL_FP32 * float(want.abs().max()), pair
 
 
 @pytest.mark.parametrize("B,grid,C", [(2, (4, 16, 16), 256), (1, (3, 5, 7), 128), (2, (2, 4, 4), 64), (1, (16, 16, 16), 256), (1, (1, 32, 2), 64)])
@@ -140,6 +142,8 @@ def test_native_decoder_against_reference_fixture(name):
     assert (got - want).abs().max().item() <= 5e-5 * scale
     fast = decode.decode(vq, tokens, table, decode.NativeDecoder(vq.decoder, precision="tf32")).cpu()
     assert (fast - want).abs().max().item() <= 2e-2 * scale
+    paired = decode.decode(vq, tokens, table, decode.NativeDecoder(vq.decoder, cta_pair=True)).cpu()
+    assert (paired - want).abs().max().item() <= 5e-5 * scale
     # the reference's own entry: Decoder.forward on the channels-first tensor
     again = decode.NativeDecoder(vq.decoder)(torch.from_numpy(fx["h"]).to(DEV)).cpu()
     assert (again - want).abs().max().item() <= 5e-5 * scale

@@ -49,7 +49,7 @@ def decoder_flops(B, grid, C, n_res, strides):
     return total
 
 
-def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None):
+def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None, cta_pair=False):
     import torch
     from baseline import reference_loader as RL
     from d3pm_b200 import decode
@@ -90,7 +90,7 @@ def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
     scale = float(want.abs().max())
     for prec in ("fp32", "tf32"):
-        nd = decode.NativeDecoder(vq.decoder, precision=prec, n_tile=n_tile)
+        nd = decode.NativeDecoder(vq.decoder, precision=prec, n_tile=n_tile, cta_pair=cta_pair)
         got = decode.decode(vq, tokens, table, nd)
         ms = _timed(lambda: decode.decode(vq, tokens, table, nd), reps, dev)
         res[f"native_{prec}_ms"] = ms
@@ -144,5 +144,6 @@ if __name__ == "__main__":
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--n-tile", type=int, default=None, help="force the GEMM tile width (128 / 256) of every layer")
+    ap.add_argument("--pairs", action="store_true", help="run every GEMM on pairs of CTAs (cta_group::2)")
     a = ap.parse_args()
-    run(videos=a.videos, reps=a.reps, layers=a.layers, n_tile=a.n_tile)
+    run(videos=a.videos, reps=a.reps, layers=a.layers, n_tile=a.n_tile, cta_pair=a.pairs)
