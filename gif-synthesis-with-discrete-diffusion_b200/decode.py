@@ -266,11 +266,28 @@ class NativeDecoder:
     def from_autoencoder(cls, autoencoder, precision: str = "fp32") -> "NativeDecoder":
         return cls(autoencoder.decoder, precision)
 
+    max_elements = 2 ** 32 - 1   # the kernels form 32-bit element offsets into a layer's input
+
+    def videos_per_pass(self, grid) -> int:
+        """How many videos one pass can take: the largest layer input (the last transposed convolution's) must stay below
+        `max_elements` elements; `forward_rows` splits larger batches (which also bounds the activation memory)."""
+        rows = int(grid[0]) * int(grid[1]) * int(grid[2])
+        worst = rows * 3 * self.C   # the attention output feeding `fc`
+        for item in self.convts:
+            worst = max(worst, rows * item[1].cin)
+            rows *= item[2][0] * item[2][1] * item[2][2]
+        return max(1, self.max_elements // worst)
+
     def forward_rows(self, x: torch.Tensor, B: int, grid) -> torch.Tensor:
         """Channels-last rows `[B * T * H * W, C]` -> video `[B, Cout, T', H', W']`."""
         T, H, W = (int(v) for v in grid)
         if max(T, H, W) > 32:
             raise D3PMError(f"latent grid {T}x{H}x{W}: the axial attention kernel covers axes of up to 32 positions")
+        per_pass = self.videos_per_pass((T, H, W))
+        if B > per_pass:
+            n = T * H * W
+            return torch.cat([self.forward_rows(x[b * n:min(B, b + per_pass) * n], min(B, b + per_pass) - b, (T, H, W))
+                              for b in range(0, B, per_pass)], 0)
         lib = _lib.load_library()
         dev = x.device
         M = B * T * H * W

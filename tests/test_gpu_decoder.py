@@ -144,6 +144,11 @@ def test_native_decoder_against_reference_fixture(name):
     assert (fast - want).abs().max().item() <= 2e-2 * scale
     paired = decode.decode(vq, tokens, table, decode.NativeDecoder(vq.decoder, cta_pair=True)).cpu()
     assert (paired - want).abs().max().item() <= 5e-5 * scale
+    if tokens.shape[0] > 1:  # a batch too large for the 32-bit element offsets is decoded in passes of whole videos
+        small = decode.NativeDecoder(vq.decoder)
+        small.max_elements = small.max_elements // (small.videos_per_pass(tokens.shape[1:])) + 1   # room for exactly one video
+        assert small.videos_per_pass(tokens.shape[1:]) == 1
+        assert torch.equal(decode.decode(vq, tokens, table, small).cpu(), got)
     # the reference's own entry: Decoder.forward on the channels-first tensor
     again = decode.NativeDecoder(vq.decoder)(torch.from_numpy(fx["h"]).to(DEV)).cpu()
     assert (again - want).abs().max().item() <= 5e-5 * scale
