@@ -96,8 +96,8 @@ def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None,
         res[f"native_{prec}_ms"] = ms
         res[f"native_{prec}_useful_TFLOPs"] = flops / (ms * 1e-3) / 1e12
         res[f"native_{prec}_max_err_over_scale"] = float((got - want).abs().max()) / scale
-        if layers and prec == "fp32":
-            res["layers_fp32"] = layer_table(nd, vq, tokens, table, dev)
+        if layers:
+            res[f"layers_{prec}"] = layer_table(nd, vq, tokens, table, dev)
     res["reference_default_tf32_conv_max_err_over_scale"] = err_ref_tf32 / scale
     res["speedup_fp32"] = res["reference_fp32_ms"] / res["native_fp32_ms"]
     res["speedup_tf32"] = res["reference_default_tf32_conv_ms"] / res["native_tf32_ms"]
