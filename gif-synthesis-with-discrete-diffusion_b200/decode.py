@@ -215,19 +215,26 @@ class _Layer:
                     self.desc.tap[c][i][e] = d[e]
 
     def __call__(self, x: torch.Tensor, B: int, grid, *, terms: int, residual: Optional[torch.Tensor] = None,
-                 transposed: bool = False) -> torch.Tensor:
+                 transposed: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """-> rows `[B * T' * H' * W', Nout]`, or with `transposed` planes `[B * T', Nout, H' * W']` (what d3pm_dec_col2im reads)."""
         T, H, W = grid
         rows_out = B * T * H * W * self.stride[0] * self.stride[1] * self.stride[2]
         if x.shape != (B * T * H * W, self.cin) or not x.is_contiguous() or x.dtype != torch.float32:
             raise D3PMError(f"expected contiguous float32 rows [{B * T * H * W}, {self.cin}], got {tuple(x.shape)}")
         plane = H * W * self.stride[1] * self.stride[2]
-        out = torch.empty((rows_out // plane, self.nout, plane) if transposed else (rows_out, self.nout), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((rows_out // plane, self.nout, plane) if transposed else (rows_out, self.nout), dtype=torch.float32,
+                              device=x.device)
+        elif transposed or out.dim() != 2 or out.shape[0] != rows_out or out.shape[1] < self.nout or out.stride(1) != 1 or out.stride(0) % 4:
+            raise D3PMError("out must be float32 rows [output positions, >= Nout] with a pitch that is a multiple of 4")
         d = self.desc
         d.x, d.in_scale, d.in_shift = x.data_ptr(), ops._ptr(self.in_scale), ops._ptr(self.in_shift)
+        if residual is not None and (residual.shape != out.shape or residual.stride() != out.stride()):
+            raise D3PMError("residual must be laid out like the output rows")
         d.w_image, d.bias, d.residual, d.out = self.image.data_ptr(), ops._ptr(self.bias), ops._ptr(residual), out.data_ptr()
         d.B, d.T, d.H, d.W, d.Cin = B, T, H, W, self.cin
-        d.ntaps, d.nclass, d.Nout, d.ldo, d.out_transposed = self.ntaps, self.nclass, self.nout, out.shape[-1], int(transposed)
+        d.ntaps, d.nclass, d.Nout, d.out_transposed = self.ntaps, self.nclass, self.nout, int(transposed)
+        d.ldo = out.shape[-1] if transposed else out.stride(0)
         d.stride_t, d.stride_h, d.stride_w = self.stride
         d.relu_out, d.terms, d.n_tile, d.cta_pair = int(self.relu_out), terms, self.n_tile, int(self.cta_pair)
         d.stream = ops._stream(x.device)

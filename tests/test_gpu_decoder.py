@@ -223,3 +223,23 @@ def test_sample_then_decode_like_the_reference_caller():
         want = vq.decode(tokens.view(B, *grid))
     assert video.shape == want.shape == (B, 3, grid[0], 4 * grid[1], 4 * grid[2])
     assert (video - want).abs().max().item() <= 2e-3 * float(want.abs().max())   # the reference arm runs cuDNN's default TF32 here
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("name", ["conv3_ragged_two_tiles", "nout_192_padded", "pointwise_bias_relu_res"])
+def test_dec_conv_writes_nothing_outside_its_rows_and_columns(name, pair):
+    """Canaries around the output: rows past the last position and the columns between Nout and the row pitch stay untouched
+    (ragged last tile, padded last N tile, the shared-memory-staged epilogue)."""
+    B, grid, kw, with_res, n_tile = CONV_CASES[name]
+    g = torch.Generator().manual_seed(11)
+    spec = _spec(g, **kw)
+    M = B * grid[0] * grid[1] * grid[2]
+    x = torch.randn(M, spec.cin, generator=g).to(DEV)
+    layer = decode._Layer(spec, torch.device(DEV), n_tile, cta_pair=pair)
+    plain = layer(x, B, grid, terms=3)
+    pitch, guard = spec.nout + 8, 5
+    buf = torch.full((M + guard, pitch), 777.0, device=DEV)
+    got = layer(x, B, grid, terms=3, out=buf[:M])
+    assert got.data_ptr() == buf.data_ptr()
+    assert torch.equal(buf[:M, :spec.nout], plain)
+    assert bool((buf[M:] == 777.0).all()) and bool((buf[:M, spec.nout:] == 777.0).all())
