@@ -635,6 +635,16 @@ def measure_16bit(dev, model, table, videos=VIDEOS_PER_GPU, steps=30):
         gbps = videos * N * (2 * K * 2 + 16) / (ms * 1e-3) / 1e9
         res[name] = {"ms_per_step": ms, "value": videos * N / (ms * 1e-3), "unit": UNIT, "GBps_algorithmic": gbps,
                      "frac_of_measured_peak": gbps / peak, "ms_per_step_cast_then_fp32_step": ms_cast}
+        if dt is torch.float16:  # the same from pinned HOST logits through the C handle (d3pm_host_step_set_logits_dtype): half of `e2e`'s bytes
+            host = ops.HostStep(videos, N, K, table, guidance=True, T=T_STEPS, logits_dtype=dt)
+            h_c, h_u, h_x, h_t = lc.cpu().pin_memory(), lu.cpu().pin_memory(), x.cpu().pin_memory(), t.cpu().pin_memory()
+            ms_h = _timed_steps(lambda i: host(h_c, h_u, h_x, h_t, guidance_scale=GUIDANCE, seed=9, offset=i), 5, dev, warm=2)
+            res["e2e_host_float16_logits"] = {"ms_per_step": ms_h, "value": videos * N / (ms_h * 1e-3), "unit": UNIT,
+                                              "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
+                                              "what": "d3pm_host_step_run on float16 host logits (a caller whose denoiser emits half precision): "
+                                                      "informational, the headline e2e stays the fp32 workload"}
+            host.close()
+            del h_c, h_u
         del lc, lu
     torch.cuda.empty_cache()
     return res

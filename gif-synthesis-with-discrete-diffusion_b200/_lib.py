@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "d3pm_dec_image_floats", "d3pm_dec_weight_image", "d3pm_dec_conv", "d3pm_dec_embed_rows", "d3pm_dec_axial_attention",
     "d3pm_dec_col2im",
     "d3pm_host_step_create", "d3pm_host_step_destroy", "d3pm_host_step_h2d_bytes", "d3pm_host_step_d2h_bytes",
-    "d3pm_host_step_run", "d3pm_host_head_step_run",
+    "d3pm_host_step_run", "d3pm_host_head_step_run", "d3pm_host_step_set_logits_dtype",
 )
 
 COEF_STRIDE = 32
@@ -173,6 +173,8 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_host_step_h2d_bytes.argtypes = [c_void_p]
     lib.d3pm_host_step_d2h_bytes.restype = c_int64
     lib.d3pm_host_step_d2h_bytes.argtypes = [c_void_p]
+    lib.d3pm_host_step_set_logits_dtype.restype = c_int
+    lib.d3pm_host_step_set_logits_dtype.argtypes = [c_void_p, c_int]
     lib.d3pm_host_step_run.restype = c_int
     lib.d3pm_host_step_run.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_uint64,
                                        c_int64, c_void_p, POINTER(c_uint32)]

@@ -476,6 +476,7 @@ int d3pm_to_token_major(const float* src, float* dst, int64_t pitch, int B, int 
 struct d3pm_host_step {
   int device = 0;
   int B = 0, N = 0, K = 0, T = 0, D = 0, chunks = 1;
+  int logits_dtype = D3PM_LOGITS_F32;  // element type of the HOST logits handed to d3pm_host_step_run
   bool guidance = false;
   float *logits_c = nullptr, *logits_u = nullptr, *hidden_c = nullptr, *hidden_u = nullptr;
   int64_t *x_t = nullptr, *t = nullptr, *x_prev = nullptr;
@@ -566,26 +567,36 @@ extern "C" int64_t d3pm_host_step_h2d_bytes(const d3pm_host_step* h) {
   if (h == nullptr) return 0;
   const int64_t rows = static_cast<int64_t>(h->B) * h->N;
   const int64_t width = h->D == 0 ? h->K : h->D;
-  return rows * width * 4 * (h->guidance ? 2 : 1) + rows * 8 + static_cast<int64_t>(h->B) * 8;
+  const int64_t elem = (h->D == 0 && h->logits_dtype != D3PM_LOGITS_F32) ? 2 : 4;
+  return rows * width * elem * (h->guidance ? 2 : 1) + rows * 8 + static_cast<int64_t>(h->B) * 8;
+}
+
+extern "C" int d3pm_host_step_set_logits_dtype(d3pm_host_step* h, int logits_dtype) {
+  if (h == nullptr || h->D != 0) return d3pm::host::fail(D3PM_ERR_INVALID, "host_step_set_logits_dtype: needs a handle created for logits (D = 0)");
+  if (logits_dtype < D3PM_LOGITS_F32 || logits_dtype > D3PM_LOGITS_BF16)
+    return d3pm::host::fail(D3PM_ERR_INVALID, "host_step_set_logits_dtype: unknown dtype %d", logits_dtype);
+  if (logits_dtype != D3PM_LOGITS_F32 && h->K % 8 != 0) return d3pm::host::fail(D3PM_ERR_ALIGN, "host_step_set_logits_dtype: 16-bit rows need K %% 8 == 0");
+  h->logits_dtype = logits_dtype;
+  return D3PM_OK;
 }
 extern "C" int64_t d3pm_host_step_d2h_bytes(const d3pm_host_step* h) { return h == nullptr ? 0 : static_cast<int64_t>(h->B) * h->N * 8; }
 
 // shared driver of the two run calls: `launch(b0, nb)` enqueues the step of videos [b0, b0 + nb) on h->compute
 template <typename Launch>
 static int host_step_run(d3pm_host_step* h, const float* in_c, const float* in_u, float* dev_c, float* dev_u, int64_t width,
-                         const int64_t* x_t, const int64_t* t, int64_t* x_prev, uint32_t* status_out, Launch launch) {
+                         const int64_t* x_t, const int64_t* t, int64_t* x_prev, uint32_t* status_out, Launch launch, size_t elem = 4) {
   const SetDevice on(h->device);
   const size_t rows = static_cast<size_t>(h->B) * h->N;
   D3PM_CUDA_OK(cudaMemcpyAsync(h->x_t, x_t, rows * 8, cudaMemcpyHostToDevice, h->compute), "host_step: x_t copy");
   D3PM_CUDA_OK(cudaMemcpyAsync(h->t, t, static_cast<size_t>(h->B) * 8, cudaMemcpyHostToDevice, h->compute), "host_step: t copy");
   const int per = h->B / h->chunks;
-  const size_t chunk_floats = static_cast<size_t>(per) * h->N * width;
+  const size_t chunk_bytes = static_cast<size_t>(per) * h->N * width * elem;  // (16-bit logits use the front half of the staging buffers)
+  auto at = [&](const float* base, int c) { return reinterpret_cast<const unsigned char*>(base) + c * chunk_bytes; };
+  auto at_dev = [&](float* base, int c) { return reinterpret_cast<unsigned char*>(base) + c * chunk_bytes; };
   for (int c = 0; c < h->chunks; ++c) {
-    D3PM_CUDA_OK(cudaMemcpyAsync(dev_c + c * chunk_floats, in_c + c * chunk_floats, chunk_floats * 4, cudaMemcpyHostToDevice, h->copy),
-                 "host_step: input copy");
+    D3PM_CUDA_OK(cudaMemcpyAsync(at_dev(dev_c, c), at(in_c, c), chunk_bytes, cudaMemcpyHostToDevice, h->copy), "host_step: input copy");
     if (h->guidance)
-      D3PM_CUDA_OK(cudaMemcpyAsync(dev_u + c * chunk_floats, in_u + c * chunk_floats, chunk_floats * 4, cudaMemcpyHostToDevice, h->copy),
-                   "host_step: input copy");
+      D3PM_CUDA_OK(cudaMemcpyAsync(at_dev(dev_u, c), at(in_u, c), chunk_bytes, cudaMemcpyHostToDevice, h->copy), "host_step: input copy");
     D3PM_CUDA_OK(cudaEventRecord(h->landed[c], h->copy), "host_step: event");
     D3PM_CUDA_OK(cudaStreamWaitEvent(h->compute, h->landed[c], 0), "host_step: wait");
     const int rc = launch(c * per, per);
@@ -613,7 +624,10 @@ extern "C" int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, cons
   auto launch = [&](int b0, int nb) {
     d3pm_step_desc d = {};
     const size_t at = static_cast<size_t>(b0) * h->N;
-    d.logits_c = h->logits_c + at * h->K, d.logits_u = h->guidance ? h->logits_u + at * h->K : nullptr;
+    const size_t esz = h->logits_dtype == D3PM_LOGITS_F32 ? 4 : 2;
+    auto row_ptr = [&](float* base) { return reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(base) + at * h->K * esz); };
+    d.logits_c = row_ptr(h->logits_c), d.logits_u = h->guidance ? row_ptr(h->logits_u) : nullptr;
+    d.logits_dtype = h->logits_dtype;
     d.x_t = h->x_t + at, d.t = h->t + b0, d.coef_table = coef_table, d.x_prev = h->x_prev + at, d.status = h->status;
     d.B = nb, d.N = h->N, d.K = h->K, d.T = h->T, d.pitch_logits = h->K;
     d.guidance_scale = guidance_scale, d.sample_mode = D3PM_SAMPLE_PHILOX;
@@ -621,7 +635,8 @@ extern "C" int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, cons
     d.kernel = D3PM_KERNEL_AUTO, d.stream = h->compute;
     return d3pm_fused_step(&d);
   };
-  return host_step_run(h, logits_c, logits_u, h->logits_c, h->logits_u, h->K, x_t, t, x_prev, status_out, launch);
+  return host_step_run(h, logits_c, logits_u, h->logits_c, h->logits_u, h->K, x_t, t, x_prev, status_out, launch,
+                       h->logits_dtype == D3PM_LOGITS_F32 ? 4 : 2);
 }
 
 extern "C" int d3pm_host_head_step_run(d3pm_host_step* h, const float* hidden_c, const float* hidden_u, const int64_t* x_t, const int64_t* t,

@@ -295,7 +295,7 @@ class HostStep:
     """
 
     def __init__(self, B: int, N: int, K: int, coef_table: torch.Tensor, guidance: bool = True, *, T: Optional[int] = None,
-                 hidden_dim: int = 0, chunks: int = 0):
+                 hidden_dim: int = 0, chunks: int = 0, logits_dtype: torch.dtype = torch.float32):
         dev = coef_table.device
         if dev.type != "cuda":
             raise D3PMError("HostStep needs the coefficient table on a CUDA device")
@@ -307,6 +307,11 @@ class HostStep:
                                                    B, N, K, int(T if T is not None else coef_table.shape[0]), hidden_dim,
                                                    1 if guidance else 0, chunks), "d3pm_host_step_create")
         self._handle = handle
+        self.logits_dtype = logits_dtype
+        if logits_dtype != torch.float32:  # host logits in float16 / bfloat16: half the bytes on the bus, stepped in place
+            if hidden_dim or logits_dtype not in LOGITS_DTYPES:
+                raise D3PMError("logits_dtype applies to a logits handle (hidden_dim = 0) and must be float32, float16 or bfloat16")
+            _lib.check(self._lib.d3pm_host_step_set_logits_dtype(handle, LOGITS_DTYPES[logits_dtype]), "d3pm_host_step_set_logits_dtype")
         self.x_prev_host = torch.empty(B, N, dtype=torch.int64).pin_memory()
         self.h2d_bytes = int(self._lib.d3pm_host_step_h2d_bytes(handle))
         self.d2h_bytes = int(self._lib.d3pm_host_step_d2h_bytes(handle))
@@ -325,7 +330,8 @@ class HostStep:
 
     def _check_host(self, width, a, b, x_t, t):
         B, N, _ = self.shape
-        for name, ten, shape, dt in (("conditional input", a, (B, N, width), torch.float32), ("unconditional input", b, (B, N, width), torch.float32),
+        fdt = torch.float32 if self.hidden_dim else self.logits_dtype
+        for name, ten, shape, dt in (("conditional input", a, (B, N, width), fdt), ("unconditional input", b, (B, N, width), fdt),
                                      ("x_t", x_t, (B, N), torch.int64), ("t", t, (B,), torch.int64)):
             if ten is None:
                 continue

@@ -357,6 +357,10 @@ int d3pm_host_step_create(d3pm_host_step** out, int device, int B, int N, int K,
 int d3pm_host_step_destroy(d3pm_host_step* h);
 int64_t d3pm_host_step_h2d_bytes(const d3pm_host_step* h); /* bytes one run moves host -> device */
 int64_t d3pm_host_step_d2h_bytes(const d3pm_host_step* h); /* and device -> host */
+/* Element type of the HOST logits of a D = 0 handle (D3PM_LOGITS_*; default F32): float16 / bfloat16 rows cross the bus at half
+ * the bytes and are stepped in place (d3pm_step_desc.logits_dtype); logits_c / logits_u of d3pm_host_step_run then point at
+ * 16-bit rows.  K % 8 == 0.                                                                                              */
+int d3pm_host_step_set_logits_dtype(d3pm_host_step* h, int logits_dtype);
 int d3pm_host_step_run(d3pm_host_step* h, const float* logits_c, const float* logits_u, const int64_t* x_t, const int64_t* t,
                        const float* coef_table, float guidance_scale, uint64_t seed, uint64_t offset, int64_t row_offset,
                        int64_t* x_prev, uint32_t* status_out);

@@ -206,3 +206,25 @@ def test_16bit_denoiser_logits_are_stepped_in_place(dtype):
     pa, pb = m16.p_pred(log_x, cond, cf, t), m32.p_pred(log_x, cond, cf, t)
     assert torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
     m16.check_status()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_host_step_with_16bit_host_logits(dtype):
+    """Host logits in half precision: half the bytes on the bus, the tokens of the device-resident 16-bit step."""
+    from d3pm_b200 import _lib
+    K, B, N, Tn = 4096, 4, 1024, 100
+    g = torch.Generator().manual_seed(12)
+    lc, lu = torch.randn(B, N, K, generator=g).to(dtype), torch.randn(B, N, K, generator=g).to(dtype)
+    x_t = torch.randint(0, K + 1, (B, N), generator=g)
+    t = torch.full((B,), 30, dtype=torch.long)
+    table = ops.build_coef_table(O.pack_schedule(O.make_schedule(Tn, K)).to(DEV), Tn, K)
+    hs = ops.HostStep(B, N, K, table, guidance=True, logits_dtype=dtype)
+    ref32 = ops.HostStep(B, N, K, table, guidance=True)
+    assert hs.h2d_bytes - B * N * 8 - B * 8 == (ref32.h2d_bytes - B * N * 8 - B * 8) // 2
+    got = hs(lc.pin_memory(), lu.pin_memory(), x_t.pin_memory(), t.pin_memory(), guidance_scale=2.0, seed=4, offset=9).clone()
+    want = ops.fused_step(lc.to(DEV), lu.to(DEV), x_t.to(DEV), t.to(DEV), table, guidance_scale=2.0, sample_mode=_lib.SAMPLE_PHILOX,
+                          seed=4, offset=9)["x_prev"].cpu()
+    assert torch.equal(got, want) and hs.last_status & 3 == 0
+    with pytest.raises(Exception):
+        hs(lc.float().pin_memory(), lu.float().pin_memory(), x_t, t, guidance_scale=2.0, seed=4, offset=9)
+    hs.close(), ref32.close()
