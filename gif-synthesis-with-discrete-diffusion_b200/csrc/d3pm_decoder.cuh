@@ -563,6 +563,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           const bool col_ok = n0 + 4 * pc < p.Nout;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias != nullptr && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + pc);
+          float4 r4[8];
+          const bool has_res = p.residual != nullptr;
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // all eight residual loads in flight before the first one is used
+              const int rr = 4 * j + rsub;
+              const long long orr = __shfl_sync(0xffffffffu, orow, rr);
+              const bool ok = __shfl_sync(0xffffffffu, live ? 1 : 0, rr) != 0 && col_ok;
+              r4[j] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + orr * p.ldo + n0) + pc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int rr = 4 * j + rsub;
@@ -571,10 +582,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             float4 o = *reinterpret_cast<const float4*>(&stg[rr][4 * pc]);
             if (ok) {
               o.x += b4.x, o.y += b4.y, o.z += b4.z, o.w += b4.w;
-              if (p.residual != nullptr) {
-                const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + orr * p.ldo + n0) + pc);
-                o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
-              }
+              if (has_res) o.x += r4[j].x, o.y += r4[j].y, o.z += r4[j].z, o.w += r4[j].w;
               if (p.relu_out) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
               reinterpret_cast<float4*>(p.out + orr * p.ldo + n0)[pc] = o;
             }
