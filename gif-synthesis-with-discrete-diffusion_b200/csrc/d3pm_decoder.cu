@@ -166,8 +166,14 @@ int d3pm_dec_col2im(const float* y_t, const float* bias, float* out, int B, int 
   const DeviceGuard on_device(out);
   const long long total = static_cast<long long>(B) * T * st * H * sh * W;
   if ((total + 255) / 256 > 2147483647LL) return fail(D3PM_ERR_UNSUPPORTED, "dec_col2im: output too large");
-  d3pm::dec::col2im_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y_t, bias, out, B, T, H, W,
-                                                                                                                      Cout, st, sh, sw);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (sh == 2 && sw == 2 && Cout <= 3) {  // the shape of the decoder's last layer: straight-line loads
+    if (st == 1) d3pm::dec::col2im_s22_kernel<1><<<grid, 256, 0, s>>>(y_t, bias, out, B, T, H, W, Cout);
+    else d3pm::dec::col2im_s22_kernel<2><<<grid, 256, 0, s>>>(y_t, bias, out, B, T, H, W, Cout);
+  } else {
+    d3pm::dec::col2im_kernel<<<grid, 256, 0, s>>>(y_t, bias, out, B, T, H, W, Cout, st, sh, sw);
+  }
   return check_launch("dec_col2im");
 }
 

@@ -509,6 +509,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     // =========================== epilogue (warps 10..13) ===========================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = 32 * q + lane;
+    // transposed output of a plain product (output row = input row) with 4-aligned planes: whole-column stores
+    const bool tfast = p.out_transposed && p.st == 1 && p.sh == 1 && p.sw == 1 && p.nclass == 1 && (p.ldo & 3) == 0 && (M & 3) == 0;
     uint32_t tc = 0;
     for (long long tile = unit0; tile < total; tile += nunits, ++tc) {
       const int cls = static_cast<int>(tile / per_class);
@@ -535,7 +537,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         uint32_t v[32];
         tmem_ld32(t_lane + c0, v);
         tmem_ld_wait();
-        if (live && p.out_transposed) {
+        if (p.out_transposed && tfast) {
+          // The four epilogue warps exchange their 32 x 32 blocks through shared memory ([column][128 rows]) so that a warp
+          // writes whole columns: 512 contiguous bytes per store instruction instead of 128.
+          float* stT = &C.stage[0][0][0];
+          asm volatile("bar.sync 2, 128;" ::: "memory");  // the previous block has been read
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stT[i * kTileM + r] = __uint_as_float(v[i]);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const long long m0 = mtile * kTileM + 4 * lane;  // rows 4 lane .. 4 lane + 3 of the tile (same plane: ldo % 4 == 0)
+          if (m0 < M) {
+            const long long plane = m0 / p.ldo;
+            float* dst0 = p.out + (plane * p.Nout + n0) * p.ldo + (m0 - plane * p.ldo);
+            const int cw = 8 * (warp - (2 + kProdWarps));
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const int c = cw + cc;
+              if (n0 + c < p.Nout) {
+                float4 o = *reinterpret_cast<const float4*>(stT + c * kTileM + 4 * lane);
+                if (p.bias != nullptr) {
+                  const float bc = __ldg(p.bias + n0 + c);
+                  o.x += bc, o.y += bc, o.z += bc, o.w += bc;
+                }
+                if (p.relu_out) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                *reinterpret_cast<float4*>(dst0 + static_cast<long long>(c) * p.ldo) = o;
+              }
+            }
+          }
+        } else if (live && p.out_transposed) {
           // lanes = consecutive rows: every column is one coalesced 128-byte store of the warp
           const long long plane = orow / p.ldo;
           float* dst = p.out + (plane * p.Nout + n0) * p.ldo + (orow - plane * p.ldo);
@@ -811,6 +840,60 @@ __global__ void col2im_kernel(const float* __restrict__ yT, const float* __restr
     if (sw == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0][c] + bc, acc[1][c] + bc);
     else dst[0] = acc[0][c] + bc;
   }
+}
+
+// The same for the strides the decoder's last layer has in practice, (ST, 2, 2): the taps that land on a voxel are known up
+// to the parities of yt / yh, so the 16 (ST = 1) or 8 (ST = 2) x 2 x 3 loads of a thread are straight-line code with range
+// predicates only - they are all in flight together instead of one per loop iteration.
+template <int ST>
+__global__ void __launch_bounds__(256) col2im_s22_kernel(const float* __restrict__ yT, const float* __restrict__ bias, float* __restrict__ out,
+                                                         int B, int T, int H, int W, int Cout) {
+  const int To = T * ST, Ho = H * 2;
+  const long long Wo = 2LL * W;
+  const long long total = static_cast<long long>(B) * To * Ho * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int mw = static_cast<int>(idx % W);
+  const int yh = static_cast<int>((idx / W) % Ho);
+  const int yt = static_cast<int>((idx / (static_cast<long long>(W) * Ho)) % To);
+  const long long b = idx / (static_cast<long long>(W) * Ho * To);
+  const long long P = static_cast<long long>(H) * W;
+  constexpr int NKT = 4 / ST;
+  const int kt0 = ST == 1 ? 0 : ((yt + 1) & 1);   // taps kt0, kt0 + ST, ...
+  const int kh0 = (yh + 1) & 1;                   // taps kh0, kh0 + 2
+  float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int a = 0; a < NKT; ++a) {
+    const int kt = kt0 + a * ST;
+    const int it = (yt + 3 - kt) / ST - (ST == 1 ? 2 : 1);
+    const bool okt = it >= 0 && it < T;
+    const float* plane = yT + (b * T + (okt ? it : 0)) * (64LL * Cout) * P;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kh = kh0 + 2 * e;
+      const int ih = (yh + 3 - kh) / 2 - 1;
+      const bool okh = okt && ih >= 0 && ih < H;
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const int kw = ((pw + 1) & 1) + 2 * f;
+          const int iw = (2 * mw + pw + 3 - kw) / 2 - 1;
+          const bool ok = okh && iw >= 0 && iw < W;
+          const float* src = plane + static_cast<long long>(((kt * 4 + kh) * 4 + kw) * Cout) * P + (okh ? ih : 0) * W + (ok ? iw : 0);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < Cout) acc[pw][c] += ok ? __ldg(src + c * P) : 0.f;
+        }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    if (c < Cout) {
+      const float bc = bias != nullptr ? bias[c] : 0.f;
+      float* dst = out + (((b * Cout + c) * To + yt) * Ho + yh) * Wo + 2LL * mw;
+      *reinterpret_cast<float2*>(dst) = make_float2(acc[0][c] + bc, acc[1][c] + bc);
+    }
 }
 
 }  // namespace dec
