@@ -140,8 +140,9 @@ int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, 
     const long long jobs = M / L * heads;
     auto launch = [&](auto vpl, auto lmax) {
       constexpr int V = decltype(vpl)::value, LM = decltype(lmax)::value;
-      constexpr int NW = D::attn_warps(V, LM);
-      D::axial_attention_kernel<V, LM><<<static_cast<unsigned>((jobs + NW - 1) / NW), 32 * NW, 0, s>>>(qkv, att, B, T, H, W, heads, axis);
+      constexpr D::AttnShape SH = D::attn_shape(LM);
+      D::axial_attention_kernel<V, LM><<<static_cast<unsigned>((jobs + SH.jpb - 1) / SH.jpb), 32 * SH.bw, 0, s>>>(qkv, att, B, T, H, W, heads,
+                                                                                                                 axis);
     };
     auto by_len = [&](auto vpl) {
       if (L <= 4) launch(vpl, std::integral_constant<int, 4>{});

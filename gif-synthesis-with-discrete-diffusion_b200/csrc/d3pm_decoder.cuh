@@ -660,10 +660,15 @@ __global__ void embed_rows_kernel(const int64_t* __restrict__ tokens, const floa
 // every vector.  Per query the LMAX partial dot products of a lane are reduced over the warp by a transposing butterfly
 // (at every level a lane keeps half of its values and hands the other half to its partner: LMAX - 1 shuffles instead of
 // 5 LMAX), after which lane l holds the complete score of key l >> (5 - log2 LMAX); the softmax then runs across lanes.
-// warps per block: as many as fit the 48 KiB of static shared memory, at most 4
-__host__ __device__ constexpr int attn_warps(int vpl, int lmax) {
-  const int per_warp = 2 * lmax * 32 * vpl * 4;
-  return per_warp * 4 <= 49152 ? 4 : (per_warp * 2 <= 49152 ? 2 : 1);
+// Several warps share a job (four queries each), so that a job's Q / K / V tile (24 KiB at 16 positions x 128 channels) serves
+// four warps: 36 warps per SM instead of 8, and the load burst of one job overlaps the arithmetic of the others.
+struct AttnShape {
+  int wj, bw, jpb;  // warps per job, warps per block, jobs per block
+};
+__host__ __device__ constexpr AttnShape attn_shape(int lmax) {
+  const int wj = lmax >= 8 ? lmax / 4 : 1;
+  const int bw = wj > 4 ? wj : 4;
+  return AttnShape{wj, bw, bw / wj};
 }
 
 template <int N>
@@ -681,23 +686,25 @@ __device__ __forceinline__ void transpose_reduce(float (&s)[N], int lane, int o)
 }
 
 template <int VPL, int LMAX>
-__global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
-                                                                                     int T, int H, int W, int heads, int axis) {
+__global__ void __launch_bounds__(32 * attn_shape(LMAX).bw) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
+                                                                                   int T, int H, int W, int heads, int axis) {
   constexpr int DH = 32 * VPL;
-  constexpr int kAttnWarps = attn_warps(VPL, LMAX);
+  constexpr AttnShape SH = attn_shape(LMAX);
+  constexpr int QPW = LMAX / SH.wj;  // queries (and rows to load) per warp
   constexpr int LOG = LMAX == 32 ? 5 : (LMAX == 16 ? 4 : (LMAX == 8 ? 3 : 2));
   constexpr int REP = 32 / LMAX;  // lanes that end up holding the same key's score
   static_assert(LMAX == 4 || LMAX == 8 || LMAX == 16 || LMAX == 32, "LMAX must be 4, 8, 16 or 32");
-  __shared__ __align__(16) float kv_smem[kAttnWarps][2][LMAX][DH];
+  __shared__ __align__(16) float kv_smem[SH.jpb][3][LMAX][DH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jl = warp / SH.wj, wj = warp % SH.wj;  // job of this warp inside the block, and its part of the job
   // axis 0: along W (attn_w, axial_dim -2), 1: along H, 2: along T
   const int L = axis == 0 ? W : (axis == 1 ? H : T);
   const long long M = static_cast<long long>(B) * T * H * W;
   const long long nseq = M / L;
-  const long long job = static_cast<long long>(blockIdx.x) * kAttnWarps + warp;
-  if (job >= nseq * heads) return;
-  const long long seq = job / heads;
-  const int head = static_cast<int>(job - seq * heads);
+  const long long job = static_cast<long long>(blockIdx.x) * SH.jpb + jl;
+  const bool have = job < nseq * heads;
+  const long long seq = have ? job / heads : 0;
+  const int head = have ? static_cast<int>(job - seq * heads) : 0;
   long long row0, rstride;
   const long long HW = static_cast<long long>(H) * W;
   if (axis == 0) row0 = seq * W, rstride = 1;
@@ -705,8 +712,9 @@ __global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_ke
   else row0 = (seq / HW) * (T * HW) + seq % HW, rstride = HW;
   const int C = heads * DH;
   const int ldq = 9 * C;  // floats per row of qkv
-  float (*ks)[DH] = kv_smem[warp][0];
-  float (*vs)[DH] = kv_smem[warp][1];
+  float (*ks)[DH] = kv_smem[jl][0];
+  float (*vs)[DH] = kv_smem[jl][1];
+  float (*qs)[DH] = kv_smem[jl][2];
   const float* qbase = qkv + static_cast<size_t>(axis) * 3 * C + head * DH + lane * VPL;
   auto load_vec = [](const float* src, float (&dst)[VPL]) {
     if constexpr (VPL == 4) {
@@ -719,29 +727,30 @@ __global__ void __launch_bounds__(32 * attn_warps(VPL, LMAX)) axial_attention_ke
       dst[0] = __ldg(src);
     }
   };
+  // this warp's rows of the job's Q / K / V tile (rows past the sequence are zero)
 #pragma unroll
-  for (int j = 0; j < LMAX; ++j) {
-    float kk[VPL], vv[VPL];
+  for (int jj = 0; jj < QPW; ++jj) {
+    const int j = wj * QPW + jj;
+    float qq[VPL], kk[VPL], vv[VPL];
 #pragma unroll
-    for (int e = 0; e < VPL; ++e) kk[e] = 0.f, vv[e] = 0.f;
-    if (j < L) {
+    for (int e = 0; e < VPL; ++e) qq[e] = 0.f, kk[e] = 0.f, vv[e] = 0.f;
+    if (have && j < L) {
       const float* rowp = qbase + (row0 + j * rstride) * ldq;
+      load_vec(rowp, qq);
       load_vec(rowp + C, kk);
       load_vec(rowp + 2 * C, vv);
     }
 #pragma unroll
-    for (int e = 0; e < VPL; ++e) ks[j][lane * VPL + e] = kk[e], vs[j][lane * VPL + e] = vv[e];
+    for (int e = 0; e < VPL; ++e) qs[j][lane * VPL + e] = qq[e], ks[j][lane * VPL + e] = kk[e], vs[j][lane * VPL + e] = vv[e];
   }
-  __syncwarp();
+  __syncthreads();
+  if (!have) return;
   const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // scores in log2 units
   const int myj = lane >> (5 - LOG);  // the key whose score this lane holds after the reduction
-  float qn[VPL];
-  load_vec(qbase + row0 * ldq, qn);
-  for (int i = 0; i < L; ++i) {
+  for (int i = wj * QPW; i < (wj + 1) * QPW && i < L; ++i) {
     float qv[VPL];
 #pragma unroll
-    for (int e = 0; e < VPL; ++e) qv[e] = qn[e];
-    if (i + 1 < L) load_vec(qbase + (row0 + (i + 1) * rstride) * ldq, qn);
+    for (int e = 0; e < VPL; ++e) qv[e] = qs[i][lane * VPL + e];
     float s[LMAX];
 #pragma unroll
     for (int j = 0; j < LMAX; ++j) {
