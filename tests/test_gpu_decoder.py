@@ -243,3 +243,27 @@ def test_dec_conv_writes_nothing_outside_its_rows_and_columns(name, pair):
     assert got.data_ptr() == buf.data_ptr()
     assert torch.equal(buf[:M, :spec.nout], plain)
     assert bool((buf[M:] == 777.0).all()) and bool((buf[:M, spec.nout:] == 777.0).all())
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_dec_conv_random_shapes(seed):
+    """Randomised shapes against the float64 emulation of the contract: odd grids, arbitrary tap sets, every stride / parity-class
+    combination, padded N tiles, bias / affine / ReLU / residual in all mixes, both tile widths, single CTAs and pairs."""
+    import random
+    rnd = random.Random(1000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    B, grid = rnd.randint(1, 3), tuple(rnd.randint(1, 7) for _ in range(3))
+    cin, nout = rnd.choice([32, 64, 96]), 4 * rnd.randint(1, 75)
+    stride = tuple(rnd.choice([1, 2]) for _ in range(3))
+    classes = [(a, b, c) for a in range(stride[0]) for b in range(stride[1]) for c in range(stride[2])]
+    ntaps = rnd.randint(1, 6)
+    taps = [[tuple(rnd.randint(-2, 2) for _ in range(3)) for _ in range(ntaps)] for _ in classes]
+    spec = _spec(g, nclass=len(classes), nout=nout, cin=cin, taps=taps, classes=classes, stride=stride, bias=rnd.random() < 0.5,
+                 affine=rnd.random() < 0.5, relu=rnd.random() < 0.5)
+    M = B * grid[0] * grid[1] * grid[2]
+    x = torch.randn(M, cin, generator=g)
+    res = torch.randn(M * stride[0] * stride[1] * stride[2], nout, generator=g) if rnd.random() < 0.5 else None
+    want = emulate_conv(spec, x, B, grid, residual=res)
+    layer = decode._Layer(spec, torch.device(DEV), rnd.choice([128, 256]), cta_pair=rnd.random() < 0.5)
+    got = layer(x.to(DEV), B, grid, terms=3, residual=None if res is None else res.to(DEV)).cpu()
+    assert (got - want).abs().max().item() <= TOL_FP32 * max(1.0, float(want.abs().max()))
