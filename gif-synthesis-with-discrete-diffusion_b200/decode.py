@@ -184,7 +184,8 @@ def decoder_plan(decoder: torch.nn.Module) -> dict:
 
 
 class _Layer:
-    """A `LayerSpec` bound to a device: the weight image and the static part of the launch descriptor."""
+    """A `LayerSpec` bound to a device: the weight image and the static part of the launch descriptor.  (The descriptor is
+    reused between calls: one `NativeDecoder` serves one stream / thread at a time, like an `nn.Module` with buffers.)"""
 
     def __init__(self, spec: LayerSpec, dev, n_tile: Optional[int] = None, cta_pair: bool = False):
         nclass, nout, ktot = spec.wmat.shape
