@@ -191,7 +191,7 @@ def load_library() -> ctypes.CDLL:
     lib.d3pm_dec_embed_rows.restype = c_int
     lib.d3pm_dec_embed_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
     lib.d3pm_dec_axial_attention.restype = c_int
-    lib.d3pm_dec_axial_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.d3pm_dec_axial_attention.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]
     lib.d3pm_dec_col2im.restype = c_int
     lib.d3pm_dec_col2im.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]

@@ -125,7 +125,8 @@ int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int
   return check_launch("dec_embed_rows");
 }
 
-int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, int W, int heads, int head_dim, d3pm_stream_t stream) {
+int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, int W, int heads, int head_dim, float softmax_scale,
+                             d3pm_stream_t stream) {
   namespace D = d3pm::dec;
   if (qkv == nullptr || att == nullptr || B <= 0 || T <= 0 || H <= 0 || W <= 0 || heads <= 0)
     return fail(D3PM_ERR_INVALID, "dec_axial_attention: bad arguments");
@@ -142,7 +143,7 @@ int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, 
       constexpr int V = decltype(vpl)::value, LM = decltype(lmax)::value;
       constexpr D::AttnShape SH = D::attn_shape(LM);
       D::axial_attention_kernel<V, LM><<<static_cast<unsigned>((jobs + SH.jpb - 1) / SH.jpb), 32 * SH.bw, 0, s>>>(qkv, att, B, T, H, W, heads,
-                                                                                                                 axis);
+                                                                                                                 axis, softmax_scale);
     };
     auto by_len = [&](auto vpl) {
       if (L <= 4) launch(vpl, std::integral_constant<int, 4>{});

@@ -687,7 +687,7 @@ __device__ __forceinline__ void transpose_reduce(float (&s)[N], int lane, int o)
 
 template <int VPL, int LMAX>
 __global__ void __launch_bounds__(32 * attn_shape(LMAX).bw) axial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int B,
-                                                                                   int T, int H, int W, int heads, int axis) {
+                                                                                   int T, int H, int W, int heads, int axis, float softmax_scale) {
   constexpr int DH = 32 * VPL;
   constexpr AttnShape SH = attn_shape(LMAX);
   constexpr int QPW = LMAX / SH.wj;  // queries (and rows to load) per warp
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(32 * attn_shape(LMAX).bw) axial_attention_kern
   }
   __syncthreads();
   if (!have) return;
-  const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // scores in log2 units
+  const float scale = (softmax_scale > 0.f ? softmax_scale : rsqrtf(static_cast<float>(DH))) * 1.4426950408889634f;  // scores in log2 units
   const int myj = lane >> (5 - LOG);  // the key whose score this lane holds after the reduction
   for (int i = wj * QPW; i < (wj + 1) * QPW && i < L; ++i) {
     float qv[VPL];

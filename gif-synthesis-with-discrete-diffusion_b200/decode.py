@@ -131,11 +131,35 @@ def decoder_plan(decoder: torch.nn.Module) -> dict:
     blocks = list(decoder.res_stack)
     bn_final, res_blocks = blocks[-2], blocks[:-2]
     C = bn_final.num_features
-    if C % 64 != 0 or (C // 2) not in (32, 64, 128):
-        raise D3PMError(f"n_hiddens={C}: the native decoder is built for n_hiddens in (64, 128, 256) (two heads of 32 / 64 / 128)")
+    if C % 2 != 0 or C > 256:
+        raise D3PMError(f"n_hiddens={C}: the native decoder covers even n_hiddens up to 256 (two heads of up to 128 channels)")
+    # The kernels work on multiples of 32 channels with heads of 32 / 64 / 128: every channel vector is ZERO-PADDED to
+    # Cp = C rounded up to 64 (the half-width tensors and the two attention heads to Cp / 2).  Padded weights, biases and
+    # BatchNorm affines are zero, so padded channels stay exactly zero through every layer and never reach a real one.
+    Cp = (C + 63) // 64 * 64
+    if Cp // 2 not in (32, 64, 128):
+        Cp = 256 if Cp > 128 else 128   # (192 -> 256: heads of 96 become 128)
+    Ch, Chp = C // 2, Cp // 2
+
+    def pad(t, dim, n):
+        if t.shape[dim] == n:
+            return t
+        shape = list(t.shape)
+        shape[dim] = n - t.shape[dim]
+        return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim)
+
+    def pad_heads(t, dim):   # a C-vector that is [2 heads][C / 2] -> [2][Cp / 2]
+        shape = list(t.shape)
+        t = t.reshape(shape[:dim] + [2, Ch] + shape[dim + 1:])
+        t = pad(t, dim + 1, Chp)
+        return t.reshape(shape[:dim] + [Cp] + shape[dim + 1:])
+
+    def pad_affine(aff, n):
+        return tuple(pad(a, 0, n) for a in aff)
+
     one = [(0, 0, 0)]
     conv3_taps = [(kt - 1, kh - 1, kw - 1) for kt in range(3) for kh in range(3) for kw in range(3)]
-    plan = {"C": C, "heads": 2, "blocks": [], "convts": []}
+    plan = {"C": Cp, "C_model": C, "heads": 2, "softmax_scale": float(Ch) ** -0.5, "blocks": [], "convts": []}
     with torch.no_grad():
         for rb in res_blocks:
             bn1, _, conv3, bn2, _, conv1, bn3, _, axial = list(rb.block)
@@ -144,40 +168,47 @@ def decoder_plan(decoder: torch.nn.Module) -> dict:
                 raise D3PMError("AttentionResidualBlock: expected a bias-free 3x3x3 and a bias-free 1x1x1 convolution (:124-131)")
             s2, b2 = _bn_affine(bn2)
             s3, b3 = _bn_affine(bn3)
-            m3 = (w3 * s2.view(-1, 1, 1, 1, 1)).permute(0, 2, 3, 4, 1).reshape(1, w3.shape[0], -1)   # [n][tap][cin]
-            m1 = (w1 * s3.view(-1, 1, 1, 1, 1)).reshape(1, w1.shape[0], -1)
-            L3 = LayerSpec(m3, cin=C, taps=[conv3_taps], classes=[(0, 0, 0)], bias=b2, in_affine=_bn_affine(bn1), relu_out=True)
-            L1 = LayerSpec(m1, cin=C // 2, taps=[one], classes=[(0, 0, 0)], bias=b3, relu_out=True)
-            if axial.attn_w.n_head != 2 or axial.attn_w.d_k != C // 2:
+            w3 = pad(pad(w3 * s2.view(-1, 1, 1, 1, 1), 0, Chp), 1, Cp)
+            w1 = pad(pad(w1 * s3.view(-1, 1, 1, 1, 1), 0, Cp), 1, Chp)
+            m3 = w3.permute(0, 2, 3, 4, 1).reshape(1, Chp, -1)   # [n][tap][cin]
+            m1 = w1.reshape(1, Cp, -1)
+            L3 = LayerSpec(m3, cin=Cp, taps=[conv3_taps], classes=[(0, 0, 0)], bias=pad(b2, 0, Chp), in_affine=pad_affine(_bn_affine(bn1), Cp),
+                           relu_out=True)
+            L1 = LayerSpec(m1, cin=Chp, taps=[one], classes=[(0, 0, 0)], bias=pad(b3, 0, Cp), relu_out=True)
+            if axial.attn_w.n_head != 2 or axial.attn_w.d_k != Ch:
                 raise D3PMError("AxialBlock: expected two heads of n_hiddens / 2 channels (:103-111)")
             att = (axial.attn_w, axial.attn_h, axial.attn_t)  # axes W, H, T = the kernel's axis 0, 1, 2
-            wqkv = torch.cat([torch.cat([a.w_qs.weight, a.w_ks.weight, a.w_vs.weight], 0) for a in att], 0).detach()
-            Lq = LayerSpec(wqkv.unsqueeze(0), cin=C, taps=[one], classes=[(0, 0, 0)])
-            wfc = torch.cat([a.fc.weight for a in att], 1).detach()
-            bfc = sum(a.fc.bias.detach().double() for a in att)
-            Lf = LayerSpec(wfc.unsqueeze(0), cin=3 * C, taps=[one], classes=[(0, 0, 0)], bias=bfc)
+            wqkv = torch.cat([torch.cat([pad(pad_heads(w.weight.detach(), 0), 1, Cp) for w in (a.w_qs, a.w_ks, a.w_vs)], 0) for a in att], 0)
+            Lq = LayerSpec(wqkv.unsqueeze(0), cin=Cp, taps=[one], classes=[(0, 0, 0)])
+            wfc = torch.cat([pad(pad_heads(a.fc.weight.detach(), 1), 0, Cp) for a in att], 1)
+            bfc = pad(sum(a.fc.bias.detach().double() for a in att), 0, Cp)
+            Lf = LayerSpec(wfc.unsqueeze(0), cin=3 * Cp, taps=[one], classes=[(0, 0, 0)], bias=bfc)
             plan["blocks"].append((L3, L1, Lq, Lf))
-        in_aff = _bn_affine(bn_final)
+        in_aff = pad_affine(_bn_affine(bn_final), Cp)
         n = len(decoder.convts)
         for i, ct in enumerate(decoder.convts):
             w = ct.convt.weight.detach()   # [Cin, Cout, 4, 4, 4]
             stride = tuple(int(v) for v in ct.convt.stride)
-            if tuple(w.shape[2:]) != (4, 4, 4) or tuple(ct.convt.padding) != (3, 3, 3):
-                raise D3PMError("SamePadConvTranspose3d: expected kernel 4 and padding 3 (:330-332)")
+            if tuple(w.shape[2:]) != (4, 4, 4) or tuple(ct.convt.padding) != (3, 3, 3) or w.shape[0] != C:
+                raise D3PMError("SamePadConvTranspose3d: expected n_hiddens input channels, kernel 4 and padding 3 (:330-332)")
             bias = ct.convt.bias.detach() if ct.convt.bias is not None else torch.zeros(w.shape[1], device=w.device)
+            w = pad(w, 0, Cp)
             if i < n - 1:
+                if w.shape[1] != C:
+                    raise D3PMError("SamePadConvTranspose3d: an inner layer is expected to keep n_hiddens channels (:271-275)")
+                w, bias = pad(w, 1, Cp), pad(bias, 0, Cp)
                 classes = _convt_taps(stride)
-                mats = [torch.stack([w[:, :, kt, kh, kw].t() for (kt, kh, kw), _ in taps], 1).reshape(w.shape[1], -1)
+                mats = [torch.stack([w[:, :, kt, kh, kw].t() for (kt, kh, kw), _ in taps], 1).reshape(Cp, -1)
                         for _, taps in classes]   # [Cout][tap][Cin]
-                spec = LayerSpec(torch.stack(mats, 0), cin=w.shape[0], taps=[[d for _, d in taps] for _, taps in classes],
+                spec = LayerSpec(torch.stack(mats, 0), cin=Cp, taps=[[d for _, d in taps] for _, taps in classes],
                                  classes=[c for c, _ in classes], stride=stride, bias=bias, in_affine=in_aff, relu_out=True)
                 plan["convts"].append(("conv", spec, stride))
             else:
                 cout = w.shape[1]
                 if cout > 4:
                     raise D3PMError(f"last transposed convolution has {cout} output channels; col2im is built for <= 4 (RGB)")
-                m = w.permute(2, 3, 4, 1, 0).reshape(1, 64 * cout, w.shape[0])   # [(kt, kh, kw, co)][cin]
-                spec = LayerSpec(m, cin=w.shape[0], taps=[one], classes=[(0, 0, 0)], in_affine=in_aff)
+                m = w.permute(2, 3, 4, 1, 0).reshape(1, 64 * cout, Cp)   # [(kt, kh, kw, co)][cin]
+                spec = LayerSpec(m, cin=Cp, taps=[one], classes=[(0, 0, 0)], in_affine=in_aff)
                 plan["convts"].append(("col2im", spec, stride, bias.float().contiguous(), cout))
             in_aff = None  # later layers read an already activated tensor (the ReLU sits in the previous epilogue)
     return plan
@@ -260,7 +291,8 @@ class NativeDecoder:
         dev = next(decoder.parameters()).device
         if dev.type != "cuda":
             raise D3PMError("d3pm_b200 operates on CUDA tensors only (there is no CPU path)")
-        self.C, self.heads, self.device = plan["C"], plan["heads"], dev
+        self.C, self.C_model, self.heads, self.device = plan["C"], plan["C_model"], plan["heads"], dev
+        self.softmax_scale = plan["softmax_scale"]
         with torch.cuda.device(dev):
             self.blocks = [tuple(_Layer(sp, dev, n_tile, cta_pair) for sp in blk) for blk in plan["blocks"]]
             self.convts = []
@@ -291,6 +323,8 @@ class NativeDecoder:
         T, H, W = (int(v) for v in grid)
         if max(T, H, W) > 32:
             raise D3PMError(f"latent grid {T}x{H}x{W}: the axial attention kernel covers axes of up to 32 positions")
+        if x.shape[1] == self.C_model and self.C_model != self.C:   # zero channels up to the width the kernels work on
+            x = torch.nn.functional.pad(x, (0, self.C - self.C_model))
         per_pass = self.videos_per_pass((T, H, W))
         if B > per_pass:
             n = T * H * W
@@ -304,7 +338,7 @@ class NativeDecoder:
             qkv = Lq(y, B, (T, H, W), terms=self.terms)
             att = torch.empty(M, 3 * self.C, dtype=torch.float32, device=dev)
             _lib.check(lib.d3pm_dec_axial_attention(qkv.data_ptr(), att.data_ptr(), B, T, H, W, self.heads, self.C // self.heads,
-                                                    ops._stream(dev)), "d3pm_dec_axial_attention")
+                                                    self.softmax_scale, ops._stream(dev)), "d3pm_dec_axial_attention")
             x = Lf(att, B, (T, H, W), terms=self.terms, residual=x)
         grid = (T, H, W)
         for item in self.convts:
@@ -324,10 +358,10 @@ class NativeDecoder:
     def __call__(self, h: torch.Tensor) -> torch.Tensor:
         """Drop-in for `Decoder.forward(h)`: `h` is the reference's channels-first `[B, C, T, H, W]` tensor."""
         ops._need_cuda(h)
-        if h.dim() != 5 or h.shape[1] != self.C:
-            raise D3PMError(f"expected [B, {self.C}, T, H, W], got {tuple(h.shape)}")
+        if h.dim() != 5 or h.shape[1] != self.C_model:
+            raise D3PMError(f"expected [B, {self.C_model}, T, H, W], got {tuple(h.shape)}")
         B, _, T, H, W = h.shape
-        rows = h.detach().float().permute(0, 2, 3, 4, 1).reshape(B * T * H * W, self.C).contiguous()
+        rows = h.detach().float().permute(0, 2, 3, 4, 1).reshape(B * T * H * W, self.C_model).contiguous()
         return self.forward_rows(rows, B, (T, H, W))
 
 

@@ -330,9 +330,10 @@ int d3pm_dec_embed_rows(const int64_t* tokens, const float* lut, float* out, int
 
 /* AxialBlock's three attentions (videogpt_vq_vae.py:100-118; AxialAttention / scaled_dot_product_attention,
  * model_utils.py:318-336, :586-600) on qkv [M][3 axes (W, H, T)][q, k, v][heads][head_dim] -> att [M][3 axes][heads][head_dim];
- * softmax(q k^T / sqrt(head_dim)) v along one grid axis, fp32.  head_dim in {32, 64, 128}, T, H, W <= 32.             */
+ * softmax(softmax_scale * q k^T) v along one grid axis, fp32; softmax_scale <= 0 means 1 / sqrt(head_dim) (a caller whose
+ * heads are zero-padded up to head_dim passes 1 / sqrt(true width)).  head_dim in {32, 64, 128}, T, H, W <= 32.        */
 int d3pm_dec_axial_attention(const float* qkv, float* att, int B, int T, int H, int W, int heads, int head_dim,
-                             d3pm_stream_t stream);
+                             float softmax_scale, d3pm_stream_t stream);
 
 /* Last SamePadConvTranspose3d (kernel 4, stride (st, sh, sw) in {1, 2}, Cout <= 4): y_t [B*T][64 * Cout][H*W] holds the per-tap
  * contributions (row ((kt*4 + kh)*4 + kw) * Cout + c of plane (b, t), column = (h, w); from d3pm_dec_conv with one tap,

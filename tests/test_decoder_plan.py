@@ -44,15 +44,16 @@ def emulate_conv(spec, x, B, grid, residual=None):
     return out.float()
 
 
-def emulate_attention(qkv, B, grid, heads, C):
+def emulate_attention(qkv, B, grid, heads, C, scale=None):
     """d3pm_dec_axial_attention: qkv [M][3 axes (W, H, T)][q, k, v][heads][dh] -> att [M][3 axes][heads][dh]."""
     T, H, W = grid
     dh = C // heads
+    scale = dh ** -0.5 if scale is None else scale
     z = qkv.double().view(B, T, H, W, 3, 3, heads, dh)
     outs = []
     for axis, dim in ((0, 3), (1, 2), (2, 1)):
         q, k, v = (z[..., axis, j, :, :].movedim(dim, -2) for j in range(3))   # [..., heads, L, dh]
-        p = torch.softmax(q @ k.transpose(-1, -2) / dh ** 0.5, dim=-1)
+        p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
         outs.append((p @ v).movedim(-2, dim))                                  # [B, T, H, W, heads, dh]
     return torch.stack(outs, 4).reshape(B * T * H * W, 3 * C).float()
 
@@ -83,11 +84,12 @@ def emulate_col2im(y, bias, B, grid, cout, stride):
 
 
 def run_plan(plan, h):
-    B, C, T, H, W = h.shape
-    x = h.permute(0, 2, 3, 4, 1).reshape(-1, C).contiguous()
+    B, Cm, T, H, W = h.shape
+    C = plan["C"]   # the width the kernels work on: the model's channels zero-padded
+    x = torch.nn.functional.pad(h.permute(0, 2, 3, 4, 1).reshape(-1, Cm), (0, C - Cm)).contiguous()
     for L3, L1, Lq, Lf in plan["blocks"]:
         y = emulate_conv(L1, emulate_conv(L3, x, B, (T, H, W)), B, (T, H, W))
-        att = emulate_attention(emulate_conv(Lq, y, B, (T, H, W)), B, (T, H, W), plan["heads"], C)
+        att = emulate_attention(emulate_conv(Lq, y, B, (T, H, W)), B, (T, H, W), plan["heads"], C, plan["softmax_scale"])
         x = emulate_conv(Lf, att, B, (T, H, W), residual=x)
     grid = (T, H, W)
     for item in plan["convts"]:
@@ -99,7 +101,7 @@ def run_plan(plan, h):
 
 
 @pytest.mark.skipif(not RL.reference_available(), reason="the plan is read off the reference's Decoder module")
-@pytest.mark.parametrize("name", ["decode_h64", "decode_h128"])
+@pytest.mark.parametrize("name", ["decode_h64", "decode_h128", "decode_small", "decode_k512"])   # the last two: n_hiddens 24, padded to 64
 def test_plan_through_the_kernel_contracts_reproduces_the_reference_video(name):
     fx = np.load(os.path.join(GOLD, name + ".npz"))
     E, K, Hd, R, d0, d1, d2, L, res, B = (int(v) for v in fx["hparams"])

@@ -96,7 +96,7 @@ def test_axial_attention(B, grid, C):
     want = emulate_attention(qkv, B, grid, 2, C)
     att = torch.empty(M, 3 * C, device=DEV)
     lib = _lib.load_library()
-    _lib.check(lib.d3pm_dec_axial_attention(qkv.to(DEV).data_ptr(), att.data_ptr(), B, *grid, 2, C // 2, 0), "d3pm_dec_axial_attention")
+    _lib.check(lib.d3pm_dec_axial_attention(qkv.to(DEV).data_ptr(), att.data_ptr(), B, *grid, 2, C // 2, 0.0, 0), "d3pm_dec_axial_attention")
     torch.cuda.synchronize()
     assert (att.cpu() - want).abs().max().item() <= 2e-5 * float(want.abs().max())
 
@@ -125,7 +125,7 @@ def _vqvae_from_fixture(fx):
     return vq.to(DEV).eval()
 
 
-@pytest.mark.parametrize("name", ["decode_h64", "decode_h128"])
+@pytest.mark.parametrize("name", ["decode_h64", "decode_h128", "decode_small", "decode_k512"])   # the last two: n_hiddens 24, padded to 64
 def test_native_decoder_against_reference_fixture(name):
     """tokens -> video entirely on the library's kernels, against the video the imported reference's `VQVAE.decode` returned."""
     if not RL.reference_available():
