@@ -267,3 +267,29 @@ def test_dec_conv_random_shapes(seed):
     layer = decode._Layer(spec, torch.device(DEV), rnd.choice([128, 256]), cta_pair=rnd.random() < 0.5)
     got = layer(x.to(DEV), B, grid, terms=3, residual=None if res is None else res.to(DEV)).cpu()
     assert (got - want).abs().max().item() <= TOL_FP32 * max(1.0, float(want.abs().max()))
+
+
+def test_decoder_kernels_on_a_non_current_device():
+    """The decoder entry points make the device that owns the tensors current for the call, like the rest of the C ABI (cluster
+    launches and the SM count of the persistent grid included)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    other = torch.device("cuda", 1)
+    torch.cuda.set_device(0)
+    B, grid, kw, _, n_tile = CONV_CASES["conv3_affine"]
+    g = torch.Generator().manual_seed(2)
+    spec = _spec(g, **kw)
+    x = torch.randn(B * grid[0] * grid[1] * grid[2], spec.cin, generator=g)
+    want = decode._Layer(spec, torch.device(DEV), n_tile)(x.to(DEV), B, grid, terms=3).cpu()
+    for pair in (False, True):
+        got = decode._Layer(spec, other, n_tile, cta_pair=pair)(x.to(other), B, grid, terms=3)
+        assert got.device == other and torch.cuda.current_device() == 0
+        assert torch.equal(got.cpu(), want)
+    qkv = torch.randn(2 * 4 * 4 * 4, 9 * 64, generator=g)
+    outs = []
+    for dev in (torch.device(DEV), other):
+        att = torch.empty(qkv.shape[0], 3 * 64, device=dev)
+        _lib.check(_lib.load_library().d3pm_dec_axial_attention(qkv.to(dev).data_ptr(), att.data_ptr(), 2, 4, 4, 4, 2, 32, 0.0,
+                                                                torch.cuda.current_stream(dev).cuda_stream), "d3pm_dec_axial_attention")
+        outs.append(att.cpu())
+    assert torch.equal(outs[0], outs[1])
