@@ -293,3 +293,30 @@ def test_decoder_kernels_on_a_non_current_device():
                                                                 torch.cuda.current_stream(dev).cuda_stream), "d3pm_dec_axial_attention")
         outs.append(att.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_native_decode_can_be_captured_in_a_cuda_graph():
+    """Serving loops replay a captured graph: the whole native decode (gather, 3xTF32 GEMMs with cluster launches off and on,
+    attention, col2im) records into a CUDA graph and replays to the eager result on new tokens."""
+    if not RL.reference_available():
+        pytest.skip("reference not staged (baseline/_ref absent)")
+    fx = np.load(os.path.join(GOLD, "decode_h64.npz"))
+    vq = _vqvae_from_fixture(fx)
+    table = decode.DecodeTable.from_autoencoder(vq)
+    K = int(fx["hparams"][1])
+    for pair in (False, True):
+        dec = decode.NativeDecoder(vq.decoder, cta_pair=pair)
+        static_tokens = torch.from_numpy(fx["tokens"]).to(DEV)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            decode.decode(vq, static_tokens, table, dec)   # warm-up outside the capture (lazy function attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = decode.decode(vq, static_tokens, table, dec)
+        new_tokens = torch.randint(0, K, static_tokens.shape, device=DEV)
+        static_tokens.copy_(new_tokens)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_out, decode.decode(vq, new_tokens, table, dec))
