@@ -218,11 +218,12 @@ class _Layer:
     """A `LayerSpec` bound to a device: the weight image and the static part of the launch descriptor.  (The descriptor is
     reused between calls: one `NativeDecoder` serves one stream / thread at a time, like an `nn.Module` with buffers.)"""
 
-    def __init__(self, spec: LayerSpec, dev, n_tile: Optional[int] = None, cta_pair: bool = False):
+    def __init__(self, spec: LayerSpec, dev, n_tile: Optional[int] = None, cta_pair: Optional[bool] = False):
         nclass, nout, ktot = spec.wmat.shape
         self.cin, self.nout, self.nclass, self.ntaps, self.stride = spec.cin, nout, nclass, len(spec.taps[0]), spec.stride
         self.n_tile = n_tile if n_tile is not None else (128 if nout <= 128 else 256)
-        self.cta_pair = bool(cta_pair)
+        self.cta_pair = cta_pair if cta_pair is None else bool(cta_pair)   # None: decided per call from the number of tiles
+        self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
         npad = (nout + self.n_tile - 1) // self.n_tile * self.n_tile
         lib = _lib.load_library()
         self.image = torch.empty(lib.d3pm_dec_image_floats(nclass, nout, ktot, self.n_tile), dtype=torch.float32, device=dev)
@@ -268,7 +269,14 @@ class _Layer:
         d.ntaps, d.nclass, d.Nout, d.out_transposed = self.ntaps, self.nclass, self.nout, int(transposed)
         d.ldo = out.shape[-1] if transposed else out.stride(0)
         d.stride_t, d.stride_h, d.stride_w = self.stride
-        d.relu_out, d.terms, d.n_tile, d.cta_pair = int(self.relu_out), terms, self.n_tile, int(self.cta_pair)
+        pair = self.cta_pair
+        if pair is None:
+            # pairs of CTAs (cta_group::2) pay off when every pair still gets at least two 256-position tiles: the transposed
+            # convolutions, the qkv product; the 3x3x3 convolution of a small batch keeps single CTAs (more tiles than SMs matter more)
+            npad = (self.nout + self.n_tile - 1) // self.n_tile
+            pair_tiles = ((B * T * H * W + 255) // 256) * npad * self.nclass
+            pair = pair_tiles >= 2 * (self.sms // 2)
+        d.relu_out, d.terms, d.n_tile, d.cta_pair = int(self.relu_out), terms, self.n_tile, int(pair)
         d.stream = ops._stream(x.device)
         _lib.check(_lib.load_library().d3pm_dec_conv(ctypes.byref(d)), "d3pm_dec_conv")
         return out
@@ -281,9 +289,11 @@ class NativeDecoder:
     on a GPU with TF32 disabled); `"tf32"`: single TF32 products, the accuracy class of the reference's default GPU path
     (cuDNN convolutions run TF32 unless `torch.backends.cudnn.allow_tf32 = False`), about three times less tensor work.
     Rebuild the object when the module's weights or BatchNorm statistics change (they are folded at construction).
+    `cta_pair`: run the products on pairs of CTAs (tcgen05 cta_group::2) - None (default) decides per layer and batch, True /
+    False force it; the results do not depend on it.
     """
 
-    def __init__(self, decoder: torch.nn.Module, precision: str = "fp32", n_tile: Optional[int] = None, cta_pair: bool = False):
+    def __init__(self, decoder: torch.nn.Module, precision: str = "fp32", n_tile: Optional[int] = None, cta_pair: Optional[bool] = None):
         if precision not in ("fp32", "tf32"):
             raise D3PMError("precision must be 'fp32' (3xTF32) or 'tf32'")
         self.terms = 3 if precision == "fp32" else 1

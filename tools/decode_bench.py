@@ -49,7 +49,7 @@ def decoder_flops(B, grid, C, n_res, strides):
     return total
 
 
-def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None, cta_pair=False):
+def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None, cta_pair=None):
     import torch
     from baseline import reference_loader as RL
     from d3pm_b200 import decode
@@ -144,6 +144,7 @@ if __name__ == "__main__":
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--n-tile", type=int, default=None, help="force the GEMM tile width (128 / 256) of every layer")
-    ap.add_argument("--pairs", action="store_true", help="run every GEMM on pairs of CTAs (cta_group::2)")
+    ap.add_argument("--pairs", choices=["auto", "on", "off"], default="auto",
+                    help="pairs of CTAs (cta_group::2) for the GEMMs: per layer (default), everywhere, nowhere")
     a = ap.parse_args()
-    run(videos=a.videos, reps=a.reps, layers=a.layers, n_tile=a.n_tile, cta_pair=a.pairs)
+    run(videos=a.videos, reps=a.reps, layers=a.layers, n_tile=a.n_tile, cta_pair={"auto": None, "on": True, "off": False}[a.pairs])
