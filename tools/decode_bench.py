@@ -53,7 +53,6 @@ def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None,
     import torch
     from baseline import reference_loader as RL
     from d3pm_b200 import decode
-    from oracle import decoder_oracle as DO
 
     if not RL.reference_available():
         return {"skipped": "reference not staged on this box (baseline/_ref absent)"}
@@ -70,7 +69,8 @@ def run(videos=16, dev="cuda:0", reps=5, layers=False, quiet=False, n_tile=None,
     grid = (4, 16, 16)
     tokens = torch.randint(0, 4096, (videos, *grid), device=dev)
     table = decode.DecodeTable.from_autoencoder(vq)
-    flops = decoder_flops(videos, grid, C, R, DO.upsample_strides(ds))
+    strides = [tuple(int(c.convt.stride[i]) for i in range(3)) for c in vq.decoder.convts]
+    flops = decoder_flops(videos, grid, C, R, strides)
     res = {"what": f"VQVAE.decode of {videos} videos: tokens [{videos}, 4, 16, 16] -> video [{videos}, 3, 4, 128, 128]; n_hiddens 256, 3 attention "
                    f"residual blocks, 3 transposed convolutions (stride 1,2,2), fp32 weights, one B200", "useful_GFLOP": flops / 1e9}
 
